@@ -1,0 +1,161 @@
+/* libtokred_sm100a.so — C ABI of the B200 token-reduction operators.
+ *
+ * The reference (JoakimHaurum/TokenReduction) has no FFI layer: its reduction operators are Python
+ * functions/modules calling ATen.  Each entry point below replaces the ATen call sequence of the cited
+ * reference lines (paths relative to the reference root) with one hand-written sm_100a kernel launch.
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions (all entry points)
+ *   - every pointer is a DEVICE pointer to a contiguous row-major tensor allocated by the caller;
+ *     the library never allocates, never synchronises, never copies to the host: it only enqueues
+ *     kernels on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - floating tensors carry a dtype tag: TOKRED_F32 or TOKRED_BF16.  Index tensors are int64 (torch.long),
+ *     masks are uint8 (torch.bool).
+ *   - return value: 0 = enqueued; <0 = argument/shape violation detected on the host before any launch
+ *     (TOKRED_ERR_*); >0 = cudaError_t reported by the launch.  tokred_last_error() returns a thread-local
+ *     human-readable message for the last non-zero return on the calling thread.
+ *   - re-entrant and thread-safe; no global mutable state besides per-kernel shared-memory opt-in attributes.
+ *   - ordering ties are always broken toward the LOWEST index (ATen max/min/argmin semantics, stable sort).
+ *   - tokens 0..N-1 with CLS = 0; P = N-1 patches; "patch index" p = token-1.
+ */
+#ifndef TOKRED_H_
+#define TOKRED_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOKRED_ABI_VERSION 1
+#define TOKRED_API __attribute__((visibility("default")))
+
+enum { TOKRED_F32 = 0, TOKRED_BF16 = 1 };
+enum { TOKRED_OK = 0, TOKRED_ERR_ARGUMENT = -1, TOKRED_ERR_UNSUPPORTED = -2 };
+
+TOKRED_API int tokred_abi_version(void);
+TOKRED_API const char* tokred_last_error(void);
+/* Number of kernel launches enqueued by this library in the calling process (for bench.py's gpu_launches). */
+TOKRED_API uint64_t tokred_launch_count(void);
+
+/* ---- a1 Top-K / a11 DynamicViT keep -----------------------------------------------------------------
+ * models/topk.py:55-65 (cls_attn mean + torch.topk) and :89-93 (gather + cat);
+ * models/dyvit.py:231-236 + :340-356 (argsort(score)[:k], batch_index_select).
+ *   x        [B,N,C]  x_dtype
+ *   scores   [B,P] fp32 or bf16 with element stride `score_stride` between consecutive patches and
+ *            `score_batch_stride` between images (DynamicViT passes pred_score[:,:,0], stride 2); or NULL
+ *   attn     [B,H,N,N] attn_dtype, used only when scores == NULL: s_p = (sum_h attn[b,h,0,1+p]) * (1/H)
+ *   x_out    [B,k+1,C] x_dtype : row 0 = CLS, row 1+j = x[1+idx[j]]
+ *   idx_out  [B,k] int64, patch indices in descending score order                                      */
+TOKRED_API int tokred_topk_gather(const void* x, int x_dtype, const void* scores, int score_dtype, int64_t score_stride,
+                       int64_t score_batch_stride, const void* attn, int attn_dtype, int H, int B, int N, int C,
+                       int k, void* x_out, int64_t* idx_out, void* stream);
+
+/* ---- a2 EViT -----------------------------------------------------------------------------------------
+ * models/evit.py:77-87 (top-k), :25-46 (complement_idx), :111-123 (gather, inattentive-token fusion, idx -1).
+ *   x_out     [B,k+2,C]: CLS, kept tokens (descending score), fused token sum_{p in compl} s_p * x[1+p]
+ *   idx_out   [B,k+1] int64 (last column = -1)
+ *   compl_out [B,P-k] int64 ascending                                                                  */
+TOKRED_API int tokred_evit_select_fuse(const void* x, int x_dtype, const void* scores, int score_dtype, const void* attn,
+                            int attn_dtype, int H, int B, int N, int C, int k, void* x_out, int64_t* idx_out,
+                            int64_t* compl_out, void* stream);
+
+/* ---- a3 ToMe matching --------------------------------------------------------------------------------
+ * models/tome.py:230-277 bipartite_soft_matching (cosine similarity of even vs odd tokens, per-row argmax,
+ * descending edge order, CLS protected).  r is clamped to (N - protected)/2 like :252-253; the caller sizes
+ * the outputs with tokred_tome_effective_r().
+ *   metric [B,N,D] metric_dtype (= k.mean(1), models/tome.py:58)
+ *   score_lowp: 0 = fp32 similarity; 1 = operands and similarity rounded to bf16 (what CUDA autocast does)
+ *   unm_idx [B,a-r] (ascending when class_token), src_idx [B,r], dst_idx [B,r] int64; a = ceil(N/2)      */
+TOKRED_API int tokred_tome_effective_r(int N, int r, int class_token);
+TOKRED_API int tokred_tome_match(const void* metric, int metric_dtype, int B, int N, int D, int r, int class_token,
+                      int score_lowp, int64_t* unm_idx, int64_t* src_idx, int64_t* dst_idx, void* stream);
+
+/* ---- a4/a5 ToMe merge --------------------------------------------------------------------------------
+ * models/tome.py:279-289 (merge closure), :309-323 (merge_wavg), :326-337 + Block_ToMe :91-99 (source map).
+ *   x [B,N,C], size [B,N] (same dtype as x) or NULL (= ones)
+ *   x_out [B,N-r,C] = [unmerged even tokens ; odd tokens + merged sources] size-weighted mean
+ *   size_out [B,N-r]; reduced_cluster_idx [B,N-1] fp32 or NULL (output row of every input patch, minus 1)
+ * Sources are accumulated in src-list order (the CPU scatter_add order): deterministic, no atomics.      */
+TOKRED_API int tokred_tome_merge(const void* x, int x_dtype, const void* size, const int64_t* unm_idx,
+                      const int64_t* src_idx, const int64_t* dst_idx, int B, int N, int C, int r, void* x_out,
+                      void* size_out, float* reduced_cluster_idx, void* stream);
+
+/* ---- pairwise distances (building block of a6 / a8, exported for parity checks) ------------------------
+ * torch.cdist(x, x) as called at models/dpcknn.py:59 and models/kmedoids.py:68, times post_scale:
+ * matmul expansion sqrt(max(|xi|^2+|xj|^2-2xi.xj, 1e-30)) for P > 25, direct differences otherwise.
+ *   x [B,P,C] fp32 -> out [B,P,P] fp32 (bit-symmetric)                                                  */
+TOKRED_API int tokred_pairwise_dist(const float* x, int B, int P, int C, float post_scale, float* out, void* stream);
+
+/* ---- a6 DPC-KNN clustering ---------------------------------------------------------------------------
+ * models/dpcknn.py:44-100 cluster_dpc_knn (token_mask=None).
+ *   x [B,P,C] fp32; noise_u [B,P] fp32 ~ U(0,1) drawn by the caller with the reference's torch.rand call
+ *   idx_cluster [B,P] int64, index_down [B,K] int64 (descending centre score)                           */
+TOKRED_API int tokred_dpcknn_cluster(const float* x, const float* noise_u, int B, int P, int C, int K, int knn,
+                          int64_t* idx_cluster, int64_t* index_down, void* stream);
+
+/* ---- a7 DPC-KNN merge --------------------------------------------------------------------------------
+ * models/dpcknn.py:103-140 merge_tokens.  token_weight [B,P] fp32 or NULL (= ones); idx_token [B,T] int64;
+ * agg_weight [B,T] fp32 -> x_merged [B,K,C], idx_token_new [B,T], agg_weight_new [B,T].                 */
+TOKRED_API int tokred_dpcknn_merge(const float* x, const int64_t* idx_token, const float* agg_weight,
+                        const int64_t* idx_cluster, const float* token_weight, int B, int P, int C, int K, int T,
+                        float* x_merged, int64_t* idx_token_new, float* agg_weight_new, void* stream);
+
+/* ---- a8 K-Medoids ------------------------------------------------------------------------------------
+ * models/kmedoids.py:240 token weights: out[b,p] = sum_h sum_q attn[b,h,q,num_tokens+p]                 */
+TOKRED_API int tokred_attn_colsum(const void* attn, int attn_dtype, int B, int H, int N, int num_tokens, float* out,
+                       void* stream);
+/* models/kmedoids.py:62-85 k_medoids_fit with token weights (topk init, iters x {assign, re-centre}).
+ *   x [B,P,C] fp32, token_weight [B,P] fp32 -> centres [B,K,C], cluster_idx [B,K] int64, assignment [B,P] int64 */
+TOKRED_API int tokred_kmedoids_fit(const float* x, const float* token_weight, int B, int P, int C, int K, int iters,
+                        float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream);
+
+/* ---- a9 Sinkhorn -------------------------------------------------------------------------------------
+ * models/sinkhorn.py:66-86 with :25-56.  v_hat [K,C] fp32 is the already-normalised parameter.
+ *   log_norm = -log(K+P) evaluated by the caller the way the reference does (:44-47; in bf16 under autocast)
+ *   lowp = 1: both contractions round operands/result to bf16 (CUDA autocast); out dtype given by out_dtype.
+ *   out [B,K,C], weights [B,K,P] fp32                                                                   */
+TOKRED_API int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_hat, int B, int P, int C, int K, float eps,
+                          float log_norm, int iters, int lowp, void* out, int out_dtype, float* weights,
+                          void* stream);
+
+/* ---- a12 PatchMerger ---------------------------------------------------------------------------------
+ * models/patchmerger.py:35-39: LayerNorm -> queries x^T * scale -> softmax over tokens -> attn x.       */
+TOKRED_API int tokred_patchmerger(const void* x, int x_dtype, const float* ln_weight, const float* ln_bias,
+                       const float* queries, int B, int P, int C, int K, float scale, float ln_eps, int lowp,
+                       void* out, int out_dtype, float* attn, void* stream);
+
+/* ---- a13 SiT -----------------------------------------------------------------------------------------
+ * models/sit.py:37-40: w = softmax(logits * scale, over tokens)^T ; out = w x.  logits [B,P,K];
+ * scale = device pointer to the module's 1-element fp32 parameter (no host read).                       */
+TOKRED_API int tokred_sit_merge(const void* x, int x_dtype, const void* logits, int logits_dtype, const float* scale, int B,
+                     int P, int C, int K, int lowp, void* out, int out_dtype, float* weights, void* stream);
+
+/* ---- a10 ATS -----------------------------------------------------------------------------------------
+ * models/ats.py:52-82: significance score, inverse-CDF sampling, per-image sorted unique ids.
+ *   v [B,H,N,Dh] v_dtype with element strides (v_stride_b, v_stride_h, v_stride_n, 1) — the qkv view of
+ *   :112-113 is consumed in place; attn [B,H,N,N] fp32, mask [B,N] uint8, steps [n_steps] fp32 (= sample_steps, :48)
+ *   ids_out  [B,n_steps+1] int64: 0, sorted unique sampled tokens, 0-padding
+ *   mask_out [B,n_steps+1] uint8: 1, ids != 0
+ *   max_count [1] int32: max_b #unique (caller zeroes it before the call; device atomicMax)             */
+TOKRED_API int tokred_ats_sample(const void* v, int v_dtype, int64_t v_stride_b, int64_t v_stride_h, int64_t v_stride_n,
+                      const float* attn, const uint8_t* mask, const float* steps, int B, int H, int N, int Dh,
+                      int n_steps, float eps, int64_t* ids_out, uint8_t* mask_out, int32_t* max_count, void* stream);
+
+/* models/ats.py:27-41,84-87 (attention rows) and :156-157 (residual tokens): out[b,g,m,:] = src[b,g,ids[b,m],:]
+ *   src [B,G,N,W] dtype, ids [B,ids_stride] int64 (first M used) -> out [B,G,M,W]                         */
+TOKRED_API int tokred_gather_rows(const void* src, int dtype, const int64_t* ids, int64_t ids_stride, int B, int G, int N,
+                       int W, int M, void* out, void* stream);
+
+/* ---- a11 DynamicViT predictor pooling ----------------------------------------------------------------
+ * models/dyvit.py:114-118: out = [h[:,:,:C/2] | (sum_p h[:,p,C/2:]*policy[p]) / sum_p policy[p] + eps].
+ *   h [B,P,C] h_dtype (bf16 under autocast), policy [B,P] fp32 -> out [B,P,C] out_dtype (fp32 under autocast:
+ *   the reference's cat promotes)                                                                       */
+TOKRED_API int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float* policy, int B, int P, int C, float eps,
+                             void* out, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOKRED_H_ */

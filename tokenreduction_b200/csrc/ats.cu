@@ -1,0 +1,151 @@
+// ATS: adaptive token sampling (inverse-CDF sampling of the CLS-attention significance score).
+// Reference: models/ats.py:44-89.
+//
+// One CTA per image replaces 37 ATen launches plus one torch.unique (a host sync) PER IMAGE: value norms and
+// the significance score are reduced in shared memory, the CDF is a sequential fp32 scan (the order the CPU
+// reference uses), every sampling step does an exact argmin over the <= 196 CDF entries with ATen's cdist
+// arithmetic, and the per-image sorted unique ids come from a flag + count compaction — no sort, no sync.
+// The batch-wide padded width max_b #unique is produced with one atomicMax so the caller needs at most ONE
+// scalar read (exact-shape mode) or none (static mode, width = sample_count).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace tokred {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+template <typename TV>
+__global__ void __launch_bounds__(kThreads)
+ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long long vs_n,
+                  const float* __restrict__ attn, const uint8_t* __restrict__ mask, const float* __restrict__ steps,
+                  int H, int N, int Dh, int n_steps, float eps, int use_mm, int64_t* __restrict__ ids_out,
+                  uint8_t* __restrict__ mask_out, int32_t* __restrict__ max_count) {
+  extern __shared__ float smem[];
+  const int P = N - 1, b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* hp = smem;                                   // [H][P] cls_attn * ||v||
+  float* cdf = hp + H * P;                            // [P]
+  float* red = cdf + P;                               // [kWarps]
+  int* hit = reinterpret_cast<int*>(red + kWarps);    // [N]
+  int* count_s = hit + N;                             // [1]
+
+  // significance per (head, patch): one warp per pair, lanes along the head dimension (coalesced)
+  const float* ab = attn + (long long)b * H * N * N;
+  for (int e = warp; e < H * P; e += kWarps) {
+    const int h = e / P, p = e % P;
+    const TV* row = v + (long long)b * vs_b + (long long)h * vs_h + (long long)(1 + p) * vs_n;
+    float s = 0.f;
+    for (int d = lane; d < Dh; d += 32) { float x = to_f32(row[d]); s = fmaf(x, x, s); }
+    s = warp_sum(s);
+    if (lane == 0) hp[e] = ab[((long long)h * N) * N + 1 + p] * sqrtf(s);
+  }
+  for (int t = tid; t < N; t += kThreads) hit[t] = 0;
+  __syncthreads();
+  // sum over heads (in head order), then the normaliser
+  float part = 0.f;
+  for (int p = tid; p < P; p += kThreads) {
+    float s = 0.f;
+    for (int h = 0; h < H; ++h) s += hp[h * P + p];
+    cdf[p] = s;
+    part += s;
+  }
+  part = warp_sum(part);
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    float total = 0.f;
+    for (int w = 0; w < kWarps; ++w) total += red[w];
+    const float denom = total + eps;
+    float run = 0.f;
+    for (int p = 0; p < P; ++p) {            // sequential inclusive scan of the normalised score
+      run += cdf[p] / denom;
+      cdf[p] = run;
+    }
+  }
+  __syncthreads();
+  for (int p = tid; p < P; p += kThreads)
+    if (!mask[(long long)b * N + 1 + p]) cdf[p] += 0.1f;
+  __syncthreads();
+
+  // inverse-CDF sampling: nearest CDF entry to every step (lowest index on ties)
+  for (int q = tid; q < n_steps; q += kThreads) {
+    const float t = steps[q];
+    const float m2t = -2.0f * t, tt = __fmul_rn(t, t);
+    float best = CUDART_INF_F;
+    int bp = 0;
+    for (int p = 0; p < P; ++p) {
+      const float c = cdf[p];
+      float d;
+      if (use_mm) {
+        // ATen cdist matmul expansion on 1-d points: ((-2t)*c + t^2) + c^2, clamp, sqrt
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(m2t, c), tt), __fmul_rn(c, c));
+        d = sqrtf(fmaxf(d2, 1e-30f));
+      } else {
+        d = fabsf(t - c);
+      }
+      if (d < best) { best = d; bp = p; }
+    }
+    hit[1 + bp] = 1;
+  }
+  __syncthreads();
+
+  // sorted unique ids by compaction
+  const int W = n_steps + 1;
+  int64_t* ids_b = ids_out + (long long)b * W;
+  uint8_t* m_b = mask_out + (long long)b * W;
+  if (tid == 0) {
+    int c = 0;
+    for (int t = 1; t < N; ++t) c += hit[t];
+    *count_s = c;
+    atomicMax(max_count, c);
+    ids_b[0] = 0;
+    m_b[0] = 1;
+  }
+  for (int t = 1 + tid; t < N; t += kThreads) {
+    if (hit[t]) {
+      int pos = 0;
+      for (int q = 1; q < t; ++q) pos += hit[q];
+      ids_b[1 + pos] = t;
+      m_b[1 + pos] = 1;
+    }
+  }
+  __syncthreads();
+  const int cnt = *count_s;
+  for (int j = 1 + cnt + tid; j < W; j += kThreads) { ids_b[j] = 0; m_b[j] = 0; }
+}
+
+}  // namespace
+}  // namespace tokred
+
+using namespace tokred;
+
+extern "C" int tokred_ats_sample(const void* v, int v_dtype, int64_t v_stride_b, int64_t v_stride_h,
+                                 int64_t v_stride_n, const float* attn, const uint8_t* mask, const float* steps, int B,
+                                 int H, int N, int Dh, int n_steps, float eps, int64_t* ids_out, uint8_t* mask_out,
+                                 int32_t* max_count, void* stream) {
+  const char* what = "tokred_ats_sample";
+  TOKRED_REQUIRE(v && attn && mask && steps && ids_out && mask_out && max_count, "%s: null tensor", what);
+  TOKRED_REQUIRE(valid_float_dtype(v_dtype), "%s: bad v dtype %d", what, v_dtype);
+  TOKRED_REQUIRE(B >= 0 && H >= 1 && N >= 2 && Dh >= 1, "%s: bad shape B=%d H=%d N=%d Dh=%d", what, B, H, N, Dh);
+  TOKRED_REQUIRE(n_steps >= 1 && n_steps <= N - 1, "%s: n_steps=%d outside [1, %d] (a step can only select one of the "
+                 "N-1 patches)", what, n_steps, N - 1);
+  if (B == 0) return TOKRED_OK;
+  const int P = N - 1;
+  const size_t smem = ((size_t)H * P + P + kWarps + N + 1) * 4;
+  const int use_mm = (n_steps > 25 || P > 25) ? 1 : 0;     // ATen: matmul expansion when either side has > 25 points
+  cudaStream_t st = (cudaStream_t)stream;
+  if (v_dtype == TOKRED_F32) {
+    if (int e = allow_smem(ats_sample_kernel<float>, smem, what)) return e;
+    ats_sample_kernel<float><<<B, kThreads, smem, st>>>((const float*)v, v_stride_b, v_stride_h, v_stride_n, attn, mask,
+                                                        steps, H, N, Dh, n_steps, eps, use_mm, ids_out, mask_out,
+                                                        max_count);
+  } else {
+    if (int e = allow_smem(ats_sample_kernel<__nv_bfloat16>, smem, what)) return e;
+    ats_sample_kernel<__nv_bfloat16><<<B, kThreads, smem, st>>>((const __nv_bfloat16*)v, v_stride_b, v_stride_h,
+                                                                v_stride_n, attn, mask, steps, H, N, Dh, n_steps, eps,
+                                                                use_mm, ids_out, mask_out, max_count);
+  }
+  return finish_launch(what);
+}

@@ -1,0 +1,143 @@
+// Shared host/device helpers for libtokred_sm100a.so (sm_100a only; no torch headers, C ABI in include/tokred.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tokred.h"
+
+namespace tokred {
+
+// ---------------------------------------------------------------------------------------- host side
+void set_error(const char* fmt, ...);   // thread-local message returned by tokred_last_error()
+void count_launch(int n);               // feeds tokred_launch_count()
+
+#define TOKRED_REQUIRE(cond, ...)                         \
+  do {                                                    \
+    if (!(cond)) {                                        \
+      ::tokred::set_error(__VA_ARGS__);                   \
+      return TOKRED_ERR_ARGUMENT;                         \
+    }                                                     \
+  } while (0)
+
+// Called after every launch: enqueue-only API, so only launch-configuration errors surface here.
+inline int finish_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  count_launch(1);
+  return TOKRED_OK;
+}
+
+// Opt a kernel in to > 48 KB dynamic shared memory (cheap; the driver caches the attribute).
+template <typename K>
+inline int allow_smem(K kernel, size_t bytes, const char* what) {
+  if (bytes > 227 * 1024) {
+    set_error("%s: needs %zu B of shared memory per CTA (> 227 KB)", what, bytes);
+    return TOKRED_ERR_UNSUPPORTED;
+  }
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      set_error("%s: cudaFuncSetAttribute(%zu): %s", what, bytes, cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  return TOKRED_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int dtype_size(int dt) { return dt == TOKRED_BF16 ? 2 : 4; }
+inline bool valid_float_dtype(int dt) { return dt == TOKRED_F32 || dt == TOKRED_BF16; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+constexpr int kNumSMs = 148;   // B200
+
+// ---------------------------------------------------------------------------------------- device side
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+// round-trip through T: identity for fp32, round-to-nearest-even for bf16 (emulates elementwise bf16 arithmetic)
+template <typename T> __device__ __forceinline__ float round_as(float v) { return to_f32(from_f32<T>(v)); }
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// 16-byte streaming copies: rows are read once and written once, keep them out of L1.
+__device__ __forceinline__ int4 ld_stream16(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream16(void* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// One warp copies `bytes` (multiple of 16, both pointers 16-B aligned) with up to 4 requests in flight per lane.
+__device__ __forceinline__ void warp_copy_row16(void* dst, const void* src, int bytes, int lane) {
+  const char* s = reinterpret_cast<const char*>(src);
+  char* d = reinterpret_cast<char*>(dst);
+  int off = lane * 16;
+  for (; off + 3 * 512 < bytes; off += 4 * 512) {
+    int4 a = ld_stream16(s + off), b = ld_stream16(s + off + 512), c = ld_stream16(s + off + 1024),
+         e = ld_stream16(s + off + 1536);
+    st_stream16(d + off, a); st_stream16(d + off + 512, b); st_stream16(d + off + 1024, c);
+    st_stream16(d + off + 1536, e);
+  }
+  for (; off < bytes; off += 512) st_stream16(d + off, ld_stream16(s + off));
+}
+// Generic fallback (any alignment / size), element type T.
+template <typename T>
+__device__ __forceinline__ void warp_copy_row_elems(T* dst, const T* src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// (value, index) arg-reductions with lowest-index tie-break (ATen max/min semantics).
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+__device__ __forceinline__ void warp_argmin(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
+// Descending rank of element i among n keys held in shared memory: number of keys that sort before it under
+// (value desc, index asc).  O(n) broadcast reads per caller; n <= a few hundred tokens on this path, so the
+// whole ordering is O(n^2) conflict-free LDS with no barriers — cheaper than a bitonic network at this size.
+__device__ __forceinline__ int rank_desc(const float* keys, int n, int i) {
+  const float ki = keys[i];
+  int r = 0;
+  for (int j = 0; j < n; ++j) {
+    float kj = keys[j];
+    r += (kj > ki) || (kj == ki && j < i);
+  }
+  return r;
+}
+
+#endif  // __CUDACC__
+}  // namespace tokred

@@ -1,0 +1,324 @@
+// Score-ordered token selection kernels: Top-K / DynamicViT keep, EViT select+fuse, row gather, DynamicViT pooling.
+//
+// All of them are HBM-bound byte movers (0 flop/byte): one CTA-row per image orders <= a few hundred scores in
+// shared memory (rank-by-counting, lowest-index ties) and then streams token rows with 16-byte no-allocate
+// loads/stores, one warp per row.  grid = (splits, B): the ordering is recomputed by every split (196^2 LDS
+// compares, ~1 us) so that small batches still fill 148 SMs without a second launch or a cluster barrier.
+#include "common.cuh"
+
+namespace tokred {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct ScoreSrc {
+  const void* scores;      // [B,P] strided, or nullptr
+  int score_dtype;
+  long long stride, batch_stride;
+  const void* attn;        // [B,H,N,N], used when scores == nullptr
+  int attn_dtype;
+  int H;
+};
+
+__device__ __forceinline__ float load_any(const void* p, int dtype, long long i) {
+  return dtype == TOKRED_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+                              : reinterpret_cast<const float*>(p)[i];
+}
+
+// s_p for image b.  From attention: head-mean of the CLS row (models/topk.py:60-61); ATen's CUDA mean is
+// sum * (1/H) accumulated in fp32 and rounded to the tensor dtype.
+__device__ __forceinline__ float fetch_score(const ScoreSrc& s, int b, int p, int N) {
+  if (s.scores) return load_any(s.scores, s.score_dtype, (long long)b * s.batch_stride + (long long)p * s.stride);
+  float acc = 0.f;
+  for (int h = 0; h < s.H; ++h)
+    acc += load_any(s.attn, s.attn_dtype, ((long long)(b * s.H + h) * N) * N + 1 + p);
+  acc *= (1.0f / (float)s.H);
+  return s.attn_dtype == TOKRED_BF16 ? bf16_round(acc) : acc;
+}
+
+__device__ __forceinline__ void copy_row(char* dst, const char* src, int row_bytes, int vec16, int elem_size, int lane) {
+  if (vec16) {
+    warp_copy_row16(dst, src, row_bytes, lane);
+  } else if (elem_size == 4) {
+    warp_copy_row_elems(reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(src), row_bytes / 4, lane);
+  } else {
+    warp_copy_row_elems(reinterpret_cast<uint16_t*>(dst), reinterpret_cast<const uint16_t*>(src), row_bytes / 2, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ Top-K
+__global__ void __launch_bounds__(kThreads)
+topk_gather_kernel(ScoreSrc ss, const char* __restrict__ x, char* __restrict__ x_out, int64_t* __restrict__ idx_out,
+                   int N, int k, int row_bytes, int vec16, int elem_size) {
+  extern __shared__ float smem[];
+  const int P = N - 1, b = blockIdx.y, tid = threadIdx.x;
+  float* keys = smem;
+  int* sel = reinterpret_cast<int*>(keys + P);
+
+  for (int p = tid; p < P; p += kThreads) keys[p] = fetch_score(ss, b, p, N);
+  __syncthreads();
+  for (int p = tid; p < P; p += kThreads) {
+    int r = rank_desc(keys, P, p);
+    if (r < k) {
+      sel[r] = p;
+      if (blockIdx.x == 0) idx_out[(long long)b * k + r] = p;
+    }
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const char* xb = x + (long long)b * N * row_bytes;
+  char* ob = x_out + (long long)b * (k + 1) * row_bytes;
+  for (int j = blockIdx.x * kWarps + warp; j < k + 1; j += gridDim.x * kWarps) {
+    int src_row = j == 0 ? 0 : 1 + sel[j - 1];
+    copy_row(ob + (long long)j * row_bytes, xb + (long long)src_row * row_bytes, row_bytes, vec16, elem_size, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ EViT
+// grid.x = number of 512-byte column slices of a token row.  Split s gathers kept rows s*8+w, ... and owns
+// slice s of the fused token: warp w accumulates complement rows w, w+8, ... (ascending patch order), the 8
+// partials are combined in warp order through shared memory -> deterministic.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_out, int64_t* __restrict__ idx_out,
+                        int64_t* __restrict__ compl_out, int N, int C, int k, int vec16) {
+  extern __shared__ float smem[];
+  constexpr int VE = 16 / sizeof(T);            // elements per 16-byte lane chunk
+  constexpr int SLICE = 32 * VE;                // elements per 512-byte slice
+  const int P = N - 1, M = P - k, b = blockIdx.y, tid = threadIdx.x;
+  float* keys = smem;                                   // [P]
+  int* sel = reinterpret_cast<int*>(keys + P);          // [k]
+  int* cmp = sel + k;                                   // [M]
+  unsigned char* dropped = reinterpret_cast<unsigned char*>(cmp + M);   // [P]
+  float* part = reinterpret_cast<float*>(smem) + P + k + M + (P + 3) / 4;   // [kWarps][SLICE]
+
+  for (int p = tid; p < P; p += kThreads) keys[p] = fetch_score(ss, b, p, N);
+  __syncthreads();
+  for (int p = tid; p < P; p += kThreads) {
+    int r = rank_desc(keys, P, p);
+    dropped[p] = r >= k;
+    if (r < k) {
+      sel[r] = p;
+      if (blockIdx.x == 0) idx_out[(long long)b * (k + 1) + r] = p;
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) idx_out[(long long)b * (k + 1) + k] = -1;
+  __syncthreads();
+  for (int p = tid; p < P; p += kThreads) {
+    if (dropped[p]) {
+      int pos = 0;
+      for (int q = 0; q < p; ++q) pos += dropped[q];
+      cmp[pos] = p;
+      if (blockIdx.x == 0) compl_out[(long long)b * M + pos] = p;
+    }
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int row_bytes = C * (int)sizeof(T);
+  const T* xb = x + (long long)b * N * C;
+  T* ob = x_out + (long long)b * (k + 2) * C;
+  // kept rows
+  for (int j = blockIdx.x * kWarps + warp; j < k + 1; j += gridDim.x * kWarps) {
+    int src_row = j == 0 ? 0 : 1 + sel[j - 1];
+    copy_row(reinterpret_cast<char*>(ob + (long long)j * C), reinterpret_cast<const char*>(xb + (long long)src_row * C),
+             row_bytes, vec16, (int)sizeof(T), lane);
+  }
+  // fused inattentive token, slice blockIdx.x
+  const int e0 = blockIdx.x * SLICE + lane * VE;
+  float acc[VE];
+#pragma unroll
+  for (int i = 0; i < VE; ++i) acc[i] = 0.f;
+  for (int m = warp; m < M; m += kWarps) {
+    const int p = cmp[m];
+    const float w = keys[p];
+    const T* row = xb + (long long)(1 + p) * C + e0;
+    if (vec16) {
+      if (e0 < C) {
+        int4 raw = ld_stream16(row);
+        const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int i = 0; i < VE; ++i) acc[i] = fmaf(w, to_f32(v[i]), acc[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < VE; ++i)
+        if (e0 + i < C) acc[i] = fmaf(w, to_f32(row[i]), acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VE; ++i) part[warp * SLICE + lane * VE + i] = acc[i];
+  __syncthreads();
+  for (int e = tid; e < SLICE; e += kThreads) {
+    if (blockIdx.x * SLICE + e < C) {
+      float s = part[e];
+#pragma unroll
+      for (int w = 1; w < kWarps; ++w) s += part[w * SLICE + e];
+      ob[(long long)(k + 1) * C + blockIdx.x * SLICE + e] = from_f32<T>(s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ row gather
+// out[b,g,m,:] = src[b,g,ids[b,m],:]; one warp per output row, grid-stride over rows.
+__global__ void __launch_bounds__(kThreads)
+gather_rows_kernel(const char* __restrict__ src, const int64_t* __restrict__ ids, long long ids_stride, int G, int N,
+                   int M, long long rows, int row_bytes, int vec16, int elem_size, char* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * kWarps + warp; row < rows; row += (long long)gridDim.x * kWarps) {
+    const int m = (int)(row % M);
+    const long long bg = row / M;
+    const int b = (int)(bg / G);
+    long long id = ids[(long long)b * ids_stride + m];
+    id = id < 0 ? 0 : (id >= N ? N - 1 : id);
+    copy_row(out + row * row_bytes, src + (bg * N + id) * row_bytes, row_bytes, vec16, elem_size, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ DynamicViT pooling
+// grid = (64-channel slices of the global half, B); 256 threads = 4 patch-phases x 64 channels.
+// Phase 1: masked mean over patches of this slice (lanes over channels -> coalesced; each phase sums its patches
+// in order, phases combined in fixed order -> deterministic).  Phase 2: write both halves of this slice.
+constexpr int kPoolSlice = 64;
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kThreads)
+dyvit_pool_concat_kernel(const TI* __restrict__ h, const float* __restrict__ policy, TO* __restrict__ out, int P, int C,
+                         float eps) {
+  extern __shared__ float smem[];
+  float* part = smem;                    // [4][kPoolSlice]
+  float* pol = smem + 4 * kPoolSlice;    // [P]
+  const int b = blockIdx.y, tid = threadIdx.x, half = C / 2;
+  const int c = tid % kPoolSlice, q = tid / kPoolSlice;
+  const int c0 = blockIdx.x * kPoolSlice;
+  const bool live = c0 + c < half;
+  const TI* hb = h + (long long)b * P * C;
+  for (int p = tid; p < P; p += kThreads) pol[p] = policy[(long long)b * P + p];
+  __syncthreads();
+  float psum = 0.f;
+  for (int p = 0; p < P; ++p) psum += pol[p];
+  float acc = 0.f;
+  if (live) {
+    const TI* col = hb + half + c0 + c;
+#pragma unroll 4
+    for (int p = q; p < P; p += 4) acc += to_f32(col[(long long)p * C]) * pol[p];
+  }
+  part[q * kPoolSlice + c] = acc;
+  __syncthreads();
+  const float g = ((part[c] + part[kPoolSlice + c]) + part[2 * kPoolSlice + c]) + part[3 * kPoolSlice + c];
+  const float gval = g / psum + eps;
+  if (live) {
+    TO* ob = out + (long long)b * P * C;
+    for (int p = q; p < P; p += 4) {
+      ob[(long long)p * C + c0 + c] = from_f32<TO>(to_f32(hb[(long long)p * C + c0 + c]));
+      ob[(long long)p * C + half + c0 + c] = from_f32<TO>(gval);
+    }
+  }
+}
+
+int check_scores(const void* scores, int score_dtype, const void* attn, int attn_dtype, int H, const char* what) {
+  TOKRED_REQUIRE(scores || attn, "%s: neither scores nor attn given", what);
+  if (scores) TOKRED_REQUIRE(valid_float_dtype(score_dtype), "%s: bad score dtype %d", what, score_dtype);
+  else TOKRED_REQUIRE(valid_float_dtype(attn_dtype) && H > 0, "%s: bad attn dtype %d / H %d", what, attn_dtype, H);
+  return TOKRED_OK;
+}
+
+}  // namespace
+}  // namespace tokred
+
+using namespace tokred;
+
+extern "C" int tokred_topk_gather(const void* x, int x_dtype, const void* scores, int score_dtype, int64_t score_stride,
+                                  int64_t score_batch_stride, const void* attn, int attn_dtype, int H, int B, int N,
+                                  int C, int k, void* x_out, int64_t* idx_out, void* stream) {
+  const char* what = "tokred_topk_gather";
+  TOKRED_REQUIRE(x && x_out && idx_out, "%s: null tensor", what);
+  TOKRED_REQUIRE(valid_float_dtype(x_dtype), "%s: bad x dtype %d", what, x_dtype);
+  TOKRED_REQUIRE(B >= 0 && N >= 2 && C >= 1, "%s: bad shape B=%d N=%d C=%d", what, B, N, C);
+  TOKRED_REQUIRE(k >= 1 && k <= N - 1, "%s: k=%d outside [1, %d]", what, k, N - 1);
+  TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
+  if (int e = check_scores(scores, score_dtype, attn, attn_dtype, H, what)) return e;
+  if (B == 0) return TOKRED_OK;
+  const int P = N - 1, row_bytes = C * dtype_size(x_dtype);
+  const int vec16 = (row_bytes % 16 == 0) && aligned16(x) && aligned16(x_out);
+  const size_t smem = (size_t)(P + k) * 4;
+  if (int e = allow_smem(topk_gather_kernel, smem, what)) return e;
+  int splits = ceil_div(4 * kNumSMs, B);
+  splits = max(1, min(splits, ceil_div(k + 1, kWarps)));
+  ScoreSrc ss{scores, score_dtype, score_stride, score_batch_stride, attn, attn_dtype, H};
+  topk_gather_kernel<<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
+      ss, (const char*)x, (char*)x_out, idx_out, N, k, row_bytes, vec16, dtype_size(x_dtype));
+  return finish_launch(what);
+}
+
+extern "C" int tokred_evit_select_fuse(const void* x, int x_dtype, const void* scores, int score_dtype,
+                                       const void* attn, int attn_dtype, int H, int B, int N, int C, int k,
+                                       void* x_out, int64_t* idx_out, int64_t* compl_out, void* stream) {
+  const char* what = "tokred_evit_select_fuse";
+  TOKRED_REQUIRE(x && x_out && idx_out && compl_out, "%s: null tensor", what);
+  TOKRED_REQUIRE(valid_float_dtype(x_dtype), "%s: bad x dtype %d", what, x_dtype);
+  TOKRED_REQUIRE(B >= 0 && N >= 2 && C >= 1, "%s: bad shape B=%d N=%d C=%d", what, B, N, C);
+  TOKRED_REQUIRE(k >= 1 && k <= N - 1, "%s: k=%d outside [1, %d]", what, k, N - 1);
+  TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
+  if (int e = check_scores(scores, score_dtype, attn, attn_dtype, H, what)) return e;
+  if (B == 0) return TOKRED_OK;
+  const int P = N - 1, esz = dtype_size(x_dtype), row_bytes = C * esz;
+  const int vec16 = (row_bytes % 16 == 0) && aligned16(x) && aligned16(x_out);
+  const int slice = 512 / esz;
+  const int splits = ceil_div(C, slice);
+  const size_t smem = (size_t)(P + k + (P - k) + (P + 3) / 4 + kWarps * slice) * 4;
+  ScoreSrc ss{scores, score_dtype, 1, P, attn, attn_dtype, H};
+  if (x_dtype == TOKRED_F32) {
+    if (int e = allow_smem(evit_select_fuse_kernel<float>, smem, what)) return e;
+    evit_select_fuse_kernel<float><<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
+        ss, (const float*)x, (float*)x_out, idx_out, compl_out, N, C, k, vec16);
+  } else {
+    if (int e = allow_smem(evit_select_fuse_kernel<__nv_bfloat16>, smem, what)) return e;
+    evit_select_fuse_kernel<__nv_bfloat16><<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
+        ss, (const __nv_bfloat16*)x, (__nv_bfloat16*)x_out, idx_out, compl_out, N, C, k, vec16);
+  }
+  return finish_launch(what);
+}
+
+extern "C" int tokred_gather_rows(const void* src, int dtype, const int64_t* ids, int64_t ids_stride, int B, int G,
+                                  int N, int W, int M, void* out, void* stream) {
+  const char* what = "tokred_gather_rows";
+  TOKRED_REQUIRE(src && ids && out, "%s: null tensor", what);
+  TOKRED_REQUIRE(valid_float_dtype(dtype), "%s: bad dtype %d", what, dtype);
+  TOKRED_REQUIRE(B >= 0 && G >= 1 && N >= 1 && W >= 1 && M >= 0 && ids_stride >= M, "%s: bad shape", what);
+  const long long rows = (long long)B * G * M;
+  if (rows == 0) return TOKRED_OK;
+  const int row_bytes = W * dtype_size(dtype);
+  const int vec16 = (row_bytes % 16 == 0) && aligned16(src) && aligned16(out);
+  long long blocks = (rows + kWarps - 1) / kWarps;
+  if (blocks > 32LL * kNumSMs) blocks = 32LL * kNumSMs;
+  gather_rows_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+      (const char*)src, ids, ids_stride, G, N, M, rows, row_bytes, vec16, dtype_size(dtype), (char*)out);
+  return finish_launch(what);
+}
+
+extern "C" int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float* policy, int B, int P, int C,
+                                        float eps, void* out, int out_dtype, void* stream) {
+  const char* what = "tokred_dyvit_pool_concat";
+  TOKRED_REQUIRE(h && policy && out, "%s: null tensor", what);
+  TOKRED_REQUIRE(valid_float_dtype(h_dtype) && valid_float_dtype(out_dtype), "%s: bad dtype", what);
+  TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 2 && C % 2 == 0, "%s: bad shape B=%d P=%d C=%d", what, B, P, C);
+  TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
+  if (B == 0) return TOKRED_OK;
+  const int splits = ceil_div(C / 2, kPoolSlice);
+  const size_t smem = (size_t)(4 * kPoolSlice + P) * 4;
+  dim3 grid(splits, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(TI, TO)                                                                                       \
+  do {                                                                                                       \
+    if (int e = allow_smem(dyvit_pool_concat_kernel<TI, TO>, smem, what)) return e;                          \
+    dyvit_pool_concat_kernel<TI, TO><<<grid, kThreads, smem, st>>>((const TI*)h, policy, (TO*)out, P, C, eps);       \
+  } while (0)
+  if (h_dtype == TOKRED_F32 && out_dtype == TOKRED_F32) LAUNCH(float, float);
+  else if (h_dtype == TOKRED_BF16 && out_dtype == TOKRED_F32) LAUNCH(__nv_bfloat16, float);
+  else if (h_dtype == TOKRED_BF16 && out_dtype == TOKRED_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else LAUNCH(float, __nv_bfloat16);
+#undef LAUNCH
+  return finish_launch(what);
+}

@@ -1,0 +1,322 @@
+// ToMe: bipartite soft matching (tome_match) and size-weighted merge with source map (tome_merge).
+// Reference: models/tome.py:230-337 and Block_ToMe.forward :78-104.
+//
+// tome_match   one CTA per image.  Rows are L2-normalised into shared memory (fp32, optionally rounded to bf16
+//              the way the autocast matmul rounds its operands), the even x odd similarity tile is computed
+//              with 4x4 register tiles, per-row (max, argmax) by one warp per row, and the edge ordering by
+//              rank-counting.  Emits the three int64 index lists the reference closure captures.
+// tome_merge   grid (splits, B), one warp per OUTPUT row, 16-byte streaming loads.  Destination rows add
+//              their sources in src-list order (the order CPU scatter_add applies them) with unfused
+//              multiply/add so that fp32 results are bit-identical to the reference on CPU; no atomics.
+//              Also writes size_out and the float "reduced_cluster_idx" map without the [B,N,N] identity the
+//              reference pushes through the merge (models/tome.py:91-99, ~35 % of its op time).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace tokred {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// ------------------------------------------------------------------------------------------ match
+template <typename TM>
+__global__ void __launch_bounds__(kThreads)
+tome_match_kernel(const TM* __restrict__ metric, int N, int D, int r, int class_token, int lowp,
+                  int64_t* __restrict__ unm_idx, int64_t* __restrict__ src_idx, int64_t* __restrict__ dst_idx) {
+  extern __shared__ float smem[];
+  const int na = (N + 1) / 2, nb = N / 2, DP = D + 1, SP = nb + 1;
+  float* A = smem;                        // [na][DP]  normalised even tokens
+  float* Bm = A + na * DP;                // [nb][DP]  normalised odd tokens
+  float* S = Bm + nb * DP;                // [na][SP]  similarity
+  float* node_max = S + na * SP;          // [na]
+  int* node_idx = reinterpret_cast<int*>(node_max + na);   // [na]
+  unsigned char* merged = reinterpret_cast<unsigned char*>(node_idx + na);   // [na]
+
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TM* mb = metric + (long long)b * N * D;
+
+  // 1. m / ||m||  (norm accumulated in fp32; true division like the reference)
+  for (int t = warp; t < N; t += kWarps) {
+    const TM* row = mb + (long long)t * D;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { float v = to_f32(row[d]); ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    float* dst = (t & 1) ? (Bm + (t >> 1) * DP) : (A + (t >> 1) * DP);
+    for (int d = lane; d < D; d += 32) {
+      float v = to_f32(row[d]) / nrm;
+      dst[d] = lowp ? bf16_round(v) : v;
+    }
+  }
+  __syncthreads();
+
+  // 2. S = A Bm^T with 4x4 register tiles; rows/cols of a tile are strided (ti + TA*a, tj + TB*b) so that the
+  //    lanes of a warp read consecutive Bm rows (stride DP = D+1 floats -> conflict-free).
+  const int TA = (na + 3) / 4, TB = (nb + 3) / 4;
+  for (int t = tid; t < TA * TB; t += kThreads) {
+    const int ti = t / TB, tj = t % TB;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+    const float* ap[4];
+    const float* bp[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ap[a] = A + min(ti + TA * a, na - 1) * DP;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) bp[c] = Bm + min(tj + TB * c, nb - 1) * DP;
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = ap[a][d];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bv[c] = bp[c][d];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], bv[c], acc[a][c]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = ti + TA * a;
+      if (i >= na) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = tj + TB * c;
+        if (j < nb) S[i * SP + j] = lowp ? bf16_round(acc[a][c]) : acc[a][c];
+      }
+    }
+  }
+  __syncthreads();
+
+  // 3. per-row (max, argmax), lowest column on ties; CLS row (0) is protected with -inf.
+  for (int i = warp; i < na; i += kWarps) {
+    float best = -CUDART_INF_F;
+    int bj = 0x7fffffff;
+    if (!(class_token && i == 0)) {
+      for (int j = lane; j < nb; j += 32) {
+        float v = S[i * SP + j];
+        if (v > best || bj == 0x7fffffff) { best = v; bj = j; }
+      }
+    }
+    warp_argmax(best, bj);
+    if (lane == 0) { node_max[i] = best; node_idx[i] = (bj == 0x7fffffff) ? 0 : bj; }
+  }
+  __syncthreads();
+
+  // 4. edge order: descending node_max (ties -> lower row); first r rows are merged away.
+  const int n_unm = na - r;
+  for (int i = tid; i < na; i += kThreads) {
+    const int rk = rank_desc(node_max, na, i);
+    merged[i] = rk < r;
+    if (rk < r) {
+      src_idx[(long long)b * r + rk] = i;
+      dst_idx[(long long)b * r + rk] = node_idx[i];
+    } else if (!class_token) {
+      unm_idx[(long long)b * n_unm + (rk - r)] = i;
+    }
+  }
+  if (class_token) {
+    __syncthreads();
+    for (int i = tid; i < na; i += kThreads) {
+      if (!merged[i]) {
+        int pos = 0;
+        for (int q = 0; q < i; ++q) pos += !merged[q];
+        unm_idx[(long long)b * n_unm + pos] = i;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ merge
+template <typename T> struct Chunk;            // one 16-byte lane chunk
+template <> struct Chunk<float> { static constexpr int VE = 4; };
+template <> struct Chunk<__nv_bfloat16> { static constexpr int VE = 8; };
+
+// acc (rounded like T arithmetic) = x*z, acc += x*z ... with UNFUSED multiply/add (the reference materialises
+// x*size before scatter_add).
+template <typename T>
+__device__ __forceinline__ float mul_as(float x, float z) { return round_as<T>(__fmul_rn(x, z)); }
+template <typename T>
+__device__ __forceinline__ float add_as(float a, float b) { return round_as<T>(__fadd_rn(a, b)); }
+
+template <typename T, bool VEC>
+__device__ __forceinline__ void merge_row(const T* __restrict__ xb, T* __restrict__ orow, int C, int lane, int t0, float z0,
+                                          const int* __restrict__ srcs, int nsrc, const float* __restrict__ zs,
+                                          bool has_size, float zsum) {
+  constexpr int VE = VEC ? Chunk<T>::VE : 1;
+  const int nchunks = C / VE;
+  for (int c = lane; c < nchunks; c += 32) {
+    float acc[VE];
+    {
+      const T* p = xb + (long long)t0 * C + c * VE;
+      if (VEC) {
+        int4 raw = ld_stream16(p);
+        const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int i = 0; i < VE; ++i) acc[i] = has_size ? mul_as<T>(to_f32(v[i]), z0) : to_f32(v[i]);
+      } else {
+        acc[0] = has_size ? mul_as<T>(to_f32(p[0]), z0) : to_f32(p[0]);
+      }
+    }
+#pragma unroll 2
+    for (int s = 0; s < nsrc; ++s) {
+      const int ts = 2 * srcs[s];
+      const float z = has_size ? zs[ts] : 1.f;
+      const T* p = xb + (long long)ts * C + c * VE;
+      if (VEC) {
+        int4 raw = ld_stream16(p);
+        const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int i = 0; i < VE; ++i)
+          acc[i] = add_as<T>(acc[i], has_size ? mul_as<T>(to_f32(v[i]), z) : to_f32(v[i]));
+      } else {
+        acc[0] = add_as<T>(acc[0], has_size ? mul_as<T>(to_f32(p[0]), z) : to_f32(p[0]));
+      }
+    }
+    T outv[VE];
+#pragma unroll
+    for (int i = 0; i < VE; ++i) outv[i] = from_f32<T>(__fdiv_rn(acc[i], zsum));
+    if (VEC) st_stream16(orow + c * VE, *reinterpret_cast<const int4*>(outv));
+    else orow[c] = outv[0];
+  }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+tome_merge_kernel(const T* __restrict__ x, const T* __restrict__ size, const int64_t* __restrict__ unm_idx,
+                  const int64_t* __restrict__ src_idx, const int64_t* __restrict__ dst_idx, int N, int C, int r,
+                  T* __restrict__ x_out, T* __restrict__ size_out, float* __restrict__ rci) {
+  extern __shared__ float smem[];
+  const int na = (N + 1) / 2, nb = N / 2, n_unm = na - r, n_out = N - r;
+  float* zs = smem;                                   // [N]   token sizes
+  int* unm = reinterpret_cast<int*>(zs + N);          // [n_unm]
+  int* src = unm + n_unm;                             // [r]
+  int* dst = src + r;                                 // [r]
+  int* cnt = dst + r;                                 // [nb]
+  int* offs = cnt + nb;                               // [nb]
+  int* csr = offs + nb;                               // [r]   sources of each odd token, in src-list order
+  int* rowmap = csr + r;                              // [na]  output row of every even token
+
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_size = size != nullptr;
+  for (int t = tid; t < N; t += kThreads) zs[t] = has_size ? to_f32(size[(long long)b * N + t]) : 1.f;
+  for (int q = tid; q < n_unm; q += kThreads) unm[q] = (int)unm_idx[(long long)b * n_unm + q];
+  for (int s = tid; s < r; s += kThreads) {
+    src[s] = (int)src_idx[(long long)b * r + s];
+    dst[s] = (int)dst_idx[(long long)b * r + s];
+  }
+  __syncthreads();
+  for (int j = tid; j < nb; j += kThreads) {
+    int c = 0;
+    for (int s = 0; s < r; ++s) c += (dst[s] == j);
+    cnt[j] = c;
+  }
+  __syncthreads();
+  for (int j = tid; j < nb; j += kThreads) {
+    int o = 0;
+    for (int q = 0; q < j; ++q) o += cnt[q];
+    offs[j] = o;
+    for (int s = 0; s < r; ++s)
+      if (dst[s] == j) csr[o++] = src[s];
+  }
+  __syncthreads();
+
+  const T* xb = x + (long long)b * N * C;
+  T* ob = x_out + (long long)b * n_out * C;
+  for (int q = blockIdx.x * kWarps + warp; q < n_out; q += gridDim.x * kWarps) {
+    int t0, nsrc = 0;
+    const int* srcs = csr;
+    if (q < n_unm) {
+      t0 = 2 * unm[q];
+    } else {
+      const int j = q - n_unm;
+      t0 = 2 * j + 1;
+      nsrc = cnt[j];
+      srcs = csr + offs[j];
+    }
+    float zsum = zs[t0];
+    for (int s = 0; s < nsrc; ++s) zsum = add_as<T>(zsum, zs[2 * srcs[s]]);
+    merge_row<T, VEC>(xb, ob + (long long)q * C, C, lane, t0, zs[t0], srcs, nsrc, zs, has_size, zsum);
+    if (lane == 0) size_out[(long long)b * n_out + q] = from_f32<T>(zsum);
+  }
+
+  if (rci != nullptr && blockIdx.x == 0) {
+    for (int q = tid; q < n_unm; q += kThreads) rowmap[unm[q]] = q;
+    for (int s = tid; s < r; s += kThreads) rowmap[src[s]] = n_unm + dst[s];
+    __syncthreads();
+    for (int t = 1 + tid; t < N; t += kThreads) {
+      const int row = (t & 1) ? n_unm + (t >> 1) : rowmap[t >> 1];
+      rci[(long long)b * (N - 1) + (t - 1)] = (float)(row - 1);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace tokred
+
+using namespace tokred;
+
+extern "C" int tokred_tome_effective_r(int N, int r, int class_token) {
+  const int cap = (N - (class_token ? 1 : 0)) / 2;
+  const int e = r < cap ? r : cap;
+  return e > 0 ? e : 0;
+}
+
+extern "C" int tokred_tome_match(const void* metric, int metric_dtype, int B, int N, int D, int r, int class_token,
+                                 int score_lowp, int64_t* unm_idx, int64_t* src_idx, int64_t* dst_idx, void* stream) {
+  const char* what = "tokred_tome_match";
+  TOKRED_REQUIRE(metric && unm_idx && src_idx && dst_idx, "%s: null tensor", what);
+  TOKRED_REQUIRE(valid_float_dtype(metric_dtype), "%s: bad metric dtype %d", what, metric_dtype);
+  TOKRED_REQUIRE(B >= 0 && N >= 2 && D >= 1, "%s: bad shape B=%d N=%d D=%d", what, B, N, D);
+  const int re = tokred_tome_effective_r(N, r, class_token);
+  TOKRED_REQUIRE(re >= 1, "%s: effective r = %d (r=%d, N=%d): nothing to merge, caller must skip", what, re, r, N);
+  if (B == 0) return TOKRED_OK;
+  const int na = (N + 1) / 2, nb = N / 2;
+  const size_t smem = ((size_t)(na + nb) * (D + 1) + (size_t)na * (nb + 1) + 2 * na) * 4 + na;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (metric_dtype == TOKRED_F32) {
+    if (int e = allow_smem(tome_match_kernel<float>, smem, what)) return e;
+    tome_match_kernel<float><<<B, kThreads, smem, st>>>((const float*)metric, N, D, re, class_token, score_lowp,
+                                                        unm_idx, src_idx, dst_idx);
+  } else {
+    if (int e = allow_smem(tome_match_kernel<__nv_bfloat16>, smem, what)) return e;
+    tome_match_kernel<__nv_bfloat16><<<B, kThreads, smem, st>>>((const __nv_bfloat16*)metric, N, D, re, class_token,
+                                                                score_lowp, unm_idx, src_idx, dst_idx);
+  }
+  return finish_launch(what);
+}
+
+extern "C" int tokred_tome_merge(const void* x, int x_dtype, const void* size, const int64_t* unm_idx,
+                                 const int64_t* src_idx, const int64_t* dst_idx, int B, int N, int C, int r,
+                                 void* x_out, void* size_out, float* reduced_cluster_idx, void* stream) {
+  const char* what = "tokred_tome_merge";
+  TOKRED_REQUIRE(x && unm_idx && src_idx && dst_idx && x_out && size_out, "%s: null tensor", what);
+  TOKRED_REQUIRE(valid_float_dtype(x_dtype), "%s: bad x dtype %d", what, x_dtype);
+  TOKRED_REQUIRE(B >= 0 && N >= 2 && C >= 1, "%s: bad shape B=%d N=%d C=%d", what, B, N, C);
+  TOKRED_REQUIRE(r >= 1 && r <= N / 2 && r <= (N + 1) / 2, "%s: r=%d outside [1, %d]", what, r, N / 2);
+  TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
+  if (B == 0) return TOKRED_OK;
+  const int na = (N + 1) / 2, nb = N / 2, n_unm = na - r, n_out = N - r;
+  const size_t smem = (size_t)(N + n_unm + 3 * r + 2 * nb + na) * 4;
+  const int ve = x_dtype == TOKRED_F32 ? 4 : 8;
+  const bool vec = (C % ve == 0) && aligned16(x) && aligned16(x_out);
+  int splits = ceil_div(4 * kNumSMs, B);
+  splits = max(1, min(splits, ceil_div(n_out, kWarps)));
+  dim3 grid(splits, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(T, VEC)                                                                                          \
+  do {                                                                                                          \
+    if (int e = allow_smem(tome_merge_kernel<T, VEC>, smem, what)) return e;                                    \
+    tome_merge_kernel<T, VEC><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)size, unm_idx, src_idx, dst_idx, \
+                                                            N, C, r, (T*)x_out, (T*)size_out, reduced_cluster_idx); \
+  } while (0)
+  if (x_dtype == TOKRED_F32) { if (vec) LAUNCH(float, true); else LAUNCH(float, false); }
+  else { if (vec) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }
+#undef LAUNCH
+  return finish_launch(what);
+}

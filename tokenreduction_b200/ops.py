@@ -1,0 +1,570 @@
+"""``torch.ops.tokred.*`` — the reduction operators as torch.library custom ops over the C-ABI library.
+
+Every op: checks arguments on the host, allocates its outputs with torch (caching allocator, current device),
+and enqueues exactly one hand-written sm_100a kernel on the current CUDA stream through ctypes.  No op has a
+CPU implementation: calling one with CPU tensors raises.  ``register_fake`` gives shape/dtype inference so
+CPU-only CI can trace graphs with FakeTensors.  All ops are inference-only (the reference runs its
+matching / clustering under no_grad: models/tome.py:258, models/dpcknn.py:56).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import BF16, F32, TokredError
+
+__all__ = [
+    "topk_gather", "topk_gather_attn", "evit_select_fuse", "evit_select_fuse_attn", "tome_effective_r", "tome_match",
+    "tome_merge", "pairwise_dist", "dpcknn_cluster", "dpcknn_merge", "attn_colsum", "kmedoids_fit", "sinkhorn_merge", "patchmerger",
+    "sit_merge", "ats_sample", "gather_rows", "dyvit_pool_concat",
+]
+
+
+# ----------------------------------------------------------------------------------------------- plumbing
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TokredError(f"unsupported dtype {t.dtype}: tokred ops take float32 or bfloat16")
+
+
+def _tdt(code: int) -> torch.dtype:
+    return torch.float32 if code == F32 else torch.bfloat16
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(name: str, *tensors: Optional[Tensor]) -> None:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise TokredError(f"{name}: tensor on {t.device}; tokred ops run on CUDA only (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise TokredError(f"{name}: tensors on different devices ({dev} vs {t.device})")
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        raise TokredError(f"{name}: tensors on {dev} but current device is cuda:{torch.cuda.current_device()}")
+
+
+def _c(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- Top-K / DyViT
+@torch.library.custom_op("tokred::topk_gather", mutates_args=(), device_types="cuda")
+def _topk_gather(x: Tensor, scores: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    _need_cuda("topk_gather", x, scores)
+    b, n, c = x.shape
+    if scores.dim() != 2 or scores.shape[0] != b or scores.shape[1] != n - 1:
+        raise TokredError(f"topk_gather: scores {tuple(scores.shape)} does not match x {tuple(x.shape)}")
+    x = _c(x)
+    out = torch.empty((b, k + 1, c), dtype=x.dtype, device=x.device)
+    idx = torch.empty((b, k), dtype=torch.int64, device=x.device)
+    _lib.call("tokred_topk_gather", _ptr(x), _dt(x), _ptr(scores), _dt(scores), scores.stride(1), scores.stride(0),
+              None, 0, 0, b, n, c, k, _ptr(out), _ptr(idx), _stream())
+    return out, idx
+
+
+@_topk_gather.register_fake
+def _(x, scores, k):
+    b, n, c = x.shape
+    return x.new_empty((b, k + 1, c)), x.new_empty((b, k), dtype=torch.int64)
+
+
+@torch.library.custom_op("tokred::topk_gather_attn", mutates_args=(), device_types="cuda")
+def _topk_gather_attn(x: Tensor, attn: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    _need_cuda("topk_gather_attn", x, attn)
+    b, n, c = x.shape
+    if attn.dim() != 4 or attn.shape[0] != b or attn.shape[2] != n or attn.shape[3] != n:
+        raise TokredError(f"topk_gather_attn: attn {tuple(attn.shape)} does not match x {tuple(x.shape)}")
+    x, attn = _c(x), _c(attn)
+    out = torch.empty((b, k + 1, c), dtype=x.dtype, device=x.device)
+    idx = torch.empty((b, k), dtype=torch.int64, device=x.device)
+    _lib.call("tokred_topk_gather", _ptr(x), _dt(x), None, 0, 0, 0, _ptr(attn), _dt(attn), attn.shape[1], b, n, c, k,
+              _ptr(out), _ptr(idx), _stream())
+    return out, idx
+
+
+@_topk_gather_attn.register_fake
+def _(x, attn, k):
+    b, n, c = x.shape
+    return x.new_empty((b, k + 1, c)), x.new_empty((b, k), dtype=torch.int64)
+
+
+def topk_gather(x: Tensor, scores: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """models/topk.py:62 + :89-93 (also DynamicViT keep, models/dyvit.py:231-236): (x_out [B,k+1,C], idx [B,k])."""
+    return torch.ops.tokred.topk_gather(x, scores, k)
+
+
+def topk_gather_attn(x: Tensor, attn: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """Same, with the head-mean of the CLS attention row computed in-kernel (no [B,P] round trip)."""
+    return torch.ops.tokred.topk_gather_attn(x, attn, k)
+
+
+# ----------------------------------------------------------------------------------------------- EViT
+def _evit_call(x, scores, attn, k):
+    b, n, c = x.shape
+    x = _c(x)
+    out = torch.empty((b, k + 2, c), dtype=x.dtype, device=x.device)
+    idx = torch.empty((b, k + 1), dtype=torch.int64, device=x.device)
+    compl = torch.empty((b, n - 1 - k), dtype=torch.int64, device=x.device)
+    if scores is not None:
+        scores = _c(scores)
+        _lib.call("tokred_evit_select_fuse", _ptr(x), _dt(x), _ptr(scores), _dt(scores), None, 0, 0, b, n, c, k,
+                  _ptr(out), _ptr(idx), _ptr(compl), _stream())
+    else:
+        attn = _c(attn)
+        _lib.call("tokred_evit_select_fuse", _ptr(x), _dt(x), None, 0, _ptr(attn), _dt(attn), attn.shape[1], b, n, c, k,
+                  _ptr(out), _ptr(idx), _ptr(compl), _stream())
+    return out, idx, compl
+
+
+@torch.library.custom_op("tokred::evit_select_fuse", mutates_args=(), device_types="cuda")
+def _evit_select_fuse(x: Tensor, scores: Tensor, k: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("evit_select_fuse", x, scores)
+    if scores.dim() != 2 or scores.shape[0] != x.shape[0] or scores.shape[1] != x.shape[1] - 1:
+        raise TokredError(f"evit_select_fuse: scores {tuple(scores.shape)} does not match x {tuple(x.shape)}")
+    return _evit_call(x, scores, None, k)
+
+
+@_evit_select_fuse.register_fake
+def _(x, scores, k):
+    b, n, c = x.shape
+    return (x.new_empty((b, k + 2, c)), x.new_empty((b, k + 1), dtype=torch.int64),
+            x.new_empty((b, n - 1 - k), dtype=torch.int64))
+
+
+@torch.library.custom_op("tokred::evit_select_fuse_attn", mutates_args=(), device_types="cuda")
+def _evit_select_fuse_attn(x: Tensor, attn: Tensor, k: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("evit_select_fuse_attn", x, attn)
+    if attn.dim() != 4 or attn.shape[0] != x.shape[0] or attn.shape[2] != x.shape[1]:
+        raise TokredError(f"evit_select_fuse_attn: attn {tuple(attn.shape)} does not match x {tuple(x.shape)}")
+    return _evit_call(x, None, attn, k)
+
+
+@_evit_select_fuse_attn.register_fake
+def _(x, attn, k):
+    b, n, c = x.shape
+    return (x.new_empty((b, k + 2, c)), x.new_empty((b, k + 1), dtype=torch.int64),
+            x.new_empty((b, n - 1 - k), dtype=torch.int64))
+
+
+def evit_select_fuse(x: Tensor, scores: Tensor, k: int):
+    """models/evit.py:84 + :111-123: (x_out [B,k+2,C], idx [B,k+1] with trailing -1, compl [B,P-k])."""
+    return torch.ops.tokred.evit_select_fuse(x, scores, k)
+
+
+def evit_select_fuse_attn(x: Tensor, attn: Tensor, k: int):
+    return torch.ops.tokred.evit_select_fuse_attn(x, attn, k)
+
+
+# ----------------------------------------------------------------------------------------------- ToMe
+def tome_effective_r(n_tokens: int, r: int, class_token: bool = True) -> int:
+    """models/tome.py:244-253 (no distillation token on this path)."""
+    return max(min(r, (n_tokens - int(class_token)) // 2), 0)
+
+
+@torch.library.custom_op("tokred::tome_match", mutates_args=(), device_types="cuda")
+def _tome_match(metric: Tensor, r: int, class_token: bool, lowp: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("tome_match", metric)
+    b, n, d = metric.shape
+    re = tome_effective_r(n, r, class_token)
+    if re <= 0:
+        raise TokredError(f"tome_match: effective r = {re}; nothing to merge (caller must skip, models/tome.py:255)")
+    metric = _c(metric)
+    na = (n + 1) // 2
+    unm = torch.empty((b, na - re), dtype=torch.int64, device=metric.device)
+    src = torch.empty((b, re), dtype=torch.int64, device=metric.device)
+    dst = torch.empty((b, re), dtype=torch.int64, device=metric.device)
+    _lib.call("tokred_tome_match", _ptr(metric), _dt(metric), b, n, d, r, int(class_token), int(lowp), _ptr(unm),
+              _ptr(src), _ptr(dst), _stream())
+    return unm, src, dst
+
+
+@_tome_match.register_fake
+def _(metric, r, class_token, lowp):
+    b, n, d = metric.shape
+    re = tome_effective_r(n, r, class_token)
+    na = (n + 1) // 2
+    mk = lambda m: metric.new_empty((b, m), dtype=torch.int64)
+    return mk(na - re), mk(re), mk(re)
+
+
+@torch.library.custom_op("tokred::tome_merge", mutates_args=(), device_types="cuda")
+def _tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor,
+                want_map: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("tome_merge", x, size, unm, src, dst)
+    b, n, c = x.shape
+    r = src.shape[1]
+    if unm.shape != (b, (n + 1) // 2 - r) or dst.shape != (b, r) or src.shape[0] != b:
+        raise TokredError("tome_merge: index tensors do not match x")
+    x, unm, src, dst = _c(x), _c(unm), _c(src), _c(dst)
+    if size is not None:
+        if size.numel() != b * n:
+            raise TokredError(f"tome_merge: size {tuple(size.shape)} does not match x {tuple(x.shape)}")
+        size = _c(size.to(x.dtype))
+    out = torch.empty((b, n - r, c), dtype=x.dtype, device=x.device)
+    size_out = torch.empty((b, n - r, 1), dtype=x.dtype, device=x.device)
+    rci = torch.empty((b, n - 1) if want_map else (0,), dtype=torch.float32, device=x.device)
+    _lib.call("tokred_tome_merge", _ptr(x), _dt(x), _ptr(size), _ptr(unm), _ptr(src), _ptr(dst), b, n, c, r, _ptr(out),
+              _ptr(size_out), _ptr(rci) if want_map else None, _stream())
+    return out, size_out, rci
+
+
+@_tome_merge.register_fake
+def _(x, size, unm, src, dst, want_map):
+    b, n, c = x.shape
+    r = src.shape[1]
+    return (x.new_empty((b, n - r, c)), x.new_empty((b, n - r, 1)),
+            x.new_empty((b, n - 1) if want_map else (0,), dtype=torch.float32))
+
+
+def tome_match(metric: Tensor, r: int, class_token: bool = True, lowp: bool = False):
+    """models/tome.py:258-277: (unm_idx [B,a-r], src_idx [B,r], dst_idx [B,r]) int64."""
+    return torch.ops.tokred.tome_match(metric, r, class_token, lowp)
+
+
+def tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor, want_map: bool = True):
+    """models/tome.py:279-289,309-323 + Block_ToMe :91-99: (x_out [B,N-r,C], size_out [B,N-r,1], map [B,N-1] f32)."""
+    return torch.ops.tokred.tome_merge(x, size, unm, src, dst, want_map)
+
+
+# ----------------------------------------------------------------------------------------------- distances
+@torch.library.custom_op("tokred::pairwise_dist", mutates_args=(), device_types="cuda")
+def _pairwise_dist(x: Tensor, post_scale: float) -> Tensor:
+    _need_cuda("pairwise_dist", x)
+    b, p, c = x.shape
+    x = _c(x.float())
+    out = torch.empty((b, p, p), dtype=torch.float32, device=x.device)
+    _lib.call("tokred_pairwise_dist", _ptr(x), b, p, c, float(post_scale), _ptr(out), _stream())
+    return out
+
+
+@_pairwise_dist.register_fake
+def _(x, post_scale):
+    b, p, _ = x.shape
+    return x.new_empty((b, p, p), dtype=torch.float32)
+
+
+def pairwise_dist(x: Tensor, post_scale: float = 1.0) -> Tensor:
+    """torch.cdist(x, x) * post_scale with ATen's formula selection (models/dpcknn.py:59, models/kmedoids.py:68)."""
+    return torch.ops.tokred.pairwise_dist(x, post_scale)
+
+
+# ----------------------------------------------------------------------------------------------- DPC-KNN
+@torch.library.custom_op("tokred::dpcknn_cluster", mutates_args=(), device_types="cuda")
+def _dpcknn_cluster(x: Tensor, noise_u: Tensor, cluster_num: int, knn: int) -> Tuple[Tensor, Tensor]:
+    _need_cuda("dpcknn_cluster", x, noise_u)
+    b, p, c = x.shape
+    if x.dtype != torch.float32:
+        x = x.float()     # cdist runs in fp32 under autocast
+    x, noise_u = _c(x), _c(noise_u.float())
+    if noise_u.shape != (b, p):
+        raise TokredError(f"dpcknn_cluster: noise {tuple(noise_u.shape)} != {(b, p)}")
+    idx_cluster = torch.empty((b, p), dtype=torch.int64, device=x.device)
+    index_down = torch.empty((b, cluster_num), dtype=torch.int64, device=x.device)
+    _lib.call("tokred_dpcknn_cluster", _ptr(x), _ptr(noise_u), b, p, c, cluster_num, knn, _ptr(idx_cluster),
+              _ptr(index_down), _stream())
+    return idx_cluster, index_down
+
+
+@_dpcknn_cluster.register_fake
+def _(x, noise_u, cluster_num, knn):
+    b, p, _ = x.shape
+    return x.new_empty((b, p), dtype=torch.int64), x.new_empty((b, cluster_num), dtype=torch.int64)
+
+
+@torch.library.custom_op("tokred::dpcknn_merge", mutates_args=(), device_types="cuda")
+def _dpcknn_merge(x: Tensor, idx_token: Tensor, agg_weight: Tensor, idx_cluster: Tensor,
+                  token_weight: Optional[Tensor], cluster_num: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("dpcknn_merge", x, idx_token, agg_weight, idx_cluster, token_weight)
+    b, p, c = x.shape
+    t = idx_token.shape[1]
+    if x.dtype != torch.float32:
+        raise TokredError("dpcknn_merge: x must be float32 (the residual stream is fp32 under autocast)")
+    x, idx_token, idx_cluster = _c(x), _c(idx_token), _c(idx_cluster)
+    agg = _c(agg_weight.float())
+    tw = None if token_weight is None else _c(token_weight.float())
+    merged = torch.empty((b, cluster_num, c), dtype=torch.float32, device=x.device)
+    idx_token_new = torch.empty((b, t), dtype=torch.int64, device=x.device)
+    agg_new = torch.empty((b, t, 1), dtype=torch.float32, device=x.device)
+    _lib.call("tokred_dpcknn_merge", _ptr(x), _ptr(idx_token), _ptr(agg), _ptr(idx_cluster), _ptr(tw), b, p, c,
+              cluster_num, t, _ptr(merged), _ptr(idx_token_new), _ptr(agg_new), _stream())
+    return merged, idx_token_new, agg_new
+
+
+@_dpcknn_merge.register_fake
+def _(x, idx_token, agg_weight, idx_cluster, token_weight, cluster_num):
+    b, p, c = x.shape
+    t = idx_token.shape[1]
+    return (x.new_empty((b, cluster_num, c)), x.new_empty((b, t), dtype=torch.int64),
+            x.new_empty((b, t, 1), dtype=torch.float32))
+
+
+def dpcknn_cluster(x: Tensor, noise_u: Tensor, cluster_num: int, knn: int = 5):
+    """models/dpcknn.py:44-100: (idx_cluster [B,P], index_down [B,K]) int64; noise_u = torch.rand(B,P)."""
+    return torch.ops.tokred.dpcknn_cluster(x, noise_u, cluster_num, knn)
+
+
+def dpcknn_merge(x, idx_token, agg_weight, idx_cluster, token_weight, cluster_num):
+    """models/dpcknn.py:103-140: (x_merged [B,K,C], idx_token_new [B,T], agg_weight_new [B,T,1])."""
+    return torch.ops.tokred.dpcknn_merge(x, idx_token, agg_weight, idx_cluster, token_weight, cluster_num)
+
+
+# ----------------------------------------------------------------------------------------------- K-Medoids
+@torch.library.custom_op("tokred::attn_colsum", mutates_args=(), device_types="cuda")
+def _attn_colsum(attn: Tensor, num_tokens: int) -> Tensor:
+    _need_cuda("attn_colsum", attn)
+    b, h, n, n2 = attn.shape
+    if n != n2:
+        raise TokredError("attn_colsum: attention must be [B,H,N,N]")
+    attn = _c(attn)
+    out = torch.empty((b, n - num_tokens, 1), dtype=torch.float32, device=attn.device)
+    _lib.call("tokred_attn_colsum", _ptr(attn), _dt(attn), b, h, n, num_tokens, _ptr(out), _stream())
+    return out
+
+
+@_attn_colsum.register_fake
+def _(attn, num_tokens):
+    b, _, n, _ = attn.shape
+    return attn.new_empty((b, n - num_tokens, 1), dtype=torch.float32)
+
+
+@torch.library.custom_op("tokred::kmedoids_fit", mutates_args=(), device_types="cuda")
+def _kmedoids_fit(x: Tensor, token_weight: Tensor, cluster_num: int, iters: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("kmedoids_fit", x, token_weight)
+    b, p, c = x.shape
+    if x.dtype != torch.float32:
+        raise TokredError("kmedoids_fit: x must be float32 (cdist runs in fp32)")
+    if token_weight.numel() != b * p:
+        raise TokredError(f"kmedoids_fit: token_weight {tuple(token_weight.shape)} does not match x")
+    x, tw = _c(x), _c(token_weight.float())
+    centres = torch.empty((b, cluster_num, c), dtype=torch.float32, device=x.device)
+    cidx = torch.empty((b, cluster_num), dtype=torch.int64, device=x.device)
+    assign = torch.empty((b, p), dtype=torch.int64, device=x.device)
+    _lib.call("tokred_kmedoids_fit", _ptr(x), _ptr(tw), b, p, c, cluster_num, iters, _ptr(centres), _ptr(cidx),
+              _ptr(assign), _stream())
+    return centres, cidx, assign
+
+
+@_kmedoids_fit.register_fake
+def _(x, token_weight, cluster_num, iters):
+    b, p, c = x.shape
+    return (x.new_empty((b, cluster_num, c)), x.new_empty((b, cluster_num), dtype=torch.int64),
+            x.new_empty((b, p), dtype=torch.int64))
+
+
+def attn_colsum(attn: Tensor, num_tokens: int = 1) -> Tensor:
+    """models/kmedoids.py:240: token weights [B,P,1] = sum over heads and query rows of attention columns."""
+    return torch.ops.tokred.attn_colsum(attn, num_tokens)
+
+
+def kmedoids_fit(x: Tensor, token_weight: Tensor, cluster_num: int, iters: int):
+    """models/kmedoids.py:62-85: (centres [B,K,C], cluster_idx [B,K], assignment [B,P])."""
+    return torch.ops.tokred.kmedoids_fit(x, token_weight, cluster_num, iters)
+
+
+# ----------------------------------------------------------------------------------------------- soft merges
+def sinkhorn_log_norm(k: int, p: int, score_dtype: torch.dtype) -> float:
+    """-log(K+P) the way models/sinkhorn.py:43-47 evaluates it: (m*one + n*one) in the dtype of the score matrix
+    (bf16 under autocast: sums above 256 are rounded to even multiples of 2), then an fp32 log."""
+    one = torch.ones((), dtype=score_dtype)
+    return float(-((k * one).to(score_dtype) + (p * one).to(score_dtype)).float().log())
+
+
+def _soft_out_dtype(x: Tensor, lowp: bool) -> torch.dtype:
+    return torch.bfloat16 if (lowp or x.dtype == torch.bfloat16) else torch.float32
+
+
+@torch.library.custom_op("tokred::sinkhorn_merge", mutates_args=(), device_types="cuda")
+def _sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool) -> Tuple[Tensor, Tensor]:
+    _need_cuda("sinkhorn_merge", x, v_hat)
+    b, p, c = x.shape
+    k = v_hat.shape[0]
+    if v_hat.shape != (k, c):
+        raise TokredError("sinkhorn_merge: v_hat must be [K,C]")
+    x, v_hat = _c(x), _c(v_hat.float())
+    odt = _soft_out_dtype(x, lowp)
+    out = torch.empty((b, k, c), dtype=odt, device=x.device)
+    weights = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
+    _lib.call("tokred_sinkhorn_merge", _ptr(x), _dt(x), _ptr(v_hat), b, p, c, k, float(eps),
+              sinkhorn_log_norm(k, p, torch.bfloat16 if lowp else x.dtype), iters, int(lowp), _ptr(out), _dt(out),
+              _ptr(weights), _stream())
+    return out, weights
+
+
+@_sinkhorn_merge.register_fake
+def _(x, v_hat, eps, iters, lowp):
+    b, p, c = x.shape
+    k = v_hat.shape[0]
+    return x.new_empty((b, k, c), dtype=_soft_out_dtype(x, lowp)), x.new_empty((b, k, p), dtype=torch.float32)
+
+
+@torch.library.custom_op("tokred::patchmerger", mutates_args=(), device_types="cuda")
+def _patchmerger(x: Tensor, ln_weight: Tensor, ln_bias: Tensor, queries: Tensor, scale: float, ln_eps: float,
+                 lowp: bool) -> Tuple[Tensor, Tensor]:
+    _need_cuda("patchmerger", x, ln_weight, ln_bias, queries)
+    b, p, c = x.shape
+    k = queries.shape[0]
+    if queries.shape != (k, c) or ln_weight.numel() != c or ln_bias.numel() != c:
+        raise TokredError("patchmerger: parameter shapes do not match x")
+    x, queries = _c(x), _c(queries.float())
+    lw, lb = _c(ln_weight.float()), _c(ln_bias.float())
+    odt = _soft_out_dtype(x, lowp)
+    out = torch.empty((b, k, c), dtype=odt, device=x.device)
+    attn = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
+    _lib.call("tokred_patchmerger", _ptr(x), _dt(x), _ptr(lw), _ptr(lb), _ptr(queries), b, p, c, k, float(scale),
+              float(ln_eps), int(lowp), _ptr(out), _dt(out), _ptr(attn), _stream())
+    return out, attn
+
+
+@_patchmerger.register_fake
+def _(x, ln_weight, ln_bias, queries, scale, ln_eps, lowp):
+    b, p, c = x.shape
+    k = queries.shape[0]
+    return x.new_empty((b, k, c), dtype=_soft_out_dtype(x, lowp)), x.new_empty((b, k, p), dtype=torch.float32)
+
+
+@torch.library.custom_op("tokred::sit_merge", mutates_args=(), device_types="cuda")
+def _sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool) -> Tuple[Tensor, Tensor]:
+    _need_cuda("sit_merge", x, logits, scale)
+    b, p, c = x.shape
+    k = logits.shape[2]
+    if logits.shape != (b, p, k):
+        raise TokredError("sit_merge: logits must be [B,P,K]")
+    x, logits = _c(x), _c(logits)
+    if scale.numel() != 1:
+        raise TokredError("sit_merge: scale must hold one element")
+    scale = _c(scale.detach().float().reshape(1))
+    odt = _soft_out_dtype(x, lowp)
+    out = torch.empty((b, k, c), dtype=odt, device=x.device)
+    w = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
+    _lib.call("tokred_sit_merge", _ptr(x), _dt(x), _ptr(logits), _dt(logits), _ptr(scale), b, p, c, k, int(lowp),
+              _ptr(out), _dt(out), _ptr(w), _stream())
+    return out, w
+
+
+@_sit_merge.register_fake
+def _(x, logits, scale, lowp):
+    b, p, c = x.shape
+    k = logits.shape[2]
+    return x.new_empty((b, k, c), dtype=_soft_out_dtype(x, lowp)), x.new_empty((b, k, p), dtype=torch.float32)
+
+
+def sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool = False):
+    """models/sinkhorn.py:66-86: (out [B,K,C], weights [B,K,P]); v_hat = F.normalize(v)."""
+    return torch.ops.tokred.sinkhorn_merge(x, v_hat, eps, iters, lowp)
+
+
+def patchmerger(x, ln_weight, ln_bias, queries, scale: float = 1.0, ln_eps: float = 1e-5, lowp: bool = False):
+    """models/patchmerger.py:35-39: (out [B,K,C], attn [B,K,P])."""
+    return torch.ops.tokred.patchmerger(x, ln_weight, ln_bias, queries, scale, ln_eps, lowp)
+
+
+def sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool = False):
+    """models/sit.py:37-40: (out [B,K,C], weight [B,K,P])."""
+    return torch.ops.tokred.sit_merge(x, logits, scale, lowp)
+
+
+# ----------------------------------------------------------------------------------------------- ATS
+@torch.library.custom_op("tokred::ats_sample", mutates_args=(), device_types="cuda")
+def _ats_sample(v: Tensor, attn: Tensor, mask: Tensor, steps: Tensor, eps: float) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("ats_sample", v, attn, mask, steps)
+    b, h, n, dh = v.shape
+    if attn.shape != (b, h, n, n) or mask.shape != (b, n):
+        raise TokredError("ats_sample: attn/mask shapes do not match v")
+    if v.stride(3) != 1:
+        v = v.contiguous()
+    attn = _c(attn.float())
+    mask8 = _c(mask.to(torch.uint8)) if mask.dtype != torch.bool else _c(mask).view(torch.uint8)
+    steps = _c(steps.float())
+    ns = steps.numel()
+    ids = torch.empty((b, ns + 1), dtype=torch.int64, device=v.device)
+    mask_out = torch.empty((b, ns + 1), dtype=torch.bool, device=v.device)
+    max_count = torch.zeros((1,), dtype=torch.int32, device=v.device)
+    _lib.call("tokred_ats_sample", _ptr(v), _dt(v), v.stride(0), v.stride(1), v.stride(2), _ptr(attn), _ptr(mask8),
+              _ptr(steps), b, h, n, dh, ns, float(eps),
+              _ptr(ids), mask_out.data_ptr(), _ptr(max_count), _stream())
+    return ids, mask_out, max_count
+
+
+@_ats_sample.register_fake
+def _(v, attn, mask, steps, eps):
+    b = v.shape[0]
+    ns = steps.numel()
+    return (v.new_empty((b, ns + 1), dtype=torch.int64), v.new_empty((b, ns + 1), dtype=torch.bool),
+            v.new_empty((1,), dtype=torch.int32))
+
+
+@torch.library.custom_op("tokred::gather_rows", mutates_args=(), device_types="cuda")
+def _gather_rows(src: Tensor, ids: Tensor, m: int) -> Tensor:
+    _need_cuda("gather_rows", src, ids)
+    if src.dim() == 3:
+        b, n, w = src.shape
+        g = 1
+    elif src.dim() == 4:
+        b, g, n, w = src.shape
+    else:
+        raise TokredError("gather_rows: src must be [B,N,W] or [B,G,N,W]")
+    if ids.dim() != 2 or ids.shape[0] != b or ids.shape[1] < m or ids.stride(1) != 1:
+        raise TokredError("gather_rows: ids must be [B,>=M] with unit inner stride")
+    src = _c(src)
+    shape = (b, m, w) if src.dim() == 3 else (b, g, m, w)
+    out = torch.empty(shape, dtype=src.dtype, device=src.device)
+    _lib.call("tokred_gather_rows", _ptr(src), _dt(src), _ptr(ids), ids.stride(0), b, g, n, w, m, _ptr(out), _stream())
+    return out
+
+
+@_gather_rows.register_fake
+def _(src, ids, m):
+    shape = list(src.shape)
+    shape[-2] = m
+    return src.new_empty(shape)
+
+
+def ats_sample(v: Tensor, attn: Tensor, mask: Tensor, steps: Tensor, eps: float = 1e-6):
+    """models/ats.py:52-82: (ids [B,n_steps+1] zero-padded sorted unique, mask [B,n_steps+1], max_count int32[1])."""
+    return torch.ops.tokred.ats_sample(v, attn, mask, steps, eps)
+
+
+def gather_rows(src: Tensor, ids: Tensor, m: Optional[int] = None) -> Tensor:
+    """out[b,(g,)j,:] = src[b,(g,)ids[b,j],:] for j < m (models/ats.py:84-87, :156-157)."""
+    return torch.ops.tokred.gather_rows(src, ids, ids.shape[1] if m is None else m)
+
+
+# ----------------------------------------------------------------------------------------------- DynamicViT
+@torch.library.custom_op("tokred::dyvit_pool_concat", mutates_args=(), device_types="cuda")
+def _dyvit_pool_concat(h: Tensor, policy: Tensor, eps: float) -> Tensor:
+    _need_cuda("dyvit_pool_concat", h, policy)
+    b, p, c = h.shape
+    if policy.numel() != b * p:
+        raise TokredError("dyvit_pool_concat: policy must be [B,P,1]")
+    h = _c(h)
+    pol = _c(policy.float())
+    odt = torch.promote_types(h.dtype, policy.dtype)      # the reference's torch.cat promotes (models/dyvit.py:118)
+    out = torch.empty((b, p, c), dtype=odt, device=h.device)
+    _lib.call("tokred_dyvit_pool_concat", _ptr(h), _dt(h), _ptr(pol), b, p, c, float(eps), _ptr(out), _dt(out), _stream())
+    return out
+
+
+@_dyvit_pool_concat.register_fake
+def _(h, policy, eps):
+    return h.new_empty(h.shape, dtype=torch.promote_types(h.dtype, policy.dtype))
+
+
+def dyvit_pool_concat(h: Tensor, policy: Tensor, eps: float = 1e-6) -> Tensor:
+    """models/dyvit.py:114-118: [local half | masked mean of the global half + eps]."""
+    return torch.ops.tokred.dyvit_pool_concat(h, policy, eps)
