@@ -77,10 +77,11 @@ TOKRED_API int tokred_tome_match(const void* metric, int metric_dtype, int B, in
  *   x [B,N,C], size [B,N] (same dtype as x) or NULL (= ones)
  *   x_out [B,N-r,C] = [unmerged even tokens ; odd tokens + merged sources] size-weighted mean
  *   size_out [B,N-r]; reduced_cluster_idx [B,N-1] fp32 or NULL (output row of every input patch, minus 1)
+ *   divide = 1: merge_wavg (weighted mean); divide = 0: the bare merge closure (sums of x*size, no division)
  * Sources are accumulated in src-list order (the CPU scatter_add order): deterministic, no atomics.      */
 TOKRED_API int tokred_tome_merge(const void* x, int x_dtype, const void* size, const int64_t* unm_idx,
                       const int64_t* src_idx, const int64_t* dst_idx, int B, int N, int C, int r, void* x_out,
-                      void* size_out, float* reduced_cluster_idx, void* stream);
+                      void* size_out, float* reduced_cluster_idx, int divide, void* stream);
 
 /* ---- pairwise distances (building block of a6 / a8, exported for parity checks) ------------------------
  * torch.cdist(x, x) as called at models/dpcknn.py:59 and models/kmedoids.py:68, times post_scale:

@@ -404,6 +404,14 @@ def test_sit_merge(T, p, k, c, lowp):
 
 
 # ------------------------------------------------------------------------------------------------ ATS
+def ats_cdf64(v, attn, mask):
+    """float64 CDF of models/ats.py:53-70 (CPU)."""
+    v, attn, mask = v.double().cpu(), attn.double().cpu(), mask.cpu()
+    sig = (attn[:, :, 0, 1:] * v[:, :, 1:, :].norm(dim=-1)).sum(dim=1)
+    cdf = (sig / (sig.sum(dim=-1, keepdim=True) + 1e-6)).cumsum(dim=1)
+    return torch.where(mask[:, 1:], cdf, cdf + 0.1)
+
+
 def spread_attn(b, h, n, seed):
     """attention whose CLS row is far from uniform, so the inverse-CDF picks are well separated."""
     return torch.softmax(6 * torch.randn(b, h, n, n, generator=g(seed)), dim=-1)
@@ -422,14 +430,27 @@ def test_ats_sample(T, n, count, h, dh, vdtype):
     ids, mask_out, max_count = T.ats_sample(v, attn, mask, steps)
     na_ref, nm_ref, ids_ref = O.ats_sample(v, attn, mask, count)
     m = int(max_count.item())
-    assert m + 1 == ids_ref.shape[1] or abs(m + 1 - ids_ref.shape[1]) <= 1
-    w = min(m + 1, ids_ref.shape[1])
-    # sampled sets: near-identical (cdf summation order differs from torch.cumsum's parallel scan)
+    assert abs(m + 1 - ids_ref.shape[1]) <= 2
+    # Margin-aware check.  The reference measures |step - cdf| with cdist's matmul expansion (s^2 + c^2 - 2sc in
+    # fp32), so the pick between two nearly equidistant CDF entries is decided by cancellation noise (~1e-7 on
+    # d^2) and by the fp32 summation order of the CDF itself (torch.cumsum on CUDA is a parallel scan; the CPU
+    # reference scans sequentially).  With a float64 CDF: every step must have one of its near-minimal candidates
+    # (d^2 within TOL of the minimum) among the kernel's ids, and every id must be such a candidate of some step.
+    TOL = 2e-6
+    cdf64 = ats_cdf64(v, attn, mask)
+    d2 = (steps.double().cpu()[None, :, None] - cdf64[:, None, :]) ** 2          # [B, steps, P]
+    cand = d2 <= d2.min(dim=-1, keepdim=True).values + TOL
+    for i in range(b):
+        got = torch.zeros(n - 1, dtype=torch.bool)
+        body_i = ids[i, 1:m + 1].cpu()
+        got[body_i[body_i > 0] - 1] = True
+        assert bool((cand[i] & got[None, :]).any(dim=-1).all()), f"image {i}: a step has no candidate among the ids"
+        assert bool(cand[i].any(dim=0)[got].all()), f"image {i}: an id is not a near-minimal candidate of any step"
     agree = 0
     for i in range(b):
         a, r = set(ids[i, :m + 1].tolist()), set(ids_ref[i].tolist())
         agree += len(a & r) / max(len(a | r), 1)
-    assert agree / b > 0.97, f"sampled-set agreement {agree / b:.3f}"
+    assert agree / b > 0.75, f"sampled-set agreement {agree / b:.3f}"
     # structure: sorted unique, zero padding, mask == (id != 0) with CLS forced on
     body = ids[:, 1:]
     assert bool((ids[:, 0] == 0).all()) and bool(mask_out[:, 0].all())

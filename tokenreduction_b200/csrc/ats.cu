@@ -126,6 +126,7 @@ extern "C" int tokred_ats_sample(const void* v, int v_dtype, int64_t v_stride_b,
                                  int H, int N, int Dh, int n_steps, float eps, int64_t* ids_out, uint8_t* mask_out,
                                  int32_t* max_count, void* stream) {
   const char* what = "tokred_ats_sample";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(v && attn && mask && steps && ids_out && mask_out && max_count, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(v_dtype), "%s: bad v dtype %d", what, v_dtype);
   TOKRED_REQUIRE(B >= 0 && H >= 1 && N >= 2 && Dh >= 1, "%s: bad shape B=%d H=%d N=%d Dh=%d", what, B, H, N, Dh);

@@ -57,9 +57,9 @@ __device__ void pairdist_to_smem(const float* __restrict__ xb, int P, int C, flo
 // ------------------------------------------------------------------------------------------ plain cdist(x, x)
 __global__ void __launch_bounds__(kThreads, 1)
 pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale, float* __restrict__ out) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* D = smem;
-  float* xt = D + P * P;
+  float* xt = D + ((P * P + 3) & ~3);   // keep the tile 16-byte aligned for LDS.128
   float* sq = xt + P * XS;
   pairdist_to_smem(x + (long long)blockIdx.x * P * C, P, C, D, xt, sq, post_scale);
   float* ob = out + (long long)blockIdx.x * P * P;
@@ -70,9 +70,9 @@ pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale
 __global__ void __launch_bounds__(kThreads, 1)
 dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noise_u, int P, int C, int K, int knn,
                       float inv_sqrt_c, int64_t* __restrict__ idx_cluster, int64_t* __restrict__ index_down) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* D = smem;
-  float* xt = D + P * P;
+  float* xt = D + ((P * P + 3) & ~3);   // keep the tile 16-byte aligned for LDS.128
   float* sq = xt + P * XS;
   float* rho = sq + P;
   float* score = rho + P;
@@ -143,9 +143,9 @@ dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noi
 __global__ void __launch_bounds__(kThreads, 1)
 kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token_weight, int P, int C, int K, int iters,
                     float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* D = smem;
-  float* xt = D + P * P;
+  float* xt = D + ((P * P + 3) & ~3);   // keep the tile 16-byte aligned for LDS.128
   float* sq = xt + P * XS;
   float* w = sq + P;
   float* S = w + P;
@@ -212,7 +212,7 @@ dpcknn_merge_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx
                     const float* __restrict__ agg_weight, const int64_t* __restrict__ idx_cluster,
                     const float* __restrict__ token_weight, int P, int C, int K, int T, float* __restrict__ x_merged,
                     int64_t* __restrict__ idx_token_new, float* __restrict__ agg_weight_new, int vec) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* nw = smem;                                   // [P] normalised weights
   float* wsum = nw + P;                               // [K]
   int* cl = reinterpret_cast<int*>(wsum + K);         // [P] cluster of token
@@ -323,11 +323,12 @@ attn_colsum_kernel(const T* __restrict__ attn, int H, int N, int nt, float* __re
 using namespace tokred;
 
 static size_t dist_smem_bytes(int P, int extra_floats) {
-  return ((size_t)P * P + (size_t)P * XS + P + extra_floats) * 4;
+  return ((((size_t)P * P + 3) & ~(size_t)3) + (size_t)P * XS + P + extra_floats) * 4;
 }
 
 extern "C" int tokred_pairwise_dist(const float* x, int B, int P, int C, float post_scale, float* out, void* stream) {
   const char* what = "tokred_pairwise_dist";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && out, "%s: null tensor", what);
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 1, "%s: bad shape B=%d P=%d C=%d", what, B, P, C);
   if (P > kMaxP) { set_error("%s: P=%d > %d patches is not supported (distance matrix is kept in shared memory)", what, P, kMaxP); return TOKRED_ERR_UNSUPPORTED; }
@@ -341,6 +342,7 @@ extern "C" int tokred_pairwise_dist(const float* x, int B, int P, int C, float p
 extern "C" int tokred_dpcknn_cluster(const float* x, const float* noise_u, int B, int P, int C, int K, int knn,
                                      int64_t* idx_cluster, int64_t* index_down, void* stream) {
   const char* what = "tokred_dpcknn_cluster";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && noise_u && idx_cluster && index_down, "%s: null tensor", what);
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 1, "%s: bad shape B=%d P=%d C=%d", what, B, P, C);
   TOKRED_REQUIRE(K >= 1 && K <= P, "%s: cluster_num=%d outside [1, P=%d]", what, K, P);
@@ -357,6 +359,7 @@ extern "C" int tokred_dpcknn_cluster(const float* x, const float* noise_u, int B
 extern "C" int tokred_kmedoids_fit(const float* x, const float* token_weight, int B, int P, int C, int K, int iters,
                                    float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream) {
   const char* what = "tokred_kmedoids_fit";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && token_weight && centres && cluster_idx && assignment, "%s: null tensor", what);
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 1, "%s: bad shape B=%d P=%d C=%d", what, B, P, C);
   TOKRED_REQUIRE(K >= 1 && K <= P, "%s: cluster_num=%d outside [1, P=%d]", what, K, P);
@@ -374,6 +377,7 @@ extern "C" int tokred_dpcknn_merge(const float* x, const int64_t* idx_token, con
                                    const int64_t* idx_cluster, const float* token_weight, int B, int P, int C, int K,
                                    int T, float* x_merged, int64_t* idx_token_new, float* agg_weight_new, void* stream) {
   const char* what = "tokred_dpcknn_merge";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && idx_token && agg_weight && idx_cluster && x_merged && idx_token_new && agg_weight_new,
                  "%s: null tensor", what);
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 1 && K >= 1 && T >= 0, "%s: bad shape", what);
@@ -392,6 +396,7 @@ extern "C" int tokred_dpcknn_merge(const float* x, const int64_t* idx_token, con
 extern "C" int tokred_attn_colsum(const void* attn, int attn_dtype, int B, int H, int N, int num_tokens, float* out,
                                   void* stream) {
   const char* what = "tokred_attn_colsum";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(attn && out, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(attn_dtype), "%s: bad dtype %d", what, attn_dtype);
   TOKRED_REQUIRE(B >= 0 && H >= 1 && N >= 1 && num_tokens >= 0 && num_tokens < N, "%s: bad shape", what);

@@ -233,6 +233,7 @@ extern "C" int tokred_topk_gather(const void* x, int x_dtype, const void* scores
                                   int64_t score_batch_stride, const void* attn, int attn_dtype, int H, int B, int N,
                                   int C, int k, void* x_out, int64_t* idx_out, void* stream) {
   const char* what = "tokred_topk_gather";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && x_out && idx_out, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(x_dtype), "%s: bad x dtype %d", what, x_dtype);
   TOKRED_REQUIRE(B >= 0 && N >= 2 && C >= 1, "%s: bad shape B=%d N=%d C=%d", what, B, N, C);
@@ -256,6 +257,7 @@ extern "C" int tokred_evit_select_fuse(const void* x, int x_dtype, const void* s
                                        const void* attn, int attn_dtype, int H, int B, int N, int C, int k,
                                        void* x_out, int64_t* idx_out, int64_t* compl_out, void* stream) {
   const char* what = "tokred_evit_select_fuse";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && x_out && idx_out && compl_out, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(x_dtype), "%s: bad x dtype %d", what, x_dtype);
   TOKRED_REQUIRE(B >= 0 && N >= 2 && C >= 1, "%s: bad shape B=%d N=%d C=%d", what, B, N, C);
@@ -284,6 +286,7 @@ extern "C" int tokred_evit_select_fuse(const void* x, int x_dtype, const void* s
 extern "C" int tokred_gather_rows(const void* src, int dtype, const int64_t* ids, int64_t ids_stride, int B, int G,
                                   int N, int W, int M, void* out, void* stream) {
   const char* what = "tokred_gather_rows";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(src && ids && out, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(dtype), "%s: bad dtype %d", what, dtype);
   TOKRED_REQUIRE(B >= 0 && G >= 1 && N >= 1 && W >= 1 && M >= 0 && ids_stride >= M, "%s: bad shape", what);
@@ -301,6 +304,7 @@ extern "C" int tokred_gather_rows(const void* src, int dtype, const int64_t* ids
 extern "C" int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float* policy, int B, int P, int C,
                                         float eps, void* out, int out_dtype, void* stream) {
   const char* what = "tokred_dyvit_pool_concat";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(h && policy && out, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(h_dtype) && valid_float_dtype(out_dtype), "%s: bad dtype", what);
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 2 && C % 2 == 0, "%s: bad shape B=%d P=%d C=%d", what, B, P, C);

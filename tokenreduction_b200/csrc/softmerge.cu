@@ -140,7 +140,7 @@ __device__ __forceinline__ void second_contraction(const T* __restrict__ xb, con
 
 template <typename T, typename TO, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) soft_merge_kernel(SoftParams prm) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int P = prm.P, C = prm.C, K = prm.K, lowp = prm.lowp;
   const int PS = (P + 3) & ~3;
   float* Z = smem;                       // [K][PS]
@@ -312,6 +312,7 @@ extern "C" int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_
                                      float eps, float log_norm, int iters, int lowp, void* out, int out_dtype,
                                      float* weights, void* stream) {
   const char* what = "tokred_sinkhorn_merge";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && v_hat && out && weights, "%s: null tensor", what);
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
   TOKRED_REQUIRE(eps > 0.f && iters >= 0, "%s: eps=%g iters=%d", what, (double)eps, iters);
@@ -326,6 +327,7 @@ extern "C" int tokred_patchmerger(const void* x, int x_dtype, const float* ln_we
                                   const float* queries, int B, int P, int C, int K, float scale, float ln_eps, int lowp,
                                   void* out, int out_dtype, float* attn, void* stream) {
   const char* what = "tokred_patchmerger";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && ln_weight && ln_bias && queries && out && attn, "%s: null tensor", what);
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
   if (B == 0) return TOKRED_OK;
@@ -339,6 +341,7 @@ extern "C" int tokred_sit_merge(const void* x, int x_dtype, const void* logits, 
                                 int B, int P, int C, int K, int lowp, void* out, int out_dtype, float* weights,
                                 void* stream) {
   const char* what = "tokred_sit_merge";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && logits && scale && out && weights, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(logits_dtype), "%s: bad logits dtype", what);
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;

@@ -137,17 +137,18 @@ template <typename T> struct Chunk;            // one 16-byte lane chunk
 template <> struct Chunk<float> { static constexpr int VE = 4; };
 template <> struct Chunk<__nv_bfloat16> { static constexpr int VE = 8; };
 
-// acc (rounded like T arithmetic) = x*z, acc += x*z ... with UNFUSED multiply/add (the reference materialises
-// x*size before scatter_add).
+// acc = x*z (rounded to T: the reference materialises x*size), then fp32 accumulation of the sources with ONE
+// rounding to T at the end — what CPU scatter_add does for bf16 (opmath accumulation); identity for fp32.
+// Multiply and add stay UNFUSED so that fp32 results are bit-identical to the reference.
 template <typename T>
 __device__ __forceinline__ float mul_as(float x, float z) { return round_as<T>(__fmul_rn(x, z)); }
 template <typename T>
-__device__ __forceinline__ float add_as(float a, float b) { return round_as<T>(__fadd_rn(a, b)); }
+__device__ __forceinline__ float add_as(float a, float b) { return __fadd_rn(a, b); }
 
 template <typename T, bool VEC>
 __device__ __forceinline__ void merge_row(const T* __restrict__ xb, T* __restrict__ orow, int C, int lane, int t0, float z0,
                                           const int* __restrict__ srcs, int nsrc, const float* __restrict__ zs,
-                                          bool has_size, float zsum) {
+                                          bool has_size, float zsum, bool divide) {
   constexpr int VE = VEC ? Chunk<T>::VE : 1;
   const int nchunks = C / VE;
   for (int c = lane; c < nchunks; c += 32) {
@@ -180,7 +181,7 @@ __device__ __forceinline__ void merge_row(const T* __restrict__ xb, T* __restric
     }
     T outv[VE];
 #pragma unroll
-    for (int i = 0; i < VE; ++i) outv[i] = from_f32<T>(__fdiv_rn(acc[i], zsum));
+    for (int i = 0; i < VE; ++i) outv[i] = divide ? from_f32<T>(__fdiv_rn(round_as<T>(acc[i]), zsum)) : from_f32<T>(acc[i]);
     if (VEC) st_stream16(orow + c * VE, *reinterpret_cast<const int4*>(outv));
     else orow[c] = outv[0];
   }
@@ -190,7 +191,7 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(kThreads)
 tome_merge_kernel(const T* __restrict__ x, const T* __restrict__ size, const int64_t* __restrict__ unm_idx,
                   const int64_t* __restrict__ src_idx, const int64_t* __restrict__ dst_idx, int N, int C, int r,
-                  T* __restrict__ x_out, T* __restrict__ size_out, float* __restrict__ rci) {
+                  T* __restrict__ x_out, T* __restrict__ size_out, float* __restrict__ rci, int divide) {
   extern __shared__ float smem[];
   const int na = (N + 1) / 2, nb = N / 2, n_unm = na - r, n_out = N - r;
   float* zs = smem;                                   // [N]   token sizes
@@ -241,7 +242,8 @@ tome_merge_kernel(const T* __restrict__ x, const T* __restrict__ size, const int
     }
     float zsum = zs[t0];
     for (int s = 0; s < nsrc; ++s) zsum = add_as<T>(zsum, zs[2 * srcs[s]]);
-    merge_row<T, VEC>(xb, ob + (long long)q * C, C, lane, t0, zs[t0], srcs, nsrc, zs, has_size, zsum);
+    zsum = round_as<T>(zsum);
+    merge_row<T, VEC>(xb, ob + (long long)q * C, C, lane, t0, zs[t0], srcs, nsrc, zs, has_size, zsum, divide != 0);
     if (lane == 0) size_out[(long long)b * n_out + q] = from_f32<T>(zsum);
   }
 
@@ -270,6 +272,7 @@ extern "C" int tokred_tome_effective_r(int N, int r, int class_token) {
 extern "C" int tokred_tome_match(const void* metric, int metric_dtype, int B, int N, int D, int r, int class_token,
                                  int score_lowp, int64_t* unm_idx, int64_t* src_idx, int64_t* dst_idx, void* stream) {
   const char* what = "tokred_tome_match";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(metric && unm_idx && src_idx && dst_idx, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(metric_dtype), "%s: bad metric dtype %d", what, metric_dtype);
   TOKRED_REQUIRE(B >= 0 && N >= 2 && D >= 1, "%s: bad shape B=%d N=%d D=%d", what, B, N, D);
@@ -293,8 +296,9 @@ extern "C" int tokred_tome_match(const void* metric, int metric_dtype, int B, in
 
 extern "C" int tokred_tome_merge(const void* x, int x_dtype, const void* size, const int64_t* unm_idx,
                                  const int64_t* src_idx, const int64_t* dst_idx, int B, int N, int C, int r,
-                                 void* x_out, void* size_out, float* reduced_cluster_idx, void* stream) {
+                                 void* x_out, void* size_out, float* reduced_cluster_idx, int divide, void* stream) {
   const char* what = "tokred_tome_merge";
+  if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && unm_idx && src_idx && dst_idx && x_out && size_out, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(x_dtype), "%s: bad x dtype %d", what, x_dtype);
   TOKRED_REQUIRE(B >= 0 && N >= 2 && C >= 1, "%s: bad shape B=%d N=%d C=%d", what, B, N, C);
@@ -313,7 +317,7 @@ extern "C" int tokred_tome_merge(const void* x, int x_dtype, const void* size, c
   do {                                                                                                          \
     if (int e = allow_smem(tome_merge_kernel<T, VEC>, smem, what)) return e;                                    \
     tome_merge_kernel<T, VEC><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)size, unm_idx, src_idx, dst_idx, \
-                                                            N, C, r, (T*)x_out, (T*)size_out, reduced_cluster_idx); \
+                                                            N, C, r, (T*)x_out, (T*)size_out, reduced_cluster_idx, divide); \
   } while (0)
   if (x_dtype == TOKRED_F32) { if (vec) LAUNCH(float, true); else LAUNCH(float, false); }
   else { if (vec) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }

@@ -1,0 +1,565 @@
+"""Drop-in reduction modules and functions: same names, constructor arguments, parameter names and forward
+signatures as the reference's (cited per class), with the ATen call sequences replaced by the tokred CUDA ops.
+
+Only the attention sub-modules differ internally from the reference: they hand the *scores* the block needs
+(CLS-attention, key mean, attention probabilities) to the block, which then issues ONE fused select+gather /
+match+merge launch instead of topk -> expand -> gather -> cat.  Block-level signatures are unchanged.
+
+Precision: ``_lowp()`` is True under ``torch.autocast('cuda', dtype=torch.bfloat16)`` — the kernels then round
+exactly where the reference's autocast matmuls round.  fp16 autocast (the reference's
+validate.py default) is not supported by the kernels and raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import ops
+from .vit import DropPath, Mlp
+
+
+def _lowp() -> bool:
+    if not torch.is_autocast_enabled("cuda"):
+        return False
+    dt = torch.get_autocast_dtype("cuda")
+    if dt != torch.bfloat16:
+        raise RuntimeError(f"tokred kernels support float32 and bfloat16 autocast, not {dt}")
+    return True
+
+
+def _train_guard(mod: nn.Module) -> None:
+    if mod.training and torch.is_grad_enabled():
+        raise NotImplementedError(
+            f"{type(mod).__name__}: the tokred reduction kernels are inference-only (no autograd formula); "
+            "call .eval() and run under torch.no_grad()")
+
+
+class _AttentionBase(nn.Module):
+    """qkv / proj layout shared by every reference attention variant (e.g. models/topk.py:27-52)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0.0, proj_drop=0.0):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+    def _qkv(self, x):
+        b, n, c = x.shape
+        qkv = self.qkv(x).reshape(b, n, 3, self.num_heads, c // self.num_heads).permute(2, 0, 3, 1, 4)
+        return qkv[0], qkv[1], qkv[2]
+
+    def _out(self, attn, v):
+        b, _, n, _ = attn.shape
+        x = (attn @ v).transpose(1, 2).reshape(b, n, -1)
+        return self.proj_drop(self.proj(x))
+
+
+# =============================================================================================== Top-K
+class Attention_TopK(_AttentionBase):
+    """models/topk.py:27-67.  forward(x) -> (x, cls_attn [B,N-1] | None, left_tokens | None)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0.0, proj_drop=0.0, keep_rate=1.0):
+        super().__init__(dim, num_heads, qkv_bias, attn_drop, proj_drop)
+        assert 0 < keep_rate <= 1, "keep_rate must > 0 and <= 1, got {0}".format(keep_rate)
+        self.keep_rate = keep_rate
+        self.init_n = 14 * 14
+
+    def forward(self, x):
+        n = x.shape[1]
+        q, k, v = self._qkv(x)
+        attn = self.attn_drop(((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1))
+        x = self._out(attn, v)
+        if self.keep_rate < 1:
+            left_tokens = int(self.keep_rate * self.init_n)
+            if left_tokens == n - 1:
+                return x, None, None
+            assert left_tokens >= 1
+            cls_attn = attn[:, :, 0, 1:].mean(dim=1)           # identical ATen call -> bit-identical decision input
+            return x, cls_attn, left_tokens
+        return x, None, None
+
+
+class Block_TopK(nn.Module):
+    """models/topk.py:70-99.  forward(x) -> (x, n_tokens, idx | None)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, drop=0.0, attn_drop=0.0, drop_path=0.0,
+                 act_layer=nn.GELU, norm_layer=nn.LayerNorm, keep_rate=0.0):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention_TopK(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop,
+                                   keep_rate=keep_rate)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+    def forward(self, x):
+        tmp, cls_attn, left_tokens = self.attn(self.norm1(x))
+        x = x + self.drop_path(tmp)
+        idx = None
+        if cls_attn is not None:
+            _train_guard(self)
+            x, idx = ops.topk_gather(x, cls_attn, left_tokens)          # select + gather + cat in one launch
+        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        return x, x.shape[1] - 1, idx
+
+
+# =============================================================================================== EViT
+def complement_idx(idx: Tensor, dim: int) -> Tensor:
+    """models/evit.py:25-46 — ascending indices of range(dim) not in idx (trailing dimension)."""
+    keep = torch.zeros(idx.shape[:-1] + (dim,), dtype=torch.bool, device=idx.device)
+    keep.scatter_(-1, idx, True)
+    ar = torch.arange(dim, device=idx.device).expand(keep.shape)
+    return ar[~keep].reshape(idx.shape[:-1] + (dim - idx.shape[-1],))
+
+
+class Attention_EVIT(Attention_TopK):
+    """models/evit.py:49-91 — same scores as Top-K."""
+
+
+class Block_EVIT(nn.Module):
+    """models/evit.py:94-129.  forward(x) -> (x, n_tokens, idx (trailing -1) | None, compl | None)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, drop=0.0, attn_drop=0.0, drop_path=0.0,
+                 act_layer=nn.GELU, norm_layer=nn.LayerNorm, keep_rate=0.0):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention_EVIT(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop,
+                                   keep_rate=keep_rate)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+    def forward(self, x):
+        tmp, cls_attn, left_tokens = self.attn(self.norm1(x))
+        x = x + self.drop_path(tmp)
+        idx = compl = None
+        if cls_attn is not None:
+            _train_guard(self)
+            x, idx, compl = ops.evit_select_fuse(x, cls_attn, left_tokens)
+        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        return x, x.shape[1] - 1, idx, compl
+
+
+# =============================================================================================== ToMe
+class _ToMeMerge:
+    """The ``merge`` closure of models/tome.py:279-289, carrying the three index lists on the device."""
+
+    def __init__(self, unm_idx: Tensor, src_idx: Tensor, dst_idx: Tensor, n_tokens: int):
+        self.unm_idx, self.src_idx, self.dst_idx, self.n_tokens = unm_idx, src_idx, dst_idx, n_tokens
+
+    @property
+    def r(self) -> int:
+        return self.src_idx.shape[1]
+
+    def __call__(self, x: Tensor, mode: str = "mean") -> Tensor:        # mode is ignored by the reference too
+        out, _, _ = ops.tome_merge(x, None, self.unm_idx, self.src_idx, self.dst_idx, False, False)
+        return out
+
+    def row_map(self, x: Tensor) -> Tensor:
+        _, _, rci = ops.tome_merge(x[..., :1].contiguous(), None, self.unm_idx, self.src_idx, self.dst_idx, True, False)
+        return rci
+
+
+def do_nothing(x, mode=None):
+    return x
+
+
+def bipartite_soft_matching(metric: Tensor, r: int, class_token: bool = False,
+                            distill_token: bool = False) -> Tuple[Callable, Callable]:
+    """models/tome.py:230-306.  Returns (merge, unmerge)."""
+    if distill_token:
+        raise NotImplementedError("tokred tome_match: distillation token protection is not on the accelerated path")
+    t = metric.shape[1]
+    r = min(r, (t - int(class_token)) // 2)
+    if r <= 0:
+        return do_nothing, do_nothing
+    lowp = _lowp() or metric.dtype == torch.bfloat16
+    unm_idx, src_idx, dst_idx = ops.tome_match(metric, r, class_token, lowp)
+    merge = _ToMeMerge(unm_idx, src_idx, dst_idx, t)
+
+    def unmerge(x: Tensor) -> Tensor:                                  # models/tome.py:291-304 (not on the hot path)
+        unm_len = unm_idx.shape[1]
+        unm, dst = x[..., :unm_len, :], x[..., unm_len:, :]
+        n, _, c = unm.shape
+        src = dst.gather(dim=-2, index=dst_idx.unsqueeze(-1).expand(n, r, c))
+        out = torch.zeros(n, t, c, device=x.device, dtype=x.dtype)
+        out[..., 1::2, :] = dst
+        out.scatter_(dim=-2, index=(2 * unm_idx).unsqueeze(-1).expand(n, unm_len, c), src=unm)
+        out.scatter_(dim=-2, index=(2 * src_idx).unsqueeze(-1).expand(n, r, c), src=src)
+        return out
+
+    return merge, unmerge
+
+
+def merge_wavg(merge: Callable, x: Tensor, size: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """models/tome.py:309-323 — one fused launch when ``merge`` came from bipartite_soft_matching above."""
+    if isinstance(merge, _ToMeMerge):
+        out, size_out, _ = ops.tome_merge(x, size, merge.unm_idx, merge.src_idx, merge.dst_idx, False, True)
+        return out, size_out
+    if size is None:
+        size = torch.ones_like(x[..., 0, None])
+    x = merge(x * size, mode="sum")
+    size = merge(size, mode="sum")
+    return x / size, size
+
+
+def merge_source(merge: Callable, x: Tensor, source: Optional[Tensor] = None) -> Tensor:
+    """models/tome.py:326-337 — adjacency [B, N-r, t] between input tokens and merged groups."""
+    if source is None:
+        n, t, _ = x.shape
+        if isinstance(merge, _ToMeMerge):
+            rows = (merge.row_map(x) + 1).long()                              # output row of tokens 1..t-1
+            rows = torch.cat([rows.new_zeros(n, 1), rows], dim=1)             # CLS -> row 0
+            out = torch.zeros(n, t - merge.r, t, device=x.device)
+            return out.scatter_(1, rows.unsqueeze(1), 1.0)
+        source = torch.eye(t, device=x.device)[None, ...].expand(n, t, t)
+    return merge(source, mode="amax")
+
+
+class Attention_ToMe(_AttentionBase):
+    """models/tome.py:29-59.  forward(x, size) -> (x, metric = k.mean(1))."""
+
+    def forward(self, x, size=None):
+        q, k, v = self._qkv(x)
+        attn = (q @ k.transpose(-2, -1)) * self.scale
+        if size is not None:
+            attn = attn + size.log()[:, None, None, :, 0]        # proportional attention
+        attn = self.attn_drop(attn.softmax(dim=-1))
+        return self._out(attn, v), k.mean(1)
+
+
+class Block_ToMe(nn.Module):
+    """models/tome.py:61-104.  forward(x, attn_size) -> (x, attn_size, reduced_cluster_idx | None)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, drop=0.0, attn_drop=0.0, drop_path=0.0,
+                 act_layer=nn.GELU, norm_layer=nn.LayerNorm, r=0, cls_token=True, dist_token=False):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Attention_ToMe(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.r = r
+        self.cls_token = cls_token
+        self.dist_token = dist_token
+
+    def forward(self, x, attn_size=None):
+        x_attn, metric = self.attn(self.norm1(x), attn_size)
+        x = x + self.drop_path(x_attn)
+        reduced_cluster_idx = None
+        if self.r > 0:
+            _train_guard(self)
+            if self.dist_token:
+                raise NotImplementedError("Block_ToMe: dist_token protection is not on the accelerated path")
+            if ops.tome_effective_r(x.shape[1], self.r, self.cls_token) > 0:
+                lowp = _lowp() or metric.dtype == torch.bfloat16
+                unm, src, dst = ops.tome_match(metric, self.r, self.cls_token, lowp)
+                # merged tokens, new sizes and the source map from ONE launch (the reference pushes a [B,t,t]
+                # identity through the merge to get the map, models/tome.py:91-99)
+                x, attn_size, reduced_cluster_idx = ops.tome_merge(x, attn_size, unm, src, dst, True, True)
+                if not self.cls_token:
+                    reduced_cluster_idx = None      # reference: different offset without CLS; never used on this path
+        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        return x, attn_size, reduced_cluster_idx
+
+
+# =============================================================================================== DPC-KNN
+def index_points(points: Tensor, idx: Tensor) -> Tensor:
+    """models/dpcknn.py:25-41 — points [B,N,C], idx [B,S] -> [B,S,C]."""
+    b = points.shape[0]
+    batch = torch.arange(b, dtype=torch.long, device=points.device).view(b, *([1] * (idx.dim() - 1))).expand_as(idx)
+    return points[batch, idx, :]
+
+
+def cluster_dpc_knn(x: Tensor, cluster_num: int, k: int = 5, token_mask: Optional[Tensor] = None):
+    """models/dpcknn.py:44-100 -> (idx_cluster [B,N], index_down [B,cluster_num])."""
+    if token_mask is not None:
+        raise NotImplementedError("cluster_dpc_knn: token_mask is never passed by the reference models")
+    b, n, _ = x.shape
+    # the reference draws its tie-breaking noise inside the op (:73-74); same call, same generator position
+    noise = torch.rand((b, n), device=x.device, dtype=torch.float32)
+    return ops.dpcknn_cluster(x, noise, cluster_num, k)
+
+
+def merge_tokens(x, idx_token, agg_weight, idx_cluster, cluster_num, token_weight=None):
+    """models/dpcknn.py:103-140 -> (x_merged, idx_token_new, agg_weight_new)."""
+    return ops.dpcknn_merge(x, idx_token, agg_weight, idx_cluster, token_weight, cluster_num)
+
+
+class CTM(nn.Module):
+    """models/dpcknn.py:143-172.  forward(x, idx_token, agg_weight, viz_mode) -> 6-tuple."""
+
+    def __init__(self, embed_dim, cluster_num, k=5, equal_weight=False):
+        super().__init__()
+        self.cluster_num = cluster_num
+        self.equal_weight = equal_weight
+        self.k = k
+        if not self.equal_weight:
+            self.score = nn.Linear(embed_dim, 1)
+
+    def forward(self, x, idx_token, agg_weight, viz_mode=False):
+        _train_guard(self)
+        token_weight = None if self.equal_weight else self.score(x).exp()
+        idx_cluster, idx_centers = cluster_dpc_knn(x, self.cluster_num, self.k)
+        cluster_centers = index_points(x, idx_centers) if viz_mode else None
+        x, idx_token, agg_weight = merge_tokens(x, idx_token, agg_weight, idx_cluster, self.cluster_num, token_weight)
+        if viz_mode:
+            return x, idx_token, agg_weight, idx_centers, idx_cluster, cluster_centers
+        return x, idx_token, agg_weight, None, None, None
+
+
+# =============================================================================================== K-Medoids
+def k_medoids_fit(x: Tensor, cluster_num: int, iterations: int = 5, token_weight: Optional[Tensor] = None):
+    """models/kmedoids.py:40-85 -> (centres, cluster_idx, assignment)."""
+    if token_weight is None:
+        raise NotImplementedError("k_medoids_fit: the equal_weight initialisation (numpy RNG, models/kmedoids.py:43-61) "
+                                  "is not on the accelerated path")
+    return ops.kmedoids_fit(x, token_weight, cluster_num, iterations)
+
+
+class KMedoids(nn.Module):
+    """models/kmedoids.py:135-148.  forward(x, token_weights) -> (centres, idx_center, idx_cluster)."""
+
+    def __init__(self, num_clusters, iters, equal_weights=False):
+        super().__init__()
+        self.cluster_count = num_clusters
+        self.iters = iters
+        self.equal_weights = equal_weights
+
+    def forward(self, x, token_weights):
+        _train_guard(self)
+        if self.equal_weights:
+            token_weights = None
+        return k_medoids_fit(x, self.cluster_count, self.iters, token_weights)
+
+
+class AttentionWithProbs(_AttentionBase):
+    """models/kmedoids.py:88-112.  forward(x) -> (x, attn)."""
+
+    def forward(self, x):
+        q, k, v = self._qkv(x)
+        attn = self.attn_drop(((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1))
+        return self._out(attn, v), attn
+
+
+class BlockWithProbs(nn.Module):
+    """models/kmedoids.py:115-132.  forward(x) -> (x, attn)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, drop=0.0, attn_drop=0.0, drop_path=0.0,
+                 act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = AttentionWithProbs(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+    def forward(self, x):
+        x_attn, attn = self.attn(self.norm1(x))
+        x = x + self.drop_path(x_attn)
+        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        return x, attn
+
+
+# =============================================================================================== Sinkhorn
+class Sinkhorn(nn.Module):
+    """models/sinkhorn.py:59-86.  forward(x) -> (x [B,K,C], weights [B,K,P])."""
+
+    def __init__(self, embed_dim, cluster_centers, eps, iters):
+        super().__init__()
+        self.v = nn.Parameter(torch.randn(cluster_centers, embed_dim))
+        self.eps = eps
+        self.iters = iters
+
+    def forward(self, x):
+        _train_guard(self)
+        with torch.no_grad():                       # the reference overwrites its parameter (:73-76); idempotent
+            self.v.copy_(F.normalize(self.v.clone(), p=2, dim=-1))
+        return ops.sinkhorn_merge(x, self.v.detach(), self.eps, self.iters, _lowp())
+
+
+# =============================================================================================== PatchMerger
+class PatchMerger(nn.Module):
+    """models/patchmerger.py:24-39.  forward(x) -> (x [B,K,C], attn [B,K,P])."""
+
+    def __init__(self, embed_dim, cluster_centers, scaled_attention=False):
+        super().__init__()
+        self.scale = embed_dim ** -0.5 if scaled_attention else 1.0
+        self.norm = nn.LayerNorm(embed_dim)
+        self.queries = nn.Parameter(torch.randn(cluster_centers, embed_dim))
+
+    def forward(self, x):
+        _train_guard(self)
+        return ops.patchmerger(x, self.norm.weight.detach(), self.norm.bias.detach(), self.queries.detach(), self.scale,
+                               self.norm.eps, _lowp())
+
+
+# =============================================================================================== SiT
+class TokenSlimmingModule(nn.Module):
+    """models/sit.py:25-40.  forward(x) -> (x [B,K,C], weight [B,K,P])."""
+
+    def __init__(self, embed_dim, cluster_centers, ratio=0.5):
+        super().__init__()
+        hidden_dim = int(embed_dim * ratio)
+        self.weight = nn.Sequential(nn.LayerNorm(embed_dim), nn.Linear(embed_dim, hidden_dim), nn.GELU(),
+                                    nn.Linear(hidden_dim, cluster_centers))
+        self.scale = nn.Parameter(torch.ones(1, 1, 1))
+
+    def forward(self, x):
+        _train_guard(self)
+        return ops.sit_merge(x, self.weight(x), self.scale.detach(), _lowp())
+
+
+# =============================================================================================== ATS
+def batched_index_select(values: Tensor, indices: Tensor, dim: int = 1) -> Tensor:
+    """models/ats.py:27-41 for the two shapes the reference uses (tokens [B,N,C] with ids [B,M];
+    attention [B,H,N,N] with ids [B,H,M] identical across heads)."""
+    if values.dim() == 3 and indices.dim() == 2 and dim == 1:
+        return ops.gather_rows(values, indices)
+    if values.dim() == 4 and indices.dim() == 3 and dim == 2:
+        return ops.gather_rows(values, indices[:, 0].contiguous())
+    raise NotImplementedError("batched_index_select: only the token / attention-row gathers of models/ats.py")
+
+
+class AdaptiveTokenSampling(nn.Module):
+    """models/ats.py:44-89.  forward(v, attn, mask) -> (new_attn [B,H,M+1,N], new_mask [B,M+1], ids [B,M+1]).
+
+    ``static_width=True`` pads to sample_count instead of the batch maximum of unique ids: no host read at all
+    (the padded rows are copies of CLS that new_mask switches off, so logits are unchanged); the default keeps
+    the reference's data-dependent width at the cost of ONE scalar read (the reference syncs once per image).
+    """
+
+    def __init__(self, sample_count, eps=1e-6, static_width=False):
+        super().__init__()
+        self.sample_count = sample_count
+        self.sample_steps = torch.arange(1 / (2 * sample_count), (2 * sample_count - 1) / (2 * sample_count),
+                                         2 / (2 * sample_count))
+        self.eps = eps
+        self.static_width = static_width
+        self._steps_dev = None
+
+    def forward(self, x, attn, mask):
+        _train_guard(self)
+        if self._steps_dev is None or self._steps_dev.device != attn.device:
+            self._steps_dev = self.sample_steps.to(attn.device)
+        ids, new_mask, max_count = ops.ats_sample(x, attn, mask, self._steps_dev, self.eps)
+        if not self.static_width:
+            m = int(max_count.item()) + 1
+            ids, new_mask = ids[:, :m], new_mask[:, :m]
+        new_attn = ops.gather_rows(attn, ids, ids.shape[1])
+        return new_attn, new_mask, ids
+
+
+class ATSAttention(_AttentionBase):
+    """models/ats.py:92-134.  forward(x, mask) -> (x, mask, sample_ids | None)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0.0, proj_drop=0.0, ats_sample_count=0):
+        assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        super().__init__(dim, num_heads, qkv_bias, attn_drop, proj_drop)
+        self.ats_sample_count = ats_sample_count
+        if self.ats_sample_count:
+            self.ats = AdaptiveTokenSampling(ats_sample_count)
+
+    def forward(self, x, mask):
+        q, k, v = self._qkv(x)
+        dots = (q @ k.transpose(-2, -1)) * self.scale
+        if mask is not None:
+            dots_mask = mask.unsqueeze(1).unsqueeze(3) * mask.unsqueeze(1).unsqueeze(2)
+            dots = dots.masked_fill(~dots_mask, -torch.finfo(dots.dtype).max)
+        attn = self.attn_drop(dots.softmax(dim=-1))
+        sample_ids = None
+        if self.ats_sample_count:
+            attn, mask, sample_ids = self.ats(v, attn, mask)
+        return self._out(attn, v), mask, sample_ids
+
+
+class ATSBlock(nn.Module):
+    """models/ats.py:137-162.  forward(x, mask) -> (x, mask, sample_ids | None)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, drop=0.0, attn_drop=0.0, init_values=None,
+                 drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, ats_sample_count=0):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = ATSAttention(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop,
+                                 ats_sample_count=ats_sample_count)
+        self.drop_path1 = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.drop_path2 = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+
+    def forward(self, x, mask):
+        x_tmp, mask, sample_ids = self.attn(self.norm1(x), mask)
+        if sample_ids is not None:
+            x = ops.gather_rows(x, sample_ids)
+        x = x + self.drop_path1(x_tmp)
+        x = x + self.drop_path2(self.mlp(self.norm2(x)))
+        return x, mask, sample_ids
+
+
+# =============================================================================================== DynamicViT
+def batch_index_select(x: Tensor, idx: Tensor) -> Tensor:
+    """models/dyvit.py:340-356."""
+    if x.dim() == 3:
+        return ops.gather_rows(x, idx) if x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) else \
+            torch.gather(x, 1, idx.unsqueeze(-1).expand(-1, -1, x.shape[-1]))
+    if x.dim() == 2:
+        return torch.gather(x, 1, idx)
+    raise NotImplementedError
+
+
+class PredictorLG(nn.Module):
+    """models/dyvit.py:91-119.  forward(x, policy) -> log-softmax keep/drop scores [B,P,2]."""
+
+    def __init__(self, embed_dim=384, eps=1e-6):
+        super().__init__()
+        self.in_conv = nn.Sequential(nn.LayerNorm(embed_dim), nn.Linear(embed_dim, embed_dim), nn.GELU())
+        self.out_conv = nn.Sequential(nn.Linear(embed_dim, embed_dim // 2), nn.GELU(),
+                                      nn.Linear(embed_dim // 2, embed_dim // 4), nn.GELU(),
+                                      nn.Linear(embed_dim // 4, 2), nn.LogSoftmax(dim=-1))
+        self.eps = eps
+
+    def forward(self, x, policy):
+        h = self.in_conv(x)
+        return self.out_conv(ops.dyvit_pool_concat(h, policy, self.eps))
+
+
+class Policy_Attention(_AttentionBase):
+    """models/dyvit.py:23-69 (eval branch: policy is None -> plain softmax)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0.0, proj_drop=0.0):
+        super().__init__(dim, num_heads, qkv_bias, attn_drop, proj_drop)
+        if qk_scale is not None:
+            self.scale = qk_scale
+
+    def forward(self, x, policy=None):
+        if policy is not None:
+            raise NotImplementedError("Policy_Attention: softmax_with_policy is the training path (out of scope)")
+        q, k, v = self._qkv(x)
+        attn = ((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1)
+        return self._out(attn, v)
+
+
+class Block_DyVIT(nn.Module):
+    """models/dyvit.py:72-88."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, qk_scale=None, drop=0.0, attn_drop=0.0,
+                 drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = Policy_Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop,
+                                     proj_drop=drop)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+    def forward(self, x, policy=None):
+        x = x + self.drop_path(self.attn(self.norm1(x), policy=policy))
+        return x + self.drop_path(self.mlp(self.norm2(x)))

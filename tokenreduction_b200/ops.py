@@ -204,8 +204,8 @@ def _(metric, r, class_token, lowp):
 
 
 @torch.library.custom_op("tokred::tome_merge", mutates_args=(), device_types="cuda")
-def _tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor,
-                want_map: bool) -> Tuple[Tensor, Tensor, Tensor]:
+def _tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor, want_map: bool,
+                divide: bool) -> Tuple[Tensor, Tensor, Tensor]:
     _need_cuda("tome_merge", x, size, unm, src, dst)
     b, n, c = x.shape
     r = src.shape[1]
@@ -220,12 +220,12 @@ def _tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst
     size_out = torch.empty((b, n - r, 1), dtype=x.dtype, device=x.device)
     rci = torch.empty((b, n - 1) if want_map else (0,), dtype=torch.float32, device=x.device)
     _lib.call("tokred_tome_merge", _ptr(x), _dt(x), _ptr(size), _ptr(unm), _ptr(src), _ptr(dst), b, n, c, r, _ptr(out),
-              _ptr(size_out), _ptr(rci) if want_map else None, _stream())
+              _ptr(size_out), _ptr(rci) if want_map else None, int(divide), _stream())
     return out, size_out, rci
 
 
 @_tome_merge.register_fake
-def _(x, size, unm, src, dst, want_map):
+def _(x, size, unm, src, dst, want_map, divide):
     b, n, c = x.shape
     r = src.shape[1]
     return (x.new_empty((b, n - r, c)), x.new_empty((b, n - r, 1)),
@@ -237,9 +237,11 @@ def tome_match(metric: Tensor, r: int, class_token: bool = True, lowp: bool = Fa
     return torch.ops.tokred.tome_match(metric, r, class_token, lowp)
 
 
-def tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor, want_map: bool = True):
-    """models/tome.py:279-289,309-323 + Block_ToMe :91-99: (x_out [B,N-r,C], size_out [B,N-r,1], map [B,N-1] f32)."""
-    return torch.ops.tokred.tome_merge(x, size, unm, src, dst, want_map)
+def tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor, want_map: bool = True,
+               divide: bool = True):
+    """models/tome.py:279-289,309-323 + Block_ToMe :91-99: (x_out [B,N-r,C], size_out [B,N-r,1], map [B,N-1] f32).
+    divide=False returns the bare merge closure's sums instead of the size-weighted mean."""
+    return torch.ops.tokred.tome_merge(x, size, unm, src, dst, want_map, divide)
 
 
 # ----------------------------------------------------------------------------------------------- distances
