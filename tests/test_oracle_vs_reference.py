@@ -189,3 +189,34 @@ def test_dyvit(ref):
     x_ref = Dy.batch_index_select(xx, now)
     out, idx = O.dyvit_keep(xx, score, 98)
     assert torch.equal(idx, keep) and torch.equal(out, x_ref)
+
+
+# ---------------------------------------------------------------------------------------------- model level
+import argparse
+import contextlib
+import io
+
+from oracle import model as OM
+
+_KR = {"topk": 0.7, "evit": 0.5, "tome": 0.7, "dyvit": 0.5, "dpcknn": 0.25, "kmedoids": 0.25, "sinkhorn": 0.9,
+       "patchmerger": 0.9, "ats": 0.9, "sit": 0.9}
+
+
+@pytest.mark.parametrize("name", sorted(_KR))
+def test_model_tiny_vs_reference(ref, name):
+    """oracle.model.forward == the reference model (DeiT-tiny, reduction_loc 3 6 9) on the same weights and input."""
+    from timm.models import create_model
+    args = argparse.Namespace(keep_rate=[_KR[name]], reduction_loc=[3, 6, 9], distillation_type="none", k_neighbors=5,
+                              cluster_iters=3, sinkhorn_eps=1.0, equal_weight=False, dyvit_distill=False)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = create_model(f"{name}_tiny_patch16_224", pretrained=False, num_classes=16, drop_rate=0.0,
+                             drop_path_rate=0.0, drop_block_rate=None, img_size=224, args=args).eval()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x = torch.randn(2, 3, 224, 224, generator=g(77))
+    torch.manual_seed(5)
+    with torch.no_grad():
+        y_ref = model(x)
+    torch.manual_seed(5)
+    y = OM.forward(name, sd, x, OM.cfg_for("tiny", keep_rate=[_KR[name]]))
+    assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-5), float((y - y_ref).abs().max())

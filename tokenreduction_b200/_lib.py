@@ -67,10 +67,23 @@ def load() -> ctypes.CDLL:
     return lib
 
 
+# Optional launch timeline for bench.py: when a list is installed here every entry-point call is bracketed by two
+# CUDA events recorded on the launching (current) stream; bench.py reads the elapsed times after it synchronises.
+TIMELINE = None
+
+
 def call(name: str, *args) -> None:
     """Invoke an entry point and turn a non-zero return into a TokredError carrying tokred_last_error()."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if TIMELINE is not None:
+        import torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = getattr(lib, name)(*args)
+        ev1.record()
+        TIMELINE.append((name, args, ev0, ev1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.tokred_last_error().decode("utf-8", "replace")
         kind = "argument" if rc < 0 else f"cuda error {rc}"
