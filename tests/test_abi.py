@@ -1,0 +1,134 @@
+"""CPU: the C-ABI library loads and exports exactly what include/tokred.h declares; the ctypes binding mirrors the
+header; ops trace with FakeTensors; the product path fails loudly without CUDA (no compute calls here)."""
+import os
+import re
+from argparse import Namespace
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "tokred.h")
+
+
+def declared():
+    """{name: number of parameters} parsed from the header."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"TOKRED_API\s+[\w\s\*]+?\b(tokred_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        params = m.group(2).strip()
+        out[m.group(1)] = 0 if params in ("void", "") else len([p for p in params.split(",") if p.strip()])
+    return out
+
+
+def test_build_entry_compiles_library():
+    import __graft_entry__ as ge
+    ge.build()
+
+
+def test_library_exports_every_declared_symbol():
+    from tokenreduction_b200 import _lib
+    lib = _lib.load()
+    decl = declared()
+    assert len(decl) >= 19
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/tokred.h but not exported"
+    assert set(_lib.EXPORTS) == set(decl), set(_lib.EXPORTS) ^ set(decl)
+    assert lib.tokred_abi_version() == _lib.ABI_VERSION
+    assert isinstance(lib.tokred_last_error(), bytes)
+    assert _lib.launch_count() >= 0
+
+
+def test_binding_arity_matches_header():
+    from tokenreduction_b200 import _lib
+    decl = declared()
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert len(argtypes) == decl[name], f"{name}: binding has {len(argtypes)} params, header {decl[name]}"
+
+
+def test_host_side_argument_errors_need_no_gpu():
+    """argument validation happens on the host before any launch: negative return + message, no CUDA call."""
+    from tokenreduction_b200 import _lib
+    lib = _lib.load()
+    assert lib.tokred_tome_effective_r(197, 59, 1) == 59
+    assert lib.tokred_tome_effective_r(197, 150, 1) == 98
+    assert lib.tokred_tome_effective_r(3, 5, 1) == 1
+    with pytest.raises(_lib.TokredError, match="null tensor"):
+        _lib.call("tokred_topk_gather", None, 0, None, 0, 1, 196, None, 0, 0, 2, 197, 64, 10, None, None, None)
+    with pytest.raises(_lib.TokredError, match="argument"):
+        _lib.call("tokred_dpcknn_cluster", 16, 16, 2, 196, 64, 300, 5, 16, 16, None)      # K > P
+    # empty batch is a no-op even with null tensors
+    _lib.call("tokred_topk_gather", None, 0, None, 0, 1, 196, None, 0, 0, 0, 197, 64, 10, None, None, None)
+
+
+def test_ops_have_no_cpu_path():
+    import tokenreduction_b200.ops as T
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        T.topk_gather(torch.zeros(2, 197, 64), torch.zeros(2, 196), 10)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        T.tome_match(torch.zeros(2, 197, 64), 59, True, False)
+
+
+def test_fake_tensor_shapes():
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import tokenreduction_b200.ops as T
+    with FakeTensorMode():
+        x = torch.empty(4, 197, 384, device="cuda")
+        out, idx = T.topk_gather(x, torch.empty(4, 196, device="cuda"), 137)
+        assert out.shape == (4, 138, 384) and idx.shape == (4, 137) and idx.dtype == torch.int64
+        out, idx, compl = T.evit_select_fuse(x, torch.empty(4, 196, device="cuda"), 98)
+        assert out.shape == (4, 100, 384) and idx.shape == (4, 99) and compl.shape == (4, 98)
+        unm, src, dst = T.tome_match(torch.empty(4, 197, 64, device="cuda"), 150, True, True)
+        assert unm.shape == (4, 1) and src.shape == (4, 98)          # r capped at (N-1)//2 (quirk B.4)
+        o, s, m = T.tome_merge(x, None, unm, src, dst, True, True)
+        assert o.shape == (4, 99, 384) and s.shape == (4, 99, 1) and m.shape == (4, 196)
+        xp = torch.empty(4, 196, 384, device="cuda")
+        ic, idn = T.dpcknn_cluster(xp, torch.empty(4, 196, device="cuda"), 49, 5)
+        assert ic.shape == (4, 196) and idn.shape == (4, 49)
+        c, ci, a = T.kmedoids_fit(xp, torch.empty(4, 196, 1, device="cuda"), 49, 3)
+        assert c.shape == (4, 49, 384) and ci.shape == (4, 49) and a.shape == (4, 196)
+        o, w = T.sinkhorn_merge(xp, torch.empty(176, 384, device="cuda"), 1.0, 3, True)
+        assert o.shape == (4, 176, 384) and o.dtype == torch.bfloat16 and w.shape == (4, 176, 196)
+        ids, mk, mc = T.ats_sample(torch.empty(4, 6, 197, 64, device="cuda"), torch.empty(4, 6, 197, 197, device="cuda"),
+                                   torch.empty(4, 197, dtype=torch.bool, device="cuda"), torch.empty(176, device="cuda"))
+        assert ids.shape == (4, 177) and mk.dtype == torch.bool and mc.shape == (1,)
+
+
+def test_factory_surface():
+    """the 42 reference entrypoint names exist; reduced models keep the helper methods and parameter names."""
+    import contextlib
+    import io
+    from tokenreduction_b200 import create_model, list_models
+    names = list_models()
+    assert len(names) == 42
+    for fam in ("topk", "evit", "tome", "dyvit", "dpcknn", "kmedoids", "sinkhorn", "patchmerger", "ats", "sit", "heuristic"):
+        for size in ("tiny", "small", "base"):
+            assert f"{fam}_{size}_patch16_224" in names
+    args = Namespace(keep_rate=[0.25], reduction_loc=[3, 6, 9], k_neighbors=5, equal_weight=False)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = create_model("dpcknn_tiny_patch16_224", pretrained=False, num_classes=7, drop_rate=0.0, drop_path_rate=0.0,
+                         drop_block_rate=None, img_size=224, args=args)
+    assert m.get_new_module_names() == ["cluster_layers"] and m.get_reduction_count() == [3, 6, 9]
+    assert m.cluster_count == [49, 12, 3]
+    assert "cluster_layers.0.score.weight" in m.state_dict() and m.head.out_features == 7
+    with pytest.raises(RuntimeError):
+        create_model("no_such_model")
+    with pytest.raises(NotImplementedError):
+        create_model("heuristic_small_patch16_224", args=args)
+
+
+def test_keep_rate_schedules():
+    import contextlib
+    import io
+    from tokenreduction_b200 import create_model
+    mk = lambda name, kr: create_model(name, args=Namespace(keep_rate=[kr], reduction_loc=[3, 6, 9], k_neighbors=5,
+                                                            cluster_iters=3, sinkhorn_eps=1.0, equal_weight=False,
+                                                            dyvit_distill=False, distillation_type="none"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        tome = mk("tome_tiny_patch16_224", 0.7)
+        ats = mk("ats_tiny_patch16_224", 0.9)
+        topk = mk("topk_tiny_patch16_224", 0.7)
+    assert [b.r for b in tome.blocks] == [0, 0, 0, 59, 0, 0, 41, 0, 0, 29, 0, 0]
+    assert ats.sample_count == [0, 0, 0, 177, 0, 0, 159, 0, 0, 143, 0, 0]
+    assert [round(b.attn.keep_rate, 3) for b in topk.blocks][3::3] == [0.7, 0.49, 0.343]
