@@ -37,17 +37,39 @@ tome_match_kernel(const TM* __restrict__ metric, int N, int D, int r, int class_
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const TM* mb = metric + (long long)b * N * D;
 
-  // 1. m / ||m||  (norm accumulated in fp32; true division like the reference)
+  // 1a. stage the raw metric tile into shared memory with every load of the CTA in flight at once (the first
+  //     version walked the rows one warp at a time from global memory and was latency-bound: ncu r01, 55 us)
+  {
+    constexpr int VE = 16 / sizeof(TM);
+    const bool vec = (D % VE == 0) && ((reinterpret_cast<uintptr_t>(mb) & 15u) == 0);
+    if (vec) {
+      const int per_row = D / VE;
+      for (int e = tid; e < N * per_row; e += kThreads) {
+        const int t = e / per_row, d0 = (e % per_row) * VE;
+        const int4 raw = *reinterpret_cast<const int4*>(mb + (long long)t * D + d0);
+        const TM* v = reinterpret_cast<const TM*>(&raw);
+        float* dst = ((t & 1) ? (Bm + (t >> 1) * DP) : (A + (t >> 1) * DP)) + d0;
+#pragma unroll
+        for (int i = 0; i < VE; ++i) dst[i] = to_f32(v[i]);
+      }
+    } else {
+      for (int e = tid; e < N * D; e += kThreads) {
+        const int t = e / D, d = e % D;
+        ((t & 1) ? (Bm + (t >> 1) * DP) : (A + (t >> 1) * DP))[d] = to_f32(mb[e]);
+      }
+    }
+  }
+  __syncthreads();
+  // 1b. m / ||m||  (norm accumulated in fp32; true division like the reference), in place
   for (int t = warp; t < N; t += kWarps) {
-    const TM* row = mb + (long long)t * D;
+    float* row = (t & 1) ? (Bm + (t >> 1) * DP) : (A + (t >> 1) * DP);
     float ss = 0.f;
-    for (int d = lane; d < D; d += 32) { float v = to_f32(row[d]); ss = fmaf(v, v, ss); }
+    for (int d = lane; d < D; d += 32) { float v = row[d]; ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
     const float nrm = sqrtf(ss);
-    float* dst = (t & 1) ? (Bm + (t >> 1) * DP) : (A + (t >> 1) * DP);
     for (int d = lane; d < D; d += 32) {
-      float v = to_f32(row[d]) / nrm;
-      dst[d] = lowp ? bf16_round(v) : v;
+      float v = row[d] / nrm;
+      row[d] = lowp ? bf16_round(v) : v;
     }
   }
   __syncthreads();
@@ -145,63 +167,115 @@ __device__ __forceinline__ float mul_as(float x, float z) { return round_as<T>(_
 template <typename T>
 __device__ __forceinline__ float add_as(float a, float b) { return __fadd_rn(a, b); }
 
-template <typename T, bool VEC>
-__device__ __forceinline__ void merge_row(const T* __restrict__ xb, T* __restrict__ orow, int C, int lane, int t0, float z0,
-                                          const int* __restrict__ srcs, int nsrc, const float* __restrict__ zs,
-                                          bool has_size, float zsum, bool divide) {
-  constexpr int VE = VEC ? Chunk<T>::VE : 1;
-  const int nchunks = C / VE;
-  for (int c = lane; c < nchunks; c += 32) {
-    float acc[VE];
-    {
-      const T* p = xb + (long long)t0 * C + c * VE;
-      if (VEC) {
-        int4 raw = ld_stream16(p);
-        const T* v = reinterpret_cast<const T*>(&raw);
+// One warp produces one output row.  CPL = 16-byte chunks per lane: ALL chunks of a source row are requested
+// before any is consumed (CPL x 512 B in flight per warp) — the kernel is latency-bound otherwise (ncu r01:
+// long-scoreboard stalls, 20 % DRAM utilisation).  CPL == 0 selects the generic element-wise path.
+template <typename T, int CPL>
+struct RowAcc {
+  static constexpr int VE = Chunk<T>::VE;
+  float v[CPL > 0 ? CPL : 1][VE];
+};
+
+template <typename T, int CPL>
+__device__ __forceinline__ void load_row_chunks(const T* __restrict__ row, int nchunks, int lane, int4 (&raw)[CPL]) {
 #pragma unroll
-        for (int i = 0; i < VE; ++i) acc[i] = has_size ? mul_as<T>(to_f32(v[i]), z0) : to_f32(v[i]);
-      } else {
-        acc[0] = has_size ? mul_as<T>(to_f32(p[0]), z0) : to_f32(p[0]);
-      }
-    }
-#pragma unroll 2
-    for (int s = 0; s < nsrc; ++s) {
-      const int ts = 2 * srcs[s];
-      const float z = has_size ? zs[ts] : 1.f;
-      const T* p = xb + (long long)ts * C + c * VE;
-      if (VEC) {
-        int4 raw = ld_stream16(p);
-        const T* v = reinterpret_cast<const T*>(&raw);
-#pragma unroll
-        for (int i = 0; i < VE; ++i)
-          acc[i] = add_as<T>(acc[i], has_size ? mul_as<T>(to_f32(v[i]), z) : to_f32(v[i]));
-      } else {
-        acc[0] = add_as<T>(acc[0], has_size ? mul_as<T>(to_f32(p[0]), z) : to_f32(p[0]));
-      }
-    }
-    T outv[VE];
-#pragma unroll
-    for (int i = 0; i < VE; ++i) outv[i] = divide ? from_f32<T>(__fdiv_rn(round_as<T>(acc[i]), zsum)) : from_f32<T>(acc[i]);
-    if (VEC) st_stream16(orow + c * VE, *reinterpret_cast<const int4*>(outv));
-    else orow[c] = outv[0];
+  for (int i = 0; i < CPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) raw[i] = ld_stream16(row + c * Chunk<T>::VE);
   }
 }
 
-template <typename T, bool VEC>
+template <typename T, int CPL>
+__device__ __forceinline__ void merge_row_vec(const T* __restrict__ xb, T* __restrict__ orow, int C, int lane, int t0,
+                                              int j, const int* __restrict__ src, const int* __restrict__ dst, int r,
+                                              const float* __restrict__ zs, bool has_size, bool divide, float& zsum_out) {
+  constexpr int VE = Chunk<T>::VE;
+  const int nchunks = C / VE;
+  RowAcc<T, CPL> acc;
+  int4 raw[CPL];
+  load_row_chunks<T, CPL>(xb + (long long)t0 * C, nchunks, lane, raw);
+  const float z0 = zs[t0];
+  float zsum = z0;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const T* v = reinterpret_cast<const T*>(&raw[i]);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) acc.v[i][e] = has_size ? mul_as<T>(to_f32(v[e]), z0) : to_f32(v[e]);
+  }
+  if (j >= 0) {
+    // sources of odd token j, in src-list order: ballot over the list, then walk the set bits (warp-uniform)
+    for (int base = 0; base < r; base += 32) {
+      const int sidx = base + lane;
+      unsigned m = __ballot_sync(0xffffffffu, sidx < r && dst[sidx] == j);
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int ts = 2 * src[base + bit];
+        load_row_chunks<T, CPL>(xb + (long long)ts * C, nchunks, lane, raw);
+        const float z = zs[ts];
+        zsum = add_as<T>(zsum, z);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const T* v = reinterpret_cast<const T*>(&raw[i]);
+#pragma unroll
+          for (int e = 0; e < VE; ++e)
+            acc.v[i][e] = add_as<T>(acc.v[i][e], has_size ? mul_as<T>(to_f32(v[e]), z) : to_f32(v[e]));
+        }
+      }
+    }
+  }
+  zsum = round_as<T>(zsum);
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      T outv[VE];
+#pragma unroll
+      for (int e = 0; e < VE; ++e)
+        outv[e] = divide ? from_f32<T>(__fdiv_rn(round_as<T>(acc.v[i][e]), zsum)) : from_f32<T>(acc.v[i][e]);
+      st_stream16(orow + c * VE, *reinterpret_cast<const int4*>(outv));
+    }
+  }
+  zsum_out = zsum;
+}
+
+// generic path: any C / alignment, one element per lane-step
+template <typename T>
+__device__ __forceinline__ void merge_row_any(const T* __restrict__ xb, T* __restrict__ orow, int C, int lane, int t0, int j,
+                                              const int* __restrict__ src, const int* __restrict__ dst, int r,
+                                              const float* __restrict__ zs, bool has_size, bool divide, float& zsum_out) {
+  float zsum = zs[t0];
+  if (j >= 0)
+    for (int s = 0; s < r; ++s)
+      if (dst[s] == j) zsum = add_as<T>(zsum, zs[2 * src[s]]);
+  zsum = round_as<T>(zsum);
+  for (int c = lane; c < C; c += 32) {
+    const float x0 = to_f32(xb[(long long)t0 * C + c]);
+    float acc = has_size ? mul_as<T>(x0, zs[t0]) : x0;
+    if (j >= 0)
+      for (int s = 0; s < r; ++s)
+        if (dst[s] == j) {
+          const int ts = 2 * src[s];
+          const float xv = to_f32(xb[(long long)ts * C + c]);
+          acc = add_as<T>(acc, has_size ? mul_as<T>(xv, zs[ts]) : xv);
+        }
+    orow[c] = divide ? from_f32<T>(__fdiv_rn(round_as<T>(acc), zsum)) : from_f32<T>(acc);
+  }
+  zsum_out = zsum;
+}
+
+template <typename T, int CPL>
 __global__ void __launch_bounds__(kThreads)
 tome_merge_kernel(const T* __restrict__ x, const T* __restrict__ size, const int64_t* __restrict__ unm_idx,
                   const int64_t* __restrict__ src_idx, const int64_t* __restrict__ dst_idx, int N, int C, int r,
                   T* __restrict__ x_out, T* __restrict__ size_out, float* __restrict__ rci, int divide) {
   extern __shared__ float smem[];
-  const int na = (N + 1) / 2, nb = N / 2, n_unm = na - r, n_out = N - r;
+  const int na = (N + 1) / 2, n_unm = na - r, n_out = N - r;
   float* zs = smem;                                   // [N]   token sizes
   int* unm = reinterpret_cast<int*>(zs + N);          // [n_unm]
   int* src = unm + n_unm;                             // [r]
   int* dst = src + r;                                 // [r]
-  int* cnt = dst + r;                                 // [nb]
-  int* offs = cnt + nb;                               // [nb]
-  int* csr = offs + nb;                               // [r]   sources of each odd token, in src-list order
-  int* rowmap = csr + r;                              // [na]  output row of every even token
+  int* rowmap = dst + r;                              // [na]  output row of every even token
 
   const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool has_size = size != nullptr;
@@ -212,38 +286,15 @@ tome_merge_kernel(const T* __restrict__ x, const T* __restrict__ size, const int
     dst[s] = (int)dst_idx[(long long)b * r + s];
   }
   __syncthreads();
-  for (int j = tid; j < nb; j += kThreads) {
-    int c = 0;
-    for (int s = 0; s < r; ++s) c += (dst[s] == j);
-    cnt[j] = c;
-  }
-  __syncthreads();
-  for (int j = tid; j < nb; j += kThreads) {
-    int o = 0;
-    for (int q = 0; q < j; ++q) o += cnt[q];
-    offs[j] = o;
-    for (int s = 0; s < r; ++s)
-      if (dst[s] == j) csr[o++] = src[s];
-  }
-  __syncthreads();
 
   const T* xb = x + (long long)b * N * C;
   T* ob = x_out + (long long)b * n_out * C;
   for (int q = blockIdx.x * kWarps + warp; q < n_out; q += gridDim.x * kWarps) {
-    int t0, nsrc = 0;
-    const int* srcs = csr;
-    if (q < n_unm) {
-      t0 = 2 * unm[q];
-    } else {
-      const int j = q - n_unm;
-      t0 = 2 * j + 1;
-      nsrc = cnt[j];
-      srcs = csr + offs[j];
-    }
-    float zsum = zs[t0];
-    for (int s = 0; s < nsrc; ++s) zsum = add_as<T>(zsum, zs[2 * srcs[s]]);
-    zsum = round_as<T>(zsum);
-    merge_row<T, VEC>(xb, ob + (long long)q * C, C, lane, t0, zs[t0], srcs, nsrc, zs, has_size, zsum, divide != 0);
+    const int j = q < n_unm ? -1 : q - n_unm;
+    const int t0 = q < n_unm ? 2 * unm[q] : 2 * j + 1;
+    float zsum;
+    if constexpr (CPL > 0) merge_row_vec<T, CPL>(xb, ob + (long long)q * C, C, lane, t0, j, src, dst, r, zs, has_size, divide != 0, zsum);
+    else merge_row_any<T>(xb, ob + (long long)q * C, C, lane, t0, j, src, dst, r, zs, has_size, divide != 0, zsum);
     if (lane == 0) size_out[(long long)b * n_out + q] = from_f32<T>(zsum);
   }
 
@@ -305,22 +356,32 @@ extern "C" int tokred_tome_merge(const void* x, int x_dtype, const void* size, c
   TOKRED_REQUIRE(r >= 1 && r <= N / 2 && r <= (N + 1) / 2, "%s: r=%d outside [1, %d]", what, r, N / 2);
   TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
   if (B == 0) return TOKRED_OK;
-  const int na = (N + 1) / 2, nb = N / 2, n_unm = na - r, n_out = N - r;
-  const size_t smem = (size_t)(N + n_unm + 3 * r + 2 * nb + na) * 4;
+  const int na = (N + 1) / 2, n_unm = na - r, n_out = N - r;
+  const size_t smem = (size_t)(N + n_unm + 2 * r + na) * 4;
   const int ve = x_dtype == TOKRED_F32 ? 4 : 8;
   const bool vec = (C % ve == 0) && aligned16(x) && aligned16(x_out);
-  int splits = ceil_div(4 * kNumSMs, B);
+  const int cpl = vec ? ceil_div(C / ve, 32) : 0;
+  int splits = ceil_div(6 * kNumSMs, B);
   splits = max(1, min(splits, ceil_div(n_out, kWarps)));
   dim3 grid(splits, B);
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(T, VEC)                                                                                          \
+#define LAUNCH(T, CPL)                                                                                          \
   do {                                                                                                          \
-    if (int e = allow_smem(tome_merge_kernel<T, VEC>, smem, what)) return e;                                    \
-    tome_merge_kernel<T, VEC><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)size, unm_idx, src_idx, dst_idx, \
+    if (int e = allow_smem(tome_merge_kernel<T, CPL>, smem, what)) return e;                                    \
+    tome_merge_kernel<T, CPL><<<grid, kThreads, smem, st>>>((const T*)x, (const T*)size, unm_idx, src_idx, dst_idx, \
                                                             N, C, r, (T*)x_out, (T*)size_out, reduced_cluster_idx, divide); \
   } while (0)
-  if (x_dtype == TOKRED_F32) { if (vec) LAUNCH(float, true); else LAUNCH(float, false); }
-  else { if (vec) LAUNCH(__nv_bfloat16, true); else LAUNCH(__nv_bfloat16, false); }
+#define DISPATCH(T)                         \
+  switch (cpl) {                            \
+    case 1: LAUNCH(T, 1); break;            \
+    case 2: LAUNCH(T, 2); break;            \
+    case 3: LAUNCH(T, 3); break;            \
+    case 4: LAUNCH(T, 4); break;            \
+    case 5: case 6: LAUNCH(T, 6); break;    \
+    default: LAUNCH(T, 0); break;           \
+  }
+  if (x_dtype == TOKRED_F32) { DISPATCH(float) } else { DISPATCH(__nv_bfloat16) }
+#undef DISPATCH
 #undef LAUNCH
   return finish_launch(what);
 }
