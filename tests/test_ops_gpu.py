@@ -191,6 +191,22 @@ def test_tome_match_lowp_bf16(T):
     assert same.float().mean() >= 0.9, f"only {float(same.float().mean()):.2f} of images match exactly"
 
 
+@pytest.mark.parametrize("n,r,d", [(197, 59, 64), (138, 41, 64), (97, 29, 64), (50, 30, 32), (197, 98, 64), (255, 60, 48), (33, 9, 16)])
+def test_tome_match_tensor_core_vs_ffma(T, n, r, d):
+    """the tcgen05 (UTCHMMA + TMEM) similarity path against the FFMA path with identical bf16 rounding."""
+    b = 24
+    metric = torch.randn(b, n, d, generator=g(140)).bfloat16().to(DEV)
+    tc = T.tome_match(metric, r, True, True, True)
+    ff = T.tome_match(metric, r, True, True, False)
+    same = torch.stack([(a == c).all(dim=1) for a, c in zip(tc, ff)]).all(dim=0)
+    assert same.float().mean() >= 0.95, f"only {float(same.float().mean()):.2f} of images identical"
+    # the index lists are a valid matching: src and unm partition the even tokens, dst within the odd tokens
+    unm, src, dst = tc
+    both = torch.cat([unm, src], dim=1).sort(dim=1).values
+    assert torch.equal(both, torch.arange((n + 1) // 2, device=DEV).expand(b, -1))
+    assert int(dst.min()) >= 0 and int(dst.max()) < n // 2 and bool((unm[:, 0] == 0).all())
+
+
 def test_tome_match_no_class_token(T):
     b, n, r, d = 4, 64, 16, 32
     metric = torch.randn(b, n, d, generator=g(15))

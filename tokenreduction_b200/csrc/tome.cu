@@ -13,6 +13,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace tokred {
 namespace {
@@ -60,17 +61,24 @@ tome_match_kernel(const TM* __restrict__ metric, int N, int D, int r, int class_
     }
   }
   __syncthreads();
-  // 1b. m / ||m||  (norm accumulated in fp32; true division like the reference), in place
-  for (int t = warp; t < N; t += kWarps) {
-    float* row = (t & 1) ? (Bm + (t >> 1) * DP) : (A + (t >> 1) * DP);
+  // 1b. m / ||m||  (norm accumulated in fp32; true division like the reference), in place.  8 lanes per row, so a
+  //     warp keeps 4 rows in flight and the shuffle chain is 3 deep (one row per warp was latency-bound).
+  for (int base = warp * 4; base < N; base += kWarps * 4) {      // warp-uniform trip count (full-mask shuffles inside)
+    const int t = base + (lane >> 3), sub = lane & 7;
+    const bool live = t < N;
+    float* row = ((t & 1) ? (Bm + (t >> 1) * DP) : (A + (t >> 1) * DP));
     float ss = 0.f;
-    for (int d = lane; d < D; d += 32) { float v = row[d]; ss = fmaf(v, v, ss); }
-    ss = warp_sum(ss);
+    if (live)
+      for (int d = sub; d < D; d += 8) { float v = row[d]; ss = fmaf(v, v, ss); }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
     const float nrm = sqrtf(ss);
-    for (int d = lane; d < D; d += 32) {
-      float v = row[d] / nrm;
-      row[d] = lowp ? bf16_round(v) : v;
-    }
+    if (live)
+      for (int d = sub; d < D; d += 8) {
+        float v = row[d] / nrm;
+        row[d] = lowp ? bf16_round(v) : v;
+      }
   }
   __syncthreads();
 
@@ -145,6 +153,149 @@ tome_match_kernel(const TM* __restrict__ metric, int N, int D, int r, int class_
   if (class_token) {
     __syncthreads();
     for (int i = tid; i < na; i += kThreads) {
+      if (!merged[i]) {
+        int pos = 0;
+        for (int q = 0; q < i; ++q) pos += !merged[q];
+        unm_idx[(long long)b * n_unm + pos] = i;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ match, tensor cores
+// bf16-autocast path (score_lowp = 1): the reference's `a @ b^T` IS a bf16 tensor-core matmul with fp32 accumulate
+// and a bf16-rounded result, so the similarity tile goes to tcgen05: normalised rows are written as bf16 straight
+// into the canonical K-major UMMA layout, ONE thread issues D/16 tcgen05.mma (M=128 x N<=256 x K=16) into a TMEM
+// accumulator, and the epilogue reads it with tcgen05.ld 32x32b — thread i owns accumulator row i, which is exactly
+// what the per-row (max, argmax) needs: no similarity matrix in shared memory, no cross-thread reduction.
+constexpr int kTcThreads = 256;
+
+template <typename TM>
+__global__ void __launch_bounds__(kTcThreads)
+tome_match_tc_kernel(const TM* __restrict__ metric, int N, int D, int r, int class_token,
+                     int64_t* __restrict__ unm_idx, int64_t* __restrict__ src_idx, int64_t* __restrict__ dst_idx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int na = (N + 1) / 2, nb = N / 2;
+  const int Dp = (D + 15) & ~15, Np = (nb + 15) & ~15;
+  const uint32_t sbo = (uint32_t)(Dp / 8) * 128u;            // bytes between 8-row groups
+  unsigned char* opA = smem_raw;                               // 128 rows (even tokens), canonical K-major bf16
+  unsigned char* opB = opA + 16 * sbo;                         // Np rows (odd tokens)
+  TM* raw = reinterpret_cast<TM*>(opB + (Np / 8) * sbo);       // [N][D] staged metric
+  float* node_max = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(raw) + (((size_t)N * D * sizeof(TM) + 15) & ~(size_t)15));
+  int* node_idx = reinterpret_cast<int*>(node_max + 128);
+  unsigned char* merged = reinterpret_cast<unsigned char*>(node_idx + 128);   // [128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(merged + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TM* mb = metric + (long long)b * N * D;
+  const uint32_t ncols = umma::tmem_cols_pow2((uint32_t)Np);
+
+  if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
+  if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_mbar_init(); }
+
+  // stage the raw metric (every load of the CTA in flight at once) and clear the operand tiles (padding = 0)
+  {
+    constexpr int VE = 16 / sizeof(TM);
+    const int total = N * D;
+    if ((total % VE == 0) && ((reinterpret_cast<uintptr_t>(mb) & 15u) == 0)) {
+      for (int e = tid; e < total / VE; e += kTcThreads)
+        reinterpret_cast<int4*>(raw)[e] = *reinterpret_cast<const int4*>(mb + (long long)e * VE);
+    } else {
+      for (int e = tid; e < total; e += kTcThreads) raw[e] = mb[e];
+    }
+    const int op_int4 = (int)((16 + Np / 8) * sbo / 16);
+    for (int e = tid; e < op_int4; e += kTcThreads) reinterpret_cast<int4*>(opA)[e] = make_int4(0, 0, 0, 0);
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // m / ||m|| in fp32, rounded to bf16 (what the autocast matmul does to its operands), into the UMMA layout.
+  // 8 lanes per row: lane `sub` owns elements sub, sub+8, ... so the 8 lanes of a row write one 16-byte K-chunk.
+  for (int base = warp * 4; base < N; base += (kTcThreads / 32) * 4) {   // warp-uniform trip count (full-mask shuffles)
+    const int t = base + (lane >> 3), sub = lane & 7;
+    const bool live = t < N;
+    const TM* row = raw + (size_t)t * D;
+    float ss = 0.f;
+    if (live)
+      for (int d = sub; d < D; d += 8) { float v = to_f32(row[d]); ss = fmaf(v, v, ss); }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    const float nrm = sqrtf(ss);
+    if (live) {
+      unsigned char* op = ((t & 1) ? opB : opA) + (uint32_t)(t >> 4) * sbo + (uint32_t)((t >> 1) & 7) * 16u + (uint32_t)sub * 2u;
+      for (int d = sub; d < D; d += 8)
+        *reinterpret_cast<__nv_bfloat16*>(op + (uint32_t)(d >> 3) * 128u) = __float2bfloat16_rn(to_f32(row[d]) / nrm);
+    }
+  }
+  umma::fence_proxy_async_smem();
+  __syncthreads();
+
+  if (tid == 0) {
+    umma::tc_fence_after_sync();
+    const uint32_t idesc = umma::instr_desc(umma::FMT_BF16, 128, (uint32_t)Np);
+    const uint32_t a0 = umma::smem_u32(opA), b0 = umma::smem_u32(opB);
+    for (int ks = 0; ks < Dp / 16; ++ks) {
+      const uint64_t da = umma::smem_desc_kmajor(a0 + ks * 256, 128, sbo);
+      const uint64_t db = umma::smem_desc_kmajor(b0 + ks * 256, 128, sbo);
+      umma::mma_bf16(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma::mma_commit(bar);
+  }
+  umma::mbar_wait(bar, 0);
+  umma::tc_fence_after_sync();
+
+  // per-row (max, argmax) straight from TMEM: lane quarter q = warp % 4 holds rows 32q..32q+31; warps q and q+4
+  // split the columns (a warp may only touch its own lane quarter).  Lowest column wins ties; CLS row protected.
+  {
+    const int i = (warp & 3) * 32 + lane;
+    const int half = ((Np / 16 + 1) / 2) * 16;
+    const int cbeg = warp < 4 ? 0 : half, cend = warp < 4 ? half : Np;
+    float best = -CUDART_INF_F;
+    int bj = 0x7fffffff;
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+      uint32_t v[16];
+      umma::tmem_ld16(umma::tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)c0), v);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float sc = bf16_round(__uint_as_float(v[j]));
+        if (c0 + j < nb && (sc > best || bj == 0x7fffffff)) { best = sc; bj = c0 + j; }
+      }
+    }
+    if (warp >= 4) { node_max[i] = best; node_idx[i] = bj; }
+    __syncthreads();
+    if (warp < 4) {
+      const float ob = node_max[i];
+      const int oj = node_idx[i];
+      if (oj != 0x7fffffff && (ob > best || bj == 0x7fffffff)) { best = ob; bj = oj; }   // ties keep the lower column
+      if (bj == 0x7fffffff) bj = 0;
+      if (class_token && i == 0) { best = -CUDART_INF_F; bj = 0; }
+    }
+    __syncthreads();
+    if (warp < 4) { node_max[i] = best; node_idx[i] = bj; }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, ncols);
+
+  const int n_unm = na - r;
+  for (int i = tid; i < na; i += kTcThreads) {
+    const int rk = rank_desc(node_max, na, i);
+    merged[i] = rk < r;
+    if (rk < r) {
+      src_idx[(long long)b * r + rk] = i;
+      dst_idx[(long long)b * r + rk] = node_idx[i];
+    } else if (!class_token) {
+      unm_idx[(long long)b * n_unm + (rk - r)] = i;
+    }
+  }
+  if (class_token) {
+    __syncthreads();
+    for (int i = tid; i < na; i += kTcThreads) {
       if (!merged[i]) {
         int pos = 0;
         for (int q = 0; q < i; ++q) pos += !merged[q];
@@ -331,8 +482,25 @@ extern "C" int tokred_tome_match(const void* metric, int metric_dtype, int B, in
   TOKRED_REQUIRE(re >= 1, "%s: effective r = %d (r=%d, N=%d): nothing to merge, caller must skip", what, re, r, N);
   if (B == 0) return TOKRED_OK;
   const int na = (N + 1) / 2, nb = N / 2;
-  const size_t smem = ((size_t)(na + nb) * (D + 1) + (size_t)na * (nb + 1) + 2 * na) * 4 + na;
   cudaStream_t st = (cudaStream_t)stream;
+  // tensor-core path: bf16-rounded similarity (autocast), one 128-row M tile, N <= 256 columns
+  const int Dp = (D + 15) & ~15, Np = (nb + 15) & ~15;
+  const size_t tc_smem = (size_t)(16 + Np / 8) * (Dp / 8) * 128 + (((size_t)N * D * dtype_size(metric_dtype) + 15) & ~(size_t)15) +
+                         128 * 4 + 128 * 4 + 128 + 16;
+  if (score_lowp && (score_lowp & 2) == 0 && na <= 128 && Np <= 256 && tc_smem <= 200 * 1024) {
+    if (metric_dtype == TOKRED_F32) {
+      if (int e = allow_smem(tome_match_tc_kernel<float>, tc_smem, what)) return e;
+      tome_match_tc_kernel<float><<<B, kTcThreads, tc_smem, st>>>((const float*)metric, N, D, re, class_token, unm_idx,
+                                                                  src_idx, dst_idx);
+    } else {
+      if (int e = allow_smem(tome_match_tc_kernel<__nv_bfloat16>, tc_smem, what)) return e;
+      tome_match_tc_kernel<__nv_bfloat16><<<B, kTcThreads, tc_smem, st>>>((const __nv_bfloat16*)metric, N, D, re,
+                                                                          class_token, unm_idx, src_idx, dst_idx);
+    }
+    return finish_launch(what);
+  }
+  score_lowp = score_lowp ? 1 : 0;
+  const size_t smem = ((size_t)(na + nb) * (D + 1) + (size_t)na * (nb + 1) + 2 * na) * 4 + na;
   if (metric_dtype == TOKRED_F32) {
     if (int e = allow_smem(tome_match_kernel<float>, smem, what)) return e;
     tome_match_kernel<float><<<B, kThreads, smem, st>>>((const float*)metric, N, D, re, class_token, score_lowp,

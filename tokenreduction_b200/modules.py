@@ -182,7 +182,7 @@ def bipartite_soft_matching(metric: Tensor, r: int, class_token: bool = False,
     if r <= 0:
         return do_nothing, do_nothing
     lowp = _lowp() or metric.dtype == torch.bfloat16
-    unm_idx, src_idx, dst_idx = ops.tome_match(metric, r, class_token, lowp)
+    unm_idx, src_idx, dst_idx = ops.tome_match(metric, r, class_token, lowp, True)
     merge = _ToMeMerge(unm_idx, src_idx, dst_idx, t)
 
     def unmerge(x: Tensor) -> Tensor:                                  # models/tome.py:291-304 (not on the hot path)
@@ -261,7 +261,7 @@ class Block_ToMe(nn.Module):
                 raise NotImplementedError("Block_ToMe: dist_token protection is not on the accelerated path")
             if ops.tome_effective_r(x.shape[1], self.r, self.cls_token) > 0:
                 lowp = _lowp() or metric.dtype == torch.bfloat16
-                unm, src, dst = ops.tome_match(metric, self.r, self.cls_token, lowp)
+                unm, src, dst = ops.tome_match(metric, self.r, self.cls_token, lowp, True)
                 # merged tokens, new sizes and the source map from ONE launch (the reference pushes a [B,t,t]
                 # identity through the merge to get the map, models/tome.py:91-99)
                 x, attn_size, reduced_cluster_idx = ops.tome_merge(x, attn_size, unm, src, dst, True, True)

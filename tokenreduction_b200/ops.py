@@ -178,7 +178,7 @@ def tome_effective_r(n_tokens: int, r: int, class_token: bool = True) -> int:
 
 
 @torch.library.custom_op("tokred::tome_match", mutates_args=(), device_types="cuda")
-def _tome_match(metric: Tensor, r: int, class_token: bool, lowp: bool) -> Tuple[Tensor, Tensor, Tensor]:
+def _tome_match(metric: Tensor, r: int, class_token: bool, lowp: bool, tensor_cores: bool) -> Tuple[Tensor, Tensor, Tensor]:
     _need_cuda("tome_match", metric)
     b, n, d = metric.shape
     re = tome_effective_r(n, r, class_token)
@@ -189,13 +189,14 @@ def _tome_match(metric: Tensor, r: int, class_token: bool, lowp: bool) -> Tuple[
     unm = torch.empty((b, na - re), dtype=torch.int64, device=metric.device)
     src = torch.empty((b, re), dtype=torch.int64, device=metric.device)
     dst = torch.empty((b, re), dtype=torch.int64, device=metric.device)
-    _lib.call("tokred_tome_match", _ptr(metric), _dt(metric), b, n, d, r, int(class_token), int(lowp), _ptr(unm),
+    mode = (1 if tensor_cores else 3) if lowp else 0
+    _lib.call("tokred_tome_match", _ptr(metric), _dt(metric), b, n, d, r, int(class_token), mode, _ptr(unm),
               _ptr(src), _ptr(dst), _stream())
     return unm, src, dst
 
 
 @_tome_match.register_fake
-def _(metric, r, class_token, lowp):
+def _(metric, r, class_token, lowp, tensor_cores):
     b, n, d = metric.shape
     re = tome_effective_r(n, r, class_token)
     na = (n + 1) // 2
@@ -232,9 +233,11 @@ def _(x, size, unm, src, dst, want_map, divide):
             x.new_empty((b, n - 1) if want_map else (0,), dtype=torch.float32))
 
 
-def tome_match(metric: Tensor, r: int, class_token: bool = True, lowp: bool = False):
-    """models/tome.py:258-277: (unm_idx [B,a-r], src_idx [B,r], dst_idx [B,r]) int64."""
-    return torch.ops.tokred.tome_match(metric, r, class_token, lowp)
+def tome_match(metric: Tensor, r: int, class_token: bool = True, lowp: bool = False, tensor_cores: bool = True):
+    """models/tome.py:258-277: (unm_idx [B,a-r], src_idx [B,r], dst_idx [B,r]) int64.
+    lowp=True reproduces the bf16 autocast matmul (on tcgen05 tensor cores; tensor_cores=False keeps the same
+    rounding on the FFMA path, used as a cross-check)."""
+    return torch.ops.tokred.tome_match(metric, r, class_token, lowp, tensor_cores)
 
 
 def tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor, want_map: bool = True,

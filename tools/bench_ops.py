@@ -43,6 +43,9 @@ def cases():
     def add(label, fn, *tensors):
         out.append((label, fn))
 
+    # calibration: a 1-row gather = launch + event overhead of this timing method
+    xs, ids1 = torch.randn(1, 4, 64, device=DEV), torch.zeros(1, 1, dtype=torch.int64, device=DEV)
+    out.append(("calibration: empty launch (1-row gather)", lambda: T.gather_rows(xs, ids1)))
     # config 1: Top-K S kr 0.7 B=64 ; plus B=1024 large-batch sweep point
     for b in (64, 1024):
         for n, k in ((197, 137), (138, 96), (97, 67)):
@@ -56,7 +59,8 @@ def cases():
         x = torch.randn(b, n, 384, device=DEV)
         size = torch.ones(b, n, 1, device=DEV)
         unm, src, dst = T.tome_match(m, r, True, True)
-        out.append((f"tome_match S B={b} N={n} r={r} lowp", lambda m=m, r=r: T.tome_match(m, r, True, True)))
+        out.append((f"tome_match S B={b} N={n} r={r} lowp tcgen05", lambda m=m, r=r: T.tome_match(m, r, True, True, True)))
+        out.append((f"tome_match S B={b} N={n} r={r} lowp ffma", lambda m=m, r=r: T.tome_match(m, r, True, True, False)))
         out.append((f"tome_match S B={b} N={n} r={r} fp32", lambda m=m, r=r: T.tome_match(m.float(), r, True, False)))
         out.append((f"tome_merge S B={b} N={n} r={r}", lambda x=x, size=size, u=unm, s=src, d=dst: T.tome_merge(x, size, u, s, d, True, True)))
     # config 3: EViT / DynamicViT B kr 0.5, B=128 (8-GPU shard) and B=1024
