@@ -116,7 +116,8 @@ TOKRED_API int tokred_kmedoids_fit(const float* x, const float* token_weight, in
 /* ---- a9 Sinkhorn -------------------------------------------------------------------------------------
  * models/sinkhorn.py:66-86 with :25-56.  v_hat [K,C] fp32 is the already-normalised parameter.
  *   log_norm = -log(K+P) evaluated by the caller the way the reference does (:44-47; in bf16 under autocast)
- *   lowp = 1: both contractions round operands/result to bf16 (CUDA autocast); out dtype given by out_dtype.
+ *   lowp = 1: both contractions round operands/result to bf16 (CUDA autocast) and run on tcgen05 tensor cores
+ *   when out_dtype is bf16; lowp = 3: same rounding on the FFMA path (cross-check); lowp = 0: exact fp32 (FFMA).
  *   out [B,K,C], weights [B,K,P] fp32                                                                   */
 TOKRED_API int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_hat, int B, int P, int C, int K, float eps,
                           float log_norm, int iters, int lowp, void* out, int out_dtype, float* weights,

@@ -378,6 +378,36 @@ def test_sinkhorn_lowp(T):
     assert_close_rel(out.float(), out_ref.float(), RTOL16, "merged tokens")
 
 
+@pytest.mark.parametrize("p,k,c,xdt", [(196, 176, 768, torch.float32), (176, 158, 768, torch.float32), (158, 142, 384, torch.float32),
+                                        (64, 20, 128, torch.float32), (60, 130, 200, torch.float32), (196, 176, 768, torch.bfloat16),
+                                        (97, 33, 100, torch.float32), (16, 4, 64, torch.float32)])
+def test_soft_merge_tensor_core_paths(T, p, k, c, xdt):
+    """tcgen05 Sinkhorn / PatchMerger (lowp) against the oracle's autocast emulation and against the FFMA path."""
+    b = 3
+    x = torch.randn(b, p, c, generator=g(410)).to(xdt).to(DEV)
+    v = torch.randn(k, c, generator=g(411)).to(DEV)
+    out_ref, w_ref, vh = O.sinkhorn_merge(x.float(), v, 1.0, 3, lowp=torch.bfloat16)
+    out, w = T.sinkhorn_merge(x, vh, 1.0, 3, True, True)
+    out_f, w_f = T.sinkhorn_merge(x, vh, 1.0, 3, True, False)
+    assert out.dtype == torch.bfloat16
+    assert_close_rel(w, w_ref, RTOL16, "sinkhorn weights vs oracle")
+    assert_close_rel(out.float(), out_ref.float(), RTOL16, "sinkhorn tokens vs oracle")
+    assert_close_rel(w, w_f, 2e-3, "sinkhorn weights tc vs ffma")
+    assert_close_rel(out.float(), out_f.float(), 5e-3, "sinkhorn tokens tc vs ffma")
+    col = w.sum(dim=1)
+    assert torch.allclose(col, torch.ones_like(col), rtol=1e-4, atol=1e-5)
+    lw = (torch.rand(c, generator=g(412)) + 0.5).to(DEV)
+    lb = (torch.randn(c, generator=g(413)) * 0.1).to(DEV)
+    q = (torch.randn(k, c, generator=g(414)) * 0.05).to(DEV)
+    o_ref, a_ref = O.patchmerger(x.float(), lw, lb, q, lowp=torch.bfloat16)
+    o, a = T.patchmerger(x, lw, lb, q, 1.0, 1e-5, True, True)
+    o_f, a_f = T.patchmerger(x, lw, lb, q, 1.0, 1e-5, True, False)
+    assert_close_rel(a, a_ref, RTOL16, "patchmerger attn vs oracle")
+    assert_close_rel(o.float(), o_ref.float(), RTOL16, "patchmerger tokens vs oracle")
+    assert_close_rel(a, a_f, 5e-3, "patchmerger attn tc vs ffma")
+    assert torch.allclose(a.sum(dim=-1), torch.ones(b, k, device=DEV), rtol=1e-4)
+
+
 @pytest.mark.parametrize("p,k,c", [(196, 176, 768), (176, 158, 768), (196, 176, 384), (60, 20, 100)])
 def test_patchmerger_fp32(T, p, k, c):
     b = 3

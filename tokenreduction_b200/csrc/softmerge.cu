@@ -306,6 +306,11 @@ int check_soft(const char* what, int B, int P, int C, int K, int x_dtype, int ou
 }  // namespace
 }  // namespace tokred
 
+namespace tokred {
+int launch_soft_merge_tc(int mode, const void* x, int x_dtype, const float* q, const float* ln_w, const float* ln_b,
+                         int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
+                         float* weights, void* stream, const char* what);
+}
 using namespace tokred;
 
 extern "C" int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_hat, int B, int P, int C, int K,
@@ -317,8 +322,13 @@ extern "C" int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
   TOKRED_REQUIRE(eps > 0.f && iters >= 0, "%s: eps=%g iters=%d", what, (double)eps, iters);
   if (B == 0) return TOKRED_OK;
+  if (lowp == 1 && out_dtype == TOKRED_BF16) {     // bf16 autocast semantics on tcgen05 tensor cores
+    const int rc = launch_soft_merge_tc(MODE_SINKHORN, x, x_dtype, v_hat, nullptr, nullptr, B, P, C, K, 1.0f / eps, log_norm,
+                                        0.f, iters, out, weights, stream, what);
+    if (rc != 1) return rc;
+  }
   SoftParams prm{};
-  prm.x = x; prm.q = v_hat; prm.scale = 1.0f / eps; prm.log_norm = log_norm; prm.iters = iters; prm.lowp = lowp;
+  prm.x = x; prm.q = v_hat; prm.scale = 1.0f / eps; prm.log_norm = log_norm; prm.iters = iters; prm.lowp = lowp ? 1 : 0;
   prm.P = P; prm.C = C; prm.K = K; prm.out = out; prm.weights = weights;
   return launch_soft<MODE_SINKHORN>(prm, B, x_dtype, out_dtype, what, stream);
 }
@@ -331,9 +341,14 @@ extern "C" int tokred_patchmerger(const void* x, int x_dtype, const float* ln_we
   TOKRED_REQUIRE(x && ln_weight && ln_bias && queries && out && attn, "%s: null tensor", what);
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
   if (B == 0) return TOKRED_OK;
+  if (lowp == 1 && out_dtype == TOKRED_BF16) {
+    const int rc = launch_soft_merge_tc(MODE_PATCHMERGER, x, x_dtype, queries, ln_weight, ln_bias, B, P, C, K, scale, 0.f,
+                                        ln_eps, 0, out, attn, stream, what);
+    if (rc != 1) return rc;
+  }
   SoftParams prm{};
   prm.x = x; prm.q = queries; prm.ln_w = ln_weight; prm.ln_b = ln_bias; prm.scale = scale; prm.ln_eps = ln_eps;
-  prm.lowp = lowp; prm.P = P; prm.C = C; prm.K = K; prm.out = out; prm.weights = attn;
+  prm.lowp = lowp ? 1 : 0; prm.P = P; prm.C = C; prm.K = K; prm.out = out; prm.weights = attn;
   return launch_soft<MODE_PATCHMERGER>(prm, B, x_dtype, out_dtype, what, stream);
 }
 
@@ -347,7 +362,7 @@ extern "C" int tokred_sit_merge(const void* x, int x_dtype, const void* logits, 
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
   if (B == 0) return TOKRED_OK;
   SoftParams prm{};
-  prm.x = x; prm.logits = logits; prm.logits_dtype = logits_dtype; prm.scale_ptr = scale; prm.lowp = lowp;
+  prm.x = x; prm.logits = logits; prm.logits_dtype = logits_dtype; prm.scale_ptr = scale; prm.lowp = lowp ? 1 : 0;
   prm.P = P; prm.C = C; prm.K = K; prm.out = out; prm.weights = weights;
   return launch_soft<MODE_SIT>(prm, B, x_dtype, out_dtype, what, stream);
 }

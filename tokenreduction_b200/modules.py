@@ -383,7 +383,7 @@ class Sinkhorn(nn.Module):
         _train_guard(self)
         with torch.no_grad():                       # the reference overwrites its parameter (:73-76); idempotent
             self.v.copy_(F.normalize(self.v.clone(), p=2, dim=-1))
-        return ops.sinkhorn_merge(x, self.v.detach(), self.eps, self.iters, _lowp())
+        return ops.sinkhorn_merge(x, self.v.detach(), self.eps, self.iters, _lowp(), True)
 
 
 # =============================================================================================== PatchMerger
@@ -399,7 +399,7 @@ class PatchMerger(nn.Module):
     def forward(self, x):
         _train_guard(self)
         return ops.patchmerger(x, self.norm.weight.detach(), self.norm.bias.detach(), self.queries.detach(), self.scale,
-                               self.norm.eps, _lowp())
+                               self.norm.eps, _lowp(), True)
 
 
 # =============================================================================================== SiT

@@ -390,12 +390,17 @@ def sinkhorn_log_norm(k: int, p: int, score_dtype: torch.dtype) -> float:
     return float(-((k * one).to(score_dtype) + (p * one).to(score_dtype)).float().log())
 
 
+def _lowp_mode(lowp: bool, tensor_cores: bool) -> int:
+    """C-ABI lowp code: 0 exact fp32, 1 bf16-autocast rounding on tcgen05, 3 same rounding on the FFMA path."""
+    return (1 if tensor_cores else 3) if lowp else 0
+
+
 def _soft_out_dtype(x: Tensor, lowp: bool) -> torch.dtype:
     return torch.bfloat16 if (lowp or x.dtype == torch.bfloat16) else torch.float32
 
 
 @torch.library.custom_op("tokred::sinkhorn_merge", mutates_args=(), device_types="cuda")
-def _sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool) -> Tuple[Tensor, Tensor]:
+def _sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool, tensor_cores: bool) -> Tuple[Tensor, Tensor]:
     _need_cuda("sinkhorn_merge", x, v_hat)
     b, p, c = x.shape
     k = v_hat.shape[0]
@@ -406,13 +411,13 @@ def _sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool
     out = torch.empty((b, k, c), dtype=odt, device=x.device)
     weights = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
     _lib.call("tokred_sinkhorn_merge", _ptr(x), _dt(x), _ptr(v_hat), b, p, c, k, float(eps),
-              sinkhorn_log_norm(k, p, torch.bfloat16 if lowp else x.dtype), iters, int(lowp), _ptr(out), _dt(out),
+              sinkhorn_log_norm(k, p, torch.bfloat16 if lowp else x.dtype), iters, _lowp_mode(lowp, tensor_cores), _ptr(out), _dt(out),
               _ptr(weights), _stream())
     return out, weights
 
 
 @_sinkhorn_merge.register_fake
-def _(x, v_hat, eps, iters, lowp):
+def _(x, v_hat, eps, iters, lowp, tensor_cores):
     b, p, c = x.shape
     k = v_hat.shape[0]
     return x.new_empty((b, k, c), dtype=_soft_out_dtype(x, lowp)), x.new_empty((b, k, p), dtype=torch.float32)
@@ -420,7 +425,7 @@ def _(x, v_hat, eps, iters, lowp):
 
 @torch.library.custom_op("tokred::patchmerger", mutates_args=(), device_types="cuda")
 def _patchmerger(x: Tensor, ln_weight: Tensor, ln_bias: Tensor, queries: Tensor, scale: float, ln_eps: float,
-                 lowp: bool) -> Tuple[Tensor, Tensor]:
+                 lowp: bool, tensor_cores: bool) -> Tuple[Tensor, Tensor]:
     _need_cuda("patchmerger", x, ln_weight, ln_bias, queries)
     b, p, c = x.shape
     k = queries.shape[0]
@@ -432,12 +437,12 @@ def _patchmerger(x: Tensor, ln_weight: Tensor, ln_bias: Tensor, queries: Tensor,
     out = torch.empty((b, k, c), dtype=odt, device=x.device)
     attn = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
     _lib.call("tokred_patchmerger", _ptr(x), _dt(x), _ptr(lw), _ptr(lb), _ptr(queries), b, p, c, k, float(scale),
-              float(ln_eps), int(lowp), _ptr(out), _dt(out), _ptr(attn), _stream())
+              float(ln_eps), _lowp_mode(lowp, tensor_cores), _ptr(out), _dt(out), _ptr(attn), _stream())
     return out, attn
 
 
 @_patchmerger.register_fake
-def _(x, ln_weight, ln_bias, queries, scale, ln_eps, lowp):
+def _(x, ln_weight, ln_bias, queries, scale, ln_eps, lowp, tensor_cores):
     b, p, c = x.shape
     k = queries.shape[0]
     return x.new_empty((b, k, c), dtype=_soft_out_dtype(x, lowp)), x.new_empty((b, k, p), dtype=torch.float32)
@@ -469,14 +474,15 @@ def _(x, logits, scale, lowp):
     return x.new_empty((b, k, c), dtype=_soft_out_dtype(x, lowp)), x.new_empty((b, k, p), dtype=torch.float32)
 
 
-def sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool = False):
+def sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool = False, tensor_cores: bool = True):
     """models/sinkhorn.py:66-86: (out [B,K,C], weights [B,K,P]); v_hat = F.normalize(v)."""
-    return torch.ops.tokred.sinkhorn_merge(x, v_hat, eps, iters, lowp)
+    return torch.ops.tokred.sinkhorn_merge(x, v_hat, eps, iters, lowp, tensor_cores)
 
 
-def patchmerger(x, ln_weight, ln_bias, queries, scale: float = 1.0, ln_eps: float = 1e-5, lowp: bool = False):
+def patchmerger(x, ln_weight, ln_bias, queries, scale: float = 1.0, ln_eps: float = 1e-5, lowp: bool = False,
+                tensor_cores: bool = True):
     """models/patchmerger.py:35-39: (out [B,K,C], attn [B,K,P])."""
-    return torch.ops.tokred.patchmerger(x, ln_weight, ln_bias, queries, scale, ln_eps, lowp)
+    return torch.ops.tokred.patchmerger(x, ln_weight, ln_bias, queries, scale, ln_eps, lowp, tensor_cores)
 
 
 def sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool = False):

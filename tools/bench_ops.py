@@ -99,10 +99,9 @@ def cases():
         lw, lb = torch.ones(768, device=DEV), torch.zeros(768, device=DEV)
         logits = torch.randn(b, p, k, device=DEV).bfloat16()
         scale = torch.ones(1, device=DEV)
-        for lowp in (True, False):
-            tag = "lowp" if lowp else "fp32"
-            out.append((f"sinkhorn_merge B B={b} P={p} K={k} {tag}", lambda x=x, v=v, lowp=lowp: T.sinkhorn_merge(x, v, 1.0, 3, lowp)))
-            out.append((f"patchmerger B B={b} P={p} K={k} {tag}", lambda x=x, lw=lw, lb=lb, q=q, lowp=lowp: T.patchmerger(x, lw, lb, q, 1.0, 1e-5, lowp)))
+        for lowp, tc, tag in ((True, True, "lowp tcgen05"), (True, False, "lowp ffma"), (False, False, "fp32")):
+            out.append((f"sinkhorn_merge B B={b} P={p} K={k} {tag}", lambda x=x, v=v, lowp=lowp, tc=tc: T.sinkhorn_merge(x, v, 1.0, 3, lowp, tc)))
+            out.append((f"patchmerger B B={b} P={p} K={k} {tag}", lambda x=x, lw=lw, lb=lb, q=q, lowp=lowp, tc=tc: T.patchmerger(x, lw, lb, q, 1.0, 1e-5, lowp, tc)))
         out.append((f"sit_merge B B={b} P={p} K={k} lowp", lambda x=x, l=logits, s=scale: T.sit_merge(x, l, s, True)))
     from oracle.ops import ats_sample_steps
     for n, count in ((197, 177), (177, 159), (159, 143)):
