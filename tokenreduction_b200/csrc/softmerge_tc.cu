@@ -49,7 +49,7 @@ struct Layout {
   size_t stageA, stageB, r0, r1, total;
 };
 
-__host__ __device__ inline Layout make_layout(int P, int K) {
+__host__ __device__ inline Layout make_layout(int P, int K, int C) {
   Layout L;
   L.Np = (P + 15) & ~15;
   L.Pp = L.Np;
@@ -67,7 +67,7 @@ __host__ __device__ inline Layout make_layout(int P, int K) {
   const size_t zbytes = (size_t)K * psb * 2;
   const size_t xt = (size_t)(NC2 / 8) * L.sbo2;
   L.r1 = ((zbytes > xt ? zbytes : xt) + 127) & ~(size_t)127;
-  L.total = L.r0 + L.r1 + (size_t)(3 * P + K) * 4 + 64;
+  L.total = L.r0 + L.r1 + (size_t)(3 * P + K + 2 * ((C + 3) & ~3)) * 4 + 64;
   return L;
 }
 
@@ -110,20 +110,44 @@ struct Xform {
     if (MODE == MODE_SINKHORN) return v / s0[p];
     return g[c] * (s1[p] * (v - s0[p])) + bta[c];
   }
+  // 8 consecutive channels c0..c0+7 of token p (c0 % 4 == 0); channels >= C become 0
+  __device__ __forceinline__ void apply8(int p, int c0, int C, float (&v)[8]) const {
+    if (MODE == MODE_SINKHORN) {
+      const float d = s0[p];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (c0 + i < C) ? v[i] / d : 0.f;
+    } else {
+      const float mean = s0[p], rstd = s1[p];
+      if (c0 + 8 <= C) {
+        const float4 g0 = *reinterpret_cast<const float4*>(g + c0), g1 = *reinterpret_cast<const float4*>(g + c0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(bta + c0), b1 = *reinterpret_cast<const float4*>(bta + c0 + 4);
+        v[0] = g0.x * (rstd * (v[0] - mean)) + b0.x; v[1] = g0.y * (rstd * (v[1] - mean)) + b0.y;
+        v[2] = g0.z * (rstd * (v[2] - mean)) + b0.z; v[3] = g0.w * (rstd * (v[3] - mean)) + b0.w;
+        v[4] = g1.x * (rstd * (v[4] - mean)) + b1.x; v[5] = g1.y * (rstd * (v[5] - mean)) + b1.y;
+        v[6] = g1.z * (rstd * (v[6] - mean)) + b1.z; v[7] = g1.w * (rstd * (v[7] - mean)) + b1.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (c0 + i < C) ? g[c0 + i] * (rstd * (v[i] - mean)) + bta[c0 + i] : 0.f;
+      }
+    }
+  }
 };
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int P = prm.P, C = prm.C, K = prm.K;
-  const Layout L = make_layout(P, K);
+  const Layout L = make_layout(P, K, C);
   unsigned char* R0 = smem;
   unsigned char* R1 = smem + L.r0;
-  float* s0 = reinterpret_cast<float*>(R1 + L.r1);     // [P]
+  const int Cpad = (C + 3) & ~3;
+  float* lng = reinterpret_cast<float*>(R1 + L.r1);     // [Cpad] LayerNorm weight (patchmerger), 16-byte aligned
+  float* lnb = lng + Cpad;                               // [Cpad] LayerNorm bias
+  float* s0 = lnb + Cpad;                                // [P]
   float* s1 = s0 + P;                                    // [P]
   float* uvec = s1 + P;                                  // [K]
   float* vvec = uvec + K;                                // [P]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(vvec + P);   // [0,1]: stage / accumulator-set barriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(vvec + P) + 7) & ~(uintptr_t)7);   // stage / accumulator barriers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -132,51 +156,76 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
   const bool qvec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(prm.q) & 15u) == 0);
 
   if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+  if (MODE == MODE_PATCHMERGER)
+    for (int c = tid; c < C; c += kThreads) { lng[c] = prm.ln_w[c]; lnb[c] = prm.ln_b[c]; }
   if (tid == 0) {
     umma::mbar_init(&bars[0], 1);
     umma::mbar_init(&bars[1], 1);
     umma::fence_mbar_init();
   }
 
-  // ---- 0. token statistics
-  for (int p = warp; p < P; p += kWarps) {
-    const T* row = xb + (long long)p * C;
-    if (MODE == MODE_SINKHORN) {
-      float s = 0.f;
-      for (int c = lane * 8; c < C; c += 256) {
-        float v[8];
-        load8<T>(row + c, xvec, C - c, v);
+  // ---- 0. token statistics: one warp per token, the whole row (<= 1024 channels) held in registers so that x is
+  //         read from HBM once and every load of the row is in flight together
+  if (C <= 1024) {
+    for (int p = warp; p < P; p += kWarps) {
+      const T* row = xb + (long long)p * C;
+      float v[4][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(v[i], v[i], s);
-      }
-      s = warp_sum(s);
-      if (lane == 0) s0[p] = fmaxf(sqrtf(s), 1e-12f);
-    } else {
-      float s = 0.f;
-      for (int c = lane * 8; c < C; c += 256) {
-        float v[8];
-        load8<T>(row + c, xvec, C - c, v);
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane * 8 + j * 256;
+        if (c < C) load8<T>(row + c, xvec, C - c, v[j]);
+        else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[i];
+          for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+        }
       }
-      const float mean = warp_sum(s) / (float)C;
-      float q = 0.f;
-      for (int c = lane * 8; c < C; c += 256) {
-        float v[8];
-        load8<T>(row + c, xvec, C - c, v);
+      if (MODE == MODE_SINKHORN) {
+        float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (c + i < C) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s = fmaf(v[j][i], v[j][i], s);
+        s = warp_sum(s);
+        if (lane == 0) s0[p] = fmaxf(sqrtf(s), 1e-12f);
+      } else {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s += v[j][i];
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (lane * 8 + j * 256 + i < C) { const float d = v[j][i] - mean; q = fmaf(d, d, q); }
+        const float var = warp_sum(q) / (float)C;
+        if (lane == 0) { s0[p] = mean; s1[p] = rsqrtf(var + prm.ln_eps); }
       }
-      const float var = warp_sum(q) / (float)C;
-      if (lane == 0) { s0[p] = mean; s1[p] = rsqrtf(var + prm.ln_eps); }
+    }
+  } else {
+    for (int p = warp; p < P; p += kWarps) {
+      const T* row = xb + (long long)p * C;
+      float s = 0.f, q = 0.f;
+      for (int c = lane; c < C; c += 32) { const float v = to_f32(row[c]); s += v; q = fmaf(v, v, q); }
+      if (MODE == MODE_SINKHORN) {
+        q = warp_sum(q);
+        if (lane == 0) s0[p] = fmaxf(sqrtf(q), 1e-12f);
+      } else {
+        const float mean = warp_sum(s) / (float)C;
+        float d2 = 0.f;
+        for (int c = lane; c < C; c += 32) { const float d = to_f32(row[c]) - mean; d2 = fmaf(d, d, d2); }
+        const float var = warp_sum(d2) / (float)C;
+        if (lane == 0) { s0[p] = mean; s1[p] = rsqrtf(var + prm.ln_eps); }
+      }
     }
   }
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const Xform<MODE> xf{s0, s1, prm.ln_w, prm.ln_b};
+  const Xform<MODE> xf{s0, s1, lng, lnb};
 
   // ---- 1. Z = Q . Xn^T on tensor cores
   const int nchunk = (C + KC1 - 1) / KC1;
@@ -187,29 +236,48 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
     unsigned char* Bt = A + L.stageA;
     if (c >= 2) umma::mbar_wait(&bars[st], (uint32_t)(((c - 2) >> 1) & 1));   // MMAs of chunk c-2 released this stage
     const int k0 = c * KC1;
-    // 8 consecutive lanes = 8 consecutive rows of one 16-byte K-chunk: 128 contiguous bytes of shared memory
-    for (int gI = tid; gI < ((K + 7) / 8) * 64; gI += kThreads) {
-      const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7;
-      if (row < K) {
-        float v[8];
-        const int k = k0 + ch * 8;
-        load8<float>(prm.q + (long long)row * C + k, qvec, C - k, v);
-        *reinterpret_cast<int4*>(A + (row >> 3) * L.sbo1 + (row & 7) * 16 + ch * 128) = pack8(v);
+    // 8 consecutive lanes = 8 consecutive rows of one 16-byte K-chunk: 128 contiguous bytes of shared memory.
+    // U groups per thread-step: all 2U 16-byte loads are issued before the first convert (latency-bound otherwise).
+    constexpr int U = 4;
+    const int nga = ((K + 7) / 8) * 64, ngb = L.Np * 8;
+    for (int g0 = tid; g0 < nga; g0 += kThreads * U) {
+      float v[U][8];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gI = g0 + u * kThreads;
+        const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7, k = k0 + ch * 8;
+        if (gI < nga && row < K) load8<float>(prm.q + (long long)row * C + k, qvec, C - k, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gI = g0 + u * kThreads;
+        const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7;
+        if (gI < nga && row < K)
+          *reinterpret_cast<int4*>(A + (row >> 3) * L.sbo1 + (row & 7) * 16 + ch * 128) = pack8(v[u]);
       }
     }
-    for (int gI = tid; gI < L.Np * 8; gI += kThreads) {
-      const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7;
-      float v[8];
-      const int k = k0 + ch * 8;
-      if (row < P) {
-        load8<T>(xb + (long long)row * C + k, xvec, C - k, v);
+    for (int g0 = tid; g0 < ngb; g0 += kThreads * U) {
+      float v[U][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (k + i < C) ? xf(row, k + i, v[i]) : 0.f;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int gI = g0 + u * kThreads;
+        const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7, k = k0 + ch * 8;
+        if (gI < ngb && row < P) load8<T>(xb + (long long)row * C + k, xvec, C - k, v[u]);
       }
-      *reinterpret_cast<int4*>(Bt + (row >> 3) * L.sbo1 + (row & 7) * 16 + ch * 128) = pack8(v);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gI = g0 + u * kThreads;
+        const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7, k = k0 + ch * 8;
+        if (gI < ngb) {
+          if (row < P) {
+            xf.apply8(row, k, C, v[u]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+          }
+          *reinterpret_cast<int4*>(Bt + (row >> 3) * L.sbo1 + (row & 7) * 16 + ch * 128) = pack8(v[u]);
+        }
+      }
     }
     umma::fence_proxy_async_smem();
     __syncthreads();
@@ -341,13 +409,14 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
           const int p = pg * 8 + pp, c = c0 + cg * 8;
           if (p < P && c < C) {
             load8<T>(xb + (long long)p * C + c, xvec, C - c, v[pp]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[pp][i] = (c + i < C) ? xf(p, c + i, v[pp][i]) : 0.f;
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[pp][i] = 0.f;
           }
         }
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+          if (pg * 8 + pp < P && c0 + cg * 8 < C) xf.apply8(pg * 8 + pp, c0 + cg * 8, C, v[pp]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float col[8];
@@ -419,7 +488,7 @@ int launch_soft_merge_tc(int mode, const void* x, int x_dtype, const float* q, c
                          int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
                          float* weights, void* stream, const char* what) {
   if (P > kMaxP || K > kMaxK || P < 8 || K < 1) return 1;
-  const Layout L = make_layout(P, K);
+  const Layout L = make_layout(P, K, C);
   if (L.total > 227 * 1024) return 1;
   TcParams prm{};
   prm.x = x; prm.q = q; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.scale = scale; prm.log_norm = log_norm; prm.ln_eps = ln_eps;
