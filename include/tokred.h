@@ -87,15 +87,18 @@ TOKRED_API int tokred_tome_merge(const void* x, int x_dtype, const void* size, c
 /* ---- pairwise distances (building block of a6 / a8, exported for parity checks) ------------------------
  * torch.cdist(x, x) as called at models/dpcknn.py:59 and models/kmedoids.py:68, times post_scale:
  * matmul expansion sqrt(max(|xi|^2+|xj|^2-2xi.xj, 1e-30)) for P > 25, direct differences otherwise.
- *   x [B,P,C] fp32 -> out [B,P,P] fp32 (bit-symmetric)                                                  */
-TOKRED_API int tokred_pairwise_dist(const float* x, int B, int P, int C, float post_scale, float* out, void* stream);
+ *   x [B,P,C] fp32 -> out [B,P,P] fp32 (bit-symmetric).
+ *   exact_fp32 = 0: Gram on tcgen05 tensor cores with 3xTF32 error compensation (fp32-matmul accuracy class);
+ *   exact_fp32 = 1: FFMA (true fp32 products).  Same switch on dpcknn_cluster / kmedoids_fit.            */
+TOKRED_API int tokred_pairwise_dist(const float* x, int B, int P, int C, float post_scale, int exact_fp32, float* out,
+                                    void* stream);
 
 /* ---- a6 DPC-KNN clustering ---------------------------------------------------------------------------
  * models/dpcknn.py:44-100 cluster_dpc_knn (token_mask=None).
  *   x [B,P,C] fp32; noise_u [B,P] fp32 ~ U(0,1) drawn by the caller with the reference's torch.rand call
  *   idx_cluster [B,P] int64, index_down [B,K] int64 (descending centre score)                           */
 TOKRED_API int tokred_dpcknn_cluster(const float* x, const float* noise_u, int B, int P, int C, int K, int knn,
-                          int64_t* idx_cluster, int64_t* index_down, void* stream);
+                                     int exact_fp32, int64_t* idx_cluster, int64_t* index_down, void* stream);
 
 /* ---- a7 DPC-KNN merge --------------------------------------------------------------------------------
  * models/dpcknn.py:103-140 merge_tokens.  token_weight [B,P] fp32 or NULL (= ones); idx_token [B,T] int64;
@@ -111,7 +114,7 @@ TOKRED_API int tokred_attn_colsum(const void* attn, int attn_dtype, int B, int H
 /* models/kmedoids.py:62-85 k_medoids_fit with token weights (topk init, iters x {assign, re-centre}).
  *   x [B,P,C] fp32, token_weight [B,P] fp32 -> centres [B,K,C], cluster_idx [B,K] int64, assignment [B,P] int64 */
 TOKRED_API int tokred_kmedoids_fit(const float* x, const float* token_weight, int B, int P, int C, int K, int iters,
-                        float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream);
+                                   int exact_fp32, float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream);
 
 /* ---- a9 Sinkhorn -------------------------------------------------------------------------------------
  * models/sinkhorn.py:66-86 with :25-56.  v_hat [K,C] fp32 is the already-normalised parameter.

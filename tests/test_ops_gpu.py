@@ -257,20 +257,22 @@ def test_tome_merge_properties_full_size(T):
 
 
 # ------------------------------------------------------------------------------------------------ distances / DPC-KNN
-@pytest.mark.parametrize("p,c", [(196, 384), (49, 384), (12, 384), (196, 768), (60, 100), (25, 64), (26, 64)])
-def test_pairwise_dist(T, p, c):
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("p,c", [(196, 384), (49, 384), (12, 384), (196, 768), (60, 100), (25, 64), (26, 64), (130, 192), (208, 96)])
+def test_pairwise_dist(T, p, c, exact):
+    """exact=False: Gram on tcgen05 with 3xTF32 compensation; exact=True: FFMA.  Both must be in the accuracy class of
+    ATen's own fp32 cdist (matmul expansion) measured against float64."""
     x = torch.randn(3, p, c, generator=g(22)).to(DEV)
-    d = T.pairwise_dist(x)
+    d = T.pairwise_dist(x, 1.0, exact)
     d_ref = torch.cdist(x, x)
     d64 = torch.cdist(x.double(), x.double())
     assert torch.equal(d, d.transpose(1, 2)), "distance matrix must be bit-symmetric"
     off = ~torch.eye(p, dtype=torch.bool, device=DEV)
-    # same accuracy class as ATen's own fp32 cdist (matmul expansion): compare both to float64
     err_mine = (d.double() - d64)[:, off].abs().max()
     err_aten = (d_ref.double() - d64)[:, off].abs().max()
-    assert err_mine <= max(2.0 * float(err_aten), 1e-4)
+    assert err_mine <= max((2.0 if exact else 6.0) * float(err_aten), 1e-4), (float(err_mine), float(err_aten))
     if p > 25:
-        assert float(d.diagonal(dim1=1, dim2=2).max()) < 5e-2      # matmul form: diagonal is noise, not 0
+        assert float(d.diagonal(dim1=1, dim2=2).max()) < 1e-1      # matmul form: diagonal is noise, not an exact 0
     else:
         assert float(d.diagonal(dim1=1, dim2=2).abs().max()) == 0.0
 
@@ -282,14 +284,15 @@ def clustered_tokens(b, p, c, n_centres, seed, spread=0.35):
     return x
 
 
+@pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("p,k,c", [(196, 49, 384), (49, 12, 384), (12, 3, 384), (196, 49, 768), (100, 30, 64)])
-def test_dpcknn_cluster(T, p, k, c):
+def test_dpcknn_cluster(T, p, k, c, exact):
     b = 16
     x = clustered_tokens(b, p, c, max(k // 2, 2), 23).to(DEV)
     noise = torch.rand(b, p, generator=g(26)).to(DEV)
-    idx_cluster, index_down = T.dpcknn_cluster(x, noise, k, 5)
+    idx_cluster, index_down = T.dpcknn_cluster(x, noise, k, 5, exact)
     # decisions must be exact given the kernel's own distance matrix (identical decision inputs)
-    d = T.pairwise_dist(x)
+    d = T.pairwise_dist(x, 1.0, exact)
     ic_ref, id_ref = O.dpcknn_cluster(x, k, 5, noise, dist=d)
     img_ok = (index_down == id_ref).all(dim=1) & (idx_cluster == ic_ref).all(dim=1)
     assert img_ok.float().mean() >= 0.85, f"exact-image rate {float(img_ok.float().mean()):.2f}"
@@ -329,13 +332,14 @@ def test_attn_colsum(T, h, n):
     assert_close_rel(out, ref, 1e-6, "token weights")
 
 
+@pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("p,k,c,iters", [(196, 49, 384, 3), (49, 12, 384, 3), (12, 3, 384, 3), (196, 49, 768, 1), (100, 30, 64, 5)])
-def test_kmedoids_fit(T, p, k, c, iters):
+def test_kmedoids_fit(T, p, k, c, iters, exact):
     b = 16
     x = clustered_tokens(b, p, c, max(k // 2, 2), 33).to(DEV)
     tw = (5.5 + tie_free_scores(b, p, 36)).unsqueeze(-1).to(DEV)
-    centres, cidx, assign = T.kmedoids_fit(x, tw, k, iters)
-    d = T.pairwise_dist(x)
+    centres, cidx, assign = T.kmedoids_fit(x, tw, k, iters, exact)
+    d = T.pairwise_dist(x, 1.0, exact)
     c_ref, ci_ref, as_ref = O.kmedoids_fit(x, k, iters, tw, dist=d)
     img_ok = (cidx == ci_ref).all(dim=1) & (assign == as_ref).all(dim=1)
     assert img_ok.float().mean() >= 0.85, f"exact-image rate {float(img_ok.float().mean()):.2f}"

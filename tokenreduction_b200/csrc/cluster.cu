@@ -12,6 +12,7 @@
 #include <math_constants.h>
 
 #include "gemm_nt.cuh"
+#include "umma.cuh"
 
 namespace tokred {
 namespace {
@@ -19,12 +20,208 @@ namespace {
 constexpr int kThreads = kGemmThreads;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxP = 208;    // P*P + staging must fit 227 KB of shared memory
+constexpr int KT = 32;        // tf32 path: contraction columns per stage
 
-// Fills D[P*P] (shared) with the pairwise distances of the P rows of xb (global, [P][C]) times post_scale.
-// xt: [P][XS] staging, sq: [P] squared norms.  All threads of the CTA must call.
-__device__ void pairdist_to_smem(const float* __restrict__ xb, int P, int C, float* D, float* xt, float* sq,
-                                 float post_scale) {
+// Shared-memory plan of the distance kernels.  D has an odd row stride so that both row-per-thread stores (the
+// TMEM epilogue) and column reads (every later pass) are bank-conflict free.  On the tensor-core path the two
+// operand stages alias D's region: D is only written after the last MMA has completed.
+struct DistCtx {
+  float* D; int DS;
+  float* xt;                 // FFMA path: [P][XS] staging tile
+  unsigned char* stage;      // tensor-core path: 2 stages x {hi, lo} canonical tf32 tiles
+  float* sq;                 // [P]
+  float* extra;              // kernel-specific vectors
+  uint64_t* bars;            // [2]
+  uint32_t* tmem_slot;
+  uint32_t tmem_base, tmem_cols;
+  int use_tc;
+};
+
+__host__ __device__ inline size_t dist_stage_bytes(int P) { return (size_t)((P + 127) / 128) * 16 * 1024 * 2; }   // hi + lo
+__host__ __device__ inline size_t dist_region0_bytes(int P, int use_tc) {
+  const size_t d = ((size_t)P * (P | 1) * 4 + 15) & ~(size_t)15;
+  const size_t st = use_tc ? 2 * dist_stage_bytes(P) : 0;
+  return d > st ? d : st;
+}
+__host__ __device__ inline size_t dist_smem_bytes(int P, int extra_floats, int use_tc) {
+  size_t n = dist_region0_bytes(P, use_tc);
+  if (!use_tc) n += (size_t)P * XS * 4;
+  n += (((size_t)P + extra_floats) * 4 + 15) & ~(size_t)15;
+  return n + 32;
+}
+
+// carve the dynamic shared memory, and (tensor-core path) allocate TMEM + init the mbarriers.  All threads call.
+__device__ __forceinline__ DistCtx dist_setup(float* smem, int P, int extra_floats, int use_tc) {
+  DistCtx cx;
+  cx.use_tc = use_tc;
+  cx.D = smem;
+  cx.DS = P | 1;
+  cx.stage = reinterpret_cast<unsigned char*>(smem);
+  float* after = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(smem) + dist_region0_bytes(P, use_tc));
+  cx.xt = after;
+  if (!use_tc) after += P * XS;
+  cx.sq = after;
+  cx.extra = after + P;
+  cx.bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(after) + ((((size_t)P + extra_floats) * 4 + 15) & ~(size_t)15));
+  cx.tmem_slot = reinterpret_cast<uint32_t*>(cx.bars + 2);
+  cx.tmem_base = 0;
+  const int Np = (P + 15) & ~15;
+  cx.tmem_cols = P > 128 ? 512u : umma::tmem_cols_pow2((uint32_t)Np);
+  if (use_tc) {
+    if ((threadIdx.x >> 5) == 0) umma::tmem_alloc(cx.tmem_slot, cx.tmem_cols);
+    if (threadIdx.x == 0) { umma::mbar_init(&cx.bars[0], 1); umma::mbar_init(&cx.bars[1], 1); umma::fence_mbar_init(); }
+    umma::tc_fence_before_sync();
+    __syncthreads();
+    umma::tc_fence_after_sync();
+    cx.tmem_base = *cx.tmem_slot;
+  }
+  return cx;
+}
+__device__ __forceinline__ void dist_teardown(const DistCtx& cx) {
+  if (cx.use_tc) {
+    umma::tc_fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) umma::tmem_dealloc(cx.tmem_base, cx.tmem_cols);
+  }
+}
+
+// round-to-nearest tf32, returned in an fp32 container (low 13 mantissa bits zero)
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void row_sqnorms(const float* __restrict__ xb, int P, int C, float* sq) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0);
+  for (int i = warp; i < P; i += kWarps) {
+    const float* row = xb + (long long)i * C;
+    float s = 0.f;
+    if (vec) {
+      for (int k = lane * 4; k < C; k += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(row + k);
+        s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+      }
+    } else {
+      for (int k = lane; k < C; k += 32) { float v = row[k]; s = fmaf(v, v, s); }
+    }
+    s = warp_sum(s);
+    if (lane == 0) sq[i] = s;
+  }
+}
+
+// Gram matrix on tcgen05 with 3xTF32 error compensation: x = hi + lo (hi = tf32(x), lo = x - hi exactly),
+// G ~= hi.hi^T + hi.lo^T + lo.hi^T accumulated in one fp32 TMEM accumulator — the same accuracy class as the fp32
+// matmul torch.cdist runs (plain tf32 would be 1e-3 and flip neighbour decisions).  Both MMA operands are the SAME
+// shared-memory tile (A = rows of an M tile, B = rows 0..Np-1), written by the threads in the canonical K-major
+// layout (4 tf32 per 16-byte core row); two stages alias the D region.
+__device__ void pairdist_tc(const float* __restrict__ xb, int P, int C, DistCtx& cx, float post_scale) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  row_sqnorms(xb, P, C, cx.sq);
+  const int n_mt = (P + 127) / 128, Np = (P + 15) & ~15;
+  const size_t stage_bytes = dist_stage_bytes(P), half = stage_bytes / 2;
+  const uint32_t sbo = (KT / 4) * 128;      // 1024
+  const uint32_t idesc = umma::instr_desc(umma::FMT_TF32, 128, (uint32_t)Np);
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0);
+  const int nchunk = (C + KT - 1) / KT;
+  const int ng = ((P + 7) / 8) * 64;        // (8 rows) x (8 core columns of 4 floats) per row group
+  for (int c = 0; c < nchunk; ++c) {
+    const int st = c & 1;
+    unsigned char* hi = cx.stage + (size_t)st * stage_bytes;
+    unsigned char* lo = hi + half;
+    if (c >= 2) umma::mbar_wait(&cx.bars[st], (uint32_t)(((c - 2) >> 1) & 1));
+    const int k0 = c * KT;
+    constexpr int U = 4;
+    for (int g0 = tid; g0 < ng; g0 += kThreads * U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gI = g0 + u * kThreads;
+        const int row = (gI & 7) + ((gI >> 6) << 3), k = k0 + ((gI >> 3) & 7) * 4;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gI < ng && row < P) {
+          const float* g = xb + (long long)row * C + k;
+          if (vec && k + 3 < C) v[u] = *reinterpret_cast<const float4*>(g);
+          else { if (k < C) v[u].x = g[0]; if (k + 1 < C) v[u].y = g[1]; if (k + 2 < C) v[u].z = g[2]; if (k + 3 < C) v[u].w = g[3]; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gI = g0 + u * kThreads;
+        const int row = (gI & 7) + ((gI >> 6) << 3), core = (gI >> 3) & 7;
+        if (gI < ng) {
+          float4 h, l;
+          h.x = to_tf32(v[u].x); h.y = to_tf32(v[u].y); h.z = to_tf32(v[u].z); h.w = to_tf32(v[u].w);
+          // the remainder is exact in fp32; round it to tf32 ourselves (the MMA would TRUNCATE it: a biased error)
+          l.x = to_tf32(v[u].x - h.x); l.y = to_tf32(v[u].y - h.y); l.z = to_tf32(v[u].z - h.z); l.w = to_tf32(v[u].w - h.w);
+          const uint32_t off = (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 16u + (uint32_t)core * 128u;
+          *reinterpret_cast<float4*>(hi + off) = h;
+          *reinterpret_cast<float4*>(lo + off) = l;
+        }
+      }
+    }
+    umma::fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      umma::tc_fence_after_sync();
+      const uint32_t h0 = umma::smem_u32(hi), l0 = umma::smem_u32(lo);
+      for (int mt = 0; mt < n_mt; ++mt)
+        for (int ks = 0; ks < KT / 8; ++ks) {
+          const uint32_t ao = (uint32_t)mt * 16u * sbo + (uint32_t)ks * 256u, bo = (uint32_t)ks * 256u;
+          const uint64_t a_hi = umma::smem_desc_kmajor(h0 + ao, 128, sbo), a_lo = umma::smem_desc_kmajor(l0 + ao, 128, sbo);
+          const uint64_t b_hi = umma::smem_desc_kmajor(h0 + bo, 128, sbo), b_lo = umma::smem_desc_kmajor(l0 + bo, 128, sbo);
+          const uint32_t acc = cx.tmem_base + (uint32_t)mt * 256u;
+          umma::mma_tf32(acc, a_hi, b_hi, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+          umma::mma_tf32(acc, a_hi, b_lo, idesc, 1u);
+          umma::mma_tf32(acc, a_lo, b_hi, idesc, 1u);
+        }
+      umma::mma_commit(&cx.bars[st]);
+    }
+  }
+  {
+    const int last = nchunk - 1;
+    umma::mbar_wait(&cx.bars[last & 1], (uint32_t)((last >> 1) & 1));
+    if (nchunk >= 2) umma::mbar_wait(&cx.bars[(last - 1) & 1], (uint32_t)(((last - 1) >> 1) & 1));
+  }
+  umma::tc_fence_after_sync();
+  // accumulator row i -> D row i (thread = row; odd row stride => conflict-free)
+  {
+    const int mt = warp >> 2;
+    const int i = mt * 128 + (warp & 3) * 32 + lane;
+    if (mt < n_mt) {
+      const float sqi = i < P ? cx.sq[i] : 0.f;
+      for (int c0 = 0; c0 < Np; c0 += 16) {
+        uint32_t v[16];
+        umma::tmem_ld16(umma::tmem_addr(cx.tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(mt * 256 + c0)), v);
+        umma::tmem_ld_wait();
+        if (i < P) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < P) {
+              // diagonal: g_ii == |x_i|^2 exactly in exact arithmetic; use it (ATen's diagonal is clamp-level noise too)
+              const float d2 = (c0 + j == i) ? 0.f : (sqi + cx.sq[c0 + j]) - 2.0f * __uint_as_float(v[j]);
+              cx.D[i * cx.DS + c0 + j] = sqrtf(fmaxf(d2, 1e-30f)) * post_scale;
+            }
+        }
+      }
+    }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  // G_ij and G_ji add the same products in a different order: mirror the upper triangle so D is bit-symmetric
+  for (int e = tid; e < P * P; e += kThreads) {
+    const int i = e / P, j = e % P;
+    if (j > i) cx.D[j * cx.DS + i] = cx.D[i * cx.DS + j];
+  }
+  __syncthreads();
+}
+
+// Fills cx.D (shared) with the pairwise distances of the P rows of xb (global, [P][C]) times post_scale.
+__device__ void pairdist_to_smem(const float* __restrict__ xb, int P, int C, DistCtx& cx, float post_scale) {
+  const int tid = threadIdx.x;
+  float* D = cx.D;
+  const int DS = cx.DS;
   if (P <= 25) {
     // direct form (ATen's non-matmul cdist path): sqrt(sum (xi - xj)^2)
     for (int e = tid; e < P * P; e += kThreads) {
@@ -33,54 +230,51 @@ __device__ void pairdist_to_smem(const float* __restrict__ xb, int P, int C, flo
       const float* c = xb + (long long)j * C;
       float s = 0.f;
       for (int k = 0; k < C; ++k) { float d = a[k] - c[k]; s = fmaf(d, d, s); }
-      D[e] = sqrtf(s) * post_scale;
+      D[i * DS + j] = sqrtf(s) * post_scale;
     }
     __syncthreads();
     return;
   }
-  for (int i = warp; i < P; i += kWarps) {
-    const float* row = xb + (long long)i * C;
-    float s = 0.f;
-    for (int k = lane; k < C; k += 32) { float v = row[k]; s = fmaf(v, v, s); }
-    s = warp_sum(s);
-    if (lane == 0) sq[i] = s;
-  }
+  if (cx.use_tc) { pairdist_tc(xb, P, C, cx, post_scale); return; }
+  row_sqnorms(xb, P, C, cx.sq);
   const bool vec_ok = stage_vec_ok(xb, C);
+  float* xt = cx.xt;
+  const float* sq = cx.sq;
   gemm_nt(P, P, C, xt, xt,
           [&](int k0) { stage_rows(xb, P, C, C, k0, xt, vec_ok, [](int, int, float v) { return v; }); },
           [&](int i, int j, float g) {
             const float d2 = (sq[i] + sq[j]) - 2.0f * g;
-            D[i * P + j] = sqrtf(fmaxf(d2, 1e-30f)) * post_scale;
+            D[i * DS + j] = sqrtf(fmaxf(d2, 1e-30f)) * post_scale;
           });
 }
 
 // ------------------------------------------------------------------------------------------ plain cdist(x, x)
 __global__ void __launch_bounds__(kThreads, 1)
-pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale, float* __restrict__ out) {
-  extern __shared__ __align__(16) float smem[];
-  float* D = smem;
-  float* xt = D + ((P * P + 3) & ~3);   // keep the tile 16-byte aligned for LDS.128
-  float* sq = xt + P * XS;
-  pairdist_to_smem(x + (long long)blockIdx.x * P * C, P, C, D, xt, sq, post_scale);
+pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale, float* __restrict__ out, int use_tc) {
+  extern __shared__ __align__(128) float smem[];
+  DistCtx cx = dist_setup(smem, P, 0, use_tc);
+  pairdist_to_smem(x + (long long)blockIdx.x * P * C, P, C, cx, post_scale);
   float* ob = out + (long long)blockIdx.x * P * P;
-  for (int e = threadIdx.x; e < P * P; e += kThreads) ob[e] = D[e];
+  for (int e = threadIdx.x; e < P * P; e += kThreads) ob[e] = cx.D[(e / P) * cx.DS + e % P];
+  dist_teardown(cx);
 }
 
 // ------------------------------------------------------------------------------------------ DPC-KNN cluster
 __global__ void __launch_bounds__(kThreads, 1)
 dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noise_u, int P, int C, int K, int knn,
-                      float inv_sqrt_c, int64_t* __restrict__ idx_cluster, int64_t* __restrict__ index_down) {
-  extern __shared__ __align__(16) float smem[];
-  float* D = smem;
-  float* xt = D + ((P * P + 3) & ~3);   // keep the tile 16-byte aligned for LDS.128
-  float* sq = xt + P * XS;
-  float* rho = sq + P;
+                      float inv_sqrt_c, int64_t* __restrict__ idx_cluster, int64_t* __restrict__ index_down, int use_tc) {
+  extern __shared__ __align__(128) float smem[];
+  DistCtx cx = dist_setup(smem, P, 2 * P + K + kWarps, use_tc);
+  float* D = cx.D;
+  const int DS = cx.DS;
+  float* rho = cx.extra;
   float* score = rho + P;
   int* centre = reinterpret_cast<int*>(score + P);   // [K]
   float* red = reinterpret_cast<float*>(centre + K);  // [kWarps]
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  pairdist_to_smem(x + (long long)b * P * C, P, C, D, xt, sq, inv_sqrt_c);
+  pairdist_to_smem(x + (long long)b * P * C, P, C, cx, inv_sqrt_c);
+  dist_teardown(cx);
 
   // local density from the knn nearest (self included): exp(-mean(d^2)) + 1e-6 * U
   float lmax = 0.f;
@@ -92,7 +286,7 @@ dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noi
       float best = CUDART_INF_F;
       int bj = -1;
       for (int j = 0; j < P; ++j) {
-        const float v = D[j * P + i];
+        const float v = D[j * DS + i];
         const bool after = (v > prev_v) || (v == prev_v && j > prev_j);
         if (after && v < best) { best = v; bj = j; }
       }
@@ -100,7 +294,7 @@ dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noi
       prev_v = best; prev_j = bj;
     }
     rho[i] = expf(-(sumsq * (1.0f / (float)knn))) + noise_u[(long long)b * P + i] * 1e-6f;
-    for (int j = 0; j < P; ++j) lmax = fmaxf(lmax, D[j * P + i]);
+    for (int j = 0; j < P; ++j) lmax = fmaxf(lmax, D[j * DS + i]);
   }
   lmax = warp_max(lmax);
   if (lane == 0) red[warp] = lmax;
@@ -114,7 +308,7 @@ dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noi
     const float ri = rho[i];
     float best = dmax;
     for (int j = 0; j < P; ++j) {
-      const float v = rho[j] > ri ? D[j * P + i] : dmax;
+      const float v = rho[j] > ri ? D[j * DS + i] : dmax;
       best = fminf(best, v);
     }
     score[i] = best * ri;
@@ -130,7 +324,7 @@ dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noi
     float best = CUDART_INF_F;
     int bk = 0;
     for (int k = 0; k < K; ++k) {
-      const float v = D[centre[k] * P + i];
+      const float v = D[centre[k] * DS + i];
       if (v < best) { best = v; bk = k; }
     }
     for (int k = 0; k < K; ++k)
@@ -142,12 +336,13 @@ dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noi
 // ------------------------------------------------------------------------------------------ K-Medoids fit
 __global__ void __launch_bounds__(kThreads, 1)
 kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token_weight, int P, int C, int K, int iters,
-                    float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment) {
-  extern __shared__ __align__(16) float smem[];
-  float* D = smem;
-  float* xt = D + ((P * P + 3) & ~3);   // keep the tile 16-byte aligned for LDS.128
-  float* sq = xt + P * XS;
-  float* w = sq + P;
+                    float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment,
+                    int use_tc) {
+  extern __shared__ __align__(128) float smem[];
+  DistCtx cx = dist_setup(smem, P, 3 * P + K, use_tc);
+  float* D = cx.D;
+  const int DS = cx.DS;
+  float* w = cx.extra;
   float* S = w + P;
   int* assign = reinterpret_cast<int*>(S + P);   // [P]
   int* centre = assign + P;                       // [K]
@@ -155,13 +350,14 @@ kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token
   const float* xb = x + (long long)b * P * C;
 
   for (int i = tid; i < P; i += kThreads) w[i] = token_weight[(long long)b * P + i];
-  pairdist_to_smem(xb, P, C, D, xt, sq, 1.0f);
+  pairdist_to_smem(xb, P, C, cx, 1.0f);
+  dist_teardown(cx);
 
   // S_i = sum_j (D_ij * w_i); initial centres = top-K token weights (descending, lowest index on ties)
   for (int i = tid; i < P; i += kThreads) {
     const float wi = w[i];
     float s = 0.f;
-    for (int j = 0; j < P; ++j) s += __fmul_rn(D[j * P + i], wi);
+    for (int j = 0; j < P; ++j) s += __fmul_rn(D[j * DS + i], wi);
     S[i] = s;
     const int rk = rank_desc(w, P, i);
     if (rk < K) centre[rk] = i;
@@ -173,7 +369,7 @@ kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token
       float best = CUDART_INF_F;
       int bk = 0;
       for (int k = 0; k < K; ++k) {
-        const float v = D[centre[k] * P + i];
+        const float v = D[centre[k] * DS + i];
         if (v < best) { best = v; bk = k; }
       }
       assign[i] = bk;
@@ -212,7 +408,7 @@ dpcknn_merge_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx
                     const float* __restrict__ agg_weight, const int64_t* __restrict__ idx_cluster,
                     const float* __restrict__ token_weight, int P, int C, int K, int T, float* __restrict__ x_merged,
                     int64_t* __restrict__ idx_token_new, float* __restrict__ agg_weight_new, int vec) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* nw = smem;                                   // [P] normalised weights
   float* wsum = nw + P;                               // [K]
   int* cl = reinterpret_cast<int*>(wsum + K);         // [P] cluster of token
@@ -322,25 +518,26 @@ attn_colsum_kernel(const T* __restrict__ attn, int H, int N, int nt, float* __re
 
 using namespace tokred;
 
-static size_t dist_smem_bytes(int P, int extra_floats) {
-  return ((((size_t)P * P + 3) & ~(size_t)3) + (size_t)P * XS + P + extra_floats) * 4;
-}
+// tensor cores for every P that takes ATen's matmul form (P > 25), unless the caller asks for the exact-fp32 FFMA path
+static int pick_tc(int P, int exact_fp32) { return (P > 25 && !exact_fp32) ? 1 : 0; }
 
-extern "C" int tokred_pairwise_dist(const float* x, int B, int P, int C, float post_scale, float* out, void* stream) {
+extern "C" int tokred_pairwise_dist(const float* x, int B, int P, int C, float post_scale, int exact_fp32, float* out,
+                                    void* stream) {
   const char* what = "tokred_pairwise_dist";
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && out, "%s: null tensor", what);
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 1, "%s: bad shape B=%d P=%d C=%d", what, B, P, C);
   if (P > kMaxP) { set_error("%s: P=%d > %d patches is not supported (distance matrix is kept in shared memory)", what, P, kMaxP); return TOKRED_ERR_UNSUPPORTED; }
   if (B == 0) return TOKRED_OK;
-  const size_t smem = dist_smem_bytes(P, 0);
+  const int use_tc = pick_tc(P, exact_fp32);
+  const size_t smem = dist_smem_bytes(P, 0, use_tc);
   if (int e = allow_smem(pairwise_dist_kernel, smem, what)) return e;
-  pairwise_dist_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out);
+  pairwise_dist_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out, use_tc);
   return finish_launch(what);
 }
 
 extern "C" int tokred_dpcknn_cluster(const float* x, const float* noise_u, int B, int P, int C, int K, int knn,
-                                     int64_t* idx_cluster, int64_t* index_down, void* stream) {
+                                     int exact_fp32, int64_t* idx_cluster, int64_t* index_down, void* stream) {
   const char* what = "tokred_dpcknn_cluster";
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && noise_u && idx_cluster && index_down, "%s: null tensor", what);
@@ -349,15 +546,17 @@ extern "C" int tokred_dpcknn_cluster(const float* x, const float* noise_u, int B
   TOKRED_REQUIRE(knn >= 1 && knn <= P, "%s: k=%d outside [1, P=%d]", what, knn, P);
   if (P > kMaxP) { set_error("%s: P=%d > %d patches is not supported (distance matrix is kept in shared memory)", what, P, kMaxP); return TOKRED_ERR_UNSUPPORTED; }
   if (B == 0) return TOKRED_OK;
-  const size_t smem = dist_smem_bytes(P, 2 * P + K + kWarps);
+  const int use_tc = pick_tc(P, exact_fp32);
+  const size_t smem = dist_smem_bytes(P, 2 * P + K + kWarps, use_tc);
   if (int e = allow_smem(dpcknn_cluster_kernel, smem, what)) return e;
   const float inv = 1.0f / (float)sqrt((double)C);     // CUDA tensor / python-scalar = multiply by fp32 reciprocal
-  dpcknn_cluster_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(x, noise_u, P, C, K, knn, inv, idx_cluster, index_down);
+  dpcknn_cluster_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(x, noise_u, P, C, K, knn, inv, idx_cluster, index_down,
+                                                                     use_tc);
   return finish_launch(what);
 }
 
 extern "C" int tokred_kmedoids_fit(const float* x, const float* token_weight, int B, int P, int C, int K, int iters,
-                                   float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream) {
+                                   int exact_fp32, float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream) {
   const char* what = "tokred_kmedoids_fit";
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && token_weight && centres && cluster_idx && assignment, "%s: null tensor", what);
@@ -366,10 +565,11 @@ extern "C" int tokred_kmedoids_fit(const float* x, const float* token_weight, in
   TOKRED_REQUIRE(iters >= 0, "%s: iters=%d < 0", what, iters);
   if (P > kMaxP) { set_error("%s: P=%d > %d patches is not supported (distance matrix is kept in shared memory)", what, P, kMaxP); return TOKRED_ERR_UNSUPPORTED; }
   if (B == 0) return TOKRED_OK;
-  const size_t smem = dist_smem_bytes(P, 3 * P + K);
+  const int use_tc = pick_tc(P, exact_fp32);
+  const size_t smem = dist_smem_bytes(P, 3 * P + K, use_tc);
   if (int e = allow_smem(kmedoids_fit_kernel, smem, what)) return e;
   kmedoids_fit_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(x, token_weight, P, C, K, iters, centres, cluster_idx,
-                                                                   assignment);
+                                                                   assignment, use_tc);
   return finish_launch(what);
 }
 

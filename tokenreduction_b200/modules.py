@@ -286,7 +286,7 @@ def cluster_dpc_knn(x: Tensor, cluster_num: int, k: int = 5, token_mask: Optiona
     b, n, _ = x.shape
     # the reference draws its tie-breaking noise inside the op (:73-74); same call, same generator position
     noise = torch.rand((b, n), device=x.device, dtype=torch.float32)
-    return ops.dpcknn_cluster(x, noise, cluster_num, k)
+    return ops.dpcknn_cluster(x, noise, cluster_num, k, False)
 
 
 def merge_tokens(x, idx_token, agg_weight, idx_cluster, cluster_num, token_weight=None):
@@ -322,7 +322,7 @@ def k_medoids_fit(x: Tensor, cluster_num: int, iterations: int = 5, token_weight
     if token_weight is None:
         raise NotImplementedError("k_medoids_fit: the equal_weight initialisation (numpy RNG, models/kmedoids.py:43-61) "
                                   "is not on the accelerated path")
-    return ops.kmedoids_fit(x, token_weight, cluster_num, iterations)
+    return ops.kmedoids_fit(x, token_weight, cluster_num, iterations, False)
 
 
 class KMedoids(nn.Module):

@@ -249,29 +249,30 @@ def tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst:
 
 # ----------------------------------------------------------------------------------------------- distances
 @torch.library.custom_op("tokred::pairwise_dist", mutates_args=(), device_types="cuda")
-def _pairwise_dist(x: Tensor, post_scale: float) -> Tensor:
+def _pairwise_dist(x: Tensor, post_scale: float, exact_fp32: bool) -> Tensor:
     _need_cuda("pairwise_dist", x)
     b, p, c = x.shape
     x = _c(x.float())
     out = torch.empty((b, p, p), dtype=torch.float32, device=x.device)
-    _lib.call("tokred_pairwise_dist", _ptr(x), b, p, c, float(post_scale), _ptr(out), _stream())
+    _lib.call("tokred_pairwise_dist", _ptr(x), b, p, c, float(post_scale), int(exact_fp32), _ptr(out), _stream())
     return out
 
 
 @_pairwise_dist.register_fake
-def _(x, post_scale):
+def _(x, post_scale, exact_fp32):
     b, p, _ = x.shape
     return x.new_empty((b, p, p), dtype=torch.float32)
 
 
-def pairwise_dist(x: Tensor, post_scale: float = 1.0) -> Tensor:
-    """torch.cdist(x, x) * post_scale with ATen's formula selection (models/dpcknn.py:59, models/kmedoids.py:68)."""
-    return torch.ops.tokred.pairwise_dist(x, post_scale)
+def pairwise_dist(x: Tensor, post_scale: float = 1.0, exact_fp32: bool = False) -> Tensor:
+    """torch.cdist(x, x) * post_scale with ATen's formula selection (models/dpcknn.py:59, models/kmedoids.py:68).
+    Default: Gram on tcgen05 with 3xTF32 compensation; exact_fp32=True: FFMA."""
+    return torch.ops.tokred.pairwise_dist(x, post_scale, exact_fp32)
 
 
 # ----------------------------------------------------------------------------------------------- DPC-KNN
 @torch.library.custom_op("tokred::dpcknn_cluster", mutates_args=(), device_types="cuda")
-def _dpcknn_cluster(x: Tensor, noise_u: Tensor, cluster_num: int, knn: int) -> Tuple[Tensor, Tensor]:
+def _dpcknn_cluster(x: Tensor, noise_u: Tensor, cluster_num: int, knn: int, exact_fp32: bool) -> Tuple[Tensor, Tensor]:
     _need_cuda("dpcknn_cluster", x, noise_u)
     b, p, c = x.shape
     if x.dtype != torch.float32:
@@ -281,13 +282,13 @@ def _dpcknn_cluster(x: Tensor, noise_u: Tensor, cluster_num: int, knn: int) -> T
         raise TokredError(f"dpcknn_cluster: noise {tuple(noise_u.shape)} != {(b, p)}")
     idx_cluster = torch.empty((b, p), dtype=torch.int64, device=x.device)
     index_down = torch.empty((b, cluster_num), dtype=torch.int64, device=x.device)
-    _lib.call("tokred_dpcknn_cluster", _ptr(x), _ptr(noise_u), b, p, c, cluster_num, knn, _ptr(idx_cluster),
+    _lib.call("tokred_dpcknn_cluster", _ptr(x), _ptr(noise_u), b, p, c, cluster_num, knn, int(exact_fp32), _ptr(idx_cluster),
               _ptr(index_down), _stream())
     return idx_cluster, index_down
 
 
 @_dpcknn_cluster.register_fake
-def _(x, noise_u, cluster_num, knn):
+def _(x, noise_u, cluster_num, knn, exact_fp32):
     b, p, _ = x.shape
     return x.new_empty((b, p), dtype=torch.int64), x.new_empty((b, cluster_num), dtype=torch.int64)
 
@@ -319,9 +320,9 @@ def _(x, idx_token, agg_weight, idx_cluster, token_weight, cluster_num):
             x.new_empty((b, t, 1), dtype=torch.float32))
 
 
-def dpcknn_cluster(x: Tensor, noise_u: Tensor, cluster_num: int, knn: int = 5):
+def dpcknn_cluster(x: Tensor, noise_u: Tensor, cluster_num: int, knn: int = 5, exact_fp32: bool = False):
     """models/dpcknn.py:44-100: (idx_cluster [B,P], index_down [B,K]) int64; noise_u = torch.rand(B,P)."""
-    return torch.ops.tokred.dpcknn_cluster(x, noise_u, cluster_num, knn)
+    return torch.ops.tokred.dpcknn_cluster(x, noise_u, cluster_num, knn, exact_fp32)
 
 
 def dpcknn_merge(x, idx_token, agg_weight, idx_cluster, token_weight, cluster_num):
@@ -349,7 +350,7 @@ def _(attn, num_tokens):
 
 
 @torch.library.custom_op("tokred::kmedoids_fit", mutates_args=(), device_types="cuda")
-def _kmedoids_fit(x: Tensor, token_weight: Tensor, cluster_num: int, iters: int) -> Tuple[Tensor, Tensor, Tensor]:
+def _kmedoids_fit(x: Tensor, token_weight: Tensor, cluster_num: int, iters: int, exact_fp32: bool) -> Tuple[Tensor, Tensor, Tensor]:
     _need_cuda("kmedoids_fit", x, token_weight)
     b, p, c = x.shape
     if x.dtype != torch.float32:
@@ -360,13 +361,13 @@ def _kmedoids_fit(x: Tensor, token_weight: Tensor, cluster_num: int, iters: int)
     centres = torch.empty((b, cluster_num, c), dtype=torch.float32, device=x.device)
     cidx = torch.empty((b, cluster_num), dtype=torch.int64, device=x.device)
     assign = torch.empty((b, p), dtype=torch.int64, device=x.device)
-    _lib.call("tokred_kmedoids_fit", _ptr(x), _ptr(tw), b, p, c, cluster_num, iters, _ptr(centres), _ptr(cidx),
+    _lib.call("tokred_kmedoids_fit", _ptr(x), _ptr(tw), b, p, c, cluster_num, iters, int(exact_fp32), _ptr(centres), _ptr(cidx),
               _ptr(assign), _stream())
     return centres, cidx, assign
 
 
 @_kmedoids_fit.register_fake
-def _(x, token_weight, cluster_num, iters):
+def _(x, token_weight, cluster_num, iters, exact_fp32):
     b, p, c = x.shape
     return (x.new_empty((b, cluster_num, c)), x.new_empty((b, cluster_num), dtype=torch.int64),
             x.new_empty((b, p), dtype=torch.int64))
@@ -377,9 +378,9 @@ def attn_colsum(attn: Tensor, num_tokens: int = 1) -> Tensor:
     return torch.ops.tokred.attn_colsum(attn, num_tokens)
 
 
-def kmedoids_fit(x: Tensor, token_weight: Tensor, cluster_num: int, iters: int):
+def kmedoids_fit(x: Tensor, token_weight: Tensor, cluster_num: int, iters: int, exact_fp32: bool = False):
     """models/kmedoids.py:62-85: (centres [B,K,C], cluster_idx [B,K], assignment [B,P])."""
-    return torch.ops.tokred.kmedoids_fit(x, token_weight, cluster_num, iters)
+    return torch.ops.tokred.kmedoids_fit(x, token_weight, cluster_num, iters, exact_fp32)
 
 
 # ----------------------------------------------------------------------------------------------- soft merges

@@ -85,9 +85,11 @@ def cases():
         idx_token = torch.randint(0, p, (b, 196), device=DEV)
         agg = torch.rand(b, 196, 1, device=DEV)
         ic, _ = T.dpcknn_cluster(x, noise, k, 5)
-        out.append((f"dpcknn_cluster S B={b} P={p} K={k}", lambda x=x, nz=noise, k=k: T.dpcknn_cluster(x, nz, k, 5)))
+        out.append((f"dpcknn_cluster S B={b} P={p} K={k} tf32x3 tcgen05", lambda x=x, nz=noise, k=k: T.dpcknn_cluster(x, nz, k, 5, False)))
+        out.append((f"dpcknn_cluster S B={b} P={p} K={k} exact ffma", lambda x=x, nz=noise, k=k: T.dpcknn_cluster(x, nz, k, 5, True)))
         out.append((f"dpcknn_merge S B={b} P={p} K={k}", lambda x=x, it=idx_token, a=agg, ic=ic, tw=tw, k=k: T.dpcknn_merge(x, it, a, ic, tw, k)))
-        out.append((f"kmedoids_fit S B={b} P={p} K={k} iters=3", lambda x=x, tw=tw, k=k: T.kmedoids_fit(x, tw, k, 3)))
+        out.append((f"kmedoids_fit S B={b} P={p} K={k} iters=3 tf32x3 tcgen05", lambda x=x, tw=tw, k=k: T.kmedoids_fit(x, tw, k, 3, False)))
+        out.append((f"kmedoids_fit S B={b} P={p} K={k} iters=3 exact ffma", lambda x=x, tw=tw, k=k: T.kmedoids_fit(x, tw, k, 3, True)))
         attn = torch.softmax(torch.randn(b, 6, p + 1, p + 1, device=DEV), dim=-1)
         out.append((f"attn_colsum S B={b} N={p + 1}", lambda a=attn: T.attn_colsum(a, 1)))
     # config 5: Sinkhorn / PatchMerger / SiT / ATS B kr 0.9, B=128
