@@ -17,8 +17,9 @@
 namespace tokred {
 namespace {
 
-constexpr int kThreads = kGemmThreads;
+constexpr int kThreads = kGemmThreads;      // FFMA variants (gemm_nt.cuh is written for 256 threads)
 constexpr int kWarps = kThreads / 32;
+constexpr int kTcThreads = 512;              // tensor-core variants: no FFMA register tile -> 16 warps per CTA
 constexpr int kMaxP = 208;    // P*P + staging must fit 227 KB of shared memory
 constexpr int KT = 32;        // tf32 path: contraction columns per stage
 
@@ -93,9 +94,9 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 
 __device__ __forceinline__ void row_sqnorms(const float* __restrict__ xb, int P, int C, float* sq) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0);
-  for (int i = warp; i < P; i += kWarps) {
+  for (int i = warp; i < P; i += nwarps) {
     const float* row = xb + (long long)i * C;
     float s = 0.f;
     if (vec) {
@@ -117,7 +118,7 @@ __device__ __forceinline__ void row_sqnorms(const float* __restrict__ xb, int P,
 // shared-memory tile (A = rows of an M tile, B = rows 0..Np-1), written by the threads in the canonical K-major
 // layout (4 tf32 per 16-byte core row); two stages alias the D region.
 __device__ void pairdist_tc(const float* __restrict__ xb, int P, int C, DistCtx& cx, float post_scale) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x, nwarps = nthreads >> 5;
   row_sqnorms(xb, P, C, cx.sq);
   const int n_mt = (P + 127) / 128, Np = (P + 15) & ~15;
   const size_t stage_bytes = dist_stage_bytes(P), half = stage_bytes / 2;
@@ -133,11 +134,11 @@ __device__ void pairdist_tc(const float* __restrict__ xb, int P, int C, DistCtx&
     if (c >= 2) umma::mbar_wait(&cx.bars[st], (uint32_t)(((c - 2) >> 1) & 1));
     const int k0 = c * KT;
     constexpr int U = 4;
-    for (int g0 = tid; g0 < ng; g0 += kThreads * U) {
+    for (int g0 = tid; g0 < ng; g0 += nthreads * U) {
       float4 v[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int gI = g0 + u * kThreads;
+        const int gI = g0 + u * nthreads;
         const int row = (gI & 7) + ((gI >> 6) << 3), k = k0 + ((gI >> 3) & 7) * 4;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gI < ng && row < P) {
@@ -148,7 +149,7 @@ __device__ void pairdist_tc(const float* __restrict__ xb, int P, int C, DistCtx&
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int gI = g0 + u * kThreads;
+        const int gI = g0 + u * nthreads;
         const int row = (gI & 7) + ((gI >> 6) << 3), core = (gI >> 3) & 7;
         if (gI < ng) {
           float4 h, l;
@@ -185,15 +186,19 @@ __device__ void pairdist_tc(const float* __restrict__ xb, int P, int C, DistCtx&
     if (nchunk >= 2) umma::mbar_wait(&cx.bars[(last - 1) & 1], (uint32_t)(((last - 1) >> 1) & 1));
   }
   umma::tc_fence_after_sync();
-  // accumulator row i -> D row i (thread = row; odd row stride => conflict-free)
+  // accumulator row i -> D row i (thread = row; odd row stride => conflict-free).  Warp w owns TMEM lane quarter
+  // w % 4; the (w / 4) index enumerates (M tile, column part) pairs so that 8 or 16 warps all take part.
   {
-    const int mt = warp >> 2;
-    const int i = mt * 128 + (warp & 3) * 32 + lane;
-    if (mt < n_mt) {
+    const int q = warp & 3, slot = warp >> 2, nslots = nwarps >> 2;
+    const int parts = nslots / n_mt > 0 ? nslots / n_mt : 1;            // column parts per M tile
+    for (int s = slot; s < n_mt * parts; s += nslots) {
+      const int mt = s / parts, part = s % parts;
+      const int cbeg = ((Np / 16) * part / parts) * 16, cend = ((Np / 16) * (part + 1) / parts) * 16;
+      const int i = mt * 128 + q * 32 + lane;
       const float sqi = i < P ? cx.sq[i] : 0.f;
-      for (int c0 = 0; c0 < Np; c0 += 16) {
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
         uint32_t v[16];
-        umma::tmem_ld16(umma::tmem_addr(cx.tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(mt * 256 + c0)), v);
+        umma::tmem_ld16(umma::tmem_addr(cx.tmem_base, (uint32_t)(q * 32), (uint32_t)(mt * 256 + c0)), v);
         umma::tmem_ld_wait();
         if (i < P) {
 #pragma unroll
@@ -210,21 +215,20 @@ __device__ void pairdist_tc(const float* __restrict__ xb, int P, int C, DistCtx&
   umma::tc_fence_before_sync();
   __syncthreads();
   // G_ij and G_ji add the same products in a different order: mirror the upper triangle so D is bit-symmetric
-  for (int e = tid; e < P * P; e += kThreads) {
-    const int i = e / P, j = e % P;
-    if (j > i) cx.D[j * cx.DS + i] = cx.D[i * cx.DS + j];
-  }
+  for (int i = warp; i < P; i += nwarps)
+    for (int j = i + 1 + lane; j < P; j += 32) cx.D[j * cx.DS + i] = cx.D[i * cx.DS + j];
   __syncthreads();
 }
 
 // Fills cx.D (shared) with the pairwise distances of the P rows of xb (global, [P][C]) times post_scale.
-__device__ void pairdist_to_smem(const float* __restrict__ xb, int P, int C, DistCtx& cx, float post_scale) {
+template <bool TC>
+__device__ __forceinline__ void pairdist_to_smem(const float* __restrict__ xb, int P, int C, DistCtx& cx, float post_scale) {
   const int tid = threadIdx.x;
   float* D = cx.D;
   const int DS = cx.DS;
   if (P <= 25) {
     // direct form (ATen's non-matmul cdist path): sqrt(sum (xi - xj)^2)
-    for (int e = tid; e < P * P; e += kThreads) {
+    for (int e = tid; e < P * P; e += (int)blockDim.x) {
       const int i = e / P, j = e % P;
       const float* a = xb + (long long)i * C;
       const float* c = xb + (long long)j * C;
@@ -235,7 +239,10 @@ __device__ void pairdist_to_smem(const float* __restrict__ xb, int P, int C, Dis
     __syncthreads();
     return;
   }
-  if (cx.use_tc) { pairdist_tc(xb, P, C, cx, post_scale); return; }
+  if constexpr (TC) {
+    pairdist_tc(xb, P, C, cx, post_scale);
+    return;
+  } else {
   row_sqnorms(xb, P, C, cx.sq);
   const bool vec_ok = stage_vec_ok(xb, C);
   float* xt = cx.xt;
@@ -246,65 +253,92 @@ __device__ void pairdist_to_smem(const float* __restrict__ xb, int P, int C, Dis
             const float d2 = (sq[i] + sq[j]) - 2.0f * g;
             D[i * DS + j] = sqrtf(fmaxf(d2, 1e-30f)) * post_scale;
           });
+  }
 }
 
 // ------------------------------------------------------------------------------------------ plain cdist(x, x)
-__global__ void __launch_bounds__(kThreads, 1)
-pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale, float* __restrict__ out, int use_tc) {
+// Every distance kernel exists in two variants: TC = true (tcgen05 Gram, 512 threads, no FFMA register tile) and
+// TC = false (exact fp32 FFMA Gram, 256 threads).
+template <bool TC>
+__global__ void __launch_bounds__(TC ? kTcThreads : kThreads, 1)
+pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale, float* __restrict__ out) {
+  constexpr int NT = TC ? kTcThreads : kThreads;
   extern __shared__ __align__(128) float smem[];
-  DistCtx cx = dist_setup(smem, P, 0, use_tc);
-  pairdist_to_smem(x + (long long)blockIdx.x * P * C, P, C, cx, post_scale);
+  DistCtx cx = dist_setup(smem, P, 0, TC ? 1 : 0);
+  pairdist_to_smem<TC>(x + (long long)blockIdx.x * P * C, P, C, cx, post_scale);
   float* ob = out + (long long)blockIdx.x * P * P;
-  for (int e = threadIdx.x; e < P * P; e += kThreads) ob[e] = cx.D[(e / P) * cx.DS + e % P];
+  for (int i = threadIdx.x >> 5; i < P; i += NT / 32)
+    for (int j = threadIdx.x & 31; j < P; j += 32) ob[i * P + j] = cx.D[i * cx.DS + j];
   dist_teardown(cx);
 }
 
 // ------------------------------------------------------------------------------------------ DPC-KNN cluster
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool TC>
+__global__ void __launch_bounds__(TC ? kTcThreads : kThreads, 1)
 dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noise_u, int P, int C, int K, int knn,
-                      float inv_sqrt_c, int64_t* __restrict__ idx_cluster, int64_t* __restrict__ index_down, int use_tc) {
+                      float inv_sqrt_c, int64_t* __restrict__ idx_cluster, int64_t* __restrict__ index_down) {
+  constexpr int NT = TC ? kTcThreads : kThreads;
   extern __shared__ __align__(128) float smem[];
-  DistCtx cx = dist_setup(smem, P, 2 * P + K + kWarps, use_tc);
+  DistCtx cx = dist_setup(smem, P, 2 * P + K + kTcThreads / 32, TC ? 1 : 0);
   float* D = cx.D;
   const int DS = cx.DS;
   float* rho = cx.extra;
   float* score = rho + P;
   int* centre = reinterpret_cast<int*>(score + P);   // [K]
-  float* red = reinterpret_cast<float*>(centre + K);  // [kWarps]
+  float* red = reinterpret_cast<float*>(centre + K);  // [NT / 32]
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  pairdist_to_smem(x + (long long)b * P * C, P, C, cx, inv_sqrt_c);
+  pairdist_to_smem<TC>(x + (long long)b * P * C, P, C, cx, inv_sqrt_c);
   dist_teardown(cx);
 
   // local density from the knn nearest (self included): exp(-mean(d^2)) + 1e-6 * U
   float lmax = 0.f;
-  for (int i = tid; i < P; i += kThreads) {
-    float prev_v = -1.f;
-    int prev_j = -1;
+  for (int i = tid; i < P; i += NT) {
     float sumsq = 0.f;
-    for (int t = 0; t < knn; ++t) {
-      float best = CUDART_INF_F;
-      int bj = -1;
+    if (knn <= 8) {
+      // one pass: the 8 smallest of column i kept sorted in registers (strict < keeps the lower index first on ties)
+      float nb[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) nb[t] = CUDART_INF_F;
       for (int j = 0; j < P; ++j) {
-        const float v = D[j * DS + i];
-        const bool after = (v > prev_v) || (v == prev_v && j > prev_j);
-        if (after && v < best) { best = v; bj = j; }
+        float cur = D[j * DS + i];
+        lmax = fmaxf(lmax, cur);
+        if (cur < nb[7]) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (cur < nb[t]) { const float tmp = nb[t]; nb[t] = cur; cur = tmp; }
+        }
       }
-      sumsq += best * best;
-      prev_v = best; prev_j = bj;
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (t < knn) sumsq += nb[t] * nb[t];
+    } else {
+      float prev_v = -1.f;
+      int prev_j = -1;
+      for (int t = 0; t < knn; ++t) {
+        float best = CUDART_INF_F;
+        int bj = -1;
+        for (int j = 0; j < P; ++j) {
+          const float v = D[j * DS + i];
+          const bool after = (v > prev_v) || (v == prev_v && j > prev_j);
+          if (after && v < best) { best = v; bj = j; }
+        }
+        sumsq += best * best;
+        prev_v = best; prev_j = bj;
+      }
+      for (int j = 0; j < P; ++j) lmax = fmaxf(lmax, D[j * DS + i]);
     }
     rho[i] = expf(-(sumsq * (1.0f / (float)knn))) + noise_u[(long long)b * P + i] * 1e-6f;
-    for (int j = 0; j < P; ++j) lmax = fmaxf(lmax, D[j * DS + i]);
   }
   lmax = warp_max(lmax);
   if (lane == 0) red[warp] = lmax;
   __syncthreads();
   float dmax = red[0];
 #pragma unroll
-  for (int w = 1; w < kWarps; ++w) dmax = fmaxf(dmax, red[w]);
+  for (int w = 1; w < NT / 32; ++w) dmax = fmaxf(dmax, red[w]);
 
   // distance to the nearest denser token (or the global max), centre score
-  for (int i = tid; i < P; i += kThreads) {
+  for (int i = tid; i < P; i += NT) {
     const float ri = rho[i];
     float best = dmax;
     for (int j = 0; j < P; ++j) {
@@ -314,13 +348,13 @@ dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noi
     score[i] = best * ri;
   }
   __syncthreads();
-  for (int i = tid; i < P; i += kThreads) {
+  for (int i = tid; i < P; i += NT) {
     const int rk = rank_desc(score, P, i);
     if (rk < K) { centre[rk] = i; index_down[(long long)b * K + rk] = i; }
   }
   __syncthreads();
   // nearest centre (lowest k on ties); centres belong to their own cluster
-  for (int i = tid; i < P; i += kThreads) {
+  for (int i = tid; i < P; i += NT) {
     float best = CUDART_INF_F;
     int bk = 0;
     for (int k = 0; k < K; ++k) {
@@ -334,12 +368,13 @@ dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noi
 }
 
 // ------------------------------------------------------------------------------------------ K-Medoids fit
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool TC>
+__global__ void __launch_bounds__(TC ? kTcThreads : kThreads, 1)
 kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token_weight, int P, int C, int K, int iters,
-                    float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment,
-                    int use_tc) {
+                    float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment) {
+  constexpr int NT = TC ? kTcThreads : kThreads;
   extern __shared__ __align__(128) float smem[];
-  DistCtx cx = dist_setup(smem, P, 3 * P + K, use_tc);
+  DistCtx cx = dist_setup(smem, P, 3 * P + K, TC ? 1 : 0);
   float* D = cx.D;
   const int DS = cx.DS;
   float* w = cx.extra;
@@ -349,12 +384,12 @@ kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* xb = x + (long long)b * P * C;
 
-  for (int i = tid; i < P; i += kThreads) w[i] = token_weight[(long long)b * P + i];
-  pairdist_to_smem(xb, P, C, cx, 1.0f);
+  for (int i = tid; i < P; i += NT) w[i] = token_weight[(long long)b * P + i];
+  pairdist_to_smem<TC>(xb, P, C, cx, 1.0f);
   dist_teardown(cx);
 
   // S_i = sum_j (D_ij * w_i); initial centres = top-K token weights (descending, lowest index on ties)
-  for (int i = tid; i < P; i += kThreads) {
+  for (int i = tid; i < P; i += NT) {
     const float wi = w[i];
     float s = 0.f;
     for (int j = 0; j < P; ++j) s += __fmul_rn(D[j * DS + i], wi);
@@ -365,7 +400,7 @@ kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token
   __syncthreads();
   const float big = 1.0e6f * (float)P;     // P masked columns of 1e6 sum exactly in fp32
   for (int it = 0; it <= iters; ++it) {
-    for (int i = tid; i < P; i += kThreads) {
+    for (int i = tid; i < P; i += NT) {
       float best = CUDART_INF_F;
       int bk = 0;
       for (int k = 0; k < K; ++k) {
@@ -376,7 +411,7 @@ kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token
     }
     __syncthreads();
     if (it == iters) break;
-    for (int k = tid; k < K; k += kThreads) {
+    for (int k = tid; k < K; k += NT) {
       float best = CUDART_INF_F;
       int bi = 0;
       for (int i = 0; i < P; ++i) {
@@ -387,13 +422,13 @@ kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token
     }
     __syncthreads();
   }
-  for (int i = tid; i < P; i += kThreads) assignment[(long long)b * P + i] = assign[i];
-  for (int k = tid; k < K; k += kThreads) cluster_idx[(long long)b * K + k] = centre[k];
+  for (int i = tid; i < P; i += NT) assignment[(long long)b * P + i] = assign[i];
+  for (int k = tid; k < K; k += NT) cluster_idx[(long long)b * K + k] = centre[k];
   // medoid rows verbatim
   float* cb = centres + (long long)b * K * C;
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0) &&
                    ((reinterpret_cast<uintptr_t>(cb) & 15u) == 0);
-  for (int k = warp; k < K; k += kWarps) {
+  for (int k = warp; k < K; k += NT / 32) {
     const float* src = xb + (long long)centre[k] * C;
     if (vec) warp_copy_row16(cb + (long long)k * C, src, C * 4, lane);
     else warp_copy_row_elems(cb + (long long)k * C, src, C, lane);
@@ -531,8 +566,13 @@ extern "C" int tokred_pairwise_dist(const float* x, int B, int P, int C, float p
   if (B == 0) return TOKRED_OK;
   const int use_tc = pick_tc(P, exact_fp32);
   const size_t smem = dist_smem_bytes(P, 0, use_tc);
-  if (int e = allow_smem(pairwise_dist_kernel, smem, what)) return e;
-  pairwise_dist_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out, use_tc);
+  if (use_tc) {
+    if (int e = allow_smem(pairwise_dist_kernel<true>, smem, what)) return e;
+    pairwise_dist_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out);
+  } else {
+    if (int e = allow_smem(pairwise_dist_kernel<false>, smem, what)) return e;
+    pairwise_dist_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out);
+  }
   return finish_launch(what);
 }
 
@@ -547,11 +587,17 @@ extern "C" int tokred_dpcknn_cluster(const float* x, const float* noise_u, int B
   if (P > kMaxP) { set_error("%s: P=%d > %d patches is not supported (distance matrix is kept in shared memory)", what, P, kMaxP); return TOKRED_ERR_UNSUPPORTED; }
   if (B == 0) return TOKRED_OK;
   const int use_tc = pick_tc(P, exact_fp32);
-  const size_t smem = dist_smem_bytes(P, 2 * P + K + kWarps, use_tc);
-  if (int e = allow_smem(dpcknn_cluster_kernel, smem, what)) return e;
+  const size_t smem = dist_smem_bytes(P, 2 * P + K + kTcThreads / 32, use_tc);
   const float inv = 1.0f / (float)sqrt((double)C);     // CUDA tensor / python-scalar = multiply by fp32 reciprocal
-  dpcknn_cluster_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(x, noise_u, P, C, K, knn, inv, idx_cluster, index_down,
-                                                                     use_tc);
+  if (use_tc) {
+    if (int e = allow_smem(dpcknn_cluster_kernel<true>, smem, what)) return e;
+    dpcknn_cluster_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, noise_u, P, C, K, knn, inv, idx_cluster,
+                                                                              index_down);
+  } else {
+    if (int e = allow_smem(dpcknn_cluster_kernel<false>, smem, what)) return e;
+    dpcknn_cluster_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, noise_u, P, C, K, knn, inv, idx_cluster,
+                                                                             index_down);
+  }
   return finish_launch(what);
 }
 
@@ -567,9 +613,15 @@ extern "C" int tokred_kmedoids_fit(const float* x, const float* token_weight, in
   if (B == 0) return TOKRED_OK;
   const int use_tc = pick_tc(P, exact_fp32);
   const size_t smem = dist_smem_bytes(P, 3 * P + K, use_tc);
-  if (int e = allow_smem(kmedoids_fit_kernel, smem, what)) return e;
-  kmedoids_fit_kernel<<<B, kThreads, smem, (cudaStream_t)stream>>>(x, token_weight, P, C, K, iters, centres, cluster_idx,
-                                                                   assignment, use_tc);
+  if (use_tc) {
+    if (int e = allow_smem(kmedoids_fit_kernel<true>, smem, what)) return e;
+    kmedoids_fit_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, token_weight, P, C, K, iters, centres,
+                                                                            cluster_idx, assignment);
+  } else {
+    if (int e = allow_smem(kmedoids_fit_kernel<false>, smem, what)) return e;
+    kmedoids_fit_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, token_weight, P, C, K, iters, centres,
+                                                                           cluster_idx, assignment);
+  }
   return finish_launch(what);
 }
 
