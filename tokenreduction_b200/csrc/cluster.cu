@@ -436,20 +436,19 @@ kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token
 }
 
 // ------------------------------------------------------------------------------------------ DPC-KNN merge
-// grid (splits, B); one warp per cluster row.  Members are accumulated in ascending token order with unfused
-// multiply/add: the order and rounding of CPU index_add_ (models/dpcknn.py:122-131).
+// grid (splits, B); one warp per cluster row.  Members are found by ballot over the assignment vector (ascending
+// token order) and accumulated with unfused multiply/add: the order and rounding of CPU index_add_
+// (models/dpcknn.py:122-131) => bit-identical.  CPL = 16-byte chunks per lane, all in flight per member row.
+template <int CPL>
 __global__ void __launch_bounds__(kThreads)
 dpcknn_merge_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx_token,
                     const float* __restrict__ agg_weight, const int64_t* __restrict__ idx_cluster,
                     const float* __restrict__ token_weight, int P, int C, int K, int T, float* __restrict__ x_merged,
-                    int64_t* __restrict__ idx_token_new, float* __restrict__ agg_weight_new, int vec) {
-  extern __shared__ __align__(128) float smem[];
+                    int64_t* __restrict__ idx_token_new, float* __restrict__ agg_weight_new) {
+  extern __shared__ float smem[];
   float* nw = smem;                                   // [P] normalised weights
   float* wsum = nw + P;                               // [K]
   int* cl = reinterpret_cast<int*>(wsum + K);         // [P] cluster of token
-  int* cnt = cl + P;                                  // [K]
-  int* offs = cnt + K;                                // [K]
-  int* member = offs + K;                             // [P] tokens grouped by cluster, ascending
   const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < P; i += kThreads) {
@@ -460,19 +459,9 @@ dpcknn_merge_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx
   __syncthreads();
   for (int k = tid; k < K; k += kThreads) {
     float s = 0.f;
-    int c = 0;
     for (int i = 0; i < P; ++i)
-      if (cl[i] == k) { s += nw[i]; ++c; }
+      if (cl[i] == k) s += nw[i];
     wsum[k] = s + 1e-6f;
-    cnt[k] = c;
-  }
-  __syncthreads();
-  for (int k = tid; k < K; k += kThreads) {
-    int o = 0;
-    for (int q = 0; q < k; ++q) o += cnt[q];
-    offs[k] = o;
-    for (int i = 0; i < P; ++i)
-      if (cl[i] == k) member[o++] = i;
   }
   __syncthreads();
   for (int i = tid; i < P; i += kThreads) nw[i] = nw[i] / wsum[cl[i]];
@@ -480,32 +469,43 @@ dpcknn_merge_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx
 
   const float* xb = x + (long long)b * P * C;
   float* ob = x_merged + (long long)b * K * C;
+  const int nchunks = C / 4;
   for (int k = blockIdx.x * kWarps + warp; k < K; k += gridDim.x * kWarps) {
-    const int n = cnt[k];
-    const int* mem = member + offs[k];
-    if (vec) {
-      for (int c = lane * 4; c < C; c += 128) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-        for (int m = 0; m < n; ++m) {
-          const int i = mem[m];
+    if constexpr (CPL > 0) {
+      float acc[CPL][4];
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+      for (int base = 0; base < P; base += 32) {
+        const int t = base + lane;
+        unsigned m = __ballot_sync(0xffffffffu, t < P && cl[t] == k);
+        while (m) {
+          const int i = base + __ffs(m) - 1;
+          m &= m - 1;
           const float wgt = nw[i];
-          int4 raw = ld_stream16(xb + (long long)i * C + c);
-          const float* v = reinterpret_cast<const float*>(&raw);
-          acc.x = __fadd_rn(acc.x, __fmul_rn(v[0], wgt));
-          acc.y = __fadd_rn(acc.y, __fmul_rn(v[1], wgt));
-          acc.z = __fadd_rn(acc.z, __fmul_rn(v[2], wgt));
-          acc.w = __fadd_rn(acc.w, __fmul_rn(v[3], wgt));
+          int4 raw[CPL];
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const int c = lane + 32 * q;
+            if (c < nchunks) raw[q] = ld_stream16(xb + (long long)i * C + c * 4);
+          }
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const float* v = reinterpret_cast<const float*>(&raw[q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[q][e] = __fadd_rn(acc[q][e], __fmul_rn(v[e], wgt));
+          }
         }
-        st_stream16(ob + (long long)k * C + c, *reinterpret_cast<const int4*>(&acc));
+      }
+#pragma unroll
+      for (int q = 0; q < CPL; ++q) {
+        const int c = lane + 32 * q;
+        if (c < nchunks) st_stream16(ob + (long long)k * C + c * 4, *reinterpret_cast<const int4*>(acc[q]));
       }
     } else {
       for (int c = lane; c < C; c += 32) {
         float acc = 0.f;
-        for (int m = 0; m < n; ++m) {
-          const int i = mem[m];
-          acc = __fadd_rn(acc, __fmul_rn(xb[(long long)i * C + c], nw[i]));
-        }
+        for (int i = 0; i < P; ++i)
+          if (cl[i] == k) acc = __fadd_rn(acc, __fmul_rn(xb[(long long)i * C + c], nw[i]));
         ob[(long long)k * C + c] = acc;
       }
     }
@@ -521,31 +521,66 @@ dpcknn_merge_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx
 }
 
 // ------------------------------------------------------------------------------------------ attention column sums
-// out[b,p] = sum_q ( sum_h attn[b,h,q,nt+p] ): heads first, then query rows (the reference's two torch.sum calls).
-// One CTA per image, 1024 threads = 4 row-phases x 256 columns; lanes run along columns -> coalesced 128-byte
-// rows; the H loads of one (q, column) are independent -> H requests in flight per thread.
+// out[b,p] = sum_h sum_q attn[b,h,q,nt+p]  (models/kmedoids.py:240).  The [H,N,N] block of an image is one flat run
+// of H*N rows of N elements, so the column of flat element e is (e mod N).  Threads stream ALIGNED 16-byte vectors
+// of that run; a "group" is Tg = N / gcd(N, VE) threads, whose combined stride VE*Tg is a multiple of N — so a
+// thread hits the same VE columns in every iteration and keeps VE register accumulators.  G groups interleave
+// iterations.  Combine: G*VE rounds in which the Tg threads of one group add one accumulator each to DISTINCT
+// columns of a shared array (plain adds, fixed order => deterministic, no atomics).
 template <typename T>
 __global__ void __launch_bounds__(1024)
-attn_colsum_kernel(const T* __restrict__ attn, int H, int N, int nt, float* __restrict__ out) {
-  __shared__ float part[4][256];
-  const int b = blockIdx.y, tid = threadIdx.x, ph = tid >> 8, lc = tid & 255;
-  const int col = blockIdx.x * 256 + lc;
-  const T* ab = attn + (long long)b * H * N * N;
-  float acc = 0.f;
-  if (col < N) {
-    for (int q = ph; q < N; q += 4) {
-      float t = 0.f;
-#pragma unroll 4
-      for (int h = 0; h < H; ++h) t += to_f32(ab[((long long)h * N + q) * N + col]);
-      acc += t;
+attn_colsum_kernel(const T* __restrict__ attn, int H, int N, int nt, int Tg, int G, float* __restrict__ out) {
+  constexpr int VE = 16 / sizeof(T);
+  extern __shared__ float colsum[];     // [N]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const long long len = (long long)H * N * N;
+  const T* base = attn + (long long)b * len;
+  // first 16-byte aligned element of this image's run
+  const int mis = (int)((reinterpret_cast<uintptr_t>(base) & 15u) / sizeof(T));
+  const int head = mis ? VE - mis : 0;            // scalar prologue elements [0, head)
+  for (int c = tid; c < N; c += blockDim.x) colsum[c] = 0.f;
+  const int grp = tid / Tg, t = tid % Tg;
+  float acc[VE];
+#pragma unroll
+  for (int i = 0; i < VE; ++i) acc[i] = 0.f;
+  const bool live = grp < G;
+  const long long nvec = (len - head) / VE;       // aligned vectors
+  if (live) {
+    long long v = (long long)grp * Tg + t;
+    const long long step = (long long)G * Tg;
+    for (; v + 3 * step < nvec; v += 4 * step) {  // 4 independent 16-byte loads in flight
+      int4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = ld_stream16(base + head + (v + u * step) * VE);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const T* e = reinterpret_cast<const T*>(&r[u]);
+#pragma unroll
+        for (int i = 0; i < VE; ++i) acc[i] += to_f32(e[i]);
+      }
+    }
+    for (; v < nvec; v += step) {
+      const int4 r = ld_stream16(base + head + v * VE);
+      const T* e = reinterpret_cast<const T*>(&r);
+#pragma unroll
+      for (int i = 0; i < VE; ++i) acc[i] += to_f32(e[i]);
     }
   }
-  part[ph][lc] = acc;
   __syncthreads();
-  if (ph == 0 && col < N && col >= nt) {
-    const float s = ((part[0][lc] + part[1][lc]) + part[2][lc]) + part[3][lc];
-    out[(long long)b * (N - nt) + (col - nt)] = s;
+  // combine (group-major, accumulator-minor order); columns of one (group, i) round are all distinct
+  const int col0 = (int)(((long long)head + (long long)t * VE) % N);
+  for (int g = 0; g < G; ++g)
+    for (int i = 0; i < VE; ++i) {
+      if (live && grp == g) colsum[(col0 + i) % N] += acc[i];
+      __syncthreads();
+    }
+  // scalar prologue / epilogue elements (at most 2*(VE-1) per image)
+  if (tid == 0) {
+    for (int e = 0; e < head && e < len; ++e) colsum[e % N] += to_f32(base[e]);
+    for (long long e = head + nvec * VE; e < len; ++e) colsum[(int)(e % N)] += to_f32(base[e]);
   }
+  __syncthreads();
+  for (int c = nt + tid; c < N; c += blockDim.x) out[(long long)b * (N - nt) + (c - nt)] = colsum[c];
 }
 
 }  // namespace
@@ -635,13 +670,28 @@ extern "C" int tokred_dpcknn_merge(const float* x, const int64_t* idx_token, con
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 1 && K >= 1 && T >= 0, "%s: bad shape", what);
   TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
   if (B == 0) return TOKRED_OK;
-  const size_t smem = (size_t)(3 * P + 3 * K) * 4;
-  if (int e = allow_smem(dpcknn_merge_kernel, smem, what)) return e;
-  const int vec = (C % 4 == 0) && aligned16(x) && aligned16(x_merged);
-  int splits = ceil_div(4 * kNumSMs, B);
+  const size_t smem = (size_t)(2 * P + K) * 4;
+  const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(x_merged);
+  const int cpl = vec ? ceil_div(C / 4, 32) : 0;
+  int splits = ceil_div(6 * kNumSMs, B);
   splits = max(1, min(splits, ceil_div(K, kWarps)));
-  dpcknn_merge_kernel<<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
-      x, idx_token, agg_weight, idx_cluster, token_weight, P, C, K, T, x_merged, idx_token_new, agg_weight_new, vec);
+  dim3 grid(splits, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(CPL)                                                                                                  \
+  do {                                                                                                               \
+    if (int e = allow_smem(dpcknn_merge_kernel<CPL>, smem, what)) return e;                                          \
+    dpcknn_merge_kernel<CPL><<<grid, kThreads, smem, st>>>(x, idx_token, agg_weight, idx_cluster, token_weight, P, C, K, \
+                                                           T, x_merged, idx_token_new, agg_weight_new);             \
+  } while (0)
+  switch (cpl) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    case 5: case 6: LAUNCH(6); break;
+    default: LAUNCH(0); break;
+  }
+#undef LAUNCH
   return finish_launch(what);
 }
 
@@ -654,11 +704,19 @@ extern "C" int tokred_attn_colsum(const void* attn, int attn_dtype, int B, int H
   TOKRED_REQUIRE(B >= 0 && H >= 1 && N >= 1 && num_tokens >= 0 && num_tokens < N, "%s: bad shape", what);
   TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
   if (B == 0) return TOKRED_OK;
-  dim3 grid(ceil_div(N, 256), B);
+  // group size: smallest thread count whose combined vector stride is a multiple of N
+  const int ve = attn_dtype == TOKRED_F32 ? 4 : 8;
+  int gcd = N, a = ve;
+  while (a) { const int tmp = gcd % a; gcd = a; a = tmp; }
+  const int Tg = N / gcd;
+  TOKRED_REQUIRE(Tg <= 1024, "%s: N=%d needs a %d-thread group (> 1024)", what, N, Tg);
+  const int G = 1024 / Tg > 8 ? 8 : 1024 / Tg;
+  const int threads = ((G * Tg + 31) / 32) * 32;
+  const size_t smem = (size_t)N * 4;
   if (attn_dtype == TOKRED_F32)
-    attn_colsum_kernel<float><<<grid, 1024, 0, (cudaStream_t)stream>>>((const float*)attn, H, N, num_tokens, out);
+    attn_colsum_kernel<float><<<B, threads, smem, (cudaStream_t)stream>>>((const float*)attn, H, N, num_tokens, Tg, G, out);
   else
-    attn_colsum_kernel<__nv_bfloat16><<<grid, 1024, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)attn, H, N,
-                                                                               num_tokens, out);
+    attn_colsum_kernel<__nv_bfloat16><<<B, threads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)attn, H, N,
+                                                                                  num_tokens, Tg, G, out);
   return finish_launch(what);
 }

@@ -94,8 +94,13 @@ __device__ __forceinline__ void warp_copy_row16(void* dst, const void* src, int 
 }
 // Generic fallback (any alignment / size), element type T.
 template <typename T>
-__device__ __forceinline__ void warp_copy_row_elems(T* dst, const T* src, int n, int lane) {
-  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+__device__ __forceinline__ void warp_copy_row_elems(T* __restrict__ dst, const T* __restrict__ src, int n, int lane) {
+  int i = lane;
+  for (; i + 96 < n; i += 128) {          // 4 independent loads in flight per lane
+    const T a = src[i], b = src[i + 32], c = src[i + 64], d = src[i + 96];
+    dst[i] = a; dst[i + 32] = b; dst[i + 64] = c; dst[i + 96] = d;
+  }
+  for (; i < n; i += 32) dst[i] = src[i];
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
