@@ -40,7 +40,8 @@ struct DistCtx {
 
 __host__ __device__ inline size_t dist_stage_bytes(int P) { return (size_t)((P + 127) / 128) * 16 * 1024 * 2; }   // hi + lo
 __host__ __device__ inline size_t dist_region0_bytes(int P, int use_tc) {
-  const size_t d = ((size_t)P * (P | 1) * 4 + 15) & ~(size_t)15;
+  size_t d = ((size_t)P * (P | 1) * 4 + 15) & ~(size_t)15;
+  if (P <= 25) d += (size_t)P * 257 * 4 + 16;      // direct path: staged rows [P][256+1]
   const size_t st = use_tc ? 2 * dist_stage_bytes(P) : 0;
   return d > st ? d : st;
 }
@@ -227,20 +228,40 @@ __device__ __forceinline__ void pairdist_to_smem(const float* __restrict__ xb, i
   float* D = cx.D;
   const int DS = cx.DS;
   if (P <= 25) {
-    // direct form (ATen's non-matmul cdist path): sqrt(sum (xi - xj)^2)
-    for (int e = tid; e < P * P; e += (int)blockDim.x) {
-      const int i = e / P, j = e % P;
-      const float* a = xb + (long long)i * C;
-      const float* c = xb + (long long)j * C;
-      float s = 0.f;
-      for (int k = 0; k < C; ++k) { float d = a[k] - c[k]; s = fmaf(d, d, s); }
-      D[i * DS + j] = sqrtf(s) * post_scale;
+    // direct form (ATen's non-matmul cdist path): sqrt(sum (xi - xj)^2).  The <= 25 rows are staged through shared
+    // memory in 256-column chunks (the D region is free until the end; pair sums live in registers).
+    constexpr int CH = 256;
+    float* xs = D + (((P * DS + 3) & ~3));          // [P][CH+1] after the (tiny) D matrix, inside region 0 / tile space
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;               // up to 3 pairs per thread (P*P <= 625 <= 3*256)
+    const int nthr = (int)blockDim.x;
+    for (int k0 = 0; k0 < C; k0 += CH) {
+      const int kn = min(CH, C - k0);
+      __syncthreads();
+      for (int e = tid; e < P * kn; e += nthr) xs[(e / kn) * (CH + 1) + e % kn] = xb[(long long)(e / kn) * C + k0 + e % kn];
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int e = tid + u * nthr;
+        if (e < P * P) {
+          const float* a = xs + (e / P) * (CH + 1);
+          const float* c = xs + (e % P) * (CH + 1);
+          float s = u == 0 ? s0 : (u == 1 ? s1 : s2);
+          for (int k = 0; k < kn; ++k) { const float d = a[k] - c[k]; s = fmaf(d, d, s); }
+          if (u == 0) s0 = s; else if (u == 1) s1 = s; else s2 = s;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int e = tid + u * nthr;
+      if (e < P * P) D[(e / P) * DS + e % P] = sqrtf(u == 0 ? s0 : (u == 1 ? s1 : s2)) * post_scale;
     }
     __syncthreads();
     return;
   }
   if constexpr (TC) {
-    pairdist_tc(xb, P, C, cx, post_scale);
+    pairdist_tc(xb, P, C, cx, post_scale);      // light kernels are only launched with use_tc = 1 when P > 25
     return;
   } else {
   row_sqnorms(xb, P, C, cx.sq);
@@ -261,10 +282,10 @@ __device__ __forceinline__ void pairdist_to_smem(const float* __restrict__ xb, i
 // TC = false (exact fp32 FFMA Gram, 256 threads).
 template <bool TC>
 __global__ void __launch_bounds__(TC ? kTcThreads : kThreads, 1)
-pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale, float* __restrict__ out) {
+pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale, float* __restrict__ out, int use_tc) {
   constexpr int NT = TC ? kTcThreads : kThreads;
   extern __shared__ __align__(128) float smem[];
-  DistCtx cx = dist_setup(smem, P, 0, TC ? 1 : 0);
+  DistCtx cx = dist_setup(smem, P, 0, use_tc);
   pairdist_to_smem<TC>(x + (long long)blockIdx.x * P * C, P, C, cx, post_scale);
   float* ob = out + (long long)blockIdx.x * P * P;
   for (int i = threadIdx.x >> 5; i < P; i += NT / 32)
@@ -276,10 +297,10 @@ pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale
 template <bool TC>
 __global__ void __launch_bounds__(TC ? kTcThreads : kThreads, 1)
 dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noise_u, int P, int C, int K, int knn,
-                      float inv_sqrt_c, int64_t* __restrict__ idx_cluster, int64_t* __restrict__ index_down) {
+                      float inv_sqrt_c, int64_t* __restrict__ idx_cluster, int64_t* __restrict__ index_down, int use_tc) {
   constexpr int NT = TC ? kTcThreads : kThreads;
   extern __shared__ __align__(128) float smem[];
-  DistCtx cx = dist_setup(smem, P, 2 * P + K + kTcThreads / 32, TC ? 1 : 0);
+  DistCtx cx = dist_setup(smem, P, 2 * P + K + kTcThreads / 32, use_tc);
   float* D = cx.D;
   const int DS = cx.DS;
   float* rho = cx.extra;
@@ -371,10 +392,11 @@ dpcknn_cluster_kernel(const float* __restrict__ x, const float* __restrict__ noi
 template <bool TC>
 __global__ void __launch_bounds__(TC ? kTcThreads : kThreads, 1)
 kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token_weight, int P, int C, int K, int iters,
-                    float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment) {
+                    float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment,
+                    int use_tc) {
   constexpr int NT = TC ? kTcThreads : kThreads;
   extern __shared__ __align__(128) float smem[];
-  DistCtx cx = dist_setup(smem, P, 3 * P + K, TC ? 1 : 0);
+  DistCtx cx = dist_setup(smem, P, 3 * P + K, use_tc);
   float* D = cx.D;
   const int DS = cx.DS;
   float* w = cx.extra;
@@ -590,6 +612,8 @@ using namespace tokred;
 
 // tensor cores for every P that takes ATen's matmul form (P > 25), unless the caller asks for the exact-fp32 FFMA path
 static int pick_tc(int P, int exact_fp32) { return (P > 25 && !exact_fp32) ? 1 : 0; }
+// the light 512-thread kernels (no FFMA register tile) also serve the direct-difference path of P <= 25
+static int pick_light(int P, int use_tc) { return (use_tc || P <= 25) ? 1 : 0; }
 
 extern "C" int tokred_pairwise_dist(const float* x, int B, int P, int C, float post_scale, int exact_fp32, float* out,
                                     void* stream) {
@@ -601,12 +625,12 @@ extern "C" int tokred_pairwise_dist(const float* x, int B, int P, int C, float p
   if (B == 0) return TOKRED_OK;
   const int use_tc = pick_tc(P, exact_fp32);
   const size_t smem = dist_smem_bytes(P, 0, use_tc);
-  if (use_tc) {
+  if (pick_light(P, use_tc)) {
     if (int e = allow_smem(pairwise_dist_kernel<true>, smem, what)) return e;
-    pairwise_dist_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out);
+    pairwise_dist_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out, use_tc);
   } else {
     if (int e = allow_smem(pairwise_dist_kernel<false>, smem, what)) return e;
-    pairwise_dist_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out);
+    pairwise_dist_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out, 0);
   }
   return finish_launch(what);
 }
@@ -624,14 +648,14 @@ extern "C" int tokred_dpcknn_cluster(const float* x, const float* noise_u, int B
   const int use_tc = pick_tc(P, exact_fp32);
   const size_t smem = dist_smem_bytes(P, 2 * P + K + kTcThreads / 32, use_tc);
   const float inv = 1.0f / (float)sqrt((double)C);     // CUDA tensor / python-scalar = multiply by fp32 reciprocal
-  if (use_tc) {
+  if (pick_light(P, use_tc)) {
     if (int e = allow_smem(dpcknn_cluster_kernel<true>, smem, what)) return e;
     dpcknn_cluster_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, noise_u, P, C, K, knn, inv, idx_cluster,
-                                                                              index_down);
+                                                                              index_down, use_tc);
   } else {
     if (int e = allow_smem(dpcknn_cluster_kernel<false>, smem, what)) return e;
     dpcknn_cluster_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, noise_u, P, C, K, knn, inv, idx_cluster,
-                                                                             index_down);
+                                                                             index_down, 0);
   }
   return finish_launch(what);
 }
@@ -648,14 +672,14 @@ extern "C" int tokred_kmedoids_fit(const float* x, const float* token_weight, in
   if (B == 0) return TOKRED_OK;
   const int use_tc = pick_tc(P, exact_fp32);
   const size_t smem = dist_smem_bytes(P, 3 * P + K, use_tc);
-  if (use_tc) {
+  if (pick_light(P, use_tc)) {
     if (int e = allow_smem(kmedoids_fit_kernel<true>, smem, what)) return e;
     kmedoids_fit_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, token_weight, P, C, K, iters, centres,
-                                                                            cluster_idx, assignment);
+                                                                            cluster_idx, assignment, use_tc);
   } else {
     if (int e = allow_smem(kmedoids_fit_kernel<false>, smem, what)) return e;
     kmedoids_fit_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, token_weight, P, C, K, iters, centres,
-                                                                           cluster_idx, assignment);
+                                                                           cluster_idx, assignment, 0);
   }
   return finish_launch(what);
 }

@@ -131,18 +131,35 @@ evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_
   float acc[VE];
 #pragma unroll
   for (int i = 0; i < VE; ++i) acc[i] = 0.f;
-  for (int m = warp; m < M; m += kWarps) {
-    const int p = cmp[m];
-    const float w = keys[p];
-    const T* row = xb + (long long)(1 + p) * C + e0;
-    if (vec16) {
-      if (e0 < C) {
-        int4 raw = ld_stream16(row);
-        const T* v = reinterpret_cast<const T*>(&raw);
+  if (vec16) {
+    // 4 complement rows per step: the 16-byte loads are issued together, then consumed in ascending row order
+    for (int m0 = warp; m0 < M; m0 += 4 * kWarps) {
+      int4 raw[4];
+      float w[4];
 #pragma unroll
-        for (int i = 0; i < VE; ++i) acc[i] = fmaf(w, to_f32(v[i]), acc[i]);
+      for (int u = 0; u < 4; ++u) {
+        const int m = m0 + u * kWarps;
+        w[u] = 0.f;
+        if (m < M && e0 < C) {
+          const int p = cmp[m];
+          w[u] = keys[p];
+          raw[u] = ld_stream16(xb + (long long)(1 + p) * C + e0);
+        }
       }
-    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (m0 + u * kWarps < M && e0 < C) {
+          const T* v = reinterpret_cast<const T*>(&raw[u]);
+#pragma unroll
+          for (int i = 0; i < VE; ++i) acc[i] = fmaf(w[u], to_f32(v[i]), acc[i]);
+        }
+      }
+    }
+  } else {
+    for (int m = warp; m < M; m += kWarps) {
+      const int p = cmp[m];
+      const float w = keys[p];
+      const T* row = xb + (long long)(1 + p) * C + e0;
 #pragma unroll
       for (int i = 0; i < VE; ++i)
         if (e0 + i < C) acc[i] = fmaf(w, to_f32(row[i]), acc[i]);
@@ -178,41 +195,117 @@ gather_rows_kernel(const char* __restrict__ src, const int64_t* __restrict__ ids
 }
 
 // ------------------------------------------------------------------------------------------ DynamicViT pooling
-// grid = (64-channel slices of the global half, B); 256 threads = 4 patch-phases x 64 channels.
-// Phase 1: masked mean over patches of this slice (lanes over channels -> coalesced; each phase sums its patches
-// in order, phases combined in fixed order -> deterministic).  Phase 2: write both halves of this slice.
-constexpr int kPoolSlice = 64;
+// grid = (128-channel slices of the global half, B); 256 threads = 16 patch-phases x 16 channel-threads, every
+// thread owns 8 consecutive channels (one 16-byte load of bf16, two of fp32).
+// Phase 1: masked mean over patches of this slice (each phase sums its patches in order, phases combined in fixed
+// order -> deterministic).  Phase 2: write both halves of this slice with 16-byte stores.
+constexpr int kPoolSlice = 128;
+constexpr int kPoolPhases = kThreads / (kPoolSlice / 8);   // 16
+template <typename T> __device__ __forceinline__ void ld8(const T* p, bool vec, int valid, float (&v)[8]);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, bool vec, int valid, float (&v)[8]) {
+  if (vec && valid >= 8) {
+    const int4 a = ld_stream16(p), b = ld_stream16(p + 4);
+    const float* fa = reinterpret_cast<const float*>(&a);
+    const float* fb = reinterpret_cast<const float*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = fa[i]; v[4 + i] = fb[i]; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = i < valid ? p[i] : 0.f;
+  }
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, bool vec, int valid, float (&v)[8]) {
+  if (vec && valid >= 8) {
+    const int4 a = ld_stream16(p);
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(h[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = i < valid ? __bfloat162float(p[i]) : 0.f;
+  }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, bool vec, int valid, const float (&v)[8]);
+template <> __device__ __forceinline__ void st8<float>(float* p, bool vec, int valid, const float (&v)[8]) {
+  if (vec && valid >= 8) {
+    st_stream16(p, *reinterpret_cast<const int4*>(&v[0]));
+    st_stream16(p + 4, *reinterpret_cast<const int4*>(&v[4]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < valid) p[i] = v[i];
+  }
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, bool vec, int valid, const float (&v)[8]) {
+  if (vec && valid >= 8) {
+    __nv_bfloat162 h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    st_stream16(p, *reinterpret_cast<const int4*>(h));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < valid) p[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kThreads)
 dyvit_pool_concat_kernel(const TI* __restrict__ h, const float* __restrict__ policy, TO* __restrict__ out, int P, int C,
-                         float eps) {
+                         float eps, int vec) {
   extern __shared__ float smem[];
-  float* part = smem;                    // [4][kPoolSlice]
-  float* pol = smem + 4 * kPoolSlice;    // [P]
+  float* part = smem;                              // [kPoolPhases][kPoolSlice]
+  float* pol = smem + kPoolPhases * kPoolSlice;    // [P]
   const int b = blockIdx.y, tid = threadIdx.x, half = C / 2;
-  const int c = tid % kPoolSlice, q = tid / kPoolSlice;
-  const int c0 = blockIdx.x * kPoolSlice;
-  const bool live = c0 + c < half;
+  const int ct = tid % (kPoolSlice / 8), ph = tid / (kPoolSlice / 8);
+  const int c0 = blockIdx.x * kPoolSlice + ct * 8;          // first of this thread's 8 channels (within a half)
+  const int valid = half - c0;                              // <= 0: thread idle
   const TI* hb = h + (long long)b * P * C;
   for (int p = tid; p < P; p += kThreads) pol[p] = policy[(long long)b * P + p];
   __syncthreads();
   float psum = 0.f;
   for (int p = 0; p < P; ++p) psum += pol[p];
-  float acc = 0.f;
-  if (live) {
-    const TI* col = hb + half + c0 + c;
-#pragma unroll 4
-    for (int p = q; p < P; p += 4) acc += to_f32(col[(long long)p * C]) * pol[p];
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (valid > 0) {
+    for (int p0 = ph; p0 < P; p0 += 4 * kPoolPhases) {          // 4 rows in flight per thread, consumed in ascending order
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p0 + kPoolPhases * u < P) ld8<TI>(hb + (long long)(p0 + kPoolPhases * u) * C + half + c0, vec, valid, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p0 + kPoolPhases * u < P) {
+          const float w = pol[p0 + kPoolPhases * u];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += v[u][i] * w;
+        }
+    }
   }
-  part[q * kPoolSlice + c] = acc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[ph * kPoolSlice + ct * 8 + i] = acc[i];
   __syncthreads();
-  const float g = ((part[c] + part[kPoolSlice + c]) + part[2 * kPoolSlice + c]) + part[3 * kPoolSlice + c];
-  const float gval = g / psum + eps;
-  if (live) {
+  float g[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float s = part[ct * 8 + i];
+#pragma unroll
+    for (int q = 1; q < kPoolPhases; ++q) s += part[q * kPoolSlice + ct * 8 + i];
+    g[i] = s / psum + eps;
+  }
+  if (valid > 0) {
     TO* ob = out + (long long)b * P * C;
-    for (int p = q; p < P; p += 4) {
-      ob[(long long)p * C + c0 + c] = from_f32<TO>(to_f32(hb[(long long)p * C + c0 + c]));
-      ob[(long long)p * C + half + c0 + c] = from_f32<TO>(gval);
+    for (int p0 = ph; p0 < P; p0 += 4 * kPoolPhases) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p0 + kPoolPhases * u < P) ld8<TI>(hb + (long long)(p0 + kPoolPhases * u) * C + c0, vec, valid, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p0 + kPoolPhases * u < P) {
+          const long long p = p0 + kPoolPhases * u;
+          st8<TO>(ob + p * C + c0, vec, valid, v[u]);
+          st8<TO>(ob + p * C + half + c0, vec, valid, g);
+        }
     }
   }
 }
@@ -311,13 +404,14 @@ extern "C" int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float*
   TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
   if (B == 0) return TOKRED_OK;
   const int splits = ceil_div(C / 2, kPoolSlice);
-  const size_t smem = (size_t)(4 * kPoolSlice + P) * 4;
+  const size_t smem = (size_t)(kPoolPhases * kPoolSlice + P) * 4;
+  const int vec = ((C / 2) % 8 == 0) && aligned16(h) && aligned16(out);
   dim3 grid(splits, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(TI, TO)                                                                                       \
   do {                                                                                                       \
     if (int e = allow_smem(dyvit_pool_concat_kernel<TI, TO>, smem, what)) return e;                          \
-    dyvit_pool_concat_kernel<TI, TO><<<grid, kThreads, smem, st>>>((const TI*)h, policy, (TO*)out, P, C, eps);       \
+    dyvit_pool_concat_kernel<TI, TO><<<grid, kThreads, smem, st>>>((const TI*)h, policy, (TO*)out, P, C, eps, vec);  \
   } while (0)
   if (h_dtype == TOKRED_F32 && out_dtype == TOKRED_F32) LAUNCH(float, float);
   else if (h_dtype == TOKRED_BF16 && out_dtype == TOKRED_F32) LAUNCH(__nv_bfloat16, float);
