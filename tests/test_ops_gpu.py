@@ -438,7 +438,8 @@ def test_patchmerger_lowp(T):
     assert_close_rel(out.float(), out_ref.float(), RTOL16, "merged tokens")
 
 
-@pytest.mark.parametrize("p,k,c,lowp", [(196, 176, 768, False), (176, 158, 384, False), (196, 176, 768, True)])
+@pytest.mark.parametrize("p,k,c,lowp", [(196, 176, 768, False), (176, 158, 384, False), (196, 176, 768, True), (158, 142, 384, True),
+                                        (60, 20, 100, True), (97, 130, 200, True)])
 def test_sit_merge(T, p, k, c, lowp):
     b = 3
     x = torch.randn(b, p, c, generator=g(49)).to(DEV)
@@ -447,10 +448,12 @@ def test_sit_merge(T, p, k, c, lowp):
     if lowp:
         logits = logits.bfloat16()
     out_ref, w_ref = O.sit_merge(x, logits, scale, lowp=torch.bfloat16 if lowp else None)
-    out, w = T.sit_merge(x, logits, scale, lowp)
     tol = RTOL16 if lowp else RTOL32
-    assert_close_rel(w, w_ref, tol, "weights")
-    assert_close_rel(out.float(), out_ref.float(), tol, "merged tokens")
+    for tc in ((True, False) if lowp else (False,)):      # tcgen05 and FFMA paths of the bf16-autocast mode
+        out, w = T.sit_merge(x, logits, scale, lowp, tc)
+        assert_close_rel(w, w_ref, tol, f"weights tc={tc}")
+        assert_close_rel(out.float(), out_ref.float(), tol, f"merged tokens tc={tc}")
+        assert torch.allclose(w.sum(dim=-1), torch.ones(b, k, device=DEV), rtol=1e-4)
 
 
 # ------------------------------------------------------------------------------------------------ ATS

@@ -309,7 +309,7 @@ int check_soft(const char* what, int B, int P, int C, int K, int x_dtype, int ou
 namespace tokred {
 int launch_soft_merge_tc(int mode, const void* x, int x_dtype, const float* q, const float* ln_w, const float* ln_b,
                          int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
-                         float* weights, void* stream, const char* what);
+                         float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr);
 }
 using namespace tokred;
 
@@ -324,7 +324,7 @@ extern "C" int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_
   if (B == 0) return TOKRED_OK;
   if (lowp == 1 && out_dtype == TOKRED_BF16) {     // bf16 autocast semantics on tcgen05 tensor cores
     const int rc = launch_soft_merge_tc(MODE_SINKHORN, x, x_dtype, v_hat, nullptr, nullptr, B, P, C, K, 1.0f / eps, log_norm,
-                                        0.f, iters, out, weights, stream, what);
+                                        0.f, iters, out, weights, stream, what, nullptr, nullptr);
     if (rc != 1) return rc;
   }
   SoftParams prm{};
@@ -343,7 +343,7 @@ extern "C" int tokred_patchmerger(const void* x, int x_dtype, const float* ln_we
   if (B == 0) return TOKRED_OK;
   if (lowp == 1 && out_dtype == TOKRED_BF16) {
     const int rc = launch_soft_merge_tc(MODE_PATCHMERGER, x, x_dtype, queries, ln_weight, ln_bias, B, P, C, K, scale, 0.f,
-                                        ln_eps, 0, out, attn, stream, what);
+                                        ln_eps, 0, out, attn, stream, what, nullptr, nullptr);
     if (rc != 1) return rc;
   }
   SoftParams prm{};
@@ -361,6 +361,11 @@ extern "C" int tokred_sit_merge(const void* x, int x_dtype, const void* logits, 
   TOKRED_REQUIRE(valid_float_dtype(logits_dtype), "%s: bad logits dtype", what);
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
   if (B == 0) return TOKRED_OK;
+  if (lowp == 1 && out_dtype == TOKRED_BF16 && logits_dtype == TOKRED_BF16) {
+    const int rc = launch_soft_merge_tc(MODE_SIT, x, x_dtype, nullptr, nullptr, nullptr, B, P, C, K, 1.f, 0.f, 0.f, 0, out,
+                                        weights, stream, what, logits, scale);
+    if (rc != 1) return rc;
+  }
   SoftParams prm{};
   prm.x = x; prm.logits = logits; prm.logits_dtype = logits_dtype; prm.scale_ptr = scale; prm.lowp = lowp ? 1 : 0;
   prm.P = P; prm.C = C; prm.K = K; prm.out = out; prm.weights = weights;

@@ -21,19 +21,21 @@
 namespace tokred {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int KC1 = 64;           // contraction columns per stage of the first GEMM
 constexpr int NC2 = 128;          // output columns per accumulator set of the second GEMM
 constexpr int kMaxK = 208, kMaxP = 208;
 
-enum { MODE_SINKHORN = 0, MODE_PATCHMERGER = 1 };
+enum { MODE_SINKHORN = 0, MODE_PATCHMERGER = 1, MODE_SIT = 2 };
 
 struct TcParams {
   const void* x;            // [B,P,C]
   const float* q;           // [K,C]
   const float* ln_w;
   const float* ln_b;
+  const __nv_bfloat16* logits;   // sit: [B,P,K] bf16
+  const float* scale_ptr;        // sit: device scalar
   float scale;              // patchmerger: sim * scale ; sinkhorn: 1/eps
   float log_norm;
   float ln_eps;
@@ -44,7 +46,7 @@ struct TcParams {
 };
 
 struct Layout {
-  int Np, Pp, PSb, n_mt;
+  int Np, Pp, PSb, Ks, n_mt;
   uint32_t sbo1, sbo2;
   size_t stageA, stageB, r0, r1, total;
 };
@@ -64,7 +66,11 @@ __host__ __device__ inline Layout make_layout(int P, int K, int C) {
   int psb = (P + 1) & ~1;
   if (((psb / 2) & 1) == 0) psb += 2;             // odd number of 32-bit words per row -> conflict-free row-per-thread stores
   L.PSb = psb;
-  const size_t zbytes = (size_t)K * psb * 2;
+  int ks = (K + 1) & ~1;
+  if (((ks / 2) & 1) == 0) ks += 2;               // sit: staged logits [P][Ks], odd word count per row
+  L.Ks = ks;
+  const size_t zb0 = (size_t)K * psb * 2, zb1 = (size_t)P * ks * 2;
+  const size_t zbytes = zb0 > zb1 ? zb0 : zb1;
   const size_t xt = (size_t)(NC2 / 8) * L.sbo2;
   L.r1 = ((zbytes > xt ? zbytes : xt) + 127) & ~(size_t)127;
   L.total = L.r0 + L.r1 + (size_t)(3 * P + K + 2 * ((C + 3) & ~3)) * 4 + 64;
@@ -112,7 +118,10 @@ struct Xform {
   }
   // 8 consecutive channels c0..c0+7 of token p (c0 % 4 == 0); channels >= C become 0
   __device__ __forceinline__ void apply8(int p, int c0, int C, float (&v)[8]) const {
-    if (MODE == MODE_SINKHORN) {
+    if (MODE == MODE_SIT) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (c0 + i < C) ? v[i] : 0.f;
+    } else if (MODE == MODE_SINKHORN) {
       // x * (1/||x||): the quotient is rounded to bf16 right after, so the reciprocal form (1 ulp in fp32) is
       // indistinguishable here and avoids 8 IEEE divisions per chunk (15 % of the kernel in the r01 profile)
       const float inv = s1[p];
@@ -168,7 +177,9 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
 
   // ---- 0. token statistics: one warp per token, the whole row (<= 1024 channels) held in registers so that x is
   //         read from HBM once and every load of the row is in flight together
-  if (C <= 1024) {
+  if (MODE == MODE_SIT) {
+    // no token statistics: SiT merges the raw tokens
+  } else if (C <= 1024) {
     for (int p = warp; p < P; p += kWarps) {
       const T* row = xb + (long long)p * C;
       float v[4][8];
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
   const Xform<MODE> xf{s0, s1, lng, lnb};
 
   // ---- 1. Z = Q . Xn^T on tensor cores
-  const int nchunk = (C + KC1 - 1) / KC1;
+  const int nchunk = MODE == MODE_SIT ? 0 : (C + KC1 - 1) / KC1;
   const uint32_t idesc1 = umma::instr_desc(umma::FMT_BF16, 128, (uint32_t)L.Np);
   for (int c = 0; c < nchunk; ++c) {
     const int st = c & 1;
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
     }
   }
   // all MMAs done <=> the last commit completed (tcgen05 ops of one thread complete in order)
-  {
+  if (nchunk > 0) {
     const int last = nchunk - 1;
     umma::mbar_wait(&bars[last & 1], (uint32_t)((last >> 1) & 1));
     if (nchunk >= 2) umma::mbar_wait(&bars[(last - 1) & 1], (uint32_t)(((last - 1) >> 1) & 1));
@@ -306,13 +317,17 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
   // ---- 2. accumulator -> bf16 scores in shared memory (row per thread; padded row stride = odd word count)
   __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(R1);
   const int PSb = L.PSb;
-  {
-    const int mt = warp >> 2;
-    const int k = mt * 128 + (warp & 3) * 32 + lane;
-    if (mt < L.n_mt) {
-      for (int c0 = 0; c0 < L.Np; c0 += 16) {
+  if (MODE != MODE_SIT) {
+    // warp w owns TMEM lane quarter w % 4; (w / 4) enumerates (M tile, column part) pairs
+    const int q = warp & 3, nslots = kWarps >> 2;
+    const int parts = nslots / L.n_mt > 0 ? nslots / L.n_mt : 1;
+    for (int sl = warp >> 2; sl < L.n_mt * parts; sl += nslots) {
+      const int mt = sl / parts, part = sl % parts;
+      const int cbeg = ((L.Np / 16) * part / parts) * 16, cend = ((L.Np / 16) * (part + 1) / parts) * 16;
+      const int k = mt * 128 + q * 32 + lane;
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
         uint32_t v[16];
-        umma::tmem_ld16(umma::tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)(mt * 256 + c0)), v);
+        umma::tmem_ld16(umma::tmem_addr(tmem_base, (uint32_t)(q * 32), (uint32_t)(mt * 256 + c0)), v);
         umma::tmem_ld_wait();
         if (k < K) {
 #pragma unroll
@@ -334,7 +349,32 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
   unsigned char* Wop = R0;
   for (int e = tid; e < (int)(32 * L.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
   float* wout = prm.weights + (long long)b * K * P;
-  if (MODE == MODE_SINKHORN) {
+  if (MODE == MODE_SIT) {
+    // logits [P][K] (bf16, K contiguous) -> smem [P][Ks]; softmax over TOKENS per cluster column (models/sit.py:38)
+    __nv_bfloat16* Lg = reinterpret_cast<__nv_bfloat16*>(R1);
+    const int Ks = L.Ks;
+    const __nv_bfloat16* lb = prm.logits + (long long)b * P * K;
+    for (int e = tid; e < P * K; e += kThreads) Lg[(e / K) * Ks + e % K] = lb[e];
+    const float sc = prm.scale_ptr[0];
+    __syncthreads();
+    for (int k = tid; k < K; k += kThreads) {       // per-cluster max and normaliser (lanes on consecutive columns)
+      float m = -CUDART_INF_F;
+      for (int p = 0; p < P; ++p) m = fmaxf(m, __bfloat162float(Lg[p * Ks + k]) * sc);
+      float sum = 0.f;
+      for (int p = 0; p < P; ++p) sum += expf(__bfloat162float(Lg[p * Ks + k]) * sc - m);
+      uvec[k] = m;
+      lng[k] = sum;                                   // lng/lnb are unused by SiT: lng[0..K) holds the normalisers
+    }
+    __syncthreads();
+    for (int k = warp; k < K; k += kWarps) {
+      const float m = uvec[k], sum = lng[k];
+      for (int p = lane; p < P; p += 32) {
+        const float w = expf(__bfloat162float(Lg[p * Ks + k]) * sc - m) / sum;
+        wout[(long long)k * P + p] = w;
+        *reinterpret_cast<__nv_bfloat16*>(Wop + umma::kmajor_offset((uint32_t)k, (uint32_t)p, 2, L.sbo2)) = __float2bfloat16_rn(w);
+      }
+    }
+  } else if (MODE == MODE_SINKHORN) {
     const float nrm = prm.log_norm;
     for (int k = tid; k < K; k += kThreads) uvec[k] = 0.f;
     for (int p = tid; p < P; p += kThreads) vvec[p] = 0.f;
@@ -451,13 +491,16 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
         if ((pc & 1) == 0) { umma::mbar_wait(&bars[0], ph0 & 1); ++ph0; } else { umma::mbar_wait(&bars[1], ph1 & 1); ++ph1; }
         umma::tc_fence_after_sync();
       }
-      const int mt = warp >> 2;
-      const int k = mt * 128 + (warp & 3) * 32 + lane;
-      if (mt < L.n_mt) {
+      const int q = warp & 3, nslots = kWarps >> 2;
+      const int parts = nslots / L.n_mt > 0 ? nslots / L.n_mt : 1;
+      for (int sl = warp >> 2; sl < L.n_mt * parts; sl += nslots) {
+        const int mt = sl / parts, part = sl % parts;
+        const int jbeg = ((NC2 / 16) * part / parts) * 16, jend = ((NC2 / 16) * (part + 1) / parts) * 16;
+        const int k = mt * 128 + q * 32 + lane;
         const uint32_t acc = tmem_base + (uint32_t)((pc & 1) * 256 + mt * 128);
-        for (int j0 = 0; j0 < NC2; j0 += 16) {
+        for (int j0 = jbeg; j0 < jend; j0 += 16) {
           uint32_t v[16];
-          umma::tmem_ld16(umma::tmem_addr(acc, (uint32_t)((warp & 3) * 32), (uint32_t)j0), v);
+          umma::tmem_ld16(umma::tmem_addr(acc, (uint32_t)(q * 32), (uint32_t)j0), v);
           umma::tmem_ld_wait();
           const int c = pc * NC2 + j0;
           if (k < K && c < C) {
@@ -490,20 +533,23 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
 // returns TOKRED_OK after launching, or 1 if the shape is outside what this kernel covers (caller falls back to FFMA)
 int launch_soft_merge_tc(int mode, const void* x, int x_dtype, const float* q, const float* ln_w, const float* ln_b,
                          int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
-                         float* weights, void* stream, const char* what) {
+                         float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr) {
   if (P > kMaxP || K > kMaxK || P < 8 || K < 1) return 1;
   const Layout L = make_layout(P, K, C);
   if (L.total > 227 * 1024) return 1;
   TcParams prm{};
   prm.x = x; prm.q = q; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.scale = scale; prm.log_norm = log_norm; prm.ln_eps = ln_eps;
   prm.iters = iters; prm.P = P; prm.C = C; prm.K = K; prm.out = (__nv_bfloat16*)out; prm.weights = weights;
+  prm.logits = (const __nv_bfloat16*)logits; prm.scale_ptr = scale_ptr;
+  if (mode == MODE_SIT && K > ((C + 3) & ~3)) return 1;      // the normalisers borrow the (unused) LayerNorm slot [C]
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(T, MODE)                                                                  \
   do {                                                                                   \
     if (int e = allow_smem(soft_merge_tc_kernel<T, MODE>, L.total, what)) return e;      \
     soft_merge_tc_kernel<T, MODE><<<B, kThreads, L.total, st>>>(prm);                    \
   } while (0)
-  if (mode == MODE_SINKHORN) { if (x_dtype == TOKRED_F32) LAUNCH(float, MODE_SINKHORN); else LAUNCH(__nv_bfloat16, MODE_SINKHORN); }
+  if (mode == MODE_SIT) { if (x_dtype == TOKRED_F32) LAUNCH(float, MODE_SIT); else LAUNCH(__nv_bfloat16, MODE_SIT); }
+  else if (mode == MODE_SINKHORN) { if (x_dtype == TOKRED_F32) LAUNCH(float, MODE_SINKHORN); else LAUNCH(__nv_bfloat16, MODE_SINKHORN); }
   else { if (x_dtype == TOKRED_F32) LAUNCH(float, MODE_PATCHMERGER); else LAUNCH(__nv_bfloat16, MODE_PATCHMERGER); }
 #undef LAUNCH
   return finish_launch(what);

@@ -415,7 +415,7 @@ class TokenSlimmingModule(nn.Module):
 
     def forward(self, x):
         _train_guard(self)
-        return ops.sit_merge(x, self.weight(x), self.scale.detach(), _lowp())
+        return ops.sit_merge(x, self.weight(x), self.scale.detach(), _lowp(), True)
 
 
 # =============================================================================================== ATS

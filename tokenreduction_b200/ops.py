@@ -450,7 +450,7 @@ def _(x, ln_weight, ln_bias, queries, scale, ln_eps, lowp, tensor_cores):
 
 
 @torch.library.custom_op("tokred::sit_merge", mutates_args=(), device_types="cuda")
-def _sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool) -> Tuple[Tensor, Tensor]:
+def _sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool, tensor_cores: bool) -> Tuple[Tensor, Tensor]:
     _need_cuda("sit_merge", x, logits, scale)
     b, p, c = x.shape
     k = logits.shape[2]
@@ -463,13 +463,13 @@ def _sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool) -> Tuple[Te
     odt = _soft_out_dtype(x, lowp)
     out = torch.empty((b, k, c), dtype=odt, device=x.device)
     w = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
-    _lib.call("tokred_sit_merge", _ptr(x), _dt(x), _ptr(logits), _dt(logits), _ptr(scale), b, p, c, k, int(lowp),
+    _lib.call("tokred_sit_merge", _ptr(x), _dt(x), _ptr(logits), _dt(logits), _ptr(scale), b, p, c, k, _lowp_mode(lowp, tensor_cores),
               _ptr(out), _dt(out), _ptr(w), _stream())
     return out, w
 
 
 @_sit_merge.register_fake
-def _(x, logits, scale, lowp):
+def _(x, logits, scale, lowp, tensor_cores):
     b, p, c = x.shape
     k = logits.shape[2]
     return x.new_empty((b, k, c), dtype=_soft_out_dtype(x, lowp)), x.new_empty((b, k, p), dtype=torch.float32)
@@ -486,9 +486,9 @@ def patchmerger(x, ln_weight, ln_bias, queries, scale: float = 1.0, ln_eps: floa
     return torch.ops.tokred.patchmerger(x, ln_weight, ln_bias, queries, scale, ln_eps, lowp, tensor_cores)
 
 
-def sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool = False):
+def sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool = False, tensor_cores: bool = True):
     """models/sit.py:37-40: (out [B,K,C], weight [B,K,P])."""
-    return torch.ops.tokred.sit_merge(x, logits, scale, lowp)
+    return torch.ops.tokred.sit_merge(x, logits, scale, lowp, tensor_cores)
 
 
 # ----------------------------------------------------------------------------------------------- ATS

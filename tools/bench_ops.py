@@ -104,7 +104,8 @@ def cases():
         for lowp, tc, tag in ((True, True, "lowp tcgen05"), (True, False, "lowp ffma"), (False, False, "fp32")):
             out.append((f"sinkhorn_merge B B={b} P={p} K={k} {tag}", lambda x=x, v=v, lowp=lowp, tc=tc: T.sinkhorn_merge(x, v, 1.0, 3, lowp, tc)))
             out.append((f"patchmerger B B={b} P={p} K={k} {tag}", lambda x=x, lw=lw, lb=lb, q=q, lowp=lowp, tc=tc: T.patchmerger(x, lw, lb, q, 1.0, 1e-5, lowp, tc)))
-        out.append((f"sit_merge B B={b} P={p} K={k} lowp", lambda x=x, l=logits, s=scale: T.sit_merge(x, l, s, True)))
+        out.append((f"sit_merge B B={b} P={p} K={k} lowp tcgen05", lambda x=x, l=logits, s=scale: T.sit_merge(x, l, s, True, True)))
+        out.append((f"sit_merge B B={b} P={p} K={k} lowp ffma", lambda x=x, l=logits, s=scale: T.sit_merge(x, l, s, True, False)))
     from oracle.ops import ats_sample_steps
     for n, count in ((197, 177), (177, 159), (159, 143)):
         attn = torch.softmax(4 * torch.randn(b, 12, n, n, device=DEV), dim=-1)
