@@ -4,10 +4,11 @@ measured HBM roofline.  Runs on one B200:
 
     python tools/bench_ops.py [--out profiles/ops_rNN.json] [--iters 20] [--only tome]
 
-Timing hygiene (B200_PROFILING.md): every iteration first overwrites a 512 MB buffer (> 126 MB L2: flushes it and
-keeps the GPU busy while the host enqueues), then records event / launches the kernel through the C ABI with
-preallocated outputs / records event — so the bracket contains exactly one kernel and no host latency.
-Median of the iterations after 3 warm-ups.
+Timing hygiene (B200_PROFILING.md): every iteration first READS a 1 GB buffer (> 126 MB L2: evicts the inputs and
+keeps the GPU busy while the host enqueues; a read leaves the L2 full of CLEAN lines — an overwrite would leave
+~100 MB of dirty lines whose write-back competes with the timed kernel), then records event / launches the kernel
+through the C ABI / records event — so the bracket contains exactly one kernel and no host latency.
+Median of the iterations after 3 warm-ups.  `--flush write` reproduces the pessimistic dirty-L2 variant.
 """
 from __future__ import annotations
 
@@ -125,9 +126,10 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "ops_r01.json"))
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--flush", default="read", choices=["read", "write"])
     a = ap.parse_args()
     peaks, kind = measured_peaks()
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=DEV)
+    flush = torch.zeros(256 << 20, dtype=torch.float32, device=DEV)      # 1 GB
     rows = []
     for label, fn in cases():
         if a.only and a.only not in label:
@@ -137,7 +139,10 @@ def main():
         torch.cuda.synchronize()
         times, nbytes, kname = [], 0.0, ""
         for _ in range(a.iters):
-            flush.zero_()
+            if a.flush == "read":
+                flush.sum()
+            else:
+                flush.zero_()
             _lib.TIMELINE = []
             fn()
             tl, _lib.TIMELINE = _lib.TIMELINE, None
@@ -155,7 +160,7 @@ def main():
         print(f"{label:60s} {med:9.2f} us  {nbytes / 1e6:9.2f} MB  {gbs:8.1f} GB/s  {100 * gbs / peaks['hbm_gbs']:5.1f}% of {kind} HBM peak", flush=True)
     with open(a.out, "w") as fh:
         json.dump({"peak_hbm_gbs": peaks["hbm_gbs"], "peak_source": kind, "gpu": torch.cuda.get_device_name(0),
-                   "timing": "CUDA events around one C-ABI launch, 512 MB L2 flush before each, median", "rows": rows}, fh, indent=1)
+                   "timing": f"CUDA events around one C-ABI launch, 1 GB L2 flush ({a.flush}) before each, median", "rows": rows}, fh, indent=1)
     print("wrote", a.out)
 
 
