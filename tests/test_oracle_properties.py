@@ -121,4 +121,5 @@ def test_ats_ids_sorted_unique_padded(n, count, seed):
     assert torch.equal(nm[:, 1:], nz)
     srt = torch.where(nz, body, torch.full_like(body, 10 ** 6))
     assert bool((srt[:, 1:] >= srt[:, :-1]).all())                          # ascending, zero padding at the end
-    assert ids.shape[1] <= count and na.shape == (2, 2, ids.shape[1], n)
+    # width <= #steps + 1 (torch.arange with a float step yields K-1 or K steps depending on rounding)
+    assert ids.shape[1] <= O.ats_sample_steps(count).numel() + 1 and na.shape == (2, 2, ids.shape[1], n)
