@@ -116,6 +116,11 @@ TOKRED_API int tokred_attn_colsum(const void* attn, int attn_dtype, int B, int H
 TOKRED_API int tokred_kmedoids_fit(const float* x, const float* token_weight, int B, int P, int C, int K, int iters,
                                    int exact_fp32, float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream);
 
+/* Scratch for the bulk-copy fed tensor-core path of the three soft merges (a9, a12, a13): the caller passes a device
+ * buffer of at least this many bytes, 128-byte aligned (bf16 token tiles + packed Q).  With workspace = NULL the
+ * entry points use the scratch-free tensor-core kernel instead (slower).  The library never allocates.            */
+TOKRED_API size_t tokred_soft_merge_workspace_bytes(int B, int P, int C, int K);
+
 /* ---- a9 Sinkhorn -------------------------------------------------------------------------------------
  * models/sinkhorn.py:66-86 with :25-56.  v_hat [K,C] fp32 is the already-normalised parameter.
  *   log_norm = -log(K+P) evaluated by the caller the way the reference does (:44-47; in bf16 under autocast)
@@ -124,19 +129,20 @@ TOKRED_API int tokred_kmedoids_fit(const float* x, const float* token_weight, in
  *   out [B,K,C], weights [B,K,P] fp32                                                                   */
 TOKRED_API int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_hat, int B, int P, int C, int K, float eps,
                           float log_norm, int iters, int lowp, void* out, int out_dtype, float* weights,
-                          void* stream);
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a12 PatchMerger ---------------------------------------------------------------------------------
  * models/patchmerger.py:35-39: LayerNorm -> queries x^T * scale -> softmax over tokens -> attn x.       */
 TOKRED_API int tokred_patchmerger(const void* x, int x_dtype, const float* ln_weight, const float* ln_bias,
                        const float* queries, int B, int P, int C, int K, float scale, float ln_eps, int lowp,
-                       void* out, int out_dtype, float* attn, void* stream);
+                       void* out, int out_dtype, float* attn, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a13 SiT -----------------------------------------------------------------------------------------
  * models/sit.py:37-40: w = softmax(logits * scale, over tokens)^T ; out = w x.  logits [B,P,K];
  * scale = device pointer to the module's 1-element fp32 parameter (no host read).                       */
 TOKRED_API int tokred_sit_merge(const void* x, int x_dtype, const void* logits, int logits_dtype, const float* scale, int B,
-                     int P, int C, int K, int lowp, void* out, int out_dtype, float* weights, void* stream);
+                     int P, int C, int K, int lowp, void* out, int out_dtype, float* weights, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* ---- a10 ATS -----------------------------------------------------------------------------------------
  * models/ats.py:52-82: significance score, inverse-CDF sampling, per-image sorted unique ids.

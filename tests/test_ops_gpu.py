@@ -412,6 +412,35 @@ def test_soft_merge_tensor_core_paths(T, p, k, c, xdt):
     assert torch.allclose(a.sum(dim=-1), torch.ones(b, k, device=DEV), rtol=1e-4)
 
 
+def test_soft_merge_scratch_free_kernel_and_sit_bulk_path(T):
+    """(1) the scratch-free tensor-core kernel (v1) stays equivalent to the bulk-copy fed one (v2);
+    (2) SiT takes the bulk-copy kernel only for multi-wave batches (B > 2 x 148): exercise it."""
+    b, p, k, c = 3, 196, 176, 768
+    x = torch.randn(b, p, c, generator=g(420)).to(DEV)
+    v = torch.nn.functional.normalize(torch.randn(k, c, generator=g(421)), dim=-1).to(DEV)
+    lw, lb = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+    q = (torch.randn(k, c, generator=g(422)) * 0.05).to(DEV)
+    o2, w2 = T.sinkhorn_merge(x, v, 1.0, 3, True, True)
+    po2, pa2 = T.patchmerger(x, lw, lb, q, 1.0, 1e-5, True, True)
+    T.SOFT_MERGE_SCRATCH = False
+    try:
+        o1, w1 = T.sinkhorn_merge(x, v, 1.0, 3, True, True)
+        po1, pa1 = T.patchmerger(x, lw, lb, q, 1.0, 1e-5, True, True)
+    finally:
+        T.SOFT_MERGE_SCRATCH = True
+    assert_close_rel(w2, w1, 1e-3, "sinkhorn weights v2 vs v1")
+    assert_close_rel(o2.float(), o1.float(), 5e-3, "sinkhorn tokens v2 vs v1")
+    assert torch.equal(pa2, pa1) and torch.equal(po2, po1), "patchmerger v2 and v1 round identically"
+    bb, pp, kk, cc = 300, 32, 8, 64
+    xs = torch.randn(bb, pp, cc, generator=g(423)).to(DEV)
+    logits = torch.randn(bb, pp, kk, generator=g(424)).bfloat16().to(DEV)
+    scale = torch.full((1,), 1.3, device=DEV)
+    out_ref, w_ref = O.sit_merge(xs, logits, scale, lowp=torch.bfloat16)
+    out, w = T.sit_merge(xs, logits, scale, True, True)
+    assert_close_rel(w, w_ref, RTOL16, "sit weights (bulk-copy path)")
+    assert_close_rel(out.float(), out_ref.float(), RTOL16, "sit tokens (bulk-copy path)")
+
+
 @pytest.mark.parametrize("p,k,c", [(196, 176, 768), (176, 158, 768), (196, 176, 384), (60, 20, 100)])
 def test_patchmerger_fp32(T, p, k, c):
     b = 3

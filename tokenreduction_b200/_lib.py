@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libtokred_sm100a.so")
@@ -28,9 +28,10 @@ SIGNATURES = {
     "tokred_dpcknn_merge": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tokred_attn_colsum": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "tokred_kmedoids_fit": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
-    "tokred_sinkhorn_merge": [_P, c_int, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, c_int, _P, _P],
-    "tokred_patchmerger": [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, _P, c_int, _P, _P],
-    "tokred_sit_merge": [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P],
+    "tokred_sinkhorn_merge": [_P, c_int, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P],
+    "tokred_patchmerger": [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, _P, c_int, _P, _P, c_size_t, _P],
+    "tokred_sit_merge": [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P],
+    "tokred_soft_merge_workspace_bytes": [c_int, c_int, c_int, c_int],
     "tokred_ats_sample": [_P, c_int, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P],
     "tokred_gather_rows": [_P, c_int, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "tokred_dyvit_pool_concat": [_P, c_int, _P, c_int, c_int, c_int, c_float, _P, c_int, _P],
@@ -62,7 +63,7 @@ def load() -> ctypes.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = c_int
+        fn.restype = c_size_t if name.endswith("_workspace_bytes") else c_int
     _lib = lib
     return lib
 

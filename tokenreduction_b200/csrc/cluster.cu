@@ -128,39 +128,42 @@ __device__ void pairdist_tc(const float* __restrict__ xb, int P, int C, DistCtx&
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0);
   const int nchunk = (C + KT - 1) / KT;
   const int ng = ((P + 7) / 8) * 64;        // (8 rows) x (8 core columns of 4 floats) per row group
+  // software pipeline: the loads of chunk c+1 are issued right after the barrier of chunk c and stay in registers while
+  // the MMAs of chunk c run; split + store happen one iteration later
+  constexpr int GMAX = 8;                   // float4 groups per thread: (208/8)*64 / 256 threads = 6.5
+  float4 v[GMAX];
+  auto load_chunk = [&](int c) {
+    const int k0 = c * KT;
+#pragma unroll
+    for (int u = 0; u < GMAX; ++u) {
+      const int gI = tid + u * nthreads;
+      const int row = (gI & 7) + ((gI >> 6) << 3), k = k0 + ((gI >> 3) & 7) * 4;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gI < ng && row < P) {
+        const float* g = xb + (long long)row * C + k;
+        if (vec && k + 3 < C) v[u] = *reinterpret_cast<const float4*>(g);
+        else { if (k < C) v[u].x = g[0]; if (k + 1 < C) v[u].y = g[1]; if (k + 2 < C) v[u].z = g[2]; if (k + 3 < C) v[u].w = g[3]; }
+      }
+    }
+  };
+  load_chunk(0);
   for (int c = 0; c < nchunk; ++c) {
     const int st = c & 1;
     unsigned char* hi = cx.stage + (size_t)st * stage_bytes;
     unsigned char* lo = hi + half;
     if (c >= 2) umma::mbar_wait(&cx.bars[st], (uint32_t)(((c - 2) >> 1) & 1));
-    const int k0 = c * KT;
-    constexpr int U = 4;
-    for (int g0 = tid; g0 < ng; g0 += nthreads * U) {
-      float4 v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int gI = g0 + u * nthreads;
-        const int row = (gI & 7) + ((gI >> 6) << 3), k = k0 + ((gI >> 3) & 7) * 4;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gI < ng && row < P) {
-          const float* g = xb + (long long)row * C + k;
-          if (vec && k + 3 < C) v[u] = *reinterpret_cast<const float4*>(g);
-          else { if (k < C) v[u].x = g[0]; if (k + 1 < C) v[u].y = g[1]; if (k + 2 < C) v[u].z = g[2]; if (k + 3 < C) v[u].w = g[3]; }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int gI = g0 + u * nthreads;
-        const int row = (gI & 7) + ((gI >> 6) << 3), core = (gI >> 3) & 7;
-        if (gI < ng) {
-          float4 h, l;
-          h.x = to_tf32(v[u].x); h.y = to_tf32(v[u].y); h.z = to_tf32(v[u].z); h.w = to_tf32(v[u].w);
-          // the remainder is exact in fp32; round it to tf32 ourselves (the MMA would TRUNCATE it: a biased error)
-          l.x = to_tf32(v[u].x - h.x); l.y = to_tf32(v[u].y - h.y); l.z = to_tf32(v[u].z - h.z); l.w = to_tf32(v[u].w - h.w);
-          const uint32_t off = (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 16u + (uint32_t)core * 128u;
-          *reinterpret_cast<float4*>(hi + off) = h;
-          *reinterpret_cast<float4*>(lo + off) = l;
-        }
+    for (int u = 0; u < GMAX; ++u) {
+      const int gI = tid + u * nthreads;
+      const int row = (gI & 7) + ((gI >> 6) << 3), core = (gI >> 3) & 7;
+      if (gI < ng) {
+        float4 h, l;
+        h.x = to_tf32(v[u].x); h.y = to_tf32(v[u].y); h.z = to_tf32(v[u].z); h.w = to_tf32(v[u].w);
+        // the remainder is exact in fp32; round it to tf32 ourselves (the MMA would TRUNCATE it: a biased error)
+        l.x = to_tf32(v[u].x - h.x); l.y = to_tf32(v[u].y - h.y); l.z = to_tf32(v[u].z - h.z); l.w = to_tf32(v[u].w - h.w);
+        const uint32_t off = (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 16u + (uint32_t)core * 128u;
+        *reinterpret_cast<float4*>(hi + off) = h;
+        *reinterpret_cast<float4*>(lo + off) = l;
       }
     }
     umma::fence_proxy_async_smem();
@@ -180,6 +183,7 @@ __device__ void pairdist_tc(const float* __restrict__ xb, int P, int C, DistCtx&
         }
       umma::mma_commit(&cx.bars[st]);
     }
+    if (c + 1 < nchunk) load_chunk(c + 1);
   }
   {
     const int last = nchunk - 1;

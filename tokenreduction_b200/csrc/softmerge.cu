@@ -310,12 +310,22 @@ namespace tokred {
 int launch_soft_merge_tc(int mode, const void* x, int x_dtype, const float* q, const float* ln_w, const float* ln_b,
                          int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
                          float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr);
+int launch_soft_merge_tc2(int mode, const void* x, int x_dtype, const float* q, const float* ln_w, const float* ln_b,
+                          int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
+                          float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr,
+                          void* workspace, size_t workspace_bytes);
+size_t soft_merge_tc2_workspace_bytes(int B, int P, int C, int K);
 }
 using namespace tokred;
 
+extern "C" size_t tokred_soft_merge_workspace_bytes(int B, int P, int C, int K) {
+  if (B <= 0 || P <= 0 || C <= 0 || K <= 0) return 0;
+  return soft_merge_tc2_workspace_bytes(B, P, C, K);
+}
+
 extern "C" int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_hat, int B, int P, int C, int K,
                                      float eps, float log_norm, int iters, int lowp, void* out, int out_dtype,
-                                     float* weights, void* stream) {
+                                     float* weights, void* workspace, size_t workspace_bytes, void* stream) {
   const char* what = "tokred_sinkhorn_merge";
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && v_hat && out && weights, "%s: null tensor", what);
@@ -323,6 +333,9 @@ extern "C" int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_
   TOKRED_REQUIRE(eps > 0.f && iters >= 0, "%s: eps=%g iters=%d", what, (double)eps, iters);
   if (B == 0) return TOKRED_OK;
   if (lowp == 1 && out_dtype == TOKRED_BF16) {     // bf16 autocast semantics on tcgen05 tensor cores
+    const int rc2 = launch_soft_merge_tc2(MODE_SINKHORN, x, x_dtype, v_hat, nullptr, nullptr, B, P, C, K, 1.0f / eps, log_norm,
+                                          0.f, iters, out, weights, stream, what, nullptr, nullptr, workspace, workspace_bytes);
+    if (rc2 != 1) return rc2;
     const int rc = launch_soft_merge_tc(MODE_SINKHORN, x, x_dtype, v_hat, nullptr, nullptr, B, P, C, K, 1.0f / eps, log_norm,
                                         0.f, iters, out, weights, stream, what, nullptr, nullptr);
     if (rc != 1) return rc;
@@ -335,13 +348,17 @@ extern "C" int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_
 
 extern "C" int tokred_patchmerger(const void* x, int x_dtype, const float* ln_weight, const float* ln_bias,
                                   const float* queries, int B, int P, int C, int K, float scale, float ln_eps, int lowp,
-                                  void* out, int out_dtype, float* attn, void* stream) {
+                                  void* out, int out_dtype, float* attn, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   const char* what = "tokred_patchmerger";
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && ln_weight && ln_bias && queries && out && attn, "%s: null tensor", what);
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
   if (B == 0) return TOKRED_OK;
   if (lowp == 1 && out_dtype == TOKRED_BF16) {
+    const int rc2 = launch_soft_merge_tc2(MODE_PATCHMERGER, x, x_dtype, queries, ln_weight, ln_bias, B, P, C, K, scale, 0.f,
+                                          ln_eps, 0, out, attn, stream, what, nullptr, nullptr, workspace, workspace_bytes);
+    if (rc2 != 1) return rc2;
     const int rc = launch_soft_merge_tc(MODE_PATCHMERGER, x, x_dtype, queries, ln_weight, ln_bias, B, P, C, K, scale, 0.f,
                                         ln_eps, 0, out, attn, stream, what, nullptr, nullptr);
     if (rc != 1) return rc;
@@ -354,7 +371,7 @@ extern "C" int tokred_patchmerger(const void* x, int x_dtype, const float* ln_we
 
 extern "C" int tokred_sit_merge(const void* x, int x_dtype, const void* logits, int logits_dtype, const float* scale,
                                 int B, int P, int C, int K, int lowp, void* out, int out_dtype, float* weights,
-                                void* stream) {
+                                void* workspace, size_t workspace_bytes, void* stream) {
   const char* what = "tokred_sit_merge";
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && logits && scale && out && weights, "%s: null tensor", what);
@@ -362,6 +379,13 @@ extern "C" int tokred_sit_merge(const void* x, int x_dtype, const void* logits, 
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
   if (B == 0) return TOKRED_OK;
   if (lowp == 1 && out_dtype == TOKRED_BF16 && logits_dtype == TOKRED_BF16) {
+    // SiT has no first contraction, so the tile pre-pass of the bulk-copy kernel is pure overhead for a single wave
+    // of images (82 vs 70 us at B=128); it pays off once several waves overlap their phases.
+    if (B > 2 * kNumSMs) {
+      const int rc2 = launch_soft_merge_tc2(MODE_SIT, x, x_dtype, nullptr, nullptr, nullptr, B, P, C, K, 1.f, 0.f, 0.f, 0, out,
+                                            weights, stream, what, logits, scale, workspace, workspace_bytes);
+      if (rc2 != 1) return rc2;
+    }
     const int rc = launch_soft_merge_tc(MODE_SIT, x, x_dtype, nullptr, nullptr, nullptr, B, P, C, K, 1.f, 0.f, 0.f, 0, out,
                                         weights, stream, what, logits, scale);
     if (rc != 1) return rc;

@@ -19,6 +19,7 @@
 #include "umma.cuh"
 
 namespace tokred {
+long long* g_phase_dbg = nullptr;   // set through tokred_debug_phase_buffer()
 namespace {
 
 constexpr int kThreads = 512;
@@ -43,6 +44,7 @@ struct TcParams {
   int P, C, K;
   __nv_bfloat16* out;       // [B,K,C]
   float* weights;           // [B,K,P]
+  long long* dbg;           // optional: clock64() stamps of CTA 0 at the phase boundaries (tools/phase_times.py)
 };
 
 struct Layout {
@@ -166,6 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
   const bool xvec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0);
   const bool qvec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(prm.q) & 15u) == 0);
 
+#define STAMP(i) do { if (prm.dbg && blockIdx.x == 0 && tid == 0) prm.dbg[i] = clock64(); } while (0)
+  STAMP(0);
   if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
   if (MODE == MODE_PATCHMERGER)
     for (int c = tid; c < C; c += kThreads) { lng[c] = prm.ln_w[c]; lnb[c] = prm.ln_b[c]; }
@@ -239,57 +243,48 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
   umma::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const Xform<MODE> xf{s0, s1, lng, lnb};
+  STAMP(1);   // stats done
 
   // ---- 1. Z = Q . Xn^T on tensor cores
   const int nchunk = MODE == MODE_SIT ? 0 : (C + KC1 - 1) / KC1;
   const uint32_t idesc1 = umma::instr_desc(umma::FMT_BF16, 128, (uint32_t)L.Np);
+  // Software pipeline: the global loads of chunk c+1 are issued right after the barrier of chunk c and stay in
+  // registers while the MMAs of chunk c run and the stage is handed back; convert + store happen one iteration later.
+  constexpr int GMAX = (kMaxK / 8 * 64 + kThreads - 1) / kThreads;      // groups of 8 elements per thread and operand
+  const int nga = ((K + 7) / 8) * 64, ngb = L.Np * 8;
+  float va[GMAX][8], vb[GMAX][8];
+  auto load_chunk = [&](int c) {
+    const int k0 = c * KC1;
+#pragma unroll
+    for (int u = 0; u < GMAX; ++u) {
+      const int gI = tid + u * kThreads;
+      const int row = (gI & 7) + ((gI >> 6) << 3), k = k0 + ((gI >> 3) & 7) * 8;
+      if (gI < nga && row < K) load8<float>(prm.q + (long long)row * C + k, qvec, C - k, va[u]);
+      if (gI < ngb && row < P) load8<T>(xb + (long long)row * C + k, xvec, C - k, vb[u]);
+    }
+  };
+  if (nchunk > 0) load_chunk(0);
   for (int c = 0; c < nchunk; ++c) {
     const int st = c & 1;
     unsigned char* A = R0 + (size_t)st * (L.stageA + L.stageB);
     unsigned char* Bt = A + L.stageA;
     if (c >= 2) umma::mbar_wait(&bars[st], (uint32_t)(((c - 2) >> 1) & 1));   // MMAs of chunk c-2 released this stage
     const int k0 = c * KC1;
-    // 8 consecutive lanes = 8 consecutive rows of one 16-byte K-chunk: 128 contiguous bytes of shared memory.
-    // U groups per thread-step: all 2U 16-byte loads are issued before the first convert (latency-bound otherwise).
-    constexpr int U = 4;
-    const int nga = ((K + 7) / 8) * 64, ngb = L.Np * 8;
-    for (int g0 = tid; g0 < nga; g0 += kThreads * U) {
-      float v[U][8];
+    // 8 consecutive lanes = 8 consecutive rows of one 16-byte K-chunk: 128 contiguous bytes of shared memory
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int gI = g0 + u * kThreads;
-        const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7, k = k0 + ch * 8;
-        if (gI < nga && row < K) load8<float>(prm.q + (long long)row * C + k, qvec, C - k, v[u]);
-      }
+    for (int u = 0; u < GMAX; ++u) {
+      const int gI = tid + u * kThreads;
+      const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7, k = k0 + ch * 8;
+      if (gI < nga && row < K)
+        *reinterpret_cast<int4*>(A + (row >> 3) * L.sbo1 + (row & 7) * 16 + ch * 128) = pack8(va[u]);
+      if (gI < ngb) {
+        if (row < P) {
+          xf.apply8(row, k, C, vb[u]);
+        } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int gI = g0 + u * kThreads;
-        const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7;
-        if (gI < nga && row < K)
-          *reinterpret_cast<int4*>(A + (row >> 3) * L.sbo1 + (row & 7) * 16 + ch * 128) = pack8(v[u]);
-      }
-    }
-    for (int g0 = tid; g0 < ngb; g0 += kThreads * U) {
-      float v[U][8];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int gI = g0 + u * kThreads;
-        const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7, k = k0 + ch * 8;
-        if (gI < ngb && row < P) load8<T>(xb + (long long)row * C + k, xvec, C - k, v[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int gI = g0 + u * kThreads;
-        const int row = (gI & 7) + ((gI >> 6) << 3), ch = (gI >> 3) & 7, k = k0 + ch * 8;
-        if (gI < ngb) {
-          if (row < P) {
-            xf.apply8(row, k, C, v[u]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
-          }
-          *reinterpret_cast<int4*>(Bt + (row >> 3) * L.sbo1 + (row & 7) * 16 + ch * 128) = pack8(v[u]);
+          for (int i = 0; i < 8; ++i) vb[u][i] = 0.f;
         }
+        *reinterpret_cast<int4*>(Bt + (row >> 3) * L.sbo1 + (row & 7) * 16 + ch * 128) = pack8(vb[u]);
       }
     }
     umma::fence_proxy_async_smem();
@@ -305,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
         }
       umma::mma_commit(&bars[st]);
     }
+    if (c + 1 < nchunk) load_chunk(c + 1);
   }
   // all MMAs done <=> the last commit completed (tcgen05 ops of one thread complete in order)
   if (nchunk > 0) {
@@ -313,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
     if (nchunk >= 2) umma::mbar_wait(&bars[(last - 1) & 1], (uint32_t)(((last - 1) >> 1) & 1));
   }
   umma::tc_fence_after_sync();
+  STAMP(2);   // GEMM 1 done
 
   // ---- 2. accumulator -> bf16 scores in shared memory (row per thread; padded row stride = odd word count)
   __nv_bfloat16* Z = reinterpret_cast<__nv_bfloat16*>(R1);
@@ -344,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
   }
   umma::tc_fence_before_sync();
   __syncthreads();
+  STAMP(3);   // Z in smem
 
   // ---- 3. W from Z (fp32 math), written to global (fp32) and as bf16 into the A-operand layout of GEMM 2
   unsigned char* Wop = R0;
@@ -426,6 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
     }
   }
   __syncthreads();     // Z is dead from here on: its region becomes the Xn^T chunk buffer
+  STAMP(4);   // W built
 
   // ---- 4. out = W . Xn on tensor cores, 128 output columns per accumulator set
   unsigned char* XT = R1;
@@ -525,7 +524,9 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
     }
   }
   __syncthreads();
+  STAMP(5);   // GEMM 2 + epilogue done
   if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
+#undef STAMP
 }
 
 }  // namespace
@@ -541,6 +542,7 @@ int launch_soft_merge_tc(int mode, const void* x, int x_dtype, const float* q, c
   prm.x = x; prm.q = q; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.scale = scale; prm.log_norm = log_norm; prm.ln_eps = ln_eps;
   prm.iters = iters; prm.P = P; prm.C = C; prm.K = K; prm.out = (__nv_bfloat16*)out; prm.weights = weights;
   prm.logits = (const __nv_bfloat16*)logits; prm.scale_ptr = scale_ptr;
+  prm.dbg = g_phase_dbg;
   if (mode == MODE_SIT && K > ((C + 3) & ~3)) return 1;      // the normalisers borrow the (unused) LayerNorm slot [C]
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(T, MODE)                                                                  \
@@ -556,3 +558,6 @@ int launch_soft_merge_tc(int mode, const void* x, int x_dtype, const float* q, c
 }
 
 }  // namespace tokred
+
+// debug hook (not part of the product ABI): device buffer of >= 8 int64 receiving clock64() phase stamps of CTA 0
+extern "C" __attribute__((visibility("default"))) void tokred_debug_phase_buffer(void* p) { tokred::g_phase_dbg = (long long*)p; }

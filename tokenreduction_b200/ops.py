@@ -391,6 +391,22 @@ def sinkhorn_log_norm(k: int, p: int, score_dtype: torch.dtype) -> float:
     return float(-((k * one).to(score_dtype) + (p * one).to(score_dtype)).float().log())
 
 
+# False: never hand scratch to the soft merges -> they use the scratch-free tensor-core kernel (softmerge_tc.cu)
+SOFT_MERGE_SCRATCH = True
+
+
+def _soft_workspace(x: Tensor, b: int, p: int, c: int, k: int, lowp: bool, tensor_cores: bool):
+    """scratch for the bulk-copy fed tensor-core kernels (bf16 token tiles + packed Q); (None, 0) when not used."""
+    if not (lowp and tensor_cores and SOFT_MERGE_SCRATCH):
+        return None, 0
+    n = int(_lib.load().tokred_soft_merge_workspace_bytes(b, p, c, k))
+    if n == 0:
+        return None, 0
+    ws = torch.empty(n + 128, dtype=torch.uint8, device=x.device)
+    off = (-ws.data_ptr()) % 128
+    return ws[off:off + n], n
+
+
 def _lowp_mode(lowp: bool, tensor_cores: bool) -> int:
     """C-ABI lowp code: 0 exact fp32, 1 bf16-autocast rounding on tcgen05, 3 same rounding on the FFMA path."""
     return (1 if tensor_cores else 3) if lowp else 0
@@ -411,9 +427,10 @@ def _sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool
     odt = _soft_out_dtype(x, lowp)
     out = torch.empty((b, k, c), dtype=odt, device=x.device)
     weights = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
+    ws, ws_bytes = _soft_workspace(x, b, p, c, k, lowp, tensor_cores)
     _lib.call("tokred_sinkhorn_merge", _ptr(x), _dt(x), _ptr(v_hat), b, p, c, k, float(eps),
               sinkhorn_log_norm(k, p, torch.bfloat16 if lowp else x.dtype), iters, _lowp_mode(lowp, tensor_cores), _ptr(out), _dt(out),
-              _ptr(weights), _stream())
+              _ptr(weights), _ptr(ws), ws_bytes, _stream())
     return out, weights
 
 
@@ -437,8 +454,9 @@ def _patchmerger(x: Tensor, ln_weight: Tensor, ln_bias: Tensor, queries: Tensor,
     odt = _soft_out_dtype(x, lowp)
     out = torch.empty((b, k, c), dtype=odt, device=x.device)
     attn = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
+    ws, ws_bytes = _soft_workspace(x, b, p, c, k, lowp, tensor_cores)
     _lib.call("tokred_patchmerger", _ptr(x), _dt(x), _ptr(lw), _ptr(lb), _ptr(queries), b, p, c, k, float(scale),
-              float(ln_eps), _lowp_mode(lowp, tensor_cores), _ptr(out), _dt(out), _ptr(attn), _stream())
+              float(ln_eps), _lowp_mode(lowp, tensor_cores), _ptr(out), _dt(out), _ptr(attn), _ptr(ws), ws_bytes, _stream())
     return out, attn
 
 
@@ -463,8 +481,9 @@ def _sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool, tensor_core
     odt = _soft_out_dtype(x, lowp)
     out = torch.empty((b, k, c), dtype=odt, device=x.device)
     w = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
+    ws, ws_bytes = _soft_workspace(x, b, p, c, k, lowp, tensor_cores)
     _lib.call("tokred_sit_merge", _ptr(x), _dt(x), _ptr(logits), _dt(logits), _ptr(scale), b, p, c, k, _lowp_mode(lowp, tensor_cores),
-              _ptr(out), _dt(out), _ptr(w), _stream())
+              _ptr(out), _dt(out), _ptr(w), _ptr(ws), ws_bytes, _stream())
     return out, w
 
 
