@@ -163,6 +163,86 @@ __global__ void __launch_bounds__(256) pack_q_kernel(const float* __restrict__ q
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
+template <typename T>
+__device__ __forceinline__ void tile_row_load(const T* xb, int p, int P, int C, int lane, bool xvec, float (&v)[4][8]) {
+  if (p < P) {
+    const T* row = xb + (long long)p * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane * 8 + j * 256;
+      if (c < C) load8<T>(row + c, xvec, C - c, v[j]);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+  }
+}
+
+// Normalise (Sinkhorn: unit L2 norm; PatchMerger: LayerNorm; SiT: identity) one token held by a warp and store its
+// bf16 core rows into the K-major tile image.  Rows p >= P arrive as zeros and are stored as zeros.
+template <int MODE>
+__device__ __forceinline__ void tile_row_finish(float (&v)[4][8], int p, int P, int C, int lane, const float* lng,
+                                                const float* lnb, float ln_eps, unsigned char* xh,
+                                                size_t tile_row_bytes, int Cc16) {
+  if (p < P) {
+    if (MODE == MODE_SINKHORN) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(v[j][i], v[j][i], s);
+      s = warp_sum(s);
+      const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);      // rounded to bf16 right after: reciprocal form is fine
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j][i] *= inv;
+    } else if (MODE == MODE_PATCHMERGER) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[j][i];
+      const float mean = warp_sum(s) / (float)C;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (lane * 8 + j * 256 + i < C) { const float d = v[j][i] - mean; q = fmaf(d, d, q); }
+      const float rstd = rsqrtf(warp_sum(q) / (float)C + ln_eps);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane * 8 + j * 256;
+        if (c + 8 <= C) {
+          const float4 g0 = *reinterpret_cast<const float4*>(lng + c), g1 = *reinterpret_cast<const float4*>(lng + c + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(lnb + c), b1 = *reinterpret_cast<const float4*>(lnb + c + 4);
+          v[j][0] = g0.x * (rstd * (v[j][0] - mean)) + b0.x; v[j][1] = g0.y * (rstd * (v[j][1] - mean)) + b0.y;
+          v[j][2] = g0.z * (rstd * (v[j][2] - mean)) + b0.z; v[j][3] = g0.w * (rstd * (v[j][3] - mean)) + b0.w;
+          v[j][4] = g1.x * (rstd * (v[j][4] - mean)) + b1.x; v[j][5] = g1.y * (rstd * (v[j][5] - mean)) + b1.y;
+          v[j][6] = g1.z * (rstd * (v[j][6] - mean)) + b1.z; v[j][7] = g1.w * (rstd * (v[j][7] - mean)) + b1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            v[j][i] = (c + i < C) ? lng[c + i] * (rstd * (v[j][i] - mean)) + lnb[c + i] : 0.f;
+        }
+      }
+    }
+  }
+  unsigned char* dst = xh + (size_t)(p >> 3) * tile_row_bytes + (size_t)(p & 7) * 16;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int core = lane + j * 32;
+    if (core < Cc16) *reinterpret_cast<int4*>(dst + (size_t)core * 128) = pack8(v[j]);
+  }
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params prm) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -207,87 +287,13 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
     for (int c = tid; c < C; c += kThreads) { lng[c] = prm.ln_w[c]; lnb[c] = prm.ln_b[c]; }
   __syncthreads();
 
-  // ---- 0a. token statistics: one warp per token, the row in registers (x read from HBM once; C <= 1024)
-  if (MODE != MODE_SIT) {
-    for (int p = warp; p < P; p += kThreads / 32) {
-      float v[4][8];
-      const T* row = xb + (long long)p * C;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = lane * 8 + j * 256;
-        if (c < C) load8<T>(row + c, xvec, C - c, v[j]);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
-        }
-      }
-      if (MODE == MODE_SINKHORN) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s = fmaf(v[j][i], v[j][i], s);
-        s = warp_sum(s);
-        if (lane == 0) s1[p] = 1.0f / fmaxf(sqrtf(s), 1e-12f);   // rounded to bf16 right after: reciprocal form is fine
-      } else {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s += v[j][i];
-        const float mean = warp_sum(s) / (float)C;
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (lane * 8 + j * 256 + i < C) { const float d = v[j][i] - mean; q = fmaf(d, d, q); }
-        const float var = warp_sum(q) / (float)C;
-        if (lane == 0) { s0[p] = mean; s1[p] = rsqrtf(var + prm.ln_eps); }
-      }
-    }
-    __syncthreads();
-  }
-  // ---- 0b. normalise, round to bf16, write core-matrix tiles.  Lane = (core offset 0..3, row 0..7): the 8 lanes of a
-  //          core write its 8 rows = 128 contiguous bytes, a warp store covers 4 adjacent cores = 512 B (the first
-  //          version stored 16 B per lane at a 128-byte stride and spent 55 % of the kernel here).  x is re-read from L2.
-  {
-    const int r8 = lane & 7, cq = lane >> 3;
-    const int ncq = G.Cc16 / 4;                           // core quads per token group
-    const int nitems = G.NG * ncq;
-    constexpr int U = 4;
-    for (int it0 = warp; it0 < nitems; it0 += (kThreads / 32) * U) {
-      float v[U][8];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int it = it0 + u * (kThreads / 32);
-        const int pg = it / ncq, core = (it % ncq) * 4 + cq;
-        const int p = pg * 8 + r8, c = core * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
-        if (it < nitems && p < P && c < C) load8<T>(xb + (long long)p * C + c, xvec, C - c, v[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int it = it0 + u * (kThreads / 32);
-        if (it < nitems) {
-          const int pg = it / ncq, core = (it % ncq) * 4 + cq;
-          const int p = pg * 8 + r8, c = core * 8;
-          if (p < P && c < C) {
-            if (MODE == MODE_SINKHORN) {
-              const float inv = s1[p];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[u][i] = (c + i < C) ? v[u][i] * inv : 0.f;
-            } else if (MODE == MODE_PATCHMERGER) {
-              const float mean = s0[p], rstd = s1[p];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[u][i] = (c + i < C) ? lng[c + i] * (rstd * (v[u][i] - mean)) + lnb[c + i] : 0.f;
-            }
-          }
-          *reinterpret_cast<int4*>(xh + (size_t)pg * G.tile_row_bytes + (size_t)core * 128 + (size_t)r8 * 16) = pack8(v[u]);
-        }
-      }
-    }
+  // ---- 0. token statistics + bf16 core-matrix tiles in ONE pass: one warp per token, row in registers (x read from
+  //         HBM once), 16-byte core rows stored straight into the tile.  (Measured alternatives that did not help:
+  //         two tokens in flight per warp; assembling tile rows in shared memory and storing them with cp.async.bulk.)
+  for (int p = warp; p < G.Np; p += kThreads / 32) {
+    float v[4][8];
+    tile_row_load<T>(xb, p, P, C, lane, xvec, v);
+    tile_row_finish<MODE>(v, p, P, C, lane, lng, lnb, prm.ln_eps, xh, G.tile_row_bytes, G.Cc16);
   }
   __threadfence();          // the tiles are read back through the async proxy (bulk copies) by this CTA
   asm volatile("fence.proxy.async;" ::: "memory");

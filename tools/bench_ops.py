@@ -107,6 +107,19 @@ def cases():
             out.append((f"patchmerger B B={b} P={p} K={k} {tag}", lambda x=x, lw=lw, lb=lb, q=q, lowp=lowp, tc=tc: T.patchmerger(x, lw, lb, q, 1.0, 1e-5, lowp, tc)))
         out.append((f"sit_merge B B={b} P={p} K={k} lowp tcgen05", lambda x=x, l=logits, s=scale: T.sit_merge(x, l, s, True, True)))
         out.append((f"sit_merge B B={b} P={p} K={k} lowp ffma", lambda x=x, l=logits, s=scale: T.sit_merge(x, l, s, True, False)))
+    # config 5 large-batch sweep (stage-1 shapes): several waves of per-image CTAs overlap their phases
+    for b in (256, 512, 1024):
+        p, k = 196, 176
+        x = torch.randn(b, p, 768, device=DEV)
+        v = torch.nn.functional.normalize(torch.randn(k, 768, device=DEV), dim=-1)
+        q = torch.randn(k, 768, device=DEV) * 0.05
+        lw, lb = torch.ones(768, device=DEV), torch.zeros(768, device=DEV)
+        logits = torch.randn(b, p, k, device=DEV).bfloat16()
+        scale = torch.ones(1, device=DEV)
+        out.append((f"sweep sinkhorn_merge B B={b} P={p} K={k} lowp tcgen05", lambda x=x, v=v: T.sinkhorn_merge(x, v, 1.0, 3, True, True)))
+        out.append((f"sweep patchmerger B B={b} P={p} K={k} lowp tcgen05", lambda x=x, lw=lw, lb=lb, q=q: T.patchmerger(x, lw, lb, q, 1.0, 1e-5, True, True)))
+        out.append((f"sweep sit_merge B B={b} P={p} K={k} lowp tcgen05", lambda x=x, l=logits, s=scale: T.sit_merge(x, l, s, True, True)))
+    b = 128
     from oracle.ops import ats_sample_steps
     for n, count in ((197, 177), (177, 159), (159, 143)):
         attn = torch.softmax(4 * torch.randn(b, 12, n, n, device=DEV), dim=-1)
