@@ -430,7 +430,8 @@ def test_soft_merge_scratch_free_kernel_and_sit_bulk_path(T):
         T.SOFT_MERGE_SCRATCH = True
     assert_close_rel(w2, w1, 1e-3, "sinkhorn weights v2 vs v1")
     assert_close_rel(o2.float(), o1.float(), 5e-3, "sinkhorn tokens v2 vs v1")
-    assert torch.equal(pa2, pa1) and torch.equal(po2, po1), "patchmerger v2 and v1 round identically"
+    assert_close_rel(pa2, pa1, 1e-3, "patchmerger attention v2 vs v1")
+    assert_close_rel(po2.float(), po1.float(), 5e-3, "patchmerger tokens v2 vs v1")
     bb, pp, kk, cc = 300, 32, 8, 64
     xs = torch.randn(bb, pp, cc, generator=g(423)).to(DEV)
     logits = torch.randn(bb, pp, kk, generator=g(424)).bfloat16().to(DEV)
@@ -439,6 +440,29 @@ def test_soft_merge_scratch_free_kernel_and_sit_bulk_path(T):
     out, w = T.sit_merge(xs, logits, scale, True, True)
     assert_close_rel(w, w_ref, RTOL16, "sit weights (bulk-copy path)")
     assert_close_rel(out.float(), out_ref.float(), RTOL16, "sit tokens (bulk-copy path)")
+
+
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])
+def test_soft_merge_token_ring_stress(T, xdt):
+    """Every SM busy, many repeats, every image checked on its own: the bulk-copy token ring of the tensor-core kernel
+    once released a slot before all lanes had read it (needs a cross-proxy fence), which corrupted a few tokens in
+    ~0.3 % of images and hid inside whole-batch norms."""
+    b, p, k, c = 150, 196, 176, 768
+    x = torch.randn(b, p, c, generator=g(430)).to(DEV).to(xdt)
+    v = torch.nn.functional.normalize(torch.randn(k, c, generator=g(431)), dim=-1).to(DEV)
+    lw, lb = (torch.rand(c, generator=g(432)) + 0.5).to(DEV), (torch.randn(c, generator=g(433)) * 0.1).to(DEV)
+    q = (torch.randn(k, c, generator=g(434)) * 0.05).to(DEV)
+    o_ref, w_ref = T.sinkhorn_merge(x, v, 1.0, 3, True, False)
+    po_ref, pw_ref = T.patchmerger(x, lw, lb, q, 1.0, 1e-5, True, False)
+
+    def per_image(a, ref):
+        return ((a.float() - ref.float()).flatten(1).norm(dim=1) / ref.float().flatten(1).norm(dim=1)).max().item()
+
+    for _ in range(12):
+        o, w = T.sinkhorn_merge(x, v, 1.0, 3, True, True)
+        po, pw = T.patchmerger(x, lw, lb, q, 1.0, 1e-5, True, True)
+        assert per_image(w, w_ref) < 1e-4 and per_image(o, o_ref) < 2e-3, "sinkhorn: an image deviates"
+        assert per_image(pw, pw_ref) < 3e-3 and per_image(po, po_ref) < 3e-3, "patchmerger: an image deviates"
 
 
 @pytest.mark.parametrize("p,k,c", [(196, 176, 768), (176, 158, 768), (196, 176, 384), (60, 20, 100)])

@@ -27,14 +27,16 @@ constexpr int kWorkers = 512;
 constexpr int kThreads = kWorkers + 64;
 constexpr int kWWarps = kWorkers / 32;
 constexpr int kMaxK = 208, kMaxP = 208;
-constexpr int S1 = 2;      // GEMM 1 stages
+constexpr int S1MAX = 4;   // GEMM 1 stages: as many (2..4) as fit under the Z / GEMM-2 areas, see make_geo
 constexpr int S2 = 2;      // GEMM 2 B-operand stages
 constexpr int NC2 = 128;   // output columns per accumulator set
 
 enum { MODE_SINKHORN = 0, MODE_PATCHMERGER = 1, MODE_SIT = 2 };
 
+constexpr int kRingMax = 32;      // pair slots of the phase-0 token ring
+
 struct Geo {
-  int Np, NG, K8, n_mt, Cc8, Cc16, nchunk1, nchunk2, PSb, Ks;
+  int Np, NG, K8, n_mt, Cc8, Cc16, nchunk1, nchunk2, PSb, Ks, S1;
   uint32_t sbo2;
   size_t q_chunk_bytes, q_bytes, tile_row_bytes, img_bytes;
   size_t stage1A, stage1B, z_off, xt_off, vec_off, total;
@@ -55,9 +57,11 @@ __host__ __device__ inline Geo make_geo(int P, int C, int K) {
   g.tile_row_bytes = (size_t)g.Cc16 * 128;
   g.img_bytes = (size_t)g.NG * g.tile_row_bytes;
   g.sbo2 = (uint32_t)g.NG * 128 + 16;    // W operand (K-major over p): +16 keeps 8-row groups on different banks
-  g.stage1A = (size_t)g.n_mt * 16 * 1024;
+  // A stage = the live Q rows only; the MMA of the last M tile also reads the (n_mt*128 - K) rows behind them, which
+  // are whatever follows in shared memory: garbage rows of A only produce accumulator rows >= K, never read.
+  g.stage1A = g.q_chunk_bytes;
   g.stage1B = (size_t)g.NG * 1024;
-  const size_t stages1 = S1 * (g.stage1A + g.stage1B);
+  const size_t stage1 = g.stage1A + g.stage1B;
   const size_t wop = (size_t)32 * g.sbo2;
   int psb = (P + 1) & ~1;
   if (((psb / 2) & 1) == 0) psb += 2;
@@ -68,15 +72,22 @@ __host__ __device__ inline Geo make_geo(int P, int C, int K) {
   const size_t zb = (size_t)K * psb * 2 > (size_t)P * ks * 2 ? (size_t)K * psb * 2 : (size_t)P * ks * 2;
   const size_t xt = S2 * (size_t)g.NG * 2048;
   // Shared-memory plan (bytes from the base):
-  //   [0, stages1)            GEMM-1 stages                      | later [0, wop) the W operand of GEMM 2
-  //   [z_off, z_off + zb)     Z (bf16) / staged SiT logits       (z_off = stages1: live together with the W operand)
-  //   [xt_off, xt_off + xt)   GEMM-2 B stages (xt_off = wop)     (overlaps Z, which is dead once W is built)
-  const size_t wop_al = (wop + 127) & ~(size_t)127, st_al = (stages1 + 127) & ~(size_t)127;
-  g.z_off = st_al > wop_al ? st_al : wop_al;
+  //   [0, S1*stage1)          GEMM-1 stages (phase 0: LayerNorm parameters + token ring) | later [0, wop) W operand
+  //   [z_off, z_off + zb)     Z (bf16) / staged SiT logits   (z_off = wop: live together with the W operand; written
+  //                           only after the last GEMM-1 MMA has committed, so it may overlap the stages)
+  //   [xt_off, xt_off + xt)   GEMM-2 B stages (xt_off = wop)  (overlaps Z, which is dead once W is built)
+  const size_t wop_al = (wop + 127) & ~(size_t)127;
+  g.z_off = wop_al;
   g.xt_off = wop_al;
   const size_t end0 = g.z_off + zb, end1 = g.xt_off + xt;
-  g.vec_off = ((end0 > end1 ? end0 : end1) + 127) & ~(size_t)127;
-  g.total = g.vec_off + (size_t)(3 * P + 2 * K + 2 * ((C + 3) & ~3)) * 4 + 256;
+  size_t endm = end0 > end1 ? end0 : end1;
+  const size_t tail = (size_t)g.n_mt * 16 * 1024 - g.stage1A;      // over-read of the last stage's A operand
+  int s1 = (int)((endm > tail ? endm - tail : 0) / stage1);
+  s1 = s1 > S1MAX ? S1MAX : s1;
+  if (s1 < 2) { s1 = 2; if (2 * stage1 + tail > endm) endm = 2 * stage1 + tail; }
+  g.S1 = s1;
+  g.vec_off = (endm + 127) & ~(size_t)127;
+  g.total = g.vec_off + (size_t)(3 * P + 2 * K) * 4 + 320 + 2 * kRingMax * 8;
   return g;
 }
 
@@ -110,10 +121,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 template <typename T> __device__ __forceinline__ void load8(const T* p, bool vec, int valid, float (&v)[8]);
 template <> __device__ __forceinline__ void load8<float>(const float* p, bool vec, int valid, float (&v)[8]) {
   if (vec && valid >= 8) {
-    // plain (L1-allocating) loads: a lane reads 32 contiguous bytes as two 16-byte halves of the SAME sector; with
-    // L1::no_allocate the second half re-fetches the sector from L2 (phase 0 ran 4x slower that way)
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    // one 256-bit load per lane (LDG.256; 32-byte aligned, checked by the caller): 1 KB contiguous per warp
+    // instruction.  Two 16-byte halves cost twice the L1 wavefronts, and with L1::no_allocate the second half
+    // re-fetched the sector from L2 (phase 0 ran 4x slower that way).
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = i < valid ? p[i] : 0.f;
@@ -129,6 +142,11 @@ template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bflo
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = i < valid ? __bfloat162float(p[i]) : 0.f;
   }
+}
+__device__ __forceinline__ void st_global32(void* p, const int4& a, const int4& b) {      // STG.256, 32-byte aligned
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
 }
 __device__ __forceinline__ int4 pack8(const float (&v)[8]) {
   __nv_bfloat162 h[4];
@@ -184,62 +202,140 @@ __device__ __forceinline__ void tile_row_load(const T* xb, int p, int P, int C, 
   }
 }
 
-// Normalise (Sinkhorn: unit L2 norm; PatchMerger: LayerNorm; SiT: identity) one token held by a warp and store its
-// bf16 core rows into the K-major tile image.  Rows p >= P arrive as zeros and are stored as zeros.
-template <int MODE>
-__device__ __forceinline__ void tile_row_finish(float (&v)[4][8], int p, int P, int C, int lane, const float* lng,
-                                                const float* lnb, float ln_eps, unsigned char* xh,
-                                                size_t tile_row_bytes, int Cc16) {
-  if (p < P) {
-    if (MODE == MODE_SINKHORN) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s = fmaf(v[j][i], v[j][i], s);
-      s = warp_sum(s);
-      const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);      // rounded to bf16 right after: reciprocal form is fine
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[j][i] *= inv;
-    } else if (MODE == MODE_PATCHMERGER) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[j][i];
-      const float mean = warp_sum(s) / (float)C;
-      float q = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (lane * 8 + j * 256 + i < C) { const float d = v[j][i] - mean; q = fmaf(d, d, q); }
-      const float rstd = rsqrtf(warp_sum(q) / (float)C + ln_eps);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = lane * 8 + j * 256;
-        if (c + 8 <= C) {
-          const float4 g0 = *reinterpret_cast<const float4*>(lng + c), g1 = *reinterpret_cast<const float4*>(lng + c + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(lnb + c), b1 = *reinterpret_cast<const float4*>(lnb + c + 4);
-          v[j][0] = g0.x * (rstd * (v[j][0] - mean)) + b0.x; v[j][1] = g0.y * (rstd * (v[j][1] - mean)) + b0.y;
-          v[j][2] = g0.z * (rstd * (v[j][2] - mean)) + b0.z; v[j][3] = g0.w * (rstd * (v[j][3] - mean)) + b0.w;
-          v[j][4] = g1.x * (rstd * (v[j][4] - mean)) + b1.x; v[j][5] = g1.y * (rstd * (v[j][5] - mean)) + b1.y;
-          v[j][6] = g1.z * (rstd * (v[j][6] - mean)) + b1.z; v[j][7] = g1.w * (rstd * (v[j][7] - mean)) + b1.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            v[j][i] = (c + i < C) ? lng[c + i] * (rstd * (v[j][i] - mean)) + lnb[c + i] : 0.f;
-        }
-      }
-    }
-  }
-  unsigned char* dst = xh + (size_t)(p >> 3) * tile_row_bytes + (size_t)(p & 7) * 16;
+// same lane -> channel mapping from a row staged in shared memory (C % 8 == 0 on this path)
+template <typename T>
+__device__ __forceinline__ void tile_row_load_smem(const T* row, bool live, int C, int lane, float (&v)[4][8]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int core = lane + j * 32;
-    if (core < Cc16) *reinterpret_cast<int4*>(dst + (size_t)core * 128) = pack8(v[j]);
+    const int c = lane * 8 + j * 256;
+    if (live && c < C) {
+      if constexpr (sizeof(T) == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(row + c), b = *reinterpret_cast<const float4*>(row + c + 4);
+        v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w; v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+      } else {
+        const int4 raw = *reinterpret_cast<const int4*>(row + c);
+        const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j][i] = __bfloat162float(h[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+    }
+  }
+}
+
+// Normalise (Sinkhorn: unit L2 norm; PatchMerger: LayerNorm; SiT: identity) one token held by a warp.  The LayerNorm
+// parameters sit in shared memory as float4s in (chunk j, half, lane) order so that a warp's read is 512 contiguous
+// bytes (the natural channel order is a 32-byte lane stride: 2-way bank conflicts on every read).  A dead row (token
+// index >= P) stays all-zero.
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+__device__ __forceinline__ void ln8(float (&v)[8], float rstd, float shift, const float4& g0, const float4& g1,
+                                    const float4& b0, const float4& b1) {      // shift = -mean * rstd
+  v[0] = fmaf(g0.x, fmaf(v[0], rstd, shift), b0.x); v[1] = fmaf(g0.y, fmaf(v[1], rstd, shift), b0.y);
+  v[2] = fmaf(g0.z, fmaf(v[2], rstd, shift), b0.z); v[3] = fmaf(g0.w, fmaf(v[3], rstd, shift), b0.w);
+  v[4] = fmaf(g1.x, fmaf(v[4], rstd, shift), b1.x); v[5] = fmaf(g1.y, fmaf(v[5], rstd, shift), b1.y);
+  v[6] = fmaf(g1.z, fmaf(v[6], rstd, shift), b1.z); v[7] = fmaf(g1.w, fmaf(v[7], rstd, shift), b1.w);
+}
+// FULL8: C % 8 == 0, so a lane's 8-channel chunk is either entirely inside the row or entirely padding (one test per
+// chunk instead of one per element: the per-element predicates were a third of the instructions of this phase).
+template <int MODE, bool FULL8>
+__device__ __forceinline__ void tile_row_normalise(float (&v)[4][8], bool live, int C, int lane, const float4* lng4,
+                                                   const float4* lnb4, float ln_eps) {
+  if (!live) return;
+  if (MODE == MODE_SINKHORN) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[j] = fmaf(v[j][i], v[j][i], s[j]);
+    const float t = warp_sum((s[0] + s[1]) + (s[2] + s[3]));
+    const float inv = 1.0f / fmaxf(sqrtf(t), 1e-12f);       // rounded to bf16 right after: reciprocal form is fine
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j][i] *= inv;
+  } else if (MODE == MODE_PATCHMERGER) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[j] += v[j][i];
+    const float invC = 1.0f / (float)C;
+    const float mean = warp_sum((s[0] + s[1]) + (s[2] + s[3])) * invC;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s[j] = 0.f;
+      const int c0 = lane * 8 + j * 256;
+      if (FULL8) {
+        if (c0 < C) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; s[j] = fmaf(d, d, s[j]); }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (c0 + i < C) { const float d = v[j][i] - mean; s[j] = fmaf(d, d, s[j]); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum((s[0] + s[1]) + (s[2] + s[3])) * invC + ln_eps);
+    const float shift = -mean * rstd;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (lane * 8 + j * 256 < C)            // channels past C hold gamma = beta = 0 in the padded parameter arrays
+        ln8(v[j], rstd, shift, lng4[(j * 2) * 32 + lane], lng4[(j * 2 + 1) * 32 + lane], lnb4[(j * 2) * 32 + lane],
+            lnb4[(j * 2 + 1) * 32 + lane]);
+  }
+}
+
+__device__ __forceinline__ void warp_max2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+    b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+  }
+}
+// One row of the bf16 score matrix (P <= 256) spread over a warp: lane holds token pairs lane, lane+32, ... as
+// x[2i], x[2i+1]; `add` (per-token, may be null) and `add_row` are added in fp32 in that order ((z + add_row) + add[p]
+// when both are given, matching the reference's (Z + u) + v); slots past P read as -inf.
+__device__ __forceinline__ void load_score_row(const __nv_bfloat16* zrow, const float* add, int P, int lane, float (&x)[8],
+                                               float add_row = 0.f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = 2 * (lane + 32 * i);
+    if (p < P) {
+      const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zrow + p));
+      x[2 * i] = (z.x + add_row) + (add ? add[p] : 0.f);
+      x[2 * i + 1] = p + 1 < P ? (z.y + add_row) + (add ? add[p + 1] : 0.f) : -CUDART_INF_F;
+    } else {
+      x[2 * i] = -CUDART_INF_F;
+      x[2 * i + 1] = -CUDART_INF_F;
+    }
+  }
+}
+// weights of one row: fp32 to global memory, bf16 into the K-major A operand of GEMM 2 (token pairs are adjacent there)
+__device__ __forceinline__ void store_weight_row(const float (&w)[8], float* wrow, unsigned char* Wop, int k, int P, int lane,
+                                                 uint32_t sbo2) {
+  const bool vec2 = (reinterpret_cast<uintptr_t>(wrow) & 7u) == 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = 2 * (lane + 32 * i);
+    if (p < P) {
+      const bool two = p + 1 < P;
+      if (two && vec2) *reinterpret_cast<float2*>(wrow + p) = make_float2(w[2 * i], w[2 * i + 1]);
+      else {
+        wrow[p] = w[2 * i];
+        if (two) wrow[p + 1] = w[2 * i + 1];
+      }
+      *reinterpret_cast<__nv_bfloat162*>(Wop + umma::kmajor_offset((uint32_t)k, (uint32_t)p, 2, sbo2)) =
+          __floats2bfloat162_rn(w[2 * i], two ? w[2 * i + 1] : 0.f);
+    }
   }
 }
 
@@ -249,51 +345,134 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
   const int P = prm.P, C = prm.C, K = prm.K;
   const Geo G = make_geo(P, C, K);
   unsigned char* R0 = smem;
-  const int Cpad = (C + 3) & ~3;
-  float* lng = reinterpret_cast<float*>(smem + G.vec_off);     // [Cpad]
-  float* lnb = lng + Cpad;                               // [Cpad]
-  float* s0 = lnb + Cpad;                                // [P]
+  float* lng = reinterpret_cast<float*>(smem);            // [1024] LayerNorm gamma, lane-major float4 order; lives in the
+  float* lnb = lng + 1024;                               // [1024] (idle) GEMM-1 stage area during phase 0 only
+  float* s0 = reinterpret_cast<float*>(smem + G.vec_off);      // [P]
   float* s1 = s0 + P;                                    // [P]
   float* uvec = s1 + P;                                  // [K]
   float* vvec = uvec + K;                                // [P]
   float* aux = vvec + P;                                 // [K]   sit: softmax normalisers
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(aux + K) + 7) & ~(uintptr_t)7);
-  uint64_t* full1 = bars;            // [S1]
-  uint64_t* empty1 = full1 + S1;     // [S1]
-  uint64_t* acc1 = empty1 + S1;      // [1]  GEMM 1 finished
+  uint64_t* full1 = bars;            // [S1MAX]
+  uint64_t* empty1 = full1 + S1MAX;  // [S1MAX]
+  uint64_t* acc1 = empty1 + S1MAX;   // [1]  GEMM 1 finished
   uint64_t* full2 = acc1 + 1;        // [S2]
   uint64_t* empty2 = full2 + S2;     // [S2]
   uint64_t* accfull = empty2 + S2;   // [2]
   uint64_t* accempty = accfull + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+  uint64_t* pfull = accempty + 2;    // [kRingMax] phase-0 ring: pair of token rows landed
+  uint64_t* pempty = pfull + kRingMax;  // [kRingMax] pair consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + kRingMax);
 
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool worker = warp < kWWarps;
   const T* xb = reinterpret_cast<const T*>(prm.x) + (long long)b * P * C;
   unsigned char* xh = prm.xh + (size_t)b * G.img_bytes;
-  const bool xvec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0);
+  const bool xvec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(xb) & (8 * sizeof(T) - 1)) == 0);
+
+  // phase-0 ring: pairs of adjacent token rows (contiguous in x) streamed into the idle GEMM stage area
+  const int row_bytes = C * (int)sizeof(T);
+  const size_t ring_off = MODE == MODE_PATCHMERGER ? 8192 : 0;       // after the LayerNorm parameters
+  int ring_slots = (int)((G.vec_off - ring_off) / (size_t)(2 * row_bytes));
+  ring_slots = ring_slots >= kRingMax ? kRingMax : (ring_slots >= 16 ? 16 : 0);
+  const int ring_log = ring_slots == 32 ? 5 : 4;      // 16 or 32 slots
+  const bool ring = ring_slots > 0 && xvec && (row_bytes % 16 == 0);
+  unsigned char* ring_base = smem + ring_off;
 
 #define STAMP(i) do { if (prm.dbg && blockIdx.x == 0 && tid == 0) prm.dbg[i] = clock64(); } while (0)
   STAMP(0);
   if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
   if (tid == 0) {
-    for (int i = 0; i < S1; ++i) { umma::mbar_init(&full1[i], 1); umma::mbar_init(&empty1[i], 1); }
+    for (int i = 0; i < S1MAX; ++i) { umma::mbar_init(&full1[i], 1); umma::mbar_init(&empty1[i], 1); }
     umma::mbar_init(acc1, 1);
     for (int i = 0; i < S2; ++i) { umma::mbar_init(&full2[i], 1); umma::mbar_init(&empty2[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&accfull[i], 1); umma::mbar_init(&accempty[i], kWWarps); }
+    for (int i = 0; i < kRingMax; ++i) { umma::mbar_init(&pfull[i], 1); umma::mbar_init(&pempty[i], 1); }
     umma::fence_mbar_init();
   }
   if (MODE == MODE_PATCHMERGER)
-    for (int c = tid; c < C; c += kThreads) { lng[c] = prm.ln_w[c]; lnb[c] = prm.ln_b[c]; }
+    for (int c = tid; c < 1024; c += kThreads) {        // (chunk j, half, lane, e) order, zero beyond C
+      const int j = c >> 8, ln = (c & 255) >> 3, half = (c & 7) >> 2, e = c & 3;
+      const int slot = (((j * 2 + half) * 32 + ln) << 2) + e;
+      lng[slot] = c < C ? prm.ln_w[c] : 0.f;
+      lnb[slot] = c < C ? prm.ln_b[c] : 0.f;
+    }
   __syncthreads();
 
-  // ---- 0. token statistics + bf16 core-matrix tiles in ONE pass: one warp per token, row in registers (x read from
-  //         HBM once), 16-byte core rows stored straight into the tile.  (Measured alternatives that did not help:
-  //         two tokens in flight per warp; assembling tile rows in shared memory and storing them with cp.async.bulk.)
-  for (int p = warp; p < G.Np; p += kThreads / 32) {
-    float v[4][8];
-    tile_row_load<T>(xb, p, P, C, lane, xvec, v);
-    tile_row_finish<MODE>(v, p, P, C, lane, lng, lnb, prm.ln_eps, xh, G.tile_row_bytes, G.Cc16);
+  // ---- 0. token statistics + bf16 core-matrix tiles in ONE pass over x.  One warp per PAIR of adjacent tokens, rows
+  //         in registers; each lane stores the two tokens' 16-byte core rows of a core matrix as one 32-byte STG.256.
+  //         The rows arrive through a shared-memory ring filled by the producer warp with cp.async.bulk (one copy per
+  //         pair: the two rows are contiguous), so HBM latency is hidden by 16-32 pairs in flight per SM instead of
+  //         by the 18 resident warps (direct loads left the phase a load -> reduce -> store latency chain: 58-77k
+  //         cycles of which 15k were arithmetic).
+  {
+    const float4* lng4 = reinterpret_cast<const float4*>(lng);
+    const float4* lnb4 = reinterpret_cast<const float4*>(lnb);
+    const int npairs = G.Np >> 1;
+    if (ring) {
+      if (warp == kWWarps && lane == 0) {
+        const int live_pairs = (P + 1) >> 1;
+        for (int m = 0; m < live_pairs; ++m) {
+          const int slot = m & (ring_slots - 1);
+          if (m >= ring_slots) umma::mbar_wait(&pempty[slot], (uint32_t)(((m >> ring_log) - 1) & 1));
+          const uint32_t bytes = (uint32_t)((2 * m + 1 < P ? 2 : 1) * row_bytes);
+          mbar_expect_tx(&pfull[slot], bytes);
+          bulk_g2s(ring_base + (size_t)slot * 2 * row_bytes, xb + (long long)(2 * m) * C, bytes, &pfull[slot]);
+        }
+      } else if (worker) {
+        for (int m = warp; m < npairs; m += kWWarps) {
+          const int p = 2 * m, slot = m & (ring_slots - 1);
+          int4 pa[4], pb[4];          // one row live at a time: 18 warps cap the kernel at 96 registers per thread
+          if (p < P) {
+            umma::mbar_wait(&pfull[slot], (uint32_t)((m >> ring_log) & 1));
+            const T* rows = reinterpret_cast<const T*>(ring_base + (size_t)slot * 2 * row_bytes);
+            float v[4][8];
+            tile_row_load_smem<T>(rows, true, C, lane, v);
+            tile_row_normalise<MODE, true>(v, true, C, lane, lng4, lnb4, prm.ln_eps);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pa[j] = pack8(v[j]);
+            tile_row_load_smem<T>(rows + C, p + 1 < P, C, lane, v);
+            // Generic-proxy reads followed by an async-proxy overwrite (the refill of this slot) need a cross-proxy
+            // fence: without it the release below overtook loads still queued in the load/store unit and the next
+            // occupant's rows showed up in ~0.3 % of images (a few slightly-wrong tokens).
+            umma::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pempty[slot]);
+            tile_row_normalise<MODE, true>(v, p + 1 < P, C, lane, lng4, lnb4, prm.ln_eps);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pb[j] = pack8(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { pa[j] = make_int4(0, 0, 0, 0); pb[j] = make_int4(0, 0, 0, 0); }
+          }
+          unsigned char* dst = xh + (size_t)(p >> 3) * G.tile_row_bytes + (size_t)(p & 7) * 16;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int core = lane + j * 32;
+            if (core < G.Cc16) st_global32(dst + (size_t)core * 128, pa[j], pb[j]);
+          }
+        }
+      }
+    } else {
+      for (int p = 2 * warp; p < G.Np; p += 2 * (kThreads / 32)) {       // rows not 16-byte copyable: direct loads
+        int4 pa[4], pb[4];
+        float v[4][8];
+        tile_row_load<T>(xb, p, P, C, lane, xvec, v);
+        tile_row_normalise<MODE, false>(v, p < P, C, lane, lng4, lnb4, prm.ln_eps);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pa[j] = pack8(v[j]);
+        tile_row_load<T>(xb, p + 1, P, C, lane, xvec, v);
+        tile_row_normalise<MODE, false>(v, p + 1 < P, C, lane, lng4, lnb4, prm.ln_eps);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pb[j] = pack8(v[j]);
+        unsigned char* dst = xh + (size_t)(p >> 3) * G.tile_row_bytes + (size_t)(p & 7) * 16;    // p even: 32-byte aligned
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int core = lane + j * 32;
+          if (core < G.Cc16) st_global32(dst + (size_t)core * 128, pa[j], pb[j]);
+        }
+      }
+    }
   }
   __threadfence();          // the tiles are read back through the async proxy (bulk copies) by this CTA
   asm volatile("fence.proxy.async;" ::: "memory");
@@ -305,22 +484,27 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
 
   // ---- 1. Z = Q . Xn^T : producer warp + MMA warp, workers wait on acc1
   if (MODE != MODE_SIT) {
-    if (warp == kWWarps && lane == 0) {
+    if (warp == kWWarps) {
+      // the whole producer warp issues: one lane per 1 KB token-group segment (a single thread issuing the 27 copies
+      // of a stage one after the other was the critical path of this GEMM)
       for (int c = 0; c < G.nchunk1; ++c) {
-        const int st = c % S1;
-        if (c >= S1) umma::mbar_wait(&empty1[st], (uint32_t)(((c / S1) - 1) & 1));
+        const int st = c % G.S1;
+        if (c >= G.S1) umma::mbar_wait(&empty1[st], (uint32_t)(((c / G.S1) - 1) & 1));
         unsigned char* A = R0 + (size_t)st * (G.stage1A + G.stage1B);
         unsigned char* Bt = A + G.stage1A;
-        mbar_expect_tx(&full1[st], (uint32_t)(G.q_chunk_bytes + G.stage1B));
-        bulk_g2s(A, prm.q_packed + (size_t)c * G.q_chunk_bytes, (uint32_t)G.q_chunk_bytes, &full1[st]);
-        for (int pg = 0; pg < G.NG; ++pg)
+        if (lane == 0) {
+          mbar_expect_tx(&full1[st], (uint32_t)(G.q_chunk_bytes + G.stage1B));
+          bulk_g2s(A, prm.q_packed + (size_t)c * G.q_chunk_bytes, (uint32_t)G.q_chunk_bytes, &full1[st]);
+        }
+        __syncwarp();
+        for (int pg = lane; pg < G.NG; pg += 32)
           bulk_g2s(Bt + (size_t)pg * 1024, xh + (size_t)pg * G.tile_row_bytes + (size_t)c * 1024, 1024u, &full1[st]);
       }
     } else if (warp == kWWarps + 1 && lane == 0) {
       const uint32_t idesc1 = umma::instr_desc(umma::FMT_BF16, 128, (uint32_t)G.Np);
       for (int c = 0; c < G.nchunk1; ++c) {
-        const int st = c % S1;
-        umma::mbar_wait(&full1[st], (uint32_t)((c / S1) & 1));
+        const int st = c % G.S1;
+        umma::mbar_wait(&full1[st], (uint32_t)((c / G.S1) & 1));
         umma::tc_fence_after_sync();
         const uint32_t a0 = umma::smem_u32(R0 + (size_t)st * (G.stage1A + G.stage1B)), b0 = a0 + (uint32_t)G.stage1A;
         for (int mt = 0; mt < G.n_mt; ++mt)
@@ -370,7 +554,8 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
 
   // ---- 3. W from Z: global fp32 + bf16 A operand (K-major over p) in region 0
   unsigned char* Wop = R0;
-  for (int e = tid; e < (int)(32 * G.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
+  if (MODE == MODE_SIT)
+    for (int e = tid; e < (int)(32 * G.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
   float* wout = prm.weights + (long long)b * K * P;
   if (MODE == MODE_SIT) {
     __nv_bfloat16* Lg = reinterpret_cast<__nv_bfloat16*>(smem + G.z_off);
@@ -397,63 +582,113 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
       }
     }
   } else if (MODE == MODE_SINKHORN) {
+    // Log-domain Sinkhorn on the bf16 scores.  Row passes keep a row in registers (one shared-memory sweep: max,
+    // then exp-sum), column passes split K over several threads per column PAIR with a chunked online log-sum-exp
+    // (one sweep, one rescale per 8 rows) and combine the partials through shared memory (the W-operand area, which
+    // is zero-filled only afterwards).  13 two-byte sweeps with a separate max pass cost 90k cycles before.
     const float nrm = prm.log_norm;
+    constexpr int NW = kThreads / 32;
+    const int npp = (P + 1) >> 1;                       // column pairs
+    int nsplit = kThreads / npp;
+    nsplit = nsplit > 8 ? 8 : nsplit;
+    float* part_m = reinterpret_cast<float*>(Wop);       // [nsplit][2*npp]
+    float* part_s = part_m + 8 * 256;
     for (int k = tid; k < K; k += kThreads) uvec[k] = 0.f;
     for (int p = tid; p < P; p += kThreads) vvec[p] = 0.f;
     __syncthreads();
     for (int it = 0; it < prm.iters; ++it) {
-      for (int k = warp; k < K; k += kThreads / 32) {
-        float m = -CUDART_INF_F;
-        for (int p = lane; p < P; p += 32) m = fmaxf(m, __bfloat162float(Z[(size_t)k * PSb + p]) + vvec[p]);
-        m = warp_max(m);
-        float s = 0.f;
-        for (int p = lane; p < P; p += 32) s += __expf(__bfloat162float(Z[(size_t)k * PSb + p]) + vvec[p] - m);
-        s = warp_sum(s);
-        if (lane == 0) uvec[k] = nrm - (__logf(s) + m);
+      for (int k0 = warp; k0 < K; k0 += 2 * NW) {
+        const int k1 = k0 + NW;
+        float xa[8], xb2[8];
+        load_score_row(Z + (size_t)k0 * PSb, vvec, P, lane, xa);
+        if (k1 < K) load_score_row(Z + (size_t)k1 * PSb, vvec, P, lane, xb2);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xb2[i] = 0.f;
+        }
+        float ma = xa[0], mb = xb2[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) { ma = fmaxf(ma, xa[i]); mb = fmaxf(mb, xb2[i]); }
+        warp_max2(ma, mb);
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sa += __expf(xa[i] - ma); sb += __expf(xb2[i] - mb); }
+        warp_sum2(sa, sb);
+        if (lane == 0) {
+          uvec[k0] = nrm - (__logf(sa) + ma);
+          if (k1 < K) uvec[k1] = nrm - (__logf(sb) + mb);
+        }
       }
       __syncthreads();
-      // column pass: 2 threads per column (row halves), combined through shared memory
       {
-        const int p = tid >> 1, h = tid & 1;
-        const int kb = h ? (K + 1) / 2 : 0, ke = h ? K : (K + 1) / 2;
-        float m = -CUDART_INF_F, s = 0.f;
-        if (p < P) {
-#pragma unroll 4
-          for (int k = kb; k < ke; ++k) m = fmaxf(m, __bfloat162float(Z[(size_t)k * PSb + p]) + uvec[k]);
+        const int cp = tid % npp, sp = tid / npp;
+        if (sp < nsplit) {
+          const int kb = K * sp / nsplit, ke = K * (sp + 1) / nsplit;
+          const __nv_bfloat16* zc = Z + 2 * cp;
+          float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, s0 = 0.f, s1 = 0.f;
+          for (int k = kb; k < ke; k += 8) {
+            float x0[8], x1[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (k + i < ke) {
+                const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zc + (size_t)(k + i) * PSb));
+                const float u = uvec[k + i];
+                x0[i] = z.x + u; x1[i] = z.y + u;
+              } else { x0[i] = -CUDART_INF_F; x1[i] = -CUDART_INF_F; }
+            }
+            float n0 = m0, n1 = m1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { n0 = fmaxf(n0, x0[i]); n1 = fmaxf(n1, x1[i]); }
+            s0 *= __expf(m0 - n0); s1 *= __expf(m1 - n1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s0 += __expf(x0[i] - n0); s1 += __expf(x1[i] - n1); }
+            m0 = n0; m1 = n1;
+          }
+          part_m[sp * 256 + 2 * cp] = m0; part_m[sp * 256 + 2 * cp + 1] = m1;
+          part_s[sp * 256 + 2 * cp] = s0; part_s[sp * 256 + 2 * cp + 1] = s1;
         }
-        const float mo = __shfl_xor_sync(0xffffffffu, m, 1);
-        m = fmaxf(m, mo);
-        if (p < P) {
-#pragma unroll 4
-          for (int k = kb; k < ke; ++k) s += __expf(__bfloat162float(Z[(size_t)k * PSb + p]) + uvec[k] - m);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (p < P && h == 0) vvec[p] = nrm - (__logf(s) + m);
+      }
+      __syncthreads();
+      for (int p = tid; p < P; p += kThreads) {
+        float m = part_m[p];
+        for (int sp = 1; sp < nsplit; ++sp) m = fmaxf(m, part_m[sp * 256 + p]);
+        float sum = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) sum += part_s[sp * 256 + p] * __expf(part_m[sp * 256 + p] - m);
+        vvec[p] = nrm - (__logf(sum) + m);
       }
       __syncthreads();
     }
-    for (int k = warp; k < K; k += kThreads / 32) {
-      const float uk = uvec[k];
-      for (int p = lane; p < P; p += 32) {
-        const float w = expf(((__bfloat162float(Z[(size_t)k * PSb + p]) + uk) + vvec[p]) - nrm);
-        wout[(long long)k * P + p] = w;
-        *reinterpret_cast<__nv_bfloat16*>(Wop + umma::kmajor_offset((uint32_t)k, (uint32_t)p, 2, G.sbo2)) = __float2bfloat16_rn(w);
-      }
+    STAMP(6);
+    for (int e = tid; e < (int)(32 * G.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    STAMP(7);
+    for (int k = warp; k < K; k += NW) {
+      float x[8];
+      load_score_row(Z + (size_t)k * PSb, vvec, P, lane, x, uvec[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = expf(x[i] - nrm);
+      store_weight_row(x, wout + (long long)k * P, Wop, k, P, lane, G.sbo2);
     }
   } else {
+    for (int e = tid; e < (int)(32 * G.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
     __syncthreads();
+    STAMP(7);
     for (int k = warp; k < K; k += kThreads / 32) {
-      float m = -CUDART_INF_F;
-      for (int p = lane; p < P; p += 32) m = fmaxf(m, __bfloat162float(Z[(size_t)k * PSb + p]));
+      float x[8];
+      load_score_row(Z + (size_t)k * PSb, nullptr, P, lane, x);
+      float m = x[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) m = fmaxf(m, x[i]);
       m = warp_max(m);
-      float s = 0.f;
-      for (int p = lane; p < P; p += 32) s += expf(__bfloat162float(Z[(size_t)k * PSb + p]) - m);
-      s = warp_sum(s);
-      for (int p = lane; p < P; p += 32) {
-        const float w = expf(__bfloat162float(Z[(size_t)k * PSb + p]) - m) / s;
-        wout[(long long)k * P + p] = w;
-        *reinterpret_cast<__nv_bfloat16*>(Wop + umma::kmajor_offset((uint32_t)k, (uint32_t)p, 2, G.sbo2)) = __float2bfloat16_rn(w);
-      }
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x[i] = __expf(x[i] - m); sum += x[i]; }      // scores are bf16: 2 ulp is noise
+      // one reciprocal per row: IEEE division takes its slow path for every zero numerator (the slots past P), which
+      // made this loop 11k cycles longer; the product differs from the quotient by at most 1 ulp
+      const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] *= inv;
+      store_weight_row(x, wout + (long long)k * P, Wop, k, P, lane, G.sbo2);
     }
   }
   umma::fence_proxy_async_smem();      // W operand (generic-proxy writes) -> visible to the tensor core
@@ -463,13 +698,14 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
   // ---- 4. out = W . Xn : B operand = tile segments used MN-major (N = channel, K = token)
   unsigned char* XT = smem + G.xt_off;
   __nv_bfloat16* ob = prm.out + (long long)b * K * C;
-  if (warp == kWWarps && lane == 0) {
+  if (warp == kWWarps) {
     for (int cc = 0; cc < G.nchunk2; ++cc) {
       const int st = cc % S2;
       if (cc >= S2) umma::mbar_wait(&empty2[st], (uint32_t)(((cc / S2) - 1) & 1));
       unsigned char* dstb = XT + (size_t)st * G.NG * 2048;
-      mbar_expect_tx(&full2[st], (uint32_t)(G.NG * 2048));
-      for (int pg = 0; pg < G.NG; ++pg)
+      if (lane == 0) mbar_expect_tx(&full2[st], (uint32_t)(G.NG * 2048));
+      __syncwarp();
+      for (int pg = lane; pg < G.NG; pg += 32)
         bulk_g2s(dstb + (size_t)pg * 2048, xh + (size_t)pg * G.tile_row_bytes + (size_t)cc * 2048, 2048u, &full2[st]);
     }
   } else if (warp == kWWarps + 1 && lane == 0) {
