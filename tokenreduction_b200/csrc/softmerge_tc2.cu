@@ -294,6 +294,16 @@ __device__ __forceinline__ void tile_row_normalise(float (&v)[4][8], bool live, 
   }
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void warp_max2(float& a, float& b) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -588,6 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
     // is zero-filled only afterwards).  13 two-byte sweeps with a separate max pass cost 90k cycles before.
     const float nrm = prm.log_norm;
     constexpr int NW = kThreads / 32;
+    constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
     const int npp = (P + 1) >> 1;                       // column pairs
     int nsplit = kThreads / npp;
     nsplit = nsplit > 8 ? 8 : nsplit;
@@ -595,28 +606,49 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
     float* part_s = part_m + 8 * 256;
     for (int k = tid; k < K; k += kThreads) uvec[k] = 0.f;
     for (int p = tid; p < P; p += kThreads) vvec[p] = 0.f;
+    // per-lane constants of the row passes (the phase is instruction-issue bound: 60k warp-instructions per
+    // iteration before bounds tests, potential reloads and the 6-instruction __expf were hoisted / replaced by
+    // ex2.approx.ftz(fma(x, log2e, -m*log2e)))
+    int poff[4];
+    bool ok0[4], ok1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pp = 2 * (lane + 32 * i);
+      ok0[i] = pp < P; ok1[i] = pp + 1 < P;
+      poff[i] = ok0[i] ? pp : 0;                          // dead slots re-read token 0 (finite) and add -inf
+    }
     __syncthreads();
     for (int it = 0; it < prm.iters; ++it) {
-      for (int k0 = warp; k0 < K; k0 += 2 * NW) {
-        const int k1 = k0 + NW;
-        float xa[8], xb2[8];
-        load_score_row(Z + (size_t)k0 * PSb, vvec, P, lane, xa);
-        if (k1 < K) load_score_row(Z + (size_t)k1 * PSb, vvec, P, lane, xb2);
-        else {
+      float vv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) xb2[i] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        vv[2 * i] = ok0[i] ? vvec[poff[i]] : -CUDART_INF_F;
+        vv[2 * i + 1] = ok1[i] ? vvec[poff[i] + 1] : -CUDART_INF_F;
+      }
+      for (int k0 = warp; k0 < K; k0 += 2 * NW) {
+        const bool two = k0 + NW < K;
+        const __nv_bfloat16* za = Z + (size_t)k0 * PSb;
+        const __nv_bfloat16* zb = Z + (size_t)(two ? k0 + NW : k0) * PSb;
+        float xa[8], xb2[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(za + poff[i]));
+          const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zb + poff[i]));
+          xa[2 * i] = a2.x + vv[2 * i]; xa[2 * i + 1] = a2.y + vv[2 * i + 1];
+          xb2[2 * i] = b2.x + vv[2 * i]; xb2[2 * i + 1] = b2.y + vv[2 * i + 1];
         }
         float ma = xa[0], mb = xb2[0];
 #pragma unroll
         for (int i = 1; i < 8; ++i) { ma = fmaxf(ma, xa[i]); mb = fmaxf(mb, xb2[i]); }
         warp_max2(ma, mb);
+        const float na = -ma * L2E, nb = -mb * L2E;
         float sa = 0.f, sb = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { sa += __expf(xa[i] - ma); sb += __expf(xb2[i] - mb); }
+        for (int i = 0; i < 8; ++i) { sa += ex2_ftz(fmaf(xa[i], L2E, na)); sb += ex2_ftz(fmaf(xb2[i], L2E, nb)); }
         warp_sum2(sa, sb);
         if (lane == 0) {
-          uvec[k0] = nrm - (__logf(sa) + ma);
-          if (k1 < K) uvec[k1] = nrm - (__logf(sb) + mb);
+          uvec[k0] = nrm - (lg2_fast(sa) * LN2 + ma);
+          if (two) uvec[k0 + NW] = nrm - (lg2_fast(sb) * LN2 + mb);
         }
       }
       __syncthreads();
@@ -624,14 +656,14 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
         const int cp = tid % npp, sp = tid / npp;
         if (sp < nsplit) {
           const int kb = K * sp / nsplit, ke = K * (sp + 1) / nsplit;
-          const __nv_bfloat16* zc = Z + 2 * cp;
+          const __nv_bfloat16* zc = Z + (size_t)kb * PSb + 2 * cp;
           float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, s0 = 0.f, s1 = 0.f;
-          for (int k = kb; k < ke; k += 8) {
+          for (int k = kb; k < ke; k += 8, zc += (size_t)8 * PSb) {
             float x0[8], x1[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if (k + i < ke) {
-                const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zc + (size_t)(k + i) * PSb));
+                const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zc + (size_t)i * PSb));
                 const float u = uvec[k + i];
                 x0[i] = z.x + u; x1[i] = z.y + u;
               } else { x0[i] = -CUDART_INF_F; x1[i] = -CUDART_INF_F; }
@@ -639,9 +671,10 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
             float n0 = m0, n1 = m1;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { n0 = fmaxf(n0, x0[i]); n1 = fmaxf(n1, x1[i]); }
-            s0 *= __expf(m0 - n0); s1 *= __expf(m1 - n1);
+            const float c0 = -n0 * L2E, c1 = -n1 * L2E;
+            s0 *= ex2_ftz(fmaf(m0, L2E, c0)); s1 *= ex2_ftz(fmaf(m1, L2E, c1));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s0 += __expf(x0[i] - n0); s1 += __expf(x1[i] - n1); }
+            for (int i = 0; i < 8; ++i) { s0 += ex2_ftz(fmaf(x0[i], L2E, c0)); s1 += ex2_ftz(fmaf(x1[i], L2E, c1)); }
             m0 = n0; m1 = n1;
           }
           part_m[sp * 256 + 2 * cp] = m0; part_m[sp * 256 + 2 * cp + 1] = m1;
@@ -653,8 +686,8 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
         float m = part_m[p];
         for (int sp = 1; sp < nsplit; ++sp) m = fmaxf(m, part_m[sp * 256 + p]);
         float sum = 0.f;
-        for (int sp = 0; sp < nsplit; ++sp) sum += part_s[sp * 256 + p] * __expf(part_m[sp * 256 + p] - m);
-        vvec[p] = nrm - (__logf(sum) + m);
+        for (int sp = 0; sp < nsplit; ++sp) sum += part_s[sp * 256 + p] * ex2_ftz((part_m[sp * 256 + p] - m) * L2E);
+        vvec[p] = nrm - (lg2_fast(sum) * LN2 + m);
       }
       __syncthreads();
     }
@@ -666,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
       float x[8];
       load_score_row(Z + (size_t)k * PSb, vvec, P, lane, x, uvec[k]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = expf(x[i] - nrm);
+      for (int i = 0; i < 8; ++i) x[i] = ex2_ftz((x[i] - nrm) * L2E);      // rel. error ~1e-6: the scores are bf16
       store_weight_row(x, wout + (long long)k * P, Wop, k, P, lane, G.sbo2);
     }
   } else {
@@ -680,9 +713,10 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
 #pragma unroll
       for (int i = 1; i < 8; ++i) m = fmaxf(m, x[i]);
       m = warp_max(m);
+      const float nm2 = -m * 1.4426950408889634f;
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { x[i] = __expf(x[i] - m); sum += x[i]; }      // scores are bf16: 2 ulp is noise
+      for (int i = 0; i < 8; ++i) { x[i] = ex2_ftz(fmaf(x[i], 1.4426950408889634f, nm2)); sum += x[i]; }   // scores are bf16
       // one reciprocal per row: IEEE division takes its slow path for every zero numerator (the slots past P), which
       // made this loop 11k cycles longer; the product differs from the quotient by at most 1 ulp
       const float inv = 1.0f / warp_sum(sum);
