@@ -414,7 +414,7 @@ def test_soft_merge_tensor_core_paths(T, p, k, c, xdt):
 
 def test_soft_merge_scratch_free_kernel_and_sit_bulk_path(T):
     """(1) the scratch-free tensor-core kernel (v1) stays equivalent to the bulk-copy fed one (v2);
-    (2) SiT takes the bulk-copy kernel only for multi-wave batches (B > 2 x 148): exercise it."""
+    (2) SiT through both kernels at a multi-wave batch (B > 2 x 148)."""
     b, p, k, c = 3, 196, 176, 768
     x = torch.randn(b, p, c, generator=g(420)).to(DEV)
     v = torch.nn.functional.normalize(torch.randn(k, c, generator=g(421)), dim=-1).to(DEV)
@@ -440,6 +440,13 @@ def test_soft_merge_scratch_free_kernel_and_sit_bulk_path(T):
     out, w = T.sit_merge(xs, logits, scale, True, True)
     assert_close_rel(w, w_ref, RTOL16, "sit weights (bulk-copy path)")
     assert_close_rel(out.float(), out_ref.float(), RTOL16, "sit tokens (bulk-copy path)")
+    T.SOFT_MERGE_SCRATCH = False
+    try:
+        out1, w1 = T.sit_merge(xs, logits, scale, True, True)
+    finally:
+        T.SOFT_MERGE_SCRATCH = True
+    assert_close_rel(w1, w_ref, RTOL16, "sit weights (scratch-free path)")
+    assert_close_rel(out1.float(), out_ref.float(), RTOL16, "sit tokens (scratch-free path)")
 
 
 @pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])

@@ -379,9 +379,8 @@ extern "C" int tokred_sit_merge(const void* x, int x_dtype, const void* logits, 
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
   if (B == 0) return TOKRED_OK;
   if (lowp == 1 && out_dtype == TOKRED_BF16 && logits_dtype == TOKRED_BF16) {
-    // SiT has no first contraction, so the tile pre-pass of the bulk-copy kernel is pure overhead for a single wave
-    // of images (82 vs 70 us at B=128); it pays off once several waves overlap their phases.
-    if (B > 2 * kNumSMs) {
+    // bulk-copy fed kernel first (needs the workspace); the scratch-free one covers callers without a workspace
+    {
       const int rc2 = launch_soft_merge_tc2(MODE_SIT, x, x_dtype, nullptr, nullptr, nullptr, B, P, C, K, 1.f, 0.f, 0.f, 0, out,
                                             weights, stream, what, logits, scale, workspace, workspace_bytes);
       if (rc2 != 1) return rc2;

@@ -87,7 +87,7 @@ __host__ __device__ inline Geo make_geo(int P, int C, int K) {
   if (s1 < 2) { s1 = 2; if (2 * stage1 + tail > endm) endm = 2 * stage1 + tail; }
   g.S1 = s1;
   g.vec_off = (endm + 127) & ~(size_t)127;
-  g.total = g.vec_off + (size_t)(3 * P + 2 * K) * 4 + 320 + 2 * kRingMax * 8;
+  g.total = g.vec_off + (size_t)(3 * P + 2 * K) * 4 + 328 + 2 * kRingMax * 8;
   return g;
 }
 
@@ -349,6 +349,38 @@ __device__ __forceinline__ void store_weight_row(const float (&w)[8], float* wro
   }
 }
 
+// SiT: logits [P, K] (bf16) -> shared memory TRANSPOSED as rows [K][PSb], by `nt` cooperating threads (index t).
+// Lanes take consecutive tokens for one group of 8 slots: 16-byte loads (4 kept in flight; the loop is latency bound)
+// and conflict-free 2-byte stores.
+__device__ __forceinline__ void stage_logits_transposed(__nv_bfloat16* Lt, const __nv_bfloat16* lb, int P, int K, int PSb,
+                                                        int t, int nt) {
+  if ((K & 7) == 0 && (reinterpret_cast<uintptr_t>(lb) & 15u) == 0) {
+    const int K8 = K >> 3, items = P * K8;            // item = (slot group k8, token p), p fastest
+    for (int e0 = t; e0 < items; e0 += 4 * nt) {
+      int4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        if (e < items) { const int k8 = e / P, p = e - k8 * P; raw[u] = *reinterpret_cast<const int4*>(lb + (size_t)p * K + k8 * 8); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * nt;
+        if (e < items) {
+          const int k8 = e / P, p = e - k8 * P;
+          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) Lt[(size_t)(k8 * 8 + j) * PSb + p] = h[j];
+        }
+      }
+    }
+  } else {
+    for (int e = t; e < P * K; e += nt) { const int p = e / K, k = e - p * K; Lt[(size_t)k * PSb + p] = lb[e]; }
+  }
+  if (P & 1)
+    for (int k = t; k < K; k += nt) Lt[(size_t)k * PSb + P] = __float2bfloat16_rn(0.f);      // pad column: finite
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params prm) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -372,7 +404,8 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
   uint64_t* accempty = accfull + 2;  // [2]
   uint64_t* pfull = accempty + 2;    // [kRingMax] phase-0 ring: pair of token rows landed
   uint64_t* pempty = pfull + kRingMax;  // [kRingMax] pair consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + kRingMax);
+  uint64_t* lgbar = pempty + kRingMax;  // [1] SiT: raw logits landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lgbar + 1);
 
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool worker = warp < kWWarps;
@@ -380,13 +413,17 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
   unsigned char* xh = prm.xh + (size_t)b * G.img_bytes;
   const bool xvec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(xb) & (8 * sizeof(T) - 1)) == 0);
 
-  // phase-0 ring: pairs of adjacent token rows (contiguous in x) streamed into the idle GEMM stage area
+  // phase-0 ring: pairs of adjacent token rows (contiguous in x) streamed into the idle GEMM stage area.  SiT has no
+  // GEMM 1: its ring lives in the (idle) Z / GEMM-2 stage area instead, and [0, 2PK) receives the raw logits.
   const int row_bytes = C * (int)sizeof(T);
-  const size_t ring_off = MODE == MODE_PATCHMERGER ? 8192 : 0;       // after the LayerNorm parameters
+  const size_t ring_off = MODE == MODE_SIT ? G.z_off : (MODE == MODE_PATCHMERGER ? 8192 : 0);   // 8 KB: LayerNorm parameters
   int ring_slots = (int)((G.vec_off - ring_off) / (size_t)(2 * row_bytes));
   ring_slots = ring_slots >= kRingMax ? kRingMax : (ring_slots >= 16 ? 16 : 0);
   const int ring_log = ring_slots == 32 ? 5 : 4;      // 16 or 32 slots
   const bool ring = ring_slots > 0 && xvec && (row_bytes % 16 == 0);
+  const uint32_t lg_bytes = (uint32_t)(P * K * 2);
+  const bool lg_bulk = MODE == MODE_SIT && ring && (lg_bytes % 16 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(prm.logits) & 15u) == 0);
   unsigned char* ring_base = smem + ring_off;
 
 #define STAMP(i) do { if (prm.dbg && blockIdx.x == 0 && tid == 0) prm.dbg[i] = clock64(); } while (0)
@@ -398,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
     for (int i = 0; i < S2; ++i) { umma::mbar_init(&full2[i], 1); umma::mbar_init(&empty2[i], 1); }
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&accfull[i], 1); umma::mbar_init(&accempty[i], kWWarps); }
     for (int i = 0; i < kRingMax; ++i) { umma::mbar_init(&pfull[i], 1); umma::mbar_init(&pempty[i], 1); }
+    umma::mbar_init(lgbar, 1);
     umma::fence_mbar_init();
   }
   if (MODE == MODE_PATCHMERGER)
@@ -421,6 +459,10 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
     const int npairs = G.Np >> 1;
     if (ring) {
       if (warp == kWWarps && lane == 0) {
+        if (lg_bulk) {
+          mbar_expect_tx(lgbar, lg_bytes);
+          bulk_g2s(smem, prm.logits + (long long)b * P * K, lg_bytes, lgbar);
+        }
         const int live_pairs = (P + 1) >> 1;
         for (int m = 0; m < live_pairs; ++m) {
           const int slot = m & (ring_slots - 1);
@@ -564,32 +606,55 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
 
   // ---- 3. W from Z: global fp32 + bf16 A operand (K-major over p) in region 0
   unsigned char* Wop = R0;
-  if (MODE == MODE_SIT)
-    for (int e = tid; e < (int)(32 * G.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
   float* wout = prm.weights + (long long)b * K * P;
   if (MODE == MODE_SIT) {
-    __nv_bfloat16* Lg = reinterpret_cast<__nv_bfloat16*>(smem + G.z_off);
-    const int Ks = G.Ks;
-    const __nv_bfloat16* lb = prm.logits + (long long)b * P * K;
-    for (int e = tid; e < P * K; e += kThreads) Lg[(e / K) * Ks + e % K] = lb[e];
+    // logits [P, K] -> staged TRANSPOSED as bf16 rows [K][PSb] so that the softmax over tokens is the same
+    // register-row pass as PatchMerger's (one warp per slot k, one shared-memory sweep)
+    __nv_bfloat16* Lt = reinterpret_cast<__nv_bfloat16*>(smem + G.z_off);
+    if (lg_bulk) {
+      // the raw [P, K] block was bulk-copied to the bottom of shared memory while the tiles were produced:
+      // transpose it shared -> shared (no global latency left in this phase)
+      umma::mbar_wait(lgbar, 0);
+      const __nv_bfloat16* raw = reinterpret_cast<const __nv_bfloat16*>(smem);
+      if ((K & 1) == 0) {
+        const int K2 = K >> 1;
+        for (int e = tid; e < P * K2; e += kThreads) {
+          const int p = e / K2, k = (e - p * K2) * 2;
+          const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(raw + (size_t)p * K + k);
+          Lt[(size_t)k * PSb + p] = v2.x;
+          Lt[(size_t)(k + 1) * PSb + p] = v2.y;
+        }
+      } else {
+        for (int e = tid; e < P * K; e += kThreads) { const int p = e / K, k = e - p * K; Lt[(size_t)k * PSb + p] = raw[e]; }
+      }
+      if (P & 1)
+        for (int k = tid; k < K; k += kThreads) Lt[(size_t)k * PSb + P] = __float2bfloat16_rn(0.f);
+      __syncthreads();          // the W operand below overwrites the raw block
+    } else {
+      stage_logits_transposed(Lt, prm.logits + (long long)b * P * K, P, K, PSb, tid, kThreads);
+    }
+    for (int e = tid; e < (int)(32 * G.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
     const float sc = prm.scale_ptr[0];
     __syncthreads();
-    for (int k = tid; k < K; k += kThreads) {
-      float m = -CUDART_INF_F;
-      for (int p = 0; p < P; ++p) m = fmaxf(m, __bfloat162float(Lg[p * Ks + k]) * sc);
-      float sum = 0.f;
-      for (int p = 0; p < P; ++p) sum += expf(__bfloat162float(Lg[p * Ks + k]) * sc - m);
-      uvec[k] = m;
-      aux[k] = sum;
-    }
-    __syncthreads();
     for (int k = warp; k < K; k += kThreads / 32) {
-      const float m = uvec[k], sum = aux[k];
-      for (int p = lane; p < P; p += 32) {
-        const float w = expf(__bfloat162float(Lg[p * Ks + k]) * sc - m) / sum;
-        wout[(long long)k * P + p] = w;
-        *reinterpret_cast<__nv_bfloat16*>(Wop + umma::kmajor_offset((uint32_t)k, (uint32_t)p, 2, G.sbo2)) = __float2bfloat16_rn(w);
+      float x[8];
+      load_score_row(Lt + (size_t)k * PSb, nullptr, P, lane, x);
+      float m = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int p = 2 * (lane + 32 * (i >> 1)) + (i & 1);
+        x[i] = p < P ? x[i] * sc : -CUDART_INF_F;           // the learnable scale may have either sign
+        m = fmaxf(m, x[i]);
       }
+      m = warp_max(m);
+      const float nm2 = -m * 1.4426950408889634f;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x[i] = ex2_ftz(fmaf(x[i], 1.4426950408889634f, nm2)); sum += x[i]; }   // logits are bf16
+      const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] *= inv;
+      store_weight_row(x, wout + (long long)k * P, Wop, k, P, lane, G.sbo2);
     }
   } else if (MODE == MODE_SINKHORN) {
     // Log-domain Sinkhorn on the bf16 scores.  Row passes keep a row in registers (one shared-memory sweep: max,
