@@ -850,7 +850,10 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
 #pragma unroll
             for (int i = 0; i < 8; ++i) { f[i] = __uint_as_float(v[i]); h[i] = __uint_as_float(v[8 + i]); }
             __nv_bfloat16* dst = ob + (long long)k * C + c;
-            if (xvec && c + 16 <= C && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+            if (c + 16 <= C && ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0)) {
+              st_global32(dst, pack8(f), pack8(h));          // one STG.256: every lane writes its own output row, so a
+                                                             // store instruction costs 32 L1 wavefronts whatever its width
+            } else if (c + 16 <= C && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
               *reinterpret_cast<int4*>(dst) = pack8(f);
               *reinterpret_cast<int4*>(dst + 8) = pack8(h);
             } else {
