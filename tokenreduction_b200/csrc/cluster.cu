@@ -462,19 +462,29 @@ kmedoids_fit_kernel(const float* __restrict__ x, const float* __restrict__ token
 }
 
 // ------------------------------------------------------------------------------------------ DPC-KNN merge
-// grid (splits, B); one warp per cluster row.  Members are found by ballot over the assignment vector (ascending
-// token order) and accumulated with unfused multiply/add: the order and rounding of CPU index_add_
-// (models/dpcknn.py:122-131) => bit-identical.  CPL = 16-byte chunks per lane, all in flight per member row.
+// grid (splits, B).  Member lists of ALL clusters are built at once by a stable counting sort (rank of a token inside
+// its cluster = number of earlier tokens of the same cluster: ascending token order = the order of CPU index_add_,
+// models/dpcknn.py:122-131, so the unfused multiply/add accumulation is bit-identical).  A warp then treats the
+// member rows of its clusters (k = gw, gw + W, ...) as ONE stream and keeps MB rows in flight across cluster
+// boundaries: the rows of a cluster are spread over the image, and a large cluster (30-50 tokens on random data)
+// is otherwise a chain of dependent HBM latencies that sets the kernel time (ncu: SMs active 47 % of the duration).
+// Measured alternatives that were slower: (cluster, 128-channel slice) work items (each row is then fetched by three
+// warps at different times: 55 us vs 35 us), largest-first assignment of clusters to warps (no gain: at B=256 the
+// time is set by the SMs that hold two images, ~31 GB/s per SM).
+// CPL = 16-byte chunks per lane (0: scalar fallback).
 template <int CPL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 dpcknn_merge_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx_token,
                     const float* __restrict__ agg_weight, const int64_t* __restrict__ idx_cluster,
                     const float* __restrict__ token_weight, int P, int C, int K, int T, float* __restrict__ x_merged,
                     int64_t* __restrict__ idx_token_new, float* __restrict__ agg_weight_new) {
   extern __shared__ float smem[];
-  float* nw = smem;                                   // [P] normalised weights
+  float* nw = smem;                                   // [P] token weights, then normalised weights
   float* wsum = nw + P;                               // [K]
   int* cl = reinterpret_cast<int*>(wsum + K);         // [P] cluster of token
+  int* members = cl + P;                              // [P] tokens sorted by (cluster, token)
+  int* off = members + P;                             // [K + 1] start of each cluster's list
+  int* rk = off + K + 1;                              // [P] rank of a token inside its cluster
   const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < P; i += kThreads) {
@@ -482,11 +492,30 @@ dpcknn_merge_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx
     cl[i] = c < 0 ? 0 : (c >= K ? K - 1 : c);
     nw[i] = token_weight ? token_weight[(long long)b * P + i] : 1.f;
   }
+  for (int k = tid; k <= K; k += kThreads) off[k] = 0;
+  __syncthreads();
+  for (int i = tid; i < P; i += kThreads) {
+    const int c = cl[i];
+    int before = 0, total = 0;
+    for (int j = 0; j < P; ++j) {
+      const int same = cl[j] == c;
+      total += same;
+      before += same & (j < i);
+    }
+    rk[i] = before;
+    if (before == total - 1) off[c + 1] = total;      // the last member publishes the cluster size
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k < K; ++k) { run += off[k + 1]; off[k + 1] = run; }
+  }
+  __syncthreads();
+  for (int i = tid; i < P; i += kThreads) members[off[cl[i]] + rk[i]] = i;
   __syncthreads();
   for (int k = tid; k < K; k += kThreads) {
     float s = 0.f;
-    for (int i = 0; i < P; ++i)
-      if (cl[i] == k) s += nw[i];
+    for (int j = off[k]; j < off[k + 1]; ++j) s += nw[members[j]];
     wsum[k] = s + 1e-6f;
   }
   __syncthreads();
@@ -496,42 +525,80 @@ dpcknn_merge_kernel(const float* __restrict__ x, const int64_t* __restrict__ idx
   const float* xb = x + (long long)b * P * C;
   float* ob = x_merged + (long long)b * K * C;
   const int nchunks = C / 4;
-  for (int k = blockIdx.x * kWarps + warp; k < K; k += gridDim.x * kWarps) {
-    if constexpr (CPL > 0) {
-      float acc[CPL][4];
+  const int gw = blockIdx.x * kWarps + warp, stride = gridDim.x * kWarps;
+  if constexpr (CPL > 0) {
+    constexpr int MB = 20 / CPL > 8 ? 8 : 20 / CPL;      // rows in flight: MB * CPL 16-byte registers per lane (<= 20)
+    float acc[CPL][4];
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
-      for (int base = 0; base < P; base += 32) {
-        const int t = base + lane;
-        unsigned m = __ballot_sync(0xffffffffu, t < P && cl[t] == k);
-        while (m) {
-          const int i = base + __ffs(m) - 1;
-          m &= m - 1;
-          const float wgt = nw[i];
-          int4 raw[CPL];
+    for (int q = 0; q < CPL; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f; }
+    int k = K, knext = gw, j = 0, jend = 0;
+    auto advance = [&]() {
+      k = knext < K ? knext : K;
+      knext += stride;
+      if (k < K) { j = off[k]; jend = off[k + 1]; }
+    };
+    advance();
+    while (k < K) {
+      int tok[MB], kk[MB];
+      bool last[MB];
+#pragma unroll
+      for (int u = 0; u < MB; ++u) {
+        while (k < K && j == jend) {                   // cluster finished, or empty: an empty one still owns a zero row
+          if (off[k + 1] == off[k]) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+              const int c = lane + 32 * q;
+              if (c < nchunks) st_stream16(ob + (long long)k * C + c * 4, make_int4(0, 0, 0, 0));
+            }
+          }
+          advance();
+        }
+        if (k < K) {
+          tok[u] = members[j]; kk[u] = k; ++j; last[u] = j == jend;
+        } else {
+          tok[u] = -1; kk[u] = 0; last[u] = false;
+        }
+      }
+      int4 raw[MB][CPL];
+#pragma unroll
+      for (int u = 0; u < MB; ++u) {
+        if (tok[u] >= 0) {
 #pragma unroll
           for (int q = 0; q < CPL; ++q) {
             const int c = lane + 32 * q;
-            if (c < nchunks) raw[q] = ld_stream16(xb + (long long)i * C + c * 4);
-          }
-#pragma unroll
-          for (int q = 0; q < CPL; ++q) {
-            const float* v = reinterpret_cast<const float*>(&raw[q]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[q][e] = __fadd_rn(acc[q][e], __fmul_rn(v[e], wgt));
+            if (c < nchunks) raw[u][q] = ld_stream16(xb + (long long)tok[u] * C + c * 4);
           }
         }
       }
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        const int c = lane + 32 * q;
-        if (c < nchunks) st_stream16(ob + (long long)k * C + c * 4, *reinterpret_cast<const int4*>(acc[q]));
+      for (int u = 0; u < MB; ++u) {
+        if (tok[u] >= 0) {
+          const float wgt = nw[tok[u]];
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            const float* v = reinterpret_cast<const float*>(&raw[u][q]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[q][e] = __fadd_rn(acc[q][e], __fmul_rn(v[e], wgt));
+          }
+          if (last[u]) {
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+              const int c = lane + 32 * q;
+              if (c < nchunks) st_stream16(ob + (long long)kk[u] * C + c * 4, *reinterpret_cast<const int4*>(acc[q]));
+              acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+            }
+          }
+        }
       }
-    } else {
+    }
+  } else {
+    for (int k = gw; k < K; k += stride) {
       for (int c = lane; c < C; c += 32) {
         float acc = 0.f;
-        for (int i = 0; i < P; ++i)
-          if (cl[i] == k) acc = __fadd_rn(acc, __fmul_rn(xb[(long long)i * C + c], nw[i]));
+        for (int j = off[k]; j < off[k + 1]; ++j) {
+          const int i = members[j];
+          acc = __fadd_rn(acc, __fmul_rn(xb[(long long)i * C + c], nw[i]));
+        }
         ob[(long long)k * C + c] = acc;
       }
     }
@@ -698,10 +765,10 @@ extern "C" int tokred_dpcknn_merge(const float* x, const int64_t* idx_token, con
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 1 && K >= 1 && T >= 0, "%s: bad shape", what);
   TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
   if (B == 0) return TOKRED_OK;
-  const size_t smem = (size_t)(2 * P + K) * 4;
+  const size_t smem = (size_t)(4 * P + 2 * K + 1) * 4;
   const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(x_merged);
   const int cpl = vec ? ceil_div(C / 4, 32) : 0;
-  int splits = ceil_div(6 * kNumSMs, B);
+  int splits = (2 * kNumSMs) / B;            // one wave of resident CTAs (2 per SM; see tokred_tome_merge)
   splits = max(1, min(splits, ceil_div(K, kWarps)));
   dim3 grid(splits, B);
   cudaStream_t st = (cudaStream_t)stream;

@@ -535,7 +535,11 @@ extern "C" int tokred_tome_merge(const void* x, int x_dtype, const void* size, c
   const int ve = x_dtype == TOKRED_F32 ? 4 : 8;
   const bool vec = (C % ve == 0) && aligned16(x) && aligned16(x_out);
   const int cpl = vec ? ceil_div(C / ve, 32) : 0;
-  int splits = ceil_div(6 * kNumSMs, B);
+  // ONE wave: as many CTAs as are resident at once (4 per SM up to 3 chunks per lane, else 2), never more -- a
+  // second, partly filled wave costs more than larger CTAs do (B=256, N=197: 512 CTAs 28.7 us, 1024 CTAs 30.7 us,
+  // 2304 CTAs 32.8 us); batches beyond the resident count simply queue whole images.
+  const int resident = kNumSMs * ((cpl >= 1 && cpl <= 3) ? 4 : 2);
+  int splits = resident / B;
   splits = max(1, min(splits, ceil_div(n_out, kWarps)));
   dim3 grid(splits, B);
   cudaStream_t st = (cudaStream_t)stream;
