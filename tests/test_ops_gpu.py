@@ -499,7 +499,7 @@ def test_patchmerger_lowp(T):
 
 
 @pytest.mark.parametrize("p,k,c,lowp", [(196, 176, 768, False), (176, 158, 384, False), (196, 176, 768, True), (158, 142, 384, True),
-                                        (60, 20, 100, True), (97, 130, 200, True)])
+                                        (60, 20, 100, True), (97, 130, 200, True), (64, 21, 128, True), (200, 8, 64, True)])
 def test_sit_merge(T, p, k, c, lowp):
     b = 3
     x = torch.randn(b, p, c, generator=g(49)).to(DEV)
@@ -514,6 +514,20 @@ def test_sit_merge(T, p, k, c, lowp):
         assert_close_rel(w, w_ref, tol, f"weights tc={tc}")
         assert_close_rel(out.float(), out_ref.float(), tol, f"merged tokens tc={tc}")
         assert torch.allclose(w.sum(dim=-1), torch.ones(b, k, device=DEV), rtol=1e-4)
+
+
+def test_sit_merge_negative_scale(T):
+    """the learnable scale may go negative: padded slots of the register-row softmax must not win the row maximum."""
+    b, p, k, c = 2, 100, 24, 128
+    x = torch.randn(b, p, c, generator=g(51)).to(DEV)
+    logits = torch.randn(b, p, k, generator=g(52)).bfloat16().to(DEV)
+    scale = torch.full((1, 1, 1), -0.7, device=DEV)
+    out_ref, w_ref = O.sit_merge(x, logits, scale, lowp=torch.bfloat16)
+    for tc in (True, False):
+        out, w = T.sit_merge(x, logits, scale, True, tc)
+        assert torch.isfinite(w).all()
+        assert_close_rel(w, w_ref, RTOL16, f"weights tc={tc}")
+        assert_close_rel(out.float(), out_ref.float(), RTOL16, f"merged tokens tc={tc}")
 
 
 # ------------------------------------------------------------------------------------------------ ATS

@@ -4,15 +4,24 @@
 // stamps showed it issue-bound there (GEMM 1 staging 41 %, GEMM 2 staging + store 30 % of the kernel, tensor pipe
 // 7 % active).  v2 converts each token ONCE:
 //   pack kernel   Q [K,C] fp32 -> bf16 in the canonical K-major stage image, one contiguous block per 64-column chunk.
-//   phase 0       token statistics with the row in registers; the normalised row is rounded to bf16 and written to a
-//                 per-image scratch of CORE-MATRIX TILES  [p/8][c/8][8 rows x 16 B]  (L2-resident, 2 B/element).
-//                 The same 128-byte tile is a K-major core matrix for GEMM 1 (rows = tokens, 16 B along C) and an
-//                 MN-major core matrix for GEMM 2 (rows = the contraction index p, 16 B along the N index c).
-//   phase 1       warp 16 streams stages with cp.async.bulk (1 KB per token group + one block of Q per chunk) onto
-//                 mbarriers (expect_tx); warp 17 issues tcgen05.mma and hands stages back with tcgen05.commit.
-//   phase 2/3     as v1: accumulator -> bf16 Z in smem; Sinkhorn iterations / softmax; W -> global fp32 + bf16 A operand.
+//   phase 0       token rows stream HBM -> smem through a ring of cp.async.bulk copies (one per pair of adjacent rows,
+//                 issued by warp 16, 16-32 pairs in flight); a worker warp normalises a pair in registers, rounds it
+//                 to bf16 and writes it to a per-image scratch of CORE-MATRIX TILES  [p/8][c/8][8 rows x 16 B]
+//                 (32-byte STG.256: two tokens per lane; L2-resident, 2 B/element).  The same 128-byte tile is a
+//                 K-major core matrix for GEMM 1 (rows = tokens, 16 B along C) and an MN-major core matrix for GEMM 2
+//                 (rows = the contraction index p, 16 B along the N index c).  A ring slot is released only after a
+//                 fence.proxy.async (generic reads, then async-proxy refill).  SiT: the raw logits block is
+//                 bulk-copied in the same phase.
+//   phase 1       warp 16 streams 2-4 stages with cp.async.bulk (1 KB per token group, one lane each, + one block of
+//                 Q per chunk) onto mbarriers (expect_tx); warp 17 issues tcgen05.mma and hands stages back with
+//                 tcgen05.commit.
+//   phase 2       accumulator -> bf16 Z in smem (it IS bf16 in the reference).
+//   phase 3       weights: register-row softmax (PatchMerger; SiT after a shared -> shared transpose of its logits)
+//                 or log-domain Sinkhorn (row passes in registers, column passes split over K with an online
+//                 log-sum-exp, ex2.approx/FMA exponentials); W -> global fp32 + bf16 A operand of GEMM 2.
 //   phase 4       same producer / MMA warps: B operand = 2 KB tile segments used MN-major; 16 worker warps drain two
-//                 TMEM accumulator sets (tcgen05.ld) and store bf16 rows while the next chunk's MMAs run.
+//                 TMEM accumulator sets (tcgen05.ld) and store bf16 rows (STG.256) while the next chunk's MMAs run.
+// Measured steps and dead ends: profiles/softmerge_phases_r01.txt, DESIGN.md section 7.
 // 576 threads: warps 0-15 workers, warp 16 copy producer, warp 17 MMA issuer.
 #include <math_constants.h>
 
