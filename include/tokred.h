@@ -93,17 +93,21 @@ TOKRED_API int tokred_tome_merge(const void* x, int x_dtype, const void* size, c
 TOKRED_API int tokred_pairwise_dist(const float* x, int B, int P, int C, float post_scale, int exact_fp32, float* out,
                                     void* stream);
 
+/* x_batch_stride (a6-a9, a12, a13): elements between consecutive images of x; 0 = dense (P*C).  The reference hands
+ * these operators x[:, 1:] (class token dropped: models/dpcknn.py:259, kmedoids.py:241, sinkhorn.py:167, patchmerger.py:118, sit.py:118): rows stay
+ * C apart but images are (P+1)*C apart, and the stride lets the kernels read that view in place instead of a copy. */
+
 /* ---- a6 DPC-KNN clustering ---------------------------------------------------------------------------
  * models/dpcknn.py:44-100 cluster_dpc_knn (token_mask=None).
  *   x [B,P,C] fp32; noise_u [B,P] fp32 ~ U(0,1) drawn by the caller with the reference's torch.rand call
  *   idx_cluster [B,P] int64, index_down [B,K] int64 (descending centre score)                           */
-TOKRED_API int tokred_dpcknn_cluster(const float* x, const float* noise_u, int B, int P, int C, int K, int knn,
+TOKRED_API int tokred_dpcknn_cluster(const float* x, int64_t x_batch_stride, const float* noise_u, int B, int P, int C, int K, int knn,
                                      int exact_fp32, int64_t* idx_cluster, int64_t* index_down, void* stream);
 
 /* ---- a7 DPC-KNN merge --------------------------------------------------------------------------------
  * models/dpcknn.py:103-140 merge_tokens.  token_weight [B,P] fp32 or NULL (= ones); idx_token [B,T] int64;
  * agg_weight [B,T] fp32 -> x_merged [B,K,C], idx_token_new [B,T], agg_weight_new [B,T].                 */
-TOKRED_API int tokred_dpcknn_merge(const float* x, const int64_t* idx_token, const float* agg_weight,
+TOKRED_API int tokred_dpcknn_merge(const float* x, int64_t x_batch_stride, const int64_t* idx_token, const float* agg_weight,
                         const int64_t* idx_cluster, const float* token_weight, int B, int P, int C, int K, int T,
                         float* x_merged, int64_t* idx_token_new, float* agg_weight_new, void* stream);
 
@@ -113,7 +117,7 @@ TOKRED_API int tokred_attn_colsum(const void* attn, int attn_dtype, int B, int H
                        void* stream);
 /* models/kmedoids.py:62-85 k_medoids_fit with token weights (topk init, iters x {assign, re-centre}).
  *   x [B,P,C] fp32, token_weight [B,P] fp32 -> centres [B,K,C], cluster_idx [B,K] int64, assignment [B,P] int64 */
-TOKRED_API int tokred_kmedoids_fit(const float* x, const float* token_weight, int B, int P, int C, int K, int iters,
+TOKRED_API int tokred_kmedoids_fit(const float* x, int64_t x_batch_stride, const float* token_weight, int B, int P, int C, int K, int iters,
                                    int exact_fp32, float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream);
 
 /* Scratch for the bulk-copy fed tensor-core path of the three soft merges (a9, a12, a13): the caller passes a device
@@ -127,20 +131,20 @@ TOKRED_API size_t tokred_soft_merge_workspace_bytes(int B, int P, int C, int K);
  *   lowp = 1: both contractions round operands/result to bf16 (CUDA autocast) and run on tcgen05 tensor cores
  *   when out_dtype is bf16; lowp = 3: same rounding on the FFMA path (cross-check); lowp = 0: exact fp32 (FFMA).
  *   out [B,K,C], weights [B,K,P] fp32                                                                   */
-TOKRED_API int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_hat, int B, int P, int C, int K, float eps,
+TOKRED_API int tokred_sinkhorn_merge(const void* x, int x_dtype, int64_t x_batch_stride, const float* v_hat, int B, int P, int C, int K, float eps,
                           float log_norm, int iters, int lowp, void* out, int out_dtype, float* weights,
                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a12 PatchMerger ---------------------------------------------------------------------------------
  * models/patchmerger.py:35-39: LayerNorm -> queries x^T * scale -> softmax over tokens -> attn x.       */
-TOKRED_API int tokred_patchmerger(const void* x, int x_dtype, const float* ln_weight, const float* ln_bias,
+TOKRED_API int tokred_patchmerger(const void* x, int x_dtype, int64_t x_batch_stride, const float* ln_weight, const float* ln_bias,
                        const float* queries, int B, int P, int C, int K, float scale, float ln_eps, int lowp,
                        void* out, int out_dtype, float* attn, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a13 SiT -----------------------------------------------------------------------------------------
  * models/sit.py:37-40: w = softmax(logits * scale, over tokens)^T ; out = w x.  logits [B,P,K];
  * scale = device pointer to the module's 1-element fp32 parameter (no host read).                       */
-TOKRED_API int tokred_sit_merge(const void* x, int x_dtype, const void* logits, int logits_dtype, const float* scale, int B,
+TOKRED_API int tokred_sit_merge(const void* x, int x_dtype, int64_t x_batch_stride, const void* logits, int logits_dtype, const float* scale, int B,
                      int P, int C, int K, int lowp, void* out, int out_dtype, float* weights, void* workspace,
                      size_t workspace_bytes, void* stream);
 

@@ -57,7 +57,9 @@ def test_host_side_argument_errors_need_no_gpu():
     with pytest.raises(_lib.TokredError, match="null tensor"):
         _lib.call("tokred_topk_gather", None, 0, None, 0, 1, 196, None, 0, 0, 2, 197, 64, 10, None, None, None)
     with pytest.raises(_lib.TokredError, match="argument"):
-        _lib.call("tokred_dpcknn_cluster", 16, 16, 2, 196, 64, 300, 5, 0, 16, 16, None)      # K > P
+        _lib.call("tokred_dpcknn_cluster", 16, 0, 16, 2, 196, 64, 300, 5, 0, 16, 16, None)      # K > P
+    with pytest.raises(_lib.TokredError, match="x_batch_stride"):
+        _lib.call("tokred_dpcknn_cluster", 16, 100, 16, 2, 196, 64, 49, 5, 0, 16, 16, None)     # images overlap
     # empty batch is a no-op even with null tensors
     _lib.call("tokred_topk_gather", None, 0, None, 0, 1, 196, None, 0, 0, 0, 197, 64, 10, None, None, None)
 

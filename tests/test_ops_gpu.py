@@ -530,6 +530,47 @@ def test_sit_merge_negative_scale(T):
         assert_close_rel(out.float(), out_ref.float(), RTOL16, f"merged tokens tc={tc}")
 
 
+def test_batch_strided_tokens_are_read_in_place(T):
+    """x[:, 1:] (class token dropped -- what the cluster / soft-merge layers receive, e.g. models/dpcknn.py:259) is
+    passed with its batch stride instead of being copied: results must equal those on the contiguous copy bit for bit."""
+    b, n, c, k = 5, 197, 384, 49
+    full = torch.randn(b, n, c, generator=g(700)).to(DEV)
+    view, dense = full[:, 1:], full[:, 1:].contiguous()
+    assert not view.is_contiguous() and T._rows(view)[1] == n * c
+    noise = torch.rand(b, n - 1, generator=g(701)).to(DEV)
+    tw = (torch.rand(b, n - 1, 1, generator=g(702)) + 0.5).to(DEV)
+    for exact in (False, True):
+        a, bb = T.dpcknn_cluster(view, noise, k, 5, exact), T.dpcknn_cluster(dense, noise, k, 5, exact)
+        assert all(torch.equal(u, v) for u, v in zip(a, bb))
+        a, bb = T.kmedoids_fit(view, tw, k, 3, exact), T.kmedoids_fit(dense, tw, k, 3, exact)
+        assert all(torch.equal(u, v) for u, v in zip(a, bb))
+    ic, _ = T.dpcknn_cluster(dense, noise, k, 5)
+    idx_token = torch.arange(n - 1, device=DEV).repeat(b, 1)
+    agg = torch.ones(b, n - 1, 1, device=DEV)
+    a, bb = T.dpcknn_merge(view, idx_token, agg, ic, tw, k), T.dpcknn_merge(dense, idx_token, agg, ic, tw, k)
+    assert all(torch.equal(u, v) for u, v in zip(a, bb))
+    c2, kk = 768, 176
+    full = torch.randn(b, n, c2, generator=g(703)).to(DEV)
+    view, dense = full[:, 1:], full[:, 1:].contiguous()
+    v = torch.nn.functional.normalize(torch.randn(kk, c2, generator=g(704)), dim=-1).to(DEV)
+    lw, lb = torch.ones(c2, device=DEV), torch.zeros(c2, device=DEV)
+    q = (torch.randn(kk, c2, generator=g(705)) * 0.05).to(DEV)
+    logits = torch.randn(b, n - 1, kk, generator=g(706)).to(DEV)
+    scale = torch.full((1,), 1.1, device=DEV)
+    for lowp, tc in ((False, False), (True, False), (True, True)):
+        lg = logits.bfloat16() if lowp else logits
+        for fn in (lambda t: T.sinkhorn_merge(t, v, 1.0, 3, lowp, tc), lambda t: T.patchmerger(t, lw, lb, q, 1.0, 1e-5, lowp, tc),
+                   lambda t: T.sit_merge(t, lg, scale, lowp, tc)):
+            a, bb = fn(view), fn(dense)
+            assert all(torch.equal(u, w) for u, w in zip(a, bb)), f"lowp={lowp} tc={tc}"
+    T.SOFT_MERGE_SCRATCH = False
+    try:
+        a, bb = T.sinkhorn_merge(view, v, 1.0, 3, True, True), T.sinkhorn_merge(dense, v, 1.0, 3, True, True)
+    finally:
+        T.SOFT_MERGE_SCRATCH = True
+    assert all(torch.equal(u, w) for u, w in zip(a, bb))
+
+
 # ------------------------------------------------------------------------------------------------ ATS
 def ats_cdf64(v, attn, mask):
     """float64 CDF of models/ats.py:53-70 (CPU)."""

@@ -24,13 +24,13 @@ SIGNATURES = {
     "tokred_tome_match": [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tokred_tome_merge": [_P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P],
     "tokred_pairwise_dist": [_P, c_int, c_int, c_int, c_float, c_int, _P, _P],
-    "tokred_dpcknn_cluster": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
-    "tokred_dpcknn_merge": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "tokred_dpcknn_cluster": [_P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],
+    "tokred_dpcknn_merge": [_P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tokred_attn_colsum": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
-    "tokred_kmedoids_fit": [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
-    "tokred_sinkhorn_merge": [_P, c_int, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P],
-    "tokred_patchmerger": [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, _P, c_int, _P, _P, c_size_t, _P],
-    "tokred_sit_merge": [_P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P],
+    "tokred_kmedoids_fit": [_P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "tokred_sinkhorn_merge": [_P, c_int, c_int64, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P],
+    "tokred_patchmerger": [_P, c_int, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, _P, c_int, _P, _P, c_size_t, _P],
+    "tokred_sit_merge": [_P, c_int, c_int64, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P],
     "tokred_soft_merge_workspace_bytes": [c_int, c_int, c_int, c_int],
     "tokred_ats_sample": [_P, c_int, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P],
     "tokred_gather_rows": [_P, c_int, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P],

@@ -26,7 +26,8 @@ constexpr int CT = 128;    // output columns per pass of the second contraction
 enum { MODE_SINKHORN = 0, MODE_PATCHMERGER = 1, MODE_SIT = 2 };
 
 struct SoftParams {
-  const void* x;            // [B,P,C]
+  const void* x;            // [B,P,C], images xbs elements apart
+  long long xbs;
   const float* q;           // [K,C]   (sinkhorn: v_hat, patchmerger: queries)
   const void* logits;       // [B,P,K] (sit)
   int logits_dtype;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_kernel(SoftParams prm)
   float* uvec = s1 + P;                  // [K]
   float* vvec = uvec + K;                // [P]
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const T* xb = reinterpret_cast<const T*>(prm.x) + (long long)b * P * C;
+  const T* xb = reinterpret_cast<const T*>(prm.x) + (long long)b * prm.xbs;
 
   // ---- 1. per-token statistics
   if (MODE == MODE_SINKHORN) {
@@ -309,11 +310,12 @@ int check_soft(const char* what, int B, int P, int C, int K, int x_dtype, int ou
 namespace tokred {
 int launch_soft_merge_tc(int mode, const void* x, int x_dtype, const float* q, const float* ln_w, const float* ln_b,
                          int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
-                         float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr);
+                         float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr,
+                         long long xbs);
 int launch_soft_merge_tc2(int mode, const void* x, int x_dtype, const float* q, const float* ln_w, const float* ln_b,
                           int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
                           float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr,
-                          void* workspace, size_t workspace_bytes);
+                          void* workspace, size_t workspace_bytes, long long xbs);
 size_t soft_merge_tc2_workspace_bytes(int B, int P, int C, int K);
 }
 using namespace tokred;
@@ -323,30 +325,32 @@ extern "C" size_t tokred_soft_merge_workspace_bytes(int B, int P, int C, int K) 
   return soft_merge_tc2_workspace_bytes(B, P, C, K);
 }
 
-extern "C" int tokred_sinkhorn_merge(const void* x, int x_dtype, const float* v_hat, int B, int P, int C, int K,
+extern "C" int tokred_sinkhorn_merge(const void* x, int x_dtype, int64_t x_batch_stride, const float* v_hat, int B, int P, int C, int K,
                                      float eps, float log_norm, int iters, int lowp, void* out, int out_dtype,
                                      float* weights, void* workspace, size_t workspace_bytes, void* stream) {
   const char* what = "tokred_sinkhorn_merge";
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && v_hat && out && weights, "%s: null tensor", what);
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
+  TOKRED_REQUIRE(x_batch_stride == 0 || x_batch_stride >= (int64_t)P * C, "%s: x_batch_stride=%lld < P*C", what, (long long)x_batch_stride);
+  const long long xbs = x_batch_stride ? (long long)x_batch_stride : (long long)P * C;
   TOKRED_REQUIRE(eps > 0.f && iters >= 0, "%s: eps=%g iters=%d", what, (double)eps, iters);
   if (B == 0) return TOKRED_OK;
   if (lowp == 1 && out_dtype == TOKRED_BF16) {     // bf16 autocast semantics on tcgen05 tensor cores
     const int rc2 = launch_soft_merge_tc2(MODE_SINKHORN, x, x_dtype, v_hat, nullptr, nullptr, B, P, C, K, 1.0f / eps, log_norm,
-                                          0.f, iters, out, weights, stream, what, nullptr, nullptr, workspace, workspace_bytes);
+                                          0.f, iters, out, weights, stream, what, nullptr, nullptr, workspace, workspace_bytes, xbs);
     if (rc2 != 1) return rc2;
     const int rc = launch_soft_merge_tc(MODE_SINKHORN, x, x_dtype, v_hat, nullptr, nullptr, B, P, C, K, 1.0f / eps, log_norm,
-                                        0.f, iters, out, weights, stream, what, nullptr, nullptr);
+                                        0.f, iters, out, weights, stream, what, nullptr, nullptr, xbs);
     if (rc != 1) return rc;
   }
   SoftParams prm{};
-  prm.x = x; prm.q = v_hat; prm.scale = 1.0f / eps; prm.log_norm = log_norm; prm.iters = iters; prm.lowp = lowp ? 1 : 0;
+  prm.x = x; prm.xbs = xbs; prm.q = v_hat; prm.scale = 1.0f / eps; prm.log_norm = log_norm; prm.iters = iters; prm.lowp = lowp ? 1 : 0;
   prm.P = P; prm.C = C; prm.K = K; prm.out = out; prm.weights = weights;
   return launch_soft<MODE_SINKHORN>(prm, B, x_dtype, out_dtype, what, stream);
 }
 
-extern "C" int tokred_patchmerger(const void* x, int x_dtype, const float* ln_weight, const float* ln_bias,
+extern "C" int tokred_patchmerger(const void* x, int x_dtype, int64_t x_batch_stride, const float* ln_weight, const float* ln_bias,
                                   const float* queries, int B, int P, int C, int K, float scale, float ln_eps, int lowp,
                                   void* out, int out_dtype, float* attn, void* workspace, size_t workspace_bytes,
                                   void* stream) {
@@ -354,22 +358,24 @@ extern "C" int tokred_patchmerger(const void* x, int x_dtype, const float* ln_we
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && ln_weight && ln_bias && queries && out && attn, "%s: null tensor", what);
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
+  TOKRED_REQUIRE(x_batch_stride == 0 || x_batch_stride >= (int64_t)P * C, "%s: x_batch_stride=%lld < P*C", what, (long long)x_batch_stride);
+  const long long xbs = x_batch_stride ? (long long)x_batch_stride : (long long)P * C;
   if (B == 0) return TOKRED_OK;
   if (lowp == 1 && out_dtype == TOKRED_BF16) {
     const int rc2 = launch_soft_merge_tc2(MODE_PATCHMERGER, x, x_dtype, queries, ln_weight, ln_bias, B, P, C, K, scale, 0.f,
-                                          ln_eps, 0, out, attn, stream, what, nullptr, nullptr, workspace, workspace_bytes);
+                                          ln_eps, 0, out, attn, stream, what, nullptr, nullptr, workspace, workspace_bytes, xbs);
     if (rc2 != 1) return rc2;
     const int rc = launch_soft_merge_tc(MODE_PATCHMERGER, x, x_dtype, queries, ln_weight, ln_bias, B, P, C, K, scale, 0.f,
-                                        ln_eps, 0, out, attn, stream, what, nullptr, nullptr);
+                                        ln_eps, 0, out, attn, stream, what, nullptr, nullptr, xbs);
     if (rc != 1) return rc;
   }
   SoftParams prm{};
-  prm.x = x; prm.q = queries; prm.ln_w = ln_weight; prm.ln_b = ln_bias; prm.scale = scale; prm.ln_eps = ln_eps;
+  prm.x = x; prm.xbs = xbs; prm.q = queries; prm.ln_w = ln_weight; prm.ln_b = ln_bias; prm.scale = scale; prm.ln_eps = ln_eps;
   prm.lowp = lowp ? 1 : 0; prm.P = P; prm.C = C; prm.K = K; prm.out = out; prm.weights = attn;
   return launch_soft<MODE_PATCHMERGER>(prm, B, x_dtype, out_dtype, what, stream);
 }
 
-extern "C" int tokred_sit_merge(const void* x, int x_dtype, const void* logits, int logits_dtype, const float* scale,
+extern "C" int tokred_sit_merge(const void* x, int x_dtype, int64_t x_batch_stride, const void* logits, int logits_dtype, const float* scale,
                                 int B, int P, int C, int K, int lowp, void* out, int out_dtype, float* weights,
                                 void* workspace, size_t workspace_bytes, void* stream) {
   const char* what = "tokred_sit_merge";
@@ -377,20 +383,22 @@ extern "C" int tokred_sit_merge(const void* x, int x_dtype, const void* logits, 
   TOKRED_REQUIRE(x && logits && scale && out && weights, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(logits_dtype), "%s: bad logits dtype", what);
   if (int e = check_soft(what, B, P, C, K, x_dtype, out_dtype)) return e;
+  TOKRED_REQUIRE(x_batch_stride == 0 || x_batch_stride >= (int64_t)P * C, "%s: x_batch_stride=%lld < P*C", what, (long long)x_batch_stride);
+  const long long xbs = x_batch_stride ? (long long)x_batch_stride : (long long)P * C;
   if (B == 0) return TOKRED_OK;
   if (lowp == 1 && out_dtype == TOKRED_BF16 && logits_dtype == TOKRED_BF16) {
     // bulk-copy fed kernel first (needs the workspace); the scratch-free one covers callers without a workspace
     {
       const int rc2 = launch_soft_merge_tc2(MODE_SIT, x, x_dtype, nullptr, nullptr, nullptr, B, P, C, K, 1.f, 0.f, 0.f, 0, out,
-                                            weights, stream, what, logits, scale, workspace, workspace_bytes);
+                                            weights, stream, what, logits, scale, workspace, workspace_bytes, xbs);
       if (rc2 != 1) return rc2;
     }
     const int rc = launch_soft_merge_tc(MODE_SIT, x, x_dtype, nullptr, nullptr, nullptr, B, P, C, K, 1.f, 0.f, 0.f, 0, out,
-                                        weights, stream, what, logits, scale);
+                                        weights, stream, what, logits, scale, xbs);
     if (rc != 1) return rc;
   }
   SoftParams prm{};
-  prm.x = x; prm.logits = logits; prm.logits_dtype = logits_dtype; prm.scale_ptr = scale; prm.lowp = lowp ? 1 : 0;
+  prm.x = x; prm.xbs = xbs; prm.logits = logits; prm.logits_dtype = logits_dtype; prm.scale_ptr = scale; prm.lowp = lowp ? 1 : 0;
   prm.P = P; prm.C = C; prm.K = K; prm.out = out; prm.weights = weights;
   return launch_soft<MODE_SIT>(prm, B, x_dtype, out_dtype, what, stream);
 }

@@ -31,7 +31,8 @@ constexpr int kMaxK = 208, kMaxP = 208;
 enum { MODE_SINKHORN = 0, MODE_PATCHMERGER = 1, MODE_SIT = 2 };
 
 struct TcParams {
-  const void* x;            // [B,P,C]
+  const void* x;            // [B,P,C], images xbs elements apart
+  long long xbs;
   const float* q;           // [K,C]
   const float* ln_w;
   const float* ln_b;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const T* xb = reinterpret_cast<const T*>(prm.x) + (long long)b * P * C;
+  const T* xb = reinterpret_cast<const T*>(prm.x) + (long long)b * prm.xbs;
   const bool xvec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0);
   const bool qvec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(prm.q) & 15u) == 0);
 
@@ -534,12 +535,13 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc_kernel(TcParams prm
 // returns TOKRED_OK after launching, or 1 if the shape is outside what this kernel covers (caller falls back to FFMA)
 int launch_soft_merge_tc(int mode, const void* x, int x_dtype, const float* q, const float* ln_w, const float* ln_b,
                          int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
-                         float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr) {
+                         float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr,
+                         long long xbs) {
   if (P > kMaxP || K > kMaxK || P < 8 || K < 1) return 1;
   const Layout L = make_layout(P, K, C);
   if (L.total > 227 * 1024) return 1;
   TcParams prm{};
-  prm.x = x; prm.q = q; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.scale = scale; prm.log_norm = log_norm; prm.ln_eps = ln_eps;
+  prm.x = x; prm.xbs = xbs; prm.q = q; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.scale = scale; prm.log_norm = log_norm; prm.ln_eps = ln_eps;
   prm.iters = iters; prm.P = P; prm.C = C; prm.K = K; prm.out = (__nv_bfloat16*)out; prm.weights = weights;
   prm.logits = (const __nv_bfloat16*)logits; prm.scale_ptr = scale_ptr;
   prm.dbg = g_phase_dbg;

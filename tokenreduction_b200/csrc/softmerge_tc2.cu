@@ -101,7 +101,8 @@ __host__ __device__ inline Geo make_geo(int P, int C, int K) {
 }
 
 struct Tc2Params {
-  const void* x;                  // [B,P,C]
+  const void* x;                  // [B,P,C], images xbs elements apart
+  long long xbs;
   const unsigned char* q_packed;  // pack kernel output
   unsigned char* xh;              // [B] x img_bytes scratch tiles
   const float* ln_w;
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
 
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool worker = warp < kWWarps;
-  const T* xb = reinterpret_cast<const T*>(prm.x) + (long long)b * P * C;
+  const T* xb = reinterpret_cast<const T*>(prm.x) + (long long)b * prm.xbs;
   unsigned char* xh = prm.xh + (size_t)b * G.img_bytes;
   const bool xvec = (C % 8 == 0) && ((reinterpret_cast<uintptr_t>(xb) & (8 * sizeof(T) - 1)) == 0);
 
@@ -898,7 +899,7 @@ size_t soft_merge_tc2_workspace_bytes(int B, int P, int C, int K) {
 int launch_soft_merge_tc2(int mode, const void* x, int x_dtype, const float* q, const float* ln_w, const float* ln_b,
                           int B, int P, int C, int K, float scale, float log_norm, float ln_eps, int iters, void* out,
                           float* weights, void* stream, const char* what, const void* logits, const float* scale_ptr,
-                          void* workspace, size_t workspace_bytes) {
+                          void* workspace, size_t workspace_bytes, long long xbs) {
   if (P > kMaxP || K > kMaxK || P < 8 || K < 1 || C > 1024 || C % 8 != 0) return 1;
   if (!workspace || workspace_bytes < soft_merge_tc2_workspace_bytes(B, P, C, K)) return 1;
   if (reinterpret_cast<uintptr_t>(workspace) & 127u) return 1;
@@ -912,7 +913,7 @@ int launch_soft_merge_tc2(int mode, const void* x, int x_dtype, const float* q, 
     if (int e = finish_launch(what)) return e;
   }
   Tc2Params prm{};
-  prm.x = x; prm.q_packed = qp; prm.xh = xh; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.logits = (const __nv_bfloat16*)logits;
+  prm.x = x; prm.xbs = xbs; prm.q_packed = qp; prm.xh = xh; prm.ln_w = ln_w; prm.ln_b = ln_b; prm.logits = (const __nv_bfloat16*)logits;
   prm.scale_ptr = scale_ptr; prm.scale = scale; prm.log_norm = log_norm; prm.ln_eps = ln_eps; prm.iters = iters;
   prm.P = P; prm.C = C; prm.K = K; prm.out = (__nv_bfloat16*)out; prm.weights = weights;
   prm.dbg = g_phase_dbg;

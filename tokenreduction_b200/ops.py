@@ -63,6 +63,18 @@ def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _rows(x: Tensor) -> Tuple[Tensor, int]:
+    """[B,P,C] token tensor for the entry points that take x_batch_stride: a view whose rows are dense and C apart
+    (x[:, 1:] of a contiguous [B,N,C] tensor -- what the cluster / soft-merge layers receive) is passed in place with
+    its batch stride in elements; anything else is made contiguous (stride 0 = dense)."""
+    b, p, c = x.shape
+    if x.is_contiguous():
+        return x, 0
+    if b > 0 and p > 0 and x.stride(2) == 1 and x.stride(1) == c and (b == 1 or x.stride(0) >= p * c):
+        return x, int(x.stride(0)) if b > 1 else 0
+    return x.contiguous(), 0
+
+
 # ----------------------------------------------------------------------------------------------- Top-K / DyViT
 @torch.library.custom_op("tokred::topk_gather", mutates_args=(), device_types="cuda")
 def _topk_gather(x: Tensor, scores: Tensor, k: int) -> Tuple[Tensor, Tensor]:
@@ -277,12 +289,12 @@ def _dpcknn_cluster(x: Tensor, noise_u: Tensor, cluster_num: int, knn: int, exac
     b, p, c = x.shape
     if x.dtype != torch.float32:
         x = x.float()     # cdist runs in fp32 under autocast
-    x, noise_u = _c(x), _c(noise_u.float())
+    (x, xbs), noise_u = _rows(x), _c(noise_u.float())
     if noise_u.shape != (b, p):
         raise TokredError(f"dpcknn_cluster: noise {tuple(noise_u.shape)} != {(b, p)}")
     idx_cluster = torch.empty((b, p), dtype=torch.int64, device=x.device)
     index_down = torch.empty((b, cluster_num), dtype=torch.int64, device=x.device)
-    _lib.call("tokred_dpcknn_cluster", _ptr(x), _ptr(noise_u), b, p, c, cluster_num, knn, int(exact_fp32), _ptr(idx_cluster),
+    _lib.call("tokred_dpcknn_cluster", _ptr(x), xbs, _ptr(noise_u), b, p, c, cluster_num, knn, int(exact_fp32), _ptr(idx_cluster),
               _ptr(index_down), _stream())
     return idx_cluster, index_down
 
@@ -301,13 +313,13 @@ def _dpcknn_merge(x: Tensor, idx_token: Tensor, agg_weight: Tensor, idx_cluster:
     t = idx_token.shape[1]
     if x.dtype != torch.float32:
         raise TokredError("dpcknn_merge: x must be float32 (the residual stream is fp32 under autocast)")
-    x, idx_token, idx_cluster = _c(x), _c(idx_token), _c(idx_cluster)
+    (x, xbs), idx_token, idx_cluster = _rows(x), _c(idx_token), _c(idx_cluster)
     agg = _c(agg_weight.float())
     tw = None if token_weight is None else _c(token_weight.float())
     merged = torch.empty((b, cluster_num, c), dtype=torch.float32, device=x.device)
     idx_token_new = torch.empty((b, t), dtype=torch.int64, device=x.device)
     agg_new = torch.empty((b, t, 1), dtype=torch.float32, device=x.device)
-    _lib.call("tokred_dpcknn_merge", _ptr(x), _ptr(idx_token), _ptr(agg), _ptr(idx_cluster), _ptr(tw), b, p, c,
+    _lib.call("tokred_dpcknn_merge", _ptr(x), xbs, _ptr(idx_token), _ptr(agg), _ptr(idx_cluster), _ptr(tw), b, p, c,
               cluster_num, t, _ptr(merged), _ptr(idx_token_new), _ptr(agg_new), _stream())
     return merged, idx_token_new, agg_new
 
@@ -357,11 +369,11 @@ def _kmedoids_fit(x: Tensor, token_weight: Tensor, cluster_num: int, iters: int,
         raise TokredError("kmedoids_fit: x must be float32 (cdist runs in fp32)")
     if token_weight.numel() != b * p:
         raise TokredError(f"kmedoids_fit: token_weight {tuple(token_weight.shape)} does not match x")
-    x, tw = _c(x), _c(token_weight.float())
+    (x, xbs), tw = _rows(x), _c(token_weight.float())
     centres = torch.empty((b, cluster_num, c), dtype=torch.float32, device=x.device)
     cidx = torch.empty((b, cluster_num), dtype=torch.int64, device=x.device)
     assign = torch.empty((b, p), dtype=torch.int64, device=x.device)
-    _lib.call("tokred_kmedoids_fit", _ptr(x), _ptr(tw), b, p, c, cluster_num, iters, int(exact_fp32), _ptr(centres), _ptr(cidx),
+    _lib.call("tokred_kmedoids_fit", _ptr(x), xbs, _ptr(tw), b, p, c, cluster_num, iters, int(exact_fp32), _ptr(centres), _ptr(cidx),
               _ptr(assign), _stream())
     return centres, cidx, assign
 
@@ -423,12 +435,12 @@ def _sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool
     k = v_hat.shape[0]
     if v_hat.shape != (k, c):
         raise TokredError("sinkhorn_merge: v_hat must be [K,C]")
-    x, v_hat = _c(x), _c(v_hat.float())
+    (x, xbs), v_hat = _rows(x), _c(v_hat.float())
     odt = _soft_out_dtype(x, lowp)
     out = torch.empty((b, k, c), dtype=odt, device=x.device)
     weights = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
     ws, ws_bytes = _soft_workspace(x, b, p, c, k, lowp, tensor_cores)
-    _lib.call("tokred_sinkhorn_merge", _ptr(x), _dt(x), _ptr(v_hat), b, p, c, k, float(eps),
+    _lib.call("tokred_sinkhorn_merge", _ptr(x), _dt(x), xbs, _ptr(v_hat), b, p, c, k, float(eps),
               sinkhorn_log_norm(k, p, torch.bfloat16 if lowp else x.dtype), iters, _lowp_mode(lowp, tensor_cores), _ptr(out), _dt(out),
               _ptr(weights), _ptr(ws), ws_bytes, _stream())
     return out, weights
@@ -449,13 +461,13 @@ def _patchmerger(x: Tensor, ln_weight: Tensor, ln_bias: Tensor, queries: Tensor,
     k = queries.shape[0]
     if queries.shape != (k, c) or ln_weight.numel() != c or ln_bias.numel() != c:
         raise TokredError("patchmerger: parameter shapes do not match x")
-    x, queries = _c(x), _c(queries.float())
+    (x, xbs), queries = _rows(x), _c(queries.float())
     lw, lb = _c(ln_weight.float()), _c(ln_bias.float())
     odt = _soft_out_dtype(x, lowp)
     out = torch.empty((b, k, c), dtype=odt, device=x.device)
     attn = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
     ws, ws_bytes = _soft_workspace(x, b, p, c, k, lowp, tensor_cores)
-    _lib.call("tokred_patchmerger", _ptr(x), _dt(x), _ptr(lw), _ptr(lb), _ptr(queries), b, p, c, k, float(scale),
+    _lib.call("tokred_patchmerger", _ptr(x), _dt(x), xbs, _ptr(lw), _ptr(lb), _ptr(queries), b, p, c, k, float(scale),
               float(ln_eps), _lowp_mode(lowp, tensor_cores), _ptr(out), _dt(out), _ptr(attn), _ptr(ws), ws_bytes, _stream())
     return out, attn
 
@@ -474,7 +486,7 @@ def _sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool, tensor_core
     k = logits.shape[2]
     if logits.shape != (b, p, k):
         raise TokredError("sit_merge: logits must be [B,P,K]")
-    x, logits = _c(x), _c(logits)
+    (x, xbs), logits = _rows(x), _c(logits)
     if scale.numel() != 1:
         raise TokredError("sit_merge: scale must hold one element")
     scale = _c(scale.detach().float().reshape(1))
@@ -482,7 +494,7 @@ def _sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool, tensor_core
     out = torch.empty((b, k, c), dtype=odt, device=x.device)
     w = torch.empty((b, k, p), dtype=torch.float32, device=x.device)
     ws, ws_bytes = _soft_workspace(x, b, p, c, k, lowp, tensor_cores)
-    _lib.call("tokred_sit_merge", _ptr(x), _dt(x), _ptr(logits), _dt(logits), _ptr(scale), b, p, c, k, _lowp_mode(lowp, tensor_cores),
+    _lib.call("tokred_sit_merge", _ptr(x), _dt(x), xbs, _ptr(logits), _dt(logits), _ptr(scale), b, p, c, k, _lowp_mode(lowp, tensor_cores),
               _ptr(out), _dt(out), _ptr(w), _ptr(ws), ws_bytes, _stream())
     return out, w
 
