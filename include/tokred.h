@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOKRED_ABI_VERSION 1
+#define TOKRED_ABI_VERSION 2   /* 2: x_batch_stride on a6-a9, a12, a13 */
 #define TOKRED_API __attribute__((visibility("default")))
 
 enum { TOKRED_F32 = 0, TOKRED_BF16 = 1 };
