@@ -113,64 +113,83 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ algorithmic bytes
+_ABI_ARGS = None
+
+
+def abi_arg_names():
+    """{entry point: [parameter names]} parsed from include/tokred.h, so that the byte formulas below address the
+    ctypes argument tuples by NAME (a positional table silently broke when x_batch_stride joined six signatures)."""
+    global _ABI_ARGS
+    if _ABI_ARGS is None:
+        import re
+        text = open(os.path.join(ROOT, "include", "tokred.h")).read()
+        text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+        _ABI_ARGS = {}
+        for m in re.finditer(r"TOKRED_API\s+[\w\s\*]+?\b(tokred_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+            params = [q.strip() for q in m.group(2).split(",") if q.strip() and q.strip() != "void"]
+            _ABI_ARGS[m.group(1)] = [re.findall(r"\w+", q)[-1] for q in params]
+    return _ABI_ARGS
+
+
 def algorithmic_bytes(name: str, a: tuple) -> float:
     """Bytes one launch must move (inputs read once + outputs written once), from the ctypes argument tuple.
-    Formulas: SURVEY.md §8(d) / DESIGN.md §4."""
+    Formulas: SURVEY.md §8(d) / DESIGN.md §3."""
+    names = abi_arg_names().get(name)
+    if not names or len(names) != len(a):
+        return 0.0
+    g = dict(zip(names, a))
+
     def esz(dt):
         return 2 if dt == 1 else 4
     if name == "tokred_tome_match":
-        _, mdt, b, n, d, r = a[0], a[1], a[2], a[3], a[4], a[5]
+        n, r = g["N"], g["r"]
         na = (n + 1) // 2
-        re = min(r, (n - 1) // 2)
-        return b * (n * d * esz(mdt) + 8 * (na - re) + 16 * re)
+        re_ = min(r, (n - 1) // 2)
+        return g["B"] * (n * g["D"] * esz(g["metric_dtype"]) + 8 * (na - re_) + 16 * re_)
     if name == "tokred_tome_merge":
-        xdt, size, b, n, c, r, rci = a[1], a[2], a[6], a[7], a[8], a[9], a[12]
-        e = esz(xdt)
+        n, c, r, e = g["N"], g["C"], g["r"], esz(g["x_dtype"])
         na = (n + 1) // 2
         total = n * c * e + (n - r) * c * e + (n - r) * e + 8 * (na - r) + 16 * r
-        if size:
+        if g["size"]:
             total += n * e
-        if rci:
+        if g["reduced_cluster_idx"]:
             total += 4 * (n - 1)
-        return b * total
+        return g["B"] * total
     if name == "tokred_topk_gather":
-        xdt, scores, sdt, attn, adt, h, b, n, c, k = a[1], a[2], a[3], a[6], a[7], a[8], a[9], a[10], a[11], a[12]
-        sc = (n - 1) * esz(sdt) if scores else h * (n - 1) * esz(adt)
-        return b * (sc + 2 * (k + 1) * c * esz(xdt) + 8 * k)
+        n, c, k = g["N"], g["C"], g["k"]
+        sc = (n - 1) * esz(g["score_dtype"]) if g["scores"] else g["H"] * (n - 1) * esz(g["attn_dtype"])
+        return g["B"] * (sc + 2 * (k + 1) * c * esz(g["x_dtype"]) + 8 * k)
     if name == "tokred_evit_select_fuse":
-        xdt, scores, sdt, adt, h, b, n, c, k = a[1], a[2], a[3], a[5], a[6], a[7], a[8], a[9], a[10]
-        sc = (n - 1) * esz(sdt) if scores else h * (n - 1) * esz(adt)
-        return b * (sc + n * c * esz(xdt) + (k + 2) * c * esz(xdt) + 8 * (k + 1) + 8 * (n - 1 - k))
+        n, c, k = g["N"], g["C"], g["k"]
+        sc = (n - 1) * esz(g["score_dtype"]) if g["scores"] else g["H"] * (n - 1) * esz(g["attn_dtype"])
+        return g["B"] * (sc + n * c * esz(g["x_dtype"]) + (k + 2) * c * esz(g["x_dtype"]) + 8 * (k + 1) + 8 * (n - 1 - k))
     if name == "tokred_dpcknn_cluster":
-        b, p, c, k = a[2], a[3], a[4], a[5]
-        return b * (p * c * 4 + p * 4 + 8 * p + 8 * k)
+        p, c, k = g["P"], g["C"], g["K"]
+        return g["B"] * (p * c * 4 + p * 4 + 8 * p + 8 * k)
     if name == "tokred_dpcknn_merge":
-        b, p, c, k, t = a[5], a[6], a[7], a[8], a[9]
-        return b * (p * c * 4 + p * 4 + 8 * p + k * c * 4 + t * (8 + 4) * 2)
+        p, c, k, t = g["P"], g["C"], g["K"], g["T"]
+        return g["B"] * (p * c * 4 + p * 4 + 8 * p + k * c * 4 + t * (8 + 4) * 2)
     if name == "tokred_kmedoids_fit":
-        b, p, c, k = a[2], a[3], a[4], a[5]
-        return b * (p * c * 4 + p * 4 + k * c * 4 + 8 * k + 8 * p)
+        p, c, k = g["P"], g["C"], g["K"]
+        return g["B"] * (p * c * 4 + p * 4 + k * c * 4 + 8 * k + 8 * p)
     if name == "tokred_attn_colsum":
-        dt, b, h, n = a[1], a[2], a[3], a[4]
-        return b * (h * n * n * esz(dt) + 4 * (n - 1))
+        n = g["N"]
+        return g["B"] * (g["H"] * n * n * esz(g["attn_dtype"]) + 4 * (n - 1))
     if name in ("tokred_sinkhorn_merge", "tokred_patchmerger"):
-        if name == "tokred_sinkhorn_merge":
-            xdt, b, p, c, k, odt = a[1], a[3], a[4], a[5], a[6], a[12]
-        else:
-            xdt, b, p, c, k, odt = a[1], a[5], a[6], a[7], a[8], a[13]
-        return b * (p * c * esz(xdt) + k * c * esz(odt) + k * p * 4) + k * c * 4
+        p, c, k = g["P"], g["C"], g["K"]
+        return g["B"] * (p * c * esz(g["x_dtype"]) + k * c * esz(g["out_dtype"]) + k * p * 4) + k * c * 4
     if name == "tokred_sit_merge":
-        xdt, ldt, b, p, c, k, odt = a[1], a[3], a[5], a[6], a[7], a[8], a[11]
-        return b * (p * c * esz(xdt) + p * k * esz(ldt) + k * c * esz(odt) + k * p * 4)
+        p, c, k = g["P"], g["C"], g["K"]
+        return g["B"] * (p * c * esz(g["x_dtype"]) + p * k * esz(g["logits_dtype"]) + k * c * esz(g["out_dtype"]) + k * p * 4)
     if name == "tokred_ats_sample":
-        vdt, b, h, n, dh, ns = a[1], a[8], a[9], a[10], a[11], a[12]
-        return b * (h * (n - 1) * 4 + h * n * dh * esz(vdt) + n + 9 * (ns + 1))
+        n, h = g["N"], g["H"]
+        return g["B"] * (h * (n - 1) * 4 + h * n * g["Dh"] * esz(g["v_dtype"]) + n + 9 * (g["n_steps"] + 1))
     if name == "tokred_gather_rows":
-        dt, b, g, n, w, m = a[1], a[4], a[5], a[6], a[7], a[8]
-        return b * (2 * g * m * w * esz(dt) + 8 * m)
+        m = g["M"]
+        return g["B"] * (2 * g["G"] * m * g["W"] * esz(g["dtype"]) + 8 * m)
     if name == "tokred_dyvit_pool_concat":
-        hdt, b, p, c, odt = a[1], a[3], a[4], a[5], a[8]
-        return b * (p * c * esz(hdt) + p * 4 + p * c * esz(odt))
+        p, c = g["P"], g["C"]
+        return g["B"] * (p * c * esz(g["h_dtype"]) + p * 4 + p * c * esz(g["out_dtype"]))
     return 0.0
 
 

@@ -134,3 +134,18 @@ def test_keep_rate_schedules():
     assert [b.r for b in tome.blocks] == [0, 0, 0, 59, 0, 0, 41, 0, 0, 29, 0, 0]
     assert ats.sample_count == [0, 0, 0, 177, 0, 0, 159, 0, 0, 143, 0, 0]
     assert [round(b.attn.keep_rate, 3) for b in topk.blocks][3::3] == [0.7, 0.49, 0.343]
+
+
+def test_bench_byte_formulas_follow_the_header():
+    """bench.py addresses ABI arguments by the parameter names of include/tokred.h: every entry point must parse to
+    as many names as the ctypes signature has arguments, and two known per-launch figures must come out
+    (ToMe merge stage 1 at DeiT-S fp32 = 517,160 B/image)."""
+    import bench
+    from tokenreduction_b200 import _lib
+    names = bench.abi_arg_names()
+    for fn, sig in _lib.SIGNATURES.items():
+        assert len(names[fn]) == len(sig), fn
+    args = (1, 0, None, 1, 1, 1, 256, 197, 384, 59, 1, 1, 1, 1, None)       # x, fp32, size=NULL (first stage), ..., rci, divide, stream
+    assert bench.algorithmic_bytes("tokred_tome_merge", args) == 256 * 517160
+    args = (1, 0, 197 * 768, 1, 128, 196, 768, 176, 1.0, 0.0, 3, 1, 1, 1, 1, None, 0, None)   # sinkhorn, fp32 x, bf16 out
+    assert bench.algorithmic_bytes("tokred_sinkhorn_merge", args) == 128 * (196 * 768 * 4 + 176 * 768 * 2 + 176 * 196 * 4) + 176 * 768 * 4
