@@ -321,40 +321,48 @@ __device__ __forceinline__ void warp_max2(float& a, float& b) {
     b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
   }
 }
-// One row of the bf16 score matrix (P <= 256) spread over a warp: lane holds token pairs lane, lane+32, ... as
-// x[2i], x[2i+1]; `add` (per-token, may be null) and `add_row` are added in fp32 in that order ((z + add_row) + add[p]
-// when both are given, matching the reference's (Z + u) + v); slots past P read as -inf.
-__device__ __forceinline__ void load_score_row(const __nv_bfloat16* zrow, const float* add, int P, int lane, float (&x)[8],
-                                               float add_row = 0.f) {
+// Per-lane constants of the weight-row passes (one warp per row of W, lane holds token pairs lane, lane+32, ...):
+// hoisted out of the row loops, which were ~350 instructions per row, most of them bounds tests and operand-offset
+// arithmetic.  Dead slots (token >= P) re-read token 0 (finite) and carry dead = -inf.
+struct RowMap {
+  int poff[4];        // token index of the pair (0 for dead slots)
+  uint32_t woff[4];   // byte offset of the pair inside a K-major row group of the W operand
+  float dead[8];      // 0 for live slots, -inf for dead ones (added to the score)
+  bool live0[4], live1[4];
+};
+__device__ __forceinline__ RowMap make_row_map(int P, int lane) {
+  RowMap m;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int p = 2 * (lane + 32 * i);
-    if (p < P) {
-      const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zrow + p));
-      x[2 * i] = (z.x + add_row) + (add ? add[p] : 0.f);
-      x[2 * i + 1] = p + 1 < P ? (z.y + add_row) + (add ? add[p + 1] : 0.f) : -CUDART_INF_F;
-    } else {
-      x[2 * i] = -CUDART_INF_F;
-      x[2 * i + 1] = -CUDART_INF_F;
-    }
+    m.live0[i] = p < P; m.live1[i] = p + 1 < P;
+    m.poff[i] = m.live0[i] ? p : 0;
+    m.woff[i] = (uint32_t)((p >> 3) * 128 + (p & 7) * 2);
+    m.dead[2 * i] = m.live0[i] ? 0.f : -CUDART_INF_F;
+    m.dead[2 * i + 1] = m.live1[i] ? 0.f : -CUDART_INF_F;
+  }
+  return m;
+}
+__device__ __forceinline__ void load_scores(const __nv_bfloat16* zrow, const RowMap& m, float (&x)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 z = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(zrow + m.poff[i]));
+    x[2 * i] = z.x; x[2 * i + 1] = z.y;
   }
 }
-// weights of one row: fp32 to global memory, bf16 into the K-major A operand of GEMM 2 (token pairs are adjacent there)
-__device__ __forceinline__ void store_weight_row(const float (&w)[8], float* wrow, unsigned char* Wop, int k, int P, int lane,
-                                                 uint32_t sbo2) {
+// weights of one row: fp32 to global memory (float2 when the row is 8-byte aligned), bf16 pairs into the K-major A
+// operand of GEMM 2 (wgrp = Wop + (k/8)*sbo2 + (k%8)*16); dead slots hold 0 and are not stored
+__device__ __forceinline__ void store_weights(const float (&w)[8], float* wrow, unsigned char* wgrp, const RowMap& m) {
   const bool vec2 = (reinterpret_cast<uintptr_t>(wrow) & 7u) == 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int p = 2 * (lane + 32 * i);
-    if (p < P) {
-      const bool two = p + 1 < P;
-      if (two && vec2) *reinterpret_cast<float2*>(wrow + p) = make_float2(w[2 * i], w[2 * i + 1]);
+    if (m.live0[i]) {
+      if (m.live1[i] && vec2) *reinterpret_cast<float2*>(wrow + m.poff[i]) = make_float2(w[2 * i], w[2 * i + 1]);
       else {
-        wrow[p] = w[2 * i];
-        if (two) wrow[p + 1] = w[2 * i + 1];
+        wrow[m.poff[i]] = w[2 * i];
+        if (m.live1[i]) wrow[m.poff[i] + 1] = w[2 * i + 1];
       }
-      *reinterpret_cast<__nv_bfloat162*>(Wop + umma::kmajor_offset((uint32_t)k, (uint32_t)p, 2, sbo2)) =
-          __floats2bfloat162_rn(w[2 * i], two ? w[2 * i + 1] : 0.f);
+      *reinterpret_cast<__nv_bfloat162*>(wgrp + m.woff[i]) = __floats2bfloat162_rn(w[2 * i], m.live1[i] ? w[2 * i + 1] : 0.f);
     }
   }
 }
@@ -646,16 +654,13 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
     for (int e = tid; e < (int)(32 * G.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
     const float sc = prm.scale_ptr[0];
     __syncthreads();
+    const RowMap rm = make_row_map(P, lane);
     for (int k = warp; k < K; k += kThreads / 32) {
       float x[8];
-      load_score_row(Lt + (size_t)k * PSb, nullptr, P, lane, x);
+      load_scores(Lt + (size_t)k * PSb, rm, x);
       float m = -CUDART_INF_F;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int p = 2 * (lane + 32 * (i >> 1)) + (i & 1);
-        x[i] = p < P ? x[i] * sc : -CUDART_INF_F;           // the learnable scale may have either sign
-        m = fmaxf(m, x[i]);
-      }
+      for (int i = 0; i < 8; ++i) { x[i] = x[i] * sc + rm.dead[i]; m = fmaxf(m, x[i]); }   // the scale may have either sign
       m = warp_max(m);
       const float nm2 = -m * 1.4426950408889634f;
       float sum = 0.f;
@@ -664,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
       const float inv = 1.0f / warp_sum(sum);
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] *= inv;
-      store_weight_row(x, wout + (long long)k * P, Wop, k, P, lane, G.sbo2);
+      store_weights(x, wout + (long long)k * P, Wop + (size_t)(k >> 3) * G.sbo2 + (size_t)(k & 7) * 16, rm);
     }
   } else if (MODE == MODE_SINKHORN) {
     // Log-domain Sinkhorn on the bf16 scores.  Row passes keep a row in registers (one shared-memory sweep: max,
@@ -770,23 +775,34 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
     for (int e = tid; e < (int)(32 * G.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
     __syncthreads();
     STAMP(7);
-    for (int k = warp; k < K; k += NW) {
-      float x[8];
-      load_score_row(Z + (size_t)k * PSb, vvec, P, lane, x, uvec[k]);
+    {
+      const RowMap rm = make_row_map(P, lane);
+      float vv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = ex2_ftz((x[i] - nrm) * L2E);      // rel. error ~1e-6: the scores are bf16
-      store_weight_row(x, wout + (long long)k * P, Wop, k, P, lane, G.sbo2);
+      for (int i = 0; i < 4; ++i) {
+        vv[2 * i] = rm.live0[i] ? vvec[rm.poff[i]] : -CUDART_INF_F;
+        vv[2 * i + 1] = rm.live1[i] ? vvec[rm.poff[i] + 1] : -CUDART_INF_F;
+      }
+      for (int k = warp; k < K; k += NW) {
+        float x[8];
+        load_scores(Z + (size_t)k * PSb, rm, x);
+        const float uk = uvec[k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = ex2_ftz((((x[i] + uk) + vv[i]) - nrm) * L2E);   // rel. error ~1e-6: bf16 scores
+        store_weights(x, wout + (long long)k * P, Wop + (size_t)(k >> 3) * G.sbo2 + (size_t)(k & 7) * 16, rm);
+      }
     }
   } else {
     for (int e = tid; e < (int)(32 * G.sbo2 / 16); e += kThreads) reinterpret_cast<int4*>(Wop)[e] = make_int4(0, 0, 0, 0);
     __syncthreads();
     STAMP(7);
+    const RowMap rm = make_row_map(P, lane);
     for (int k = warp; k < K; k += kThreads / 32) {
       float x[8];
-      load_score_row(Z + (size_t)k * PSb, nullptr, P, lane, x);
-      float m = x[0];
+      load_scores(Z + (size_t)k * PSb, rm, x);
+      float m = -CUDART_INF_F;
 #pragma unroll
-      for (int i = 1; i < 8; ++i) m = fmaxf(m, x[i]);
+      for (int i = 0; i < 8; ++i) { x[i] += rm.dead[i]; m = fmaxf(m, x[i]); }
       m = warp_max(m);
       const float nm2 = -m * 1.4426950408889634f;
       float sum = 0.f;
@@ -797,7 +813,7 @@ __global__ void __launch_bounds__(kThreads, 1) soft_merge_tc2_kernel(Tc2Params p
       const float inv = 1.0f / warp_sum(sum);
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] *= inv;
-      store_weight_row(x, wout + (long long)k * P, Wop, k, P, lane, G.sbo2);
+      store_weights(x, wout + (long long)k * P, Wop + (size_t)(k >> 3) * G.sbo2 + (size_t)(k & 7) * 16, rm);
     }
   }
   umma::fence_proxy_async_smem();      // W operand (generic-proxy writes) -> visible to the tensor core
