@@ -149,3 +149,23 @@ def test_bench_byte_formulas_follow_the_header():
     assert bench.algorithmic_bytes("tokred_tome_merge", args) == 256 * 517160
     args = (1, 0, 197 * 768, 1, 128, 196, 768, 176, 1.0, 0.0, 3, 1, 1, 1, 1, None, 0, None)   # sinkhorn, fp32 x, bf16 out
     assert bench.algorithmic_bytes("tokred_sinkhorn_merge", args) == 128 * (196 * 768 * 4 + 176 * 768 * 2 + 176 * 196 * 4) + 176 * 768 * 4
+
+
+def test_rows_view_helper_host_logic():
+    """ops._rows: which token tensors are handed to the kernels in place (pointer + x_batch_stride) and which are
+    copied.  Pure host logic, no launch."""
+    import tokenreduction_b200.ops as T
+    full = torch.zeros(4, 197, 64)
+    x, s = T._rows(full)
+    assert x is full and s == 0                                    # dense
+    v = full[:, 1:]
+    x, s = T._rows(v)
+    assert x.data_ptr() == v.data_ptr() and s == 197 * 64          # class token dropped: read in place
+    x, s = T._rows(full[:1, 1:])
+    assert s == 0                                                  # a single image needs no stride
+    x, s = T._rows(full[:, :, :32])
+    assert x.is_contiguous() and s == 0                            # rows not dense: copied
+    x, s = T._rows(full.transpose(1, 2)[:, :, :64].transpose(1, 2)[:, ::2])
+    assert x.is_contiguous() and s == 0                            # row stride != C: copied
+    x, s = T._rows(full[::2, 1:])
+    assert x.data_ptr() == full[::2, 1:].data_ptr() and s == 2 * 197 * 64
