@@ -44,13 +44,13 @@ ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long
       const TV* row = v + (long long)b * vs_b + (long long)h * vs_h + (long long)(1 + p) * vs_n;
       float s = 0.f;
       if (vec) {
-        for (int d = 0; d < Dh; d += 4 * VE) {
-          int4 r[4];
+        for (int d = 0; d < Dh; d += 8 * VE) {          // 8 x 16 bytes in flight: a whole 64-element bf16 row
+          int4 r[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 8; ++u)
             if (d + u * VE < Dh) r[u] = *reinterpret_cast<const int4*>(row + d + u * VE);
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int u = 0; u < 8; ++u)
             if (d + u * VE < Dh) {
               const TV* q = reinterpret_cast<const TV*>(&r[u]);
 #pragma unroll
@@ -76,13 +76,18 @@ ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long
   part = warp_sum(part);
   if (lane == 0) red[warp] = part;
   __syncthreads();
-  if (tid == 0) {
+  {
     float total = 0.f;
     for (int w = 0; w < kWarps; ++w) total += red[w];
     const float denom = total + eps;
+    for (int p = tid; p < P; p += kThreads) cdf[p] = cdf[p] / denom;     // the divisions in parallel ...
+  }
+  __syncthreads();
+  if (tid == 0) {
     float run = 0.f;
-    for (int p = 0; p < P; ++p) {            // sequential inclusive scan of the normalised score
-      run += cdf[p] / denom;
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) {            // ... the inclusive scan sequential (fp32 order of the CPU reference)
+      run += cdf[p];
       cdf[p] = run;
     }
   }
