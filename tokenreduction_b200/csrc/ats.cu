@@ -39,6 +39,43 @@ ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long
     constexpr int VE = 16 / sizeof(TV);
     const bool vec = (Dh % VE == 0) && (vs_n % VE == 0) && (vs_h % VE == 0) && (vs_b % VE == 0) &&
                      ((reinterpret_cast<uintptr_t>(v) & 15u) == 0);
+    if (vec && Dh <= 8 * VE) {
+      // two (head, patch) pairs per thread and iteration, each value row (<= 8 x 16 bytes) entirely in flight: the
+      // phase is a chain of dependent global-latency rounds, 2352 pairs / 256 threads = 9 of them with one pair
+      const int nv = Dh / VE;
+      for (int e0 = tid; e0 < H * P; e0 += 2 * kThreads) {
+        int4 r[2][8];
+        float a[2];
+        bool on[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = e0 + u * kThreads;
+          on[u] = e < H * P;
+          if (on[u]) {
+            const int h = e / P, p = e - h * P;
+            const TV* row = v + (long long)b * vs_b + (long long)h * vs_h + (long long)(1 + p) * vs_n;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+              if (w < nv) r[u][w] = *reinterpret_cast<const int4*>(row + w * VE);
+            a[u] = ab[((long long)h * N) * N + 1 + p];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (on[u]) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+              if (w < nv) {
+                const TV* q = reinterpret_cast<const TV*>(&r[u][w]);
+#pragma unroll
+                for (int i = 0; i < VE; ++i) { const float x = to_f32(q[i]); s = fmaf(x, x, s); }
+              }
+            hp[e0 + u * kThreads] = a[u] * sqrtf(s);
+          }
+        }
+      }
+    } else
     for (int e = tid; e < H * P; e += kThreads) {
       const int h = e / P, p = e % P;
       const TV* row = v + (long long)b * vs_b + (long long)h * vs_h + (long long)(1 + p) * vs_n;
