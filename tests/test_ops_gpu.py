@@ -530,6 +530,34 @@ def test_sit_merge_negative_scale(T):
         assert_close_rel(out.float(), out_ref.float(), RTOL16, f"merged tokens tc={tc}")
 
 
+def test_soft_merges_on_4_byte_aligned_tokens(T):
+    """A token tensor that is only 4-byte aligned (storage offset of one element) cannot use the bulk-copy ring or
+    vector loads: the tensor-core kernels fall back to direct loads.  Same arithmetic => same bits as on an aligned copy."""
+    b, p, c, k = 3, 196, 768, 176
+    buf = torch.randn(b * p * c + 8, generator=g(710)).to(DEV)
+    x_off = buf[1:1 + b * p * c].view(b, p, c)
+    assert x_off.data_ptr() % 16 == 4 and x_off.is_contiguous()
+    x_al = x_off.clone()
+    v = torch.nn.functional.normalize(torch.randn(k, c, generator=g(711)), dim=-1).to(DEV)
+    lw, lb = (torch.rand(c, generator=g(712)) + 0.5).to(DEV), (torch.randn(c, generator=g(713)) * 0.1).to(DEV)
+    q = (torch.randn(k, c, generator=g(714)) * 0.05).to(DEV)
+    logits = torch.randn(b, p, k, generator=g(715)).bfloat16().to(DEV)
+    scale = torch.full((1,), 0.9, device=DEV)
+    for scratch in (True, False):
+        T.SOFT_MERGE_SCRATCH = scratch
+        try:
+            for fn in (lambda t: T.sinkhorn_merge(t, v, 1.0, 3, True, True), lambda t: T.patchmerger(t, lw, lb, q, 1.0, 1e-5, True, True),
+                       lambda t: T.sit_merge(t, logits, scale, True, True)):
+                a, bb = fn(x_off), fn(x_al)
+                assert all(torch.equal(u, w) for u, w in zip(a, bb)), f"scratch={scratch}"
+        finally:
+            T.SOFT_MERGE_SCRATCH = True
+    o_ref, w_ref, vh = O.sinkhorn_merge(x_al, v, 1.0, 3, lowp=torch.bfloat16)
+    o, w = T.sinkhorn_merge(x_off, vh, 1.0, 3, True, True)
+    assert_close_rel(w, w_ref, RTOL16, "weights (misaligned tokens) vs oracle")
+    assert_close_rel(o.float(), o_ref.float(), RTOL16, "tokens (misaligned tokens) vs oracle")
+
+
 def test_batch_strided_tokens_are_read_in_place(T):
     """x[:, 1:] (class token dropped -- what the cluster / soft-merge layers receive, e.g. models/dpcknn.py:259) is
     passed with its batch stride instead of being copied: results must equal those on the contiguous copy bit for bit."""
