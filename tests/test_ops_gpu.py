@@ -384,7 +384,8 @@ def test_sinkhorn_lowp(T):
 
 @pytest.mark.parametrize("p,k,c,xdt", [(196, 176, 768, torch.float32), (176, 158, 768, torch.float32), (158, 142, 384, torch.float32),
                                         (64, 20, 128, torch.float32), (60, 130, 200, torch.float32), (196, 176, 768, torch.bfloat16),
-                                        (97, 33, 100, torch.float32), (16, 4, 64, torch.float32)])
+                                        (97, 33, 100, torch.float32), (16, 4, 64, torch.float32),
+                                        (200, 129, 1024, torch.bfloat16), (8, 1, 8, torch.float32)])
 def test_soft_merge_tensor_core_paths(T, p, k, c, xdt):
     """tcgen05 Sinkhorn / PatchMerger (lowp) against the oracle's autocast emulation and against the FFMA path."""
     b = 3
@@ -528,6 +529,32 @@ def test_sit_merge_negative_scale(T):
         assert torch.isfinite(w).all()
         assert_close_rel(w, w_ref, RTOL16, f"weights tc={tc}")
         assert_close_rel(out.float(), out_ref.float(), RTOL16, f"merged tokens tc={tc}")
+
+
+def test_soft_merge_maximum_shape(T):
+    """P = K = 208, C = 1024: the largest shape the tensor-core kernels take (shared-memory plan at its limit).  The
+    FFMA kernel keeps the fp32 score matrix in shared memory and does not fit there: it must refuse loudly."""
+    b, p, k, c = 2, 208, 208, 1024
+    x = torch.randn(b, p, c, generator=g(720)).to(DEV)
+    v = torch.randn(k, c, generator=g(721)).to(DEV)
+    o_ref, w_ref, vh = O.sinkhorn_merge(x, v, 1.0, 3, lowp=torch.bfloat16)
+    o, w = T.sinkhorn_merge(x, vh, 1.0, 3, True, True)
+    assert_close_rel(w, w_ref, RTOL16, "sinkhorn weights")
+    assert_close_rel(o.float(), o_ref.float(), RTOL16, "sinkhorn tokens")
+    lw, lb = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+    q = (torch.randn(k, c, generator=g(722)) * 0.05).to(DEV)
+    o_ref, a_ref = O.patchmerger(x, lw, lb, q, lowp=torch.bfloat16)
+    o, a = T.patchmerger(x, lw, lb, q, 1.0, 1e-5, True, True)
+    assert_close_rel(a, a_ref, RTOL16, "patchmerger attn")
+    assert_close_rel(o.float(), o_ref.float(), RTOL16, "patchmerger tokens")
+    logits = torch.randn(b, p, k, generator=g(723)).bfloat16().to(DEV)
+    scale = torch.full((1,), 1.2, device=DEV)
+    o_ref, w_ref = O.sit_merge(x, logits, scale, lowp=torch.bfloat16)
+    o, w = T.sit_merge(x, logits, scale, True, True)
+    assert_close_rel(w, w_ref, RTOL16, "sit weights")
+    assert_close_rel(o.float(), o_ref.float(), RTOL16, "sit tokens")
+    with pytest.raises(RuntimeError, match="shared memory"):
+        T.sinkhorn_merge(x, vh, 1.0, 3, True, False)
 
 
 def test_soft_merges_on_4_byte_aligned_tokens(T):
