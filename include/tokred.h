@@ -127,7 +127,7 @@ TOKRED_API size_t tokred_soft_merge_workspace_bytes(int B, int P, int C, int K);
 /* Shape limits of a9 / a12 / a13 (one image's score matrix lives in shared memory): P <= 208 and K <= 208 always
  * (TOKRED_ERR_UNSUPPORTED above); the bf16-autocast tensor-core kernels (lowp = 1, bf16 out) cover that whole range
  * for C <= 1024 (C % 8 == 0 with a workspace); the fp32 / FFMA kernel keeps the fp32 K x P matrix and needs
- * about 4*(K*P + 36*(13*ceil(K/13) + 7*ceil(P/7))) bytes <= 227 KB -- it covers every shape of the reference
+ * 4*(K*ceil4(P) + max(36*(K+P), tile) + 3P + K) bytes <= 227 KB (softmerge.cu soft_smem_bytes) -- it covers every shape of the reference
  * (P <= 196, K <= 176) and answers with an argument error naming the shortfall beyond that (e.g. P = K = 208).   */
 
 /* ---- a9 Sinkhorn -------------------------------------------------------------------------------------
