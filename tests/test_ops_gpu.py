@@ -306,7 +306,9 @@ def test_dpcknn_cluster(T, p, k, c, exact):
     assert int(idx_cluster.min()) >= 0 and int(idx_cluster.max()) < k
 
 
-@pytest.mark.parametrize("p,k,c,with_w", [(196, 49, 384, True), (49, 12, 384, True), (12, 3, 384, False), (196, 49, 100, True)])
+@pytest.mark.parametrize("p,k,c,with_w", [(196, 49, 384, True), (49, 12, 384, True), (12, 3, 384, False), (196, 49, 100, True),
+                                          (196, 49, 768, True), (64, 40, 512, True), (50, 50, 256, False), (30, 7, 99, True),
+                                          (200, 3, 1024, True)])
 def test_dpcknn_merge_bit_exact(T, p, k, c, with_w):
     b, t = 5, 196
     x = torch.randn(b, p, c, generator=g(27))
