@@ -119,18 +119,20 @@ def cases():
         out.append((f"sweep sinkhorn_merge B B={b} P={p} K={k} lowp tcgen05", lambda x=x, v=v: T.sinkhorn_merge(x, v, 1.0, 3, True, True)))
         out.append((f"sweep patchmerger B B={b} P={p} K={k} lowp tcgen05", lambda x=x, lw=lw, lb=lb, q=q: T.patchmerger(x, lw, lb, q, 1.0, 1e-5, True, True)))
         out.append((f"sweep sit_merge B B={b} P={p} K={k} lowp tcgen05", lambda x=x, l=logits, s=scale: T.sit_merge(x, l, s, True, True)))
-    b = 128
-    from oracle.ops import ats_sample_steps
-    for n, count in ((197, 177), (177, 159), (159, 143)):
-        attn = torch.softmax(4 * torch.randn(b, 12, n, n, device=DEV), dim=-1)
-        v = torch.randn(b, 12, n, 64, device=DEV).bfloat16()
-        mask = torch.ones(b, n, dtype=torch.bool, device=DEV)
-        steps = ats_sample_steps(count).to(DEV)
-        ids, _, _ = T.ats_sample(v, attn, mask, steps)
-        x = torch.randn(b, n, 768, device=DEV)
-        out.append((f"ats_sample B B={b} N={n} count={count}", lambda v=v, a=attn, m=mask, s=steps: T.ats_sample(v, a, m, s)))
-        out.append((f"ats gather attn rows B B={b} N={n} M={count}", lambda a=attn, ids=ids: T.gather_rows(a, ids)))
-        out.append((f"ats gather tokens B B={b} N={n} M={count}", lambda x=x, ids=ids: T.gather_rows(x, ids)))
+    # ATS: 8-GPU shard (B=128) and the single-GPU configuration of SURVEY section 8(d) (B=1024, stage 1)
+    for b, shapes in ((128, ((197, 177), (177, 159), (159, 143))), (1024, ((197, 177),))):
+        for n, count in shapes:
+            attn = torch.softmax(4 * torch.randn(b, 12, n, n, device=DEV), dim=-1)
+            v = torch.randn(b, 12, n, 64, device=DEV).bfloat16()
+            mask = torch.ones(b, n, dtype=torch.bool, device=DEV)
+            steps = torch.arange(1 / (2 * count), (2 * count - 1) / (2 * count), 2 / (2 * count)).to(DEV)   # models/ats.py:48
+            ids, _, _ = T.ats_sample(v, attn, mask, steps)
+            x = torch.randn(b, n, 768, device=DEV)
+            tag = "" if b == 128 else "sweep "
+            out.append((f"{tag}ats_sample B B={b} N={n} count={count}", lambda v=v, a=attn, m=mask, s=steps: T.ats_sample(v, a, m, s)))
+            out.append((f"{tag}ats gather attn rows B B={b} N={n} M={count}", lambda a=attn, ids=ids: T.gather_rows(a, ids)))
+            out.append((f"{tag}ats gather tokens B B={b} N={n} M={count}", lambda x=x, ids=ids: T.gather_rows(x, ids)))
+            del attn, v, x
     return out
 
 
