@@ -169,3 +169,37 @@ def test_rows_view_helper_host_logic():
     assert x.is_contiguous() and s == 0                            # row stride != C: copied
     x, s = T._rows(full[::2, 1:])
     assert x.data_ptr() == full[::2, 1:].data_ptr() and s == 2 * 197 * 64
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """include/tokred.h must be consumable by a C compiler (the boundary is a C ABI, not C++), and a C program linked
+    against the library must be able to call it: version query, host-side validation, error string.  No GPU needed."""
+    import shutil
+    import subprocess
+    from tokenreduction_b200 import _lib
+    from tokenreduction_b200.build import LIB_PATH
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    _lib.load()
+    src = tmp_path / "consumer.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "tokred.h"\n'
+        "int main(void) {\n"
+        "  if (tokred_abi_version() != TOKRED_ABI_VERSION) return 2;\n"
+        "  if (tokred_tome_effective_r(197, 59, 1) != 59) return 3;\n"
+        "  /* K > P: rejected on the host, nothing launched */\n"
+        "  int rc = tokred_dpcknn_cluster((const float*)16, 0, (const float*)16, 2, 196, 64, 300, 5, 0, (int64_t*)16, (int64_t*)16, 0);\n"
+        "  if (rc >= 0) return 4;\n"
+        "  if (!strstr(tokred_last_error(), \"cluster_num\")) return 5;\n"
+        '  printf("abi %d ok\\n", tokred_abi_version());\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(LIB_PATH)
+    inc = os.path.join(os.path.dirname(libdir), "include")
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe), "-L", libdir,
+           "-l:" + os.path.basename(LIB_PATH), "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi" in r.stdout, (r.returncode, r.stdout, r.stderr)
