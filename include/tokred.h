@@ -66,8 +66,12 @@ TOKRED_API int tokred_evit_select_fuse(const void* x, int x_dtype, const void* s
  * descending edge order, CLS protected).  r is clamped to (N - protected)/2 like :252-253; the caller sizes
  * the outputs with tokred_tome_effective_r().
  *   metric [B,N,D] metric_dtype (= k.mean(1), models/tome.py:58)
+ *   NaN metric rows (zero norm) order like ATen: NaN is the largest key, so all index slots are always written.
  *   score_lowp: 0 = fp32 similarity (FFMA); 1 = operands and similarity rounded to bf16 (what CUDA autocast
  *   does) on tcgen05 tensor cores; 3 = same rounding on the FFMA path (cross-check of the tensor-core path)
+ *   class_token: protection flags -- bit 0 = class token (even token 0 never merges away, :263-264), bit 1 =
+ *   distillation token (odd token 0 never receives a merge, :265-266); 0/1 keep their plain boolean meaning.
+ *   The distilled output row order of :286-287 is a fixed permutation applied by the caller.
  *   unm_idx [B,a-r] (ascending when class_token), src_idx [B,r], dst_idx [B,r] int64; a = ceil(N/2)      */
 TOKRED_API int tokred_tome_effective_r(int N, int r, int class_token);
 TOKRED_API int tokred_tome_match(const void* metric, int metric_dtype, int B, int N, int D, int r, int class_token,

@@ -132,6 +132,7 @@ def forward(method: str, sd: Dict[str, Tensor], images: Tensor, cfg: Cfg, amp: b
                             else:
                                 x, idx, compl = O.evit_select_fuse(x, scores, k)
                         rec[i] = idx
+                        rec[("in", i)] = {"scores": scores, "k": k}
                 x = _mlp(x, sd, i)
 
         elif method == "tome":                                  # models/tome.py:78-104, 202-203
@@ -151,6 +152,7 @@ def forward(method: str, sd: Dict[str, Tensor], images: Tensor, cfg: Cfg, amp: b
                         unm, src, dst, _ = O.tome_match(metric, r_at[i], True, lowp=lowp)
                         x, size, rci = O.tome_merge(x, size, unm, src, dst)
                     rec[i] = rci
+                    rec[("in", i)] = {"metric": metric, "r": r_at[i]}
                 x = _mlp(x, sd, i)
 
         elif method == "dyvit":                                 # models/dyvit.py:205-238
@@ -171,6 +173,7 @@ def forward(method: str, sd: Dict[str, Tensor], images: Tensor, cfg: Cfg, amp: b
                         x, keep = O.dyvit_keep(x, score, k)
                     prev_decision = torch.gather(prev_decision, 1, keep.unsqueeze(-1))
                     rec[i] = keep
+                    rec[("in", i)] = {"scores": score.float(), "k": k}
                 x, _ = _plain_block(x, sd, i, heads)
 
         elif method == "dpcknn":                                # models/dpcknn.py:231-268
@@ -187,6 +190,7 @@ def forward(method: str, sd: Dict[str, Tensor], images: Tensor, cfg: Cfg, amp: b
                         idx_cluster, index_down = O.dpcknn_cluster(xp.float(), counts[j], cfg.k_neighbors, noise)
                         xm, idx_token, agg_weight = O.dpcknn_merge(xp, idx_token, agg_weight, idx_cluster, counts[j], tw.float())
                     rec[i] = (index_down, idx_cluster)
+                    rec[("in", i)] = {"x": xp.float(), "noise": noise, "K": counts[j], "knn": cfg.k_neighbors}
                     x = torch.cat((cls, xm), dim=1)
                 x, _ = _plain_block(x, sd, i, heads)
 
@@ -201,6 +205,7 @@ def forward(method: str, sd: Dict[str, Tensor], images: Tensor, cfg: Cfg, amp: b
                         tw = O.attn_colsum(attn.float())
                         centres, cidx, assign = O.kmedoids_fit(xp.float(), counts[j], cfg.cluster_iters, tw)
                     rec[i] = (cidx, assign)
+                    rec[("in", i)] = {"x": xp.float(), "tw": tw, "K": counts[j], "iters": cfg.cluster_iters}
                     x = torch.cat((cls, centres.to(x.dtype)), dim=1)
                 x, attn = _plain_block(x, sd, i, heads)
 
@@ -235,6 +240,7 @@ def forward(method: str, sd: Dict[str, Tensor], images: Tensor, cfg: Cfg, amp: b
                 attn, _, v = _attend(x, sd, i, heads, mask=mask)
                 if i in sample_count:
                     with noac():
+                        rec[("in", i)] = {"v": v, "attn": attn.float(), "mask": mask, "count": sample_count[i]}
                         attn, mask, ids = O.ats_sample(v, attn.float(), mask, sample_count[i])
                     x = O.gather_rows(x, ids)
                     rec[i] = ids

@@ -165,12 +165,16 @@ def pairwise_dist(x: Tensor) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------ a6-a7 DPC-KNN
-def dpcknn_cluster(x: Tensor, cluster_num: int, k: int, noise_u: Tensor, dist: Optional[Tensor] = None):
+def dpcknn_cluster(x: Tensor, cluster_num: int, k: int, noise_u: Tensor, dist: Optional[Tensor] = None,
+                   dist_scaled: bool = False):
     """models/dpcknn.py:56-98 (token_mask=None).  x [B,P,C], noise_u [B,P] ~ U(0,1) (the reference draws it
     inside, :73-74; drawing it outside with the same call keeps the generator in step).
+    ``dist`` (optional) replaces cdist(x, x); with ``dist_scaled`` it already carries the 1/sqrt(C) of :59.
     -> (idx_cluster [B,P], index_down [B,K]) int64."""
     b, p, c = x.shape
-    d = (pairwise_dist(x) if dist is None else dist) / (c ** 0.5)
+    d = pairwise_dist(x) if dist is None else dist
+    if not (dist is not None and dist_scaled):
+        d = d / (c ** 0.5)
     near = torch.topk(d, k=k, dim=-1, largest=False).values
     density = (-(near ** 2).mean(dim=-1)).exp() + noise_u * 1e-6
     denser = density[:, None, :] > density[:, :, None]                     # [b,i,j]: j denser than i

@@ -10,6 +10,9 @@ import pytest
 import torch
 
 from oracle import model as OM
+from oracle import ops as OP
+
+import margins as MG
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -33,8 +36,107 @@ def quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
+# ------------------------------------------------------------------------------------------------ SURVEY §8c.3
+TAU = 1e-5          # relative fp32 decision margin below which an image counts as tied (SURVEY §8c.3)
+
+
+def stage_tie_free(name, inp, amp, tau=TAU, stage=1):
+    """[B] bool: every decision of this stage of the ORACLE run has a float64 margin above tau (margins.py).  Soft
+    merges make no discrete decision.  eps_d: the product kernel computes its own distances (3xTF32 Gram), measured
+    at ~5e-7 (scaled by 1/sqrt(C)) / ~1e-5 (unscaled) from the reference's cdist (test_pairwise_dist).
+    Where the product's decision inputs are bit-identical to the oracle's by construction (Top-K scores
+    come from the identical ATen call and its gather is a verbatim copy, so at EVERY stage; EViT at the first stage)
+    no margin is needed: ties break toward the lowest index on both sides."""
+    if name == "topk" or (name == "evit" and stage == 0):
+        return torch.ones(inp["scores"].shape[0], dtype=torch.bool)
+    if name in ("evit", "dyvit"):
+        return MG.topk_order_margin(inp["scores"], inp["k"], tau)
+    if name == "tome":
+        if amp:
+            return MG.tome_bf16_decidable(inp["metric"], inp["r"])[0]
+        return MG.tome_fp32_margin(inp["metric"]) > tau
+    if name == "dpcknn":
+        x = inp["x"]
+        d = OP.pairwise_dist(x) / (x.shape[-1] ** 0.5)
+        return MG.dpcknn_decidable(d, inp["noise"], inp["K"], inp["knn"], eps_d=2e-6)[0]
+    if name == "kmedoids":
+        return MG.kmedoids_decidable(OP.pairwise_dist(inp["x"]), inp["tw"], inp["K"], inp["iters"], eps_d=2e-5,
+                                     rel_w=0.0 if stage == 0 else tau)[0]
+    if name == "ats":
+        cdf = OP.ats_significance(inp["v"], inp["attn"]).cumsum(dim=1)
+        cdf = torch.where(inp["mask"][:, 1:], cdf, cdf + 0.1)
+        return MG.ats_decidable(cdf, OP.ats_sample_steps(inp["count"]))
+    raise KeyError(name)
+
+
+def product_decisions(name, viz, i):
+    """the product model's stage-i decisions from its viz dict, in the layout of the oracle's record."""
+    if name in ("topk", "evit", "dyvit", "ats"):
+        return [torch.as_tensor(viz["Kept_Tokens"][i])]
+    if name == "tome":
+        return [torch.as_tensor(viz["Assignment_Maps"][i])]
+    return [torch.as_tensor(viz["Kept_Tokens"][i]), torch.as_tensor(viz["Assignment_Maps"][i])]
+
+
+def oracle_decisions(name, rec, i):
+    r = rec[i]
+    if name == "ats":
+        return [(r[:, 1:] - 1).cpu()]
+    if isinstance(r, tuple):
+        return [t.cpu() for t in r]
+    return [r.cpu()]
+
+
+def same_rows(a, b):
+    if a.shape != b.shape:      # ATS: padded widths may differ when a tied image changes the batch maximum
+        w = min(a.shape[1], b.shape[1])
+        rest_a, rest_b = a[:, w:], b[:, w:]
+        pad_ok = (rest_a <= 0).all(dim=1) if rest_a.numel() else torch.ones(a.shape[0], dtype=torch.bool)
+        pad_ok &= (rest_b <= 0).all(dim=1) if rest_b.numel() else torch.ones(a.shape[0], dtype=torch.bool)
+        return (a[:, :w] == b[:, :w]).all(dim=1) & pad_ok
+    return (a == b).flatten(1).all(dim=1)
+
+
+def compare_with_oracle(name, model, sd, x, cfg, amp, tol, seed=7):
+    """runs product and oracle on the same device / weights / generator state; returns a dict of per-image flags."""
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed(seed)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        y, viz = model(x)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed(seed)
+    rec = {}
+    y_ref = OM.forward(name, sd, x, cfg, amp=amp, record=rec).float()
+    y = y.float()
+    b = x.shape[0]
+    stages = sorted(k for k in rec if isinstance(k, int))
+    has_decisions = name not in ("sinkhorn", "patchmerger", "sit")
+    tie_free = torch.ones(b, dtype=torch.bool)
+    first_tie_free = None
+    agree = torch.ones(b, dtype=torch.bool)
+    first_agree = None
+    for si, i in enumerate(stages):
+        if not has_decisions:
+            break
+        tf = stage_tie_free(name, rec[("in", i)], amp, stage=si)
+        eq = torch.ones(b, dtype=torch.bool)
+        for got, want in zip(product_decisions(name, viz, i), oracle_decisions(name, rec, i)):
+            eq &= same_rows(got.long() if got.dtype != want.dtype else got, want.long() if got.dtype != want.dtype else want)
+        if si == 0:
+            first_tie_free, first_agree = tf.clone(), eq.clone()
+        tie_free &= tf
+        agree &= eq
+    rel = ((y - y_ref).norm(dim=1) / y_ref.norm(dim=1)).cpu()
+    return {"tie_free": tie_free, "agree": agree, "first_tie_free": first_tie_free, "first_agree": first_agree,
+            "rel": rel, "finite": bool(torch.isfinite(y).all())}
+
+
 @pytest.mark.parametrize("name", METHODS)
-def test_micro_model_vs_reference_golden(gold, name):
+def test_micro_model_vs_reference_golden(gold, name, monkeypatch):
+    """the drop-in model with the UNMODIFIED reference's state_dict on the golden images: decisions equal the reference's
+    recorded decisions on every image the oracle run marks tie-free, logits within tolerance on those images.
+    DPC-KNN: the golden run drew its tie-break noise from the CPU generator (seed 300) -- torch.rand is redirected to the
+    CPU generator here so that both sides see the same noise."""
     from tokenreduction_b200 import factory
     ent = gold["methods"][name]
     cls = factory._METHODS[name]
@@ -42,33 +144,63 @@ def test_micro_model_vs_reference_golden(gold, name):
     model = quiet(cls, args=margs(ent["keep_rate"], gold["reduction_loc"], viz_mode=True), **gold["micro"], **extra).eval()
     model.load_state_dict(ent["state_dict"])
     model = model.cuda()
+    images = gold["images_fp16"].float().cuda()
+    orig_rand = torch.rand
+
+    def cpu_rand(*size, device=None, **kw):
+        return orig_rand(*size, **kw).to(device) if device is not None else orig_rand(*size, **kw)
+    monkeypatch.setattr(torch, "rand", cpu_rand)
     torch.manual_seed(300)
-    torch.cuda.manual_seed(300)
     with torch.no_grad():
-        logits, viz = model(gold["images_fp16"].float().cuda())
-    dec = ent["decisions"]
-    same = True
-    for key, stages in dec.items():
+        logits, viz = model(images)
+    # tie-free images according to the oracle run on this device with the same weights
+    torch.manual_seed(300)
+    rec = {}
+    micro = gold["micro"]
+    cfg = OM.Cfg(embed_dim=micro["embed_dim"], num_heads=micro["num_heads"], depth=micro["depth"],
+                 keep_rate=[ent["keep_rate"]], reduction_loc=list(gold["reduction_loc"]))
+    sd = {k: v.detach().clone().cuda() for k, v in ent["state_dict"].items()}
+    OM.forward(name, sd, images, cfg, record=rec)
+    b = images.shape[0]
+    tie_free = torch.ones(b, dtype=torch.bool)
+    if name not in ("sinkhorn", "patchmerger", "sit"):
+        for i in sorted(k for k in rec if isinstance(k, int)):
+            tie_free &= stage_tie_free(name, rec[("in", i)], False, tau=1e-4, stage=99)   # CPU backbone vs cuBLAS backbone
+    same = torch.ones(b, dtype=torch.bool)
+    for key, stages in ent["decisions"].items():
         for i, ref in stages.items():
             got = torch.as_tensor(viz[key][i])
-            if name == "dpcknn":
-                continue      # DPC-KNN draws its tie-break noise from the CUDA generator here, from the CPU one in the golden run
-            frac = (got == ref).float().mean().item() if got.shape == ref.shape else 0.0
-            same = same and frac == 1.0
-            assert frac > 0.97, f"{name} stage {i} {key}: only {frac:.3f} of decisions match the reference"
-    if same and name != "dpcknn":
-        err = float((logits.cpu() - ent["logits"]).abs().max())
-        assert err < 2e-3, f"{name}: logits differ from the reference golden by {err}"
+            same &= same_rows(got.long(), torch.as_tensor(ref).long()) if got.dim() > 1 else torch.tensor([bool((got == ref).all())] * b)
+    print(f"{name}: golden tie-free {tie_free.tolist()} decisions identical {same.tolist()}")
+    assert bool(same[tie_free].all()), f"{name}: a tie-free image differs from the reference's golden decisions"
+    ok = tie_free & same
+    if bool(ok.any()):
+        err = ((logits.cpu() - ent["logits"]).norm(dim=1) / ent["logits"].norm(dim=1))[ok].max()
+        assert float(err) < 2e-4, f"{name}: logits differ from the reference golden by {float(err):.2e} (relative)"
+
+
+# fp32 bar of north_star: 1e-5 on the merged FEATURES (op-level tests); at the logits the per-op rounding differences
+# (fp32 summation order, 3xTF32 Gram) pass through up to 9 more transformer blocks, which amplify them: the model-level
+# bar is the amplified one, measured per method and recorded in DESIGN.md §4.
+TOL_FP32 = 2e-4
+TOL_BF16 = 3e-2
 
 
 @pytest.mark.parametrize("amp", [False, True])
 @pytest.mark.parametrize("name", METHODS)
 def test_small_model_vs_oracle_same_device(name, amp):
+    """SURVEY §8c.3.  Product model vs oracle port on the SAME device, weights and generator state (identical cuBLAS
+    backbone; only the reduction operators differ), DeiT-S, 16 images:
+      * fp32: every image whose decisions are ALL above the margin (tie-free) must make identical decisions at every
+        stage and agree in the logits; the excluded fraction is printed and bounded.
+      * bf16 autocast: stage-1 decisions (bit-identical inputs on both sides) must be identical on stage-1 tie-free
+        images; later stages see inputs that differ in the last bf16 bit, where bf16 scores are full of exact ties
+        (SURVEY A.10), so the logits bar applies to images whose decisions all agree (conditioned parity)."""
     from tokenreduction_b200 import create_model
-    b = 8
+    b = 16
     size = "small"
     torch.manual_seed(0)
-    model = quiet(create_model, f"{name}_{size}_patch16_224", num_classes=100, args=margs(KR[name])).eval().cuda()
+    model = quiet(create_model, f"{name}_{size}_patch16_224", num_classes=100, args=margs(KR[name], viz_mode=True)).eval().cuda()
     with torch.no_grad():      # spread the reduction parameters: random init leaves every decision tied (SURVEY A.10)
         for n_, p_ in model.named_parameters():
             if n_.startswith("cluster_layers") and p_.dim() >= 2 and "queries" not in n_ and not n_.endswith(".v"):
@@ -77,20 +209,26 @@ def test_small_model_vs_oracle_same_device(name, amp):
                 p_.mul_(4.0)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     x = torch.randn(b, 3, 224, 224, generator=torch.Generator().manual_seed(1)).cuda()
-    torch.manual_seed(7)
-    torch.cuda.manual_seed(7)
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-        y = model(x).float()
-    torch.manual_seed(7)
-    torch.cuda.manual_seed(7)
-    y_ref = OM.forward(name, sd, x, OM.cfg_for(size, keep_rate=[KR[name]]), amp=amp).float()
-    assert torch.isfinite(y).all()
-    rel = (y - y_ref).norm(dim=1) / y_ref.norm(dim=1)
-    tol = 3e-2 if amp else 1e-3
-    good = (rel < tol).float().mean().item()
-    print(f"{name} amp={amp}: per-image rel err {rel.tolist()}")
-    # images whose discrete decisions sit on a near-tie can flip; most images must agree tightly
-    assert good >= 0.75, f"{name} amp={amp}: only {good:.2f} of images within {tol} (rel errs {rel.tolist()})"
+    r = compare_with_oracle(name, model, sd, x, OM.cfg_for(size, keep_rate=[KR[name]]), amp, None)
+    assert r["finite"]
+    tol = TOL_BF16 if amp else TOL_FP32
+    tf, ag, rel = r["tie_free"], r["agree"], r["rel"]
+    print(f"{name} amp={amp}: tie-free {int(tf.sum())}/{b}, decisions identical {int(ag.sum())}/{b}, "
+          f"worst rel err on identical-decision images {float(rel[ag].max()) if bool(ag.any()) else float('nan'):.2e}, "
+          f"all {['%.1e' % v for v in rel.tolist()]}")
+    if not amp:
+        assert bool(ag[tf].all()), f"{name}: {int((~ag[tf]).sum())} tie-free images made different decisions"
+        if bool(tf.any()):
+            assert float(rel[tf].max()) <= tol, f"{name}: tie-free image logits differ by {float(rel[tf].max()):.2e} > {tol}"
+        if name not in ("ats", "dyvit"):           # random-init ATS / DynamicViT scores are tied on every image (A.10)
+            assert int(tf.sum()) >= 2, f"{name}: only {int(tf.sum())}/{b} images tie-free -- vacuous"
+    else:
+        if r["first_tie_free"] is not None:
+            f_tf, f_ag = r["first_tie_free"], r["first_agree"]
+            assert bool(f_ag[f_tf].all()), f"{name}: stage-1 decisions differ on {int((~f_ag[f_tf]).sum())} tie-free images"
+        if bool(ag.any()):
+            assert float(rel[ag].max()) <= tol, f"{name}: logits differ by {float(rel[ag].max()):.2e} > {tol} with identical decisions"
+        assert float(ag.float().mean()) >= 0.25, f"{name} amp: only {int(ag.sum())}/{b} images with identical decisions"
 
 
 def test_batch_shard_equivalence():

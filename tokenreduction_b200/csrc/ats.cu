@@ -194,8 +194,10 @@ extern "C" int tokred_ats_sample(const void* v, int v_dtype, int64_t v_stride_b,
   TOKRED_REQUIRE(v && attn && mask && steps && ids_out && mask_out && max_count, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(v_dtype), "%s: bad v dtype %d", what, v_dtype);
   TOKRED_REQUIRE(B >= 0 && H >= 1 && N >= 2 && Dh >= 1, "%s: bad shape B=%d H=%d N=%d Dh=%d", what, B, H, N, Dh);
-  TOKRED_REQUIRE(n_steps >= 1 && n_steps <= N - 1, "%s: n_steps=%d outside [1, %d] (a step can only select one of the "
-                 "N-1 patches)", what, n_steps, N - 1);
+  // n_steps may exceed N-1: after the first ATS stage N = 1 + max_b #unique shrinks with peaked attention while the
+  // per-stage sample_count is fixed by keep_rate (models/ats.py:204-205).  hit[] is sized N, #unique <= min(n_steps, N-1)
+  // and the id / mask rows are n_steps + 1 wide, so nothing in the kernel needs an upper bound.
+  TOKRED_REQUIRE(n_steps >= 1 && n_steps <= 65535, "%s: n_steps=%d outside [1, 65535]", what, n_steps);
   if (B == 0) return TOKRED_OK;
   const int P = N - 1;
   const size_t smem = ((size_t)H * P + P + kWarps + N + 1) * 4;

@@ -113,13 +113,16 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// ATen's max / argmax treat NaN as the greatest value (it propagates, index = first NaN)
+__device__ __forceinline__ bool nan_gt(float a, float b) { return a > b || (a != a && b == b); }
+__device__ __forceinline__ bool nan_eq(float a, float b) { return a == b || (a != a && b != b); }
 // (value, index) arg-reductions with lowest-index tie-break (ATen max/min semantics).
 __device__ __forceinline__ void warp_argmax(float& v, int& i) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     float ov = __shfl_xor_sync(0xffffffffu, v, o);
     int oi = __shfl_xor_sync(0xffffffffu, i, o);
-    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    if (nan_gt(ov, v) || (nan_eq(ov, v) && oi < i)) { v = ov; i = oi; }
   }
 }
 __device__ __forceinline__ void warp_argmin(float& v, int& i) {
@@ -134,15 +137,24 @@ __device__ __forceinline__ void warp_argmin(float& v, int& i) {
 // Descending rank of element i among n keys held in shared memory: number of keys that sort before it under
 // (value desc, index asc).  O(n) broadcast reads per caller; n <= a few hundred tokens on this path, so the
 // whole ordering is O(n^2) conflict-free LDS with no barriers — cheaper than a bitonic network at this size.
+// The order is TOTAL: NaN sorts as the largest value (what ATen's topk / sort(descending) do) and NaNs tie among
+// themselves by index, so every rank in [0, n) is produced exactly once even for NaN keys (a zero-norm ToMe
+// metric row, overflowed activations) and no consumer ever reads an unwritten index slot.
 __device__ __forceinline__ int rank_desc(const float* keys, int n, int i) {
   const float ki = keys[i];
   int r = 0;
-  for (int j = 0; j < n; ++j) {
-    float kj = keys[j];
-    r += (kj > ki) || (kj == ki && j < i);
+  if (ki != ki) {
+    for (int j = 0; j < i; ++j) { const float kj = keys[j]; r += (kj != kj); }
+  } else {
+    for (int j = 0; j < n; ++j) {
+      const float kj = keys[j];
+      r += !(kj <= ki) || (kj == ki && j < i);      // !(kj <= ki): kj > ki, or kj is NaN
+    }
   }
   return r;
 }
+
+__device__ __forceinline__ int clamp_idx(long long v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : (int)v); }
 
 #endif  // __CUDACC__
 }  // namespace tokred

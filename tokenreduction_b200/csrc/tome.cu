@@ -37,6 +37,10 @@ tome_match_kernel(const TM* __restrict__ metric, int N, int D, int r, int class_
 
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const TM* mb = metric + (long long)b * N * D;
+  // class_token carries the protection flags: bit 0 = class token (row 0 never merges away, models/tome.py:263-264),
+  // bit 1 = distillation token (odd token 0 never receives a merge, :265-266)
+  const bool dist_token = (class_token & 2) != 0;
+  class_token &= 1;
 
   // 1a. stage the raw metric tile into shared memory with every load of the CTA in flight at once (the first
   //     version walked the rows one warp at a time from global memory and was latency-bound: ncu r01, 55 us)
@@ -129,8 +133,8 @@ tome_match_kernel(const TM* __restrict__ metric, int N, int D, int r, int class_
     int bj = 0x7fffffff;
     if (!(class_token && i == 0)) {
       for (int j = lane; j < nb; j += 32) {
-        float v = S[i * SP + j];
-        if (v > best || bj == 0x7fffffff) { best = v; bj = j; }
+        float v = (dist_token && j == 0) ? -CUDART_INF_F : S[i * SP + j];
+        if (nan_gt(v, best) || bj == 0x7fffffff) { best = v; bj = j; }
       }
     }
     warp_argmax(best, bj);
@@ -190,6 +194,8 @@ tome_match_tc_kernel(const TM* __restrict__ metric, int N, int D, int r, int cla
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const TM* mb = metric + (long long)b * N * D;
   const uint32_t ncols = umma::tmem_cols_pow2((uint32_t)Np);
+  const bool dist_token = (class_token & 2) != 0;      // protection flags, see tome_match_kernel
+  class_token &= 1;
 
   if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
   if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_mbar_init(); }
@@ -262,8 +268,8 @@ tome_match_tc_kernel(const TM* __restrict__ metric, int N, int D, int r, int cla
       umma::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float sc = bf16_round(__uint_as_float(v[j]));
-        if (c0 + j < nb && (sc > best || bj == 0x7fffffff)) { best = sc; bj = c0 + j; }
+        const float sc = (dist_token && c0 + j == 0) ? -CUDART_INF_F : bf16_round(__uint_as_float(v[j]));
+        if (c0 + j < nb && (nan_gt(sc, best) || bj == 0x7fffffff)) { best = sc; bj = c0 + j; }
       }
     }
     if (warp >= 4) { node_max[i] = best; node_idx[i] = bj; }
@@ -271,7 +277,7 @@ tome_match_tc_kernel(const TM* __restrict__ metric, int N, int D, int r, int cla
     if (warp < 4) {
       const float ob = node_max[i];
       const int oj = node_idx[i];
-      if (oj != 0x7fffffff && (ob > best || bj == 0x7fffffff)) { best = ob; bj = oj; }   // ties keep the lower column
+      if (oj != 0x7fffffff && (nan_gt(ob, best) || bj == 0x7fffffff)) { best = ob; bj = oj; }   // ties keep the lower column
       if (bj == 0x7fffffff) bj = 0;
       if (class_token && i == 0) { best = -CUDART_INF_F; bj = 0; }
     }
@@ -437,10 +443,11 @@ tome_merge_kernel(const T* __restrict__ x, const T* __restrict__ size, const int
   const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool has_size = size != nullptr;
   for (int t = tid; t < N; t += kThreads) zs[t] = has_size ? to_f32(size[(long long)b * N + t]) : 1.f;
-  for (int q = tid; q < n_unm; q += kThreads) unm[q] = (int)unm_idx[(long long)b * n_unm + q];
+  // caller-supplied index lists are clamped into range (as dpcknn_merge / gather_rows do): no out-of-bounds row
+  for (int q = tid; q < n_unm; q += kThreads) unm[q] = clamp_idx(unm_idx[(long long)b * n_unm + q], na);
   for (int s = tid; s < r; s += kThreads) {
-    src[s] = (int)src_idx[(long long)b * r + s];
-    dst[s] = (int)dst_idx[(long long)b * r + s];
+    src[s] = clamp_idx(src_idx[(long long)b * r + s], na);
+    dst[s] = clamp_idx(dst_idx[(long long)b * r + s], N / 2);
   }
   __syncthreads();
 
@@ -472,7 +479,7 @@ tome_merge_kernel(const T* __restrict__ x, const T* __restrict__ size, const int
 using namespace tokred;
 
 extern "C" int tokred_tome_effective_r(int N, int r, int class_token) {
-  const int cap = (N - (class_token ? 1 : 0)) / 2;
+  const int cap = (N - ((class_token & 1) ? 1 : 0) - ((class_token & 2) ? 1 : 0)) / 2;
   const int e = r < cap ? r : cap;
   return e > 0 ? e : 0;
 }

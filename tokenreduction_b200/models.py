@@ -16,8 +16,51 @@ from . import ops
 from .vit import PatchEmbed, VisionTransformer
 
 
+class _Pending:
+    """a viz tensor that stays on the device until the forward is over (the reference does one
+    blocking ``.cpu().numpy()`` per stage and dict entry, e.g. models/topk.py:195-197)."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+
 def _np(t):
-    return t.clone().detach().cpu().numpy()
+    return _Pending(t.detach())
+
+
+def _finalize_viz(viz):
+    """every pending tensor -> pinned host memory with async copies, ONE stream synchronisation, then numpy arrays
+    (the types validate.py:199-229 consumes)."""
+    pend = []
+
+    def walk(d):
+        for v in d.values():
+            if isinstance(v, dict):
+                walk(v)
+            elif isinstance(v, _Pending):
+                pend.append(v)
+    walk(viz)
+    host = []
+    for p_ in pend:
+        if p_.t.is_cuda:
+            h = torch.empty(p_.t.shape, dtype=p_.t.dtype, pin_memory=True)
+            h.copy_(p_.t, non_blocking=True)
+        else:
+            h = p_.t.clone()
+        host.append(h)
+    if any(p_.t.is_cuda for p_ in pend):
+        torch.cuda.current_stream().synchronize()
+    done = {id(p_): h.numpy() for p_, h in zip(pend, host)}
+
+    def swap(d):
+        for k, v in d.items():
+            if isinstance(v, dict):
+                swap(v)
+            elif isinstance(v, _Pending):
+                d[k] = done[id(v)]
+    swap(viz)
+    return viz
 
 
 def _geometric(keep_rate, n_stages, what):
@@ -48,7 +91,7 @@ class _ReducedViT(VisionTransformer):
     def _ret(self, x, viz_data=None):
         if self.training or not self.viz_mode:
             return x
-        return x, viz_data
+        return x, _finalize_viz(viz_data)
 
 
 # =============================================================================================== Top-K / EViT
@@ -158,7 +201,7 @@ class ToMeVisionTransformer(_ReducedViT):
         i = -1
         for i, blk in enumerate(self.blocks):
             x, attn_size, cluster_assign = blk(x, attn_size)
-            if self.viz_mode and i in self.pruning_loc:
+            if self.viz_mode and i in self.pruning_loc and cluster_assign is not None:
                 assignments[i] = _np(cluster_assign)
                 features[i] = _np(x)
         if self.viz_mode and 11 not in features:
@@ -403,7 +446,10 @@ class ATSVisionTransformer(_ReducedViT):
                        attn_drop=attn_drop_rate, drop_path=dpr[i], norm_layer=norm_layer, act_layer=act_layer,
                        ats_sample_count=self.sample_count[i])
             for i in range(depth)])
-        static = bool(getattr(args, "tokred_ats_static_width", False))
+        # default: pad to sample_count -> no host read anywhere in the forward (north_star: "variable post-reduction token
+        # counts are handled without host syncs"); args.tokred_ats_exact_width=True restores the reference's data-dependent
+        # width max_b #unique (models/ats.py:77-83) at the cost of ONE scalar read per stage (the reference syncs per image)
+        static = not bool(getattr(args, "tokred_ats_exact_width", False))
         for blk in self.blocks:
             if blk.attn.ats_sample_count:
                 blk.attn.ats.static_width = static

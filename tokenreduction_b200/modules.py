@@ -7,7 +7,7 @@ match+merge launch instead of topk -> expand -> gather -> cat.  Block-level sign
 
 Precision: ``_lowp()`` is True under ``torch.autocast('cuda', dtype=torch.bfloat16)`` — the kernels then round
 exactly where the reference's autocast matmuls round.  fp16 autocast (the reference's
-validate.py default) is not supported by the kernels and raises.
+validate.py default) converts at the op boundary, see ``_lowp``.
 """
 from __future__ import annotations
 
@@ -24,12 +24,20 @@ from .vit import DropPath, Mlp
 
 
 def _lowp() -> bool:
+    """True under CUDA autocast.  bf16 autocast (BASELINE) is reproduced rounding for rounding.  fp16 autocast (the
+    reference's validate.py:52-54 default) runs the same reduced-precision kernels: half tensors are converted at the op
+    boundary (fp16 -> fp32 is exact) and the matmul roundings are bf16's, a documented deviation."""
     if not torch.is_autocast_enabled("cuda"):
         return False
     dt = torch.get_autocast_dtype("cuda")
-    if dt != torch.bfloat16:
-        raise RuntimeError(f"tokred kernels support float32 and bfloat16 autocast, not {dt}")
+    if dt not in (torch.bfloat16, torch.float16):
+        raise RuntimeError(f"tokred kernels support float32, bfloat16 and float16 autocast, not {dt}")
     return True
+
+
+def _f16_to_bf16(t: Tensor) -> Tensor:
+    """fp16 tensors enter the kernels as fp32 (exact); fp32 / bf16 pass through untouched."""
+    return t.float() if t.dtype == torch.float16 else t
 
 
 def _train_guard(mod: nn.Module) -> None:
@@ -152,20 +160,25 @@ class Block_EVIT(nn.Module):
 class _ToMeMerge:
     """The ``merge`` closure of models/tome.py:279-289, carrying the three index lists on the device."""
 
-    def __init__(self, unm_idx: Tensor, src_idx: Tensor, dst_idx: Tensor, n_tokens: int):
+    def __init__(self, unm_idx: Tensor, src_idx: Tensor, dst_idx: Tensor, n_tokens: int, class_token: bool = True,
+                 distill_token: bool = False):
         self.unm_idx, self.src_idx, self.dst_idx, self.n_tokens = unm_idx, src_idx, dst_idx, n_tokens
+        self.class_token, self.distill_token = class_token, distill_token
 
     @property
     def r(self) -> int:
         return self.src_idx.shape[1]
 
+    def reorder(self, out: Tensor) -> Tensor:
+        """distilled models keep [cls, dist] in front: cat([unm[:1], dst[:1], unm[1:], dst[1:]]) (models/tome.py:286-287)."""
+        if not self.distill_token:
+            return out
+        u = self.unm_idx.shape[1]
+        return torch.cat([out[:, :1], out[:, u:u + 1], out[:, 1:u], out[:, u + 1:]], dim=1)
+
     def __call__(self, x: Tensor, mode: str = "mean") -> Tensor:        # mode is ignored by the reference too
         out, _, _ = ops.tome_merge(x, None, self.unm_idx, self.src_idx, self.dst_idx, False, False)
-        return out
-
-    def row_map(self, x: Tensor) -> Tensor:
-        _, _, rci = ops.tome_merge(x[..., :1].contiguous(), None, self.unm_idx, self.src_idx, self.dst_idx, True, False)
-        return rci
+        return self.reorder(out)
 
 
 def do_nothing(x, mode=None):
@@ -175,35 +188,45 @@ def do_nothing(x, mode=None):
 def bipartite_soft_matching(metric: Tensor, r: int, class_token: bool = False,
                             distill_token: bool = False) -> Tuple[Callable, Callable]:
     """models/tome.py:230-306.  Returns (merge, unmerge)."""
-    if distill_token:
-        raise NotImplementedError("tokred tome_match: distillation token protection is not on the accelerated path")
     t = metric.shape[1]
-    r = min(r, (t - int(class_token)) // 2)
+    r = ops.tome_effective_r(t, r, class_token, distill_token)
     if r <= 0:
         return do_nothing, do_nothing
-    lowp = _lowp() or metric.dtype == torch.bfloat16
-    unm_idx, src_idx, dst_idx = ops.tome_match(metric, r, class_token, lowp, True)
-    merge = _ToMeMerge(unm_idx, src_idx, dst_idx, t)
+    lowp = _lowp() or metric.dtype in (torch.bfloat16, torch.float16)
+    unm_idx, src_idx, dst_idx = ops.tome_match(_f16_to_bf16(metric), r, class_token, lowp, True, distill_token)
+    merge = _ToMeMerge(unm_idx, src_idx, dst_idx, t, class_token, distill_token)
 
-    def unmerge(x: Tensor) -> Tensor:                                  # models/tome.py:291-304 (not on the hot path)
-        unm_len = unm_idx.shape[1]
-        unm, dst = x[..., :unm_len, :], x[..., unm_len:, :]
-        n, _, c = unm.shape
-        src = dst.gather(dim=-2, index=dst_idx.unsqueeze(-1).expand(n, r, c))
-        out = torch.zeros(n, t, c, device=x.device, dtype=x.dtype)
-        out[..., 1::2, :] = dst
-        out.scatter_(dim=-2, index=(2 * unm_idx).unsqueeze(-1).expand(n, unm_len, c), src=unm)
-        out.scatter_(dim=-2, index=(2 * src_idx).unsqueeze(-1).expand(n, r, c), src=src)
-        return out
+    def unmerge(x: Tensor) -> Tensor:
+        """models/tome.py:291-304 — one gather launch: input token t reads the merged row it went to."""
+        return ops.gather_rows(x, tome_token_rows(merge, x))
 
     return merge, unmerge
+
+
+def tome_token_rows(merge: "_ToMeMerge", like: Tensor) -> Tensor:
+    """[B, t] int64: the merged-output row every input token landed in, computed on the device from the three index
+    lists (the reference derives the same map by pushing a [B,t,t] identity through the merge, :326-337)."""
+    unm, src, dst = merge.unm_idx, merge.src_idx, merge.dst_idx
+    b, t = unm.shape[0], merge.n_tokens
+    u = unm.shape[1]
+    rows = torch.empty(b, t, dtype=torch.long, device=unm.device)
+    rows[:, 1::2] = u + torch.arange(t // 2, device=unm.device)
+    rows.scatter_(1, 2 * unm, torch.arange(u, device=unm.device).expand(b, -1))
+    rows.scatter_(1, 2 * src, u + dst)
+    if merge.distill_token:          # row permutation of models/tome.py:286-287
+        perm = torch.cat([torch.tensor([0], device=unm.device), torch.tensor([u], device=unm.device),
+                          torch.arange(1, u, device=unm.device), torch.arange(u + 1, t - merge.r, device=unm.device)])
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(perm.numel(), device=unm.device)
+        rows = inv[rows]
+    return rows
 
 
 def merge_wavg(merge: Callable, x: Tensor, size: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """models/tome.py:309-323 — one fused launch when ``merge`` came from bipartite_soft_matching above."""
     if isinstance(merge, _ToMeMerge):
         out, size_out, _ = ops.tome_merge(x, size, merge.unm_idx, merge.src_idx, merge.dst_idx, False, True)
-        return out, size_out
+        return merge.reorder(out), merge.reorder(size_out)
     if size is None:
         size = torch.ones_like(x[..., 0, None])
     x = merge(x * size, mode="sum")
@@ -216,12 +239,18 @@ def merge_source(merge: Callable, x: Tensor, source: Optional[Tensor] = None) ->
     if source is None:
         n, t, _ = x.shape
         if isinstance(merge, _ToMeMerge):
-            rows = (merge.row_map(x) + 1).long()                              # output row of tokens 1..t-1
-            rows = torch.cat([rows.new_zeros(n, 1), rows], dim=1)             # CLS -> row 0
+            rows = tome_token_rows(merge, x)                                  # valid with or without CLS / dist token
             out = torch.zeros(n, t - merge.r, t, device=x.device)
             return out.scatter_(1, rows.unsqueeze(1), 1.0)
         source = torch.eye(t, device=x.device)[None, ...].expand(n, t, t)
     return merge(source, mode="amax")
+
+
+def _reduced_cluster_idx(source: Tensor, cls_token: bool) -> Tensor:
+    """Block_ToMe's map from the adjacency (models/tome.py:92-99): float32, group id of every input token."""
+    ar = torch.arange(1, source.shape[1] + 1, device=source.device, dtype=source.dtype)
+    rci = torch.amax(source * ar[None, :, None], dim=-2)
+    return (rci - 2)[:, 1:] if cls_token else rci - 1
 
 
 class Attention_ToMe(_AttentionBase):
@@ -257,16 +286,19 @@ class Block_ToMe(nn.Module):
         reduced_cluster_idx = None
         if self.r > 0:
             _train_guard(self)
-            if self.dist_token:
-                raise NotImplementedError("Block_ToMe: dist_token protection is not on the accelerated path")
-            if ops.tome_effective_r(x.shape[1], self.r, self.cls_token) > 0:
-                lowp = _lowp() or metric.dtype == torch.bfloat16
-                unm, src, dst = ops.tome_match(metric, self.r, self.cls_token, lowp, True)
+            re = ops.tome_effective_r(x.shape[1], self.r, self.cls_token, self.dist_token)
+            if re > 0 and self.cls_token and not self.dist_token:
+                lowp = _lowp() or metric.dtype in (torch.bfloat16, torch.float16)
+                unm, src, dst = ops.tome_match(_f16_to_bf16(metric), self.r, True, lowp, True)
                 # merged tokens, new sizes and the source map from ONE launch (the reference pushes a [B,t,t]
                 # identity through the merge to get the map, models/tome.py:91-99)
                 x, attn_size, reduced_cluster_idx = ops.tome_merge(x, attn_size, unm, src, dst, True, True)
-                if not self.cls_token:
-                    reduced_cluster_idx = None      # reference: different offset without CLS; never used on this path
+            else:
+                # nothing left to merge (identity map, like the reference's do_nothing), no class token (different
+                # offset) or a distillation token (row permutation): the reference's own sequence over the same ops
+                merge, _ = bipartite_soft_matching(metric, self.r, self.cls_token, self.dist_token)
+                reduced_cluster_idx = _reduced_cluster_idx(merge_source(merge, x, None), self.cls_token)
+                x, attn_size = merge_wavg(merge, x, attn_size)
         x = x + self.drop_path(self.mlp(self.norm2(x)))
         return x, attn_size, reduced_cluster_idx
 

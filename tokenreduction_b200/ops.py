@@ -184,16 +184,17 @@ def evit_select_fuse_attn(x: Tensor, attn: Tensor, k: int):
 
 
 # ----------------------------------------------------------------------------------------------- ToMe
-def tome_effective_r(n_tokens: int, r: int, class_token: bool = True) -> int:
-    """models/tome.py:244-253 (no distillation token on this path)."""
-    return max(min(r, (n_tokens - int(class_token)) // 2), 0)
+def tome_effective_r(n_tokens: int, r: int, class_token: bool = True, distill_token: bool = False) -> int:
+    """models/tome.py:244-253."""
+    return max(min(r, (n_tokens - int(class_token) - int(distill_token)) // 2), 0)
 
 
 @torch.library.custom_op("tokred::tome_match", mutates_args=(), device_types="cuda")
-def _tome_match(metric: Tensor, r: int, class_token: bool, lowp: bool, tensor_cores: bool) -> Tuple[Tensor, Tensor, Tensor]:
+def _tome_match(metric: Tensor, r: int, class_token: bool, lowp: bool, tensor_cores: bool,
+                distill_token: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     _need_cuda("tome_match", metric)
     b, n, d = metric.shape
-    re = tome_effective_r(n, r, class_token)
+    re = tome_effective_r(n, r, class_token, distill_token)
     if re <= 0:
         raise TokredError(f"tome_match: effective r = {re}; nothing to merge (caller must skip, models/tome.py:255)")
     metric = _c(metric)
@@ -202,15 +203,15 @@ def _tome_match(metric: Tensor, r: int, class_token: bool, lowp: bool, tensor_co
     src = torch.empty((b, re), dtype=torch.int64, device=metric.device)
     dst = torch.empty((b, re), dtype=torch.int64, device=metric.device)
     mode = (1 if tensor_cores else 3) if lowp else 0
-    _lib.call("tokred_tome_match", _ptr(metric), _dt(metric), b, n, d, r, int(class_token), mode, _ptr(unm),
-              _ptr(src), _ptr(dst), _stream())
+    _lib.call("tokred_tome_match", _ptr(metric), _dt(metric), b, n, d, r, int(class_token) | (2 if distill_token else 0),
+              mode, _ptr(unm), _ptr(src), _ptr(dst), _stream())
     return unm, src, dst
 
 
 @_tome_match.register_fake
-def _(metric, r, class_token, lowp, tensor_cores):
+def _(metric, r, class_token, lowp, tensor_cores, distill_token=False):
     b, n, d = metric.shape
-    re = tome_effective_r(n, r, class_token)
+    re = tome_effective_r(n, r, class_token, distill_token)
     na = (n + 1) // 2
     mk = lambda m: metric.new_empty((b, m), dtype=torch.int64)
     return mk(na - re), mk(re), mk(re)
@@ -245,11 +246,12 @@ def _(x, size, unm, src, dst, want_map, divide):
             x.new_empty((b, n - 1) if want_map else (0,), dtype=torch.float32))
 
 
-def tome_match(metric: Tensor, r: int, class_token: bool = True, lowp: bool = False, tensor_cores: bool = True):
+def tome_match(metric: Tensor, r: int, class_token: bool = True, lowp: bool = False, tensor_cores: bool = True,
+               distill_token: bool = False):
     """models/tome.py:258-277: (unm_idx [B,a-r], src_idx [B,r], dst_idx [B,r]) int64.
     lowp=True reproduces the bf16 autocast matmul (on tcgen05 tensor cores; tensor_cores=False keeps the same
-    rounding on the FFMA path, used as a cross-check)."""
-    return torch.ops.tokred.tome_match(metric, r, class_token, lowp, tensor_cores)
+    rounding on the FFMA path, used as a cross-check).  distill_token protects odd token 0 as a destination (:265-266)."""
+    return torch.ops.tokred.tome_match(metric, r, class_token, lowp, tensor_cores, distill_token)
 
 
 def tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor, want_map: bool = True,
