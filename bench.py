@@ -2,23 +2,28 @@
 """bench.py — images/s of the reduced-ViT forward with the tokred reduction kernels (driver contract).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl tokred|reference] [--workload NAME] [--batch B]
+                    [--headline-only]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
 A "step" is one forward pass of the hot path's host model over one synthetic batch (random-init weights, N(0,1)
 224x224 images): the backbone runs on PyTorch/cuBLAS exactly like the reference's, the reduction operators at
-blocks 3/6/9 are the hand-written sm_100a kernels of libtokred_sm100a.so.  Default workload = BASELINE.json
-configs[1] (DeiT-S ToMe, reduction_loc 3 6 9, batch 256 per GPU, bf16 autocast).  Multi-GPU = pure batch sharding
-(weak scaling: the per-GPU batch is fixed), with one NCCL all_gather of the logits and of the last stage's
-assignment map per step — the only exchange the path has.
+blocks 3/6/9 are the hand-written sm_100a kernels of libtokred_sm100a.so.  Headline workload = BASELINE.json
+configs[1] (DeiT-S ToMe, reduction_loc 3 6 9, batch 256 per GPU, bf16 autocast), weak scaling (per-GPU batch fixed).
+Multi-GPU = pure batch sharding with one NCCL exchange per step: all_gather of the logits AND of every stage's
+kept-token / assignment indices (north_star; the reference's consumer is validate.py:199-229).
 
 One JSON line on rank 0:
-  value      images/s, all ranks, inputs resident in HBM, CUDA events, max over ranks
+  value      images/s of the headline, all ranks, inputs resident in HBM, CUDA events, max over ranks
   e2e        same through the public API with pinned-host inputs: H2D of the batch + D2H of the logits per step
   roofline   dominant tokred kernel (largest stage): algorithmic bytes / measured duration vs MEASURED_PEAKS hbm_gbs
   kernels    every tokred launch of one step: avg us, algorithmic GB/s, fraction of peak
-  cpu_baseline  the oracle port of the reference model on the host cores, bounded sample
---impl reference: the oracle port (CPU restatement pinned to the reference, oracle/model.py) on the host cores.
+  cpu_baseline  the unmodified reference (baseline/_ref, else the oracle port) on the host cores, bounded sample
+  workloads  every other BASELINE.json config measured the same way in the same run: config 1 (Top-K S B=64), config 3
+             (EViT / DynamicViT B, global batch 1024 STRONG-scaled over the ranks), config 4 (DPC-KNN / K-Medoids S
+             B=256), config 5 (ATS / Sinkhorn / PatchMerger B, per-GPU batch sweep), SiT
+--impl reference: the reference's own CPU implementation on the host cores (kind "reference" when baseline/_ref is
+staged, "port" = oracle/model.py otherwise), at the headline's per-GPU batch.
 """
 from __future__ import annotations
 
@@ -54,9 +59,23 @@ DEFAULT_WORKLOAD = "tome_small_kr0.7_b256_bf16"
 DIMS = {"tiny": (192, 3), "small": (384, 6), "base": (768, 12)}
 
 
-def model_args(kr):
+def extra_workloads(world):
+    """(label, BASELINE config, workload key, per-GPU batch, scaling) measured after the headline in the same run."""
+    out = [("topk_small_kr0.7_b64", 1, "topk_small_kr0.7_b64", 64, "weak")]
+    for w in ("evit_base_kr0.5_b128", "dyvit_base_kr0.5_b128"):         # config 3: batch 1024 SHARDED over the GPUs
+        out.append((w.replace("_b128", f"_global1024_dp{world}"), 3, w, max(1024 // world, 1), "strong"))
+    for w in ("dpcknn_small_kr0.25_b256", "kmedoids_small_kr0.25_b256"):
+        out.append((w, 4, w, 256, "weak"))
+    for w in ("ats_base_kr0.9_b128", "sinkhorn_base_kr0.9_b128", "patchmerger_base_kr0.9_b128"):   # config 5: sweep
+        for bsz in (128, 512, 1024):
+            out.append((w.replace("_b128", f"_b{bsz}"), 5, w, bsz, "weak"))
+    out.append(("sit_base_kr0.9_b128", None, "sit_base_kr0.9_b128", 128, "weak"))
+    return out
+
+
+def model_args(kr, **kw):
     return Namespace(keep_rate=[kr], reduction_loc=[3, 6, 9], distillation_type="none", k_neighbors=5, cluster_iters=3,
-                     sinkhorn_eps=1.0, equal_weight=False, dyvit_distill=False)
+                     sinkhorn_eps=1.0, equal_weight=False, dyvit_distill=False, **kw)
 
 
 def measured_peaks():
@@ -213,26 +232,46 @@ def summarise_timeline(timeline, steps, peak_gbs):
 
 # ------------------------------------------------------------------------------------------------ reference arm
 def cpu_reference_run(method, size, kr, amp, sample_batch, steps, warmup):
-    """The oracle port of the reference model (oracle/model.py, pinned to the unmodified reference) on the host
-    cores, fp32, all threads.  Returns (images/s, ms/step, cores)."""
-    from oracle import model as OM
-    from tokenreduction_b200 import create_model
+    """The reference model on the host cores, fp32, all threads.  kind "reference": the UNMODIFIED reference classes
+    from baseline/_ref (staged by __graft_entry__.build(); imported through the timm-0.4.12 API shim, the only missing
+    dependency) built by the reference's own factory; kind "port": the oracle port (oracle/model.py, pinned to the
+    reference) when no staged copy exists.  Returns (images/s, ms/step, cores, kind)."""
     import contextlib
     import io
     torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    with contextlib.redirect_stdout(io.StringIO()):
-        sd = create_model(f"{method}_{size}_patch16_224", num_classes=1000, args=model_args(kr)).state_dict()
-    sd = {k: v.detach().clone() for k, v in sd.items()}
-    cfg = OM.cfg_for(size, keep_rate=[kr])
     x = torch.randn(sample_batch, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    from oracle import timm_shim
+    if timm_shim.reference_available():
+        kind = "reference"
+        models_act = timm_shim.import_reference()
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = timm_shim.create_model(f"{method}_{size}_patch16_224", pretrained=False, num_classes=1000, drop_rate=0.0,
+                                           drop_path_rate=0.0, drop_block_rate=None, img_size=224, args=model_args(kr)).eval()
+        del models_act
+
+        def run():
+            with torch.no_grad():
+                return model(x)
+    else:
+        kind = "port"
+        from oracle import model as OM
+        from tokenreduction_b200 import create_model
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            sd = create_model(f"{method}_{size}_patch16_224", num_classes=1000, args=model_args(kr)).state_dict()
+        sd = {k: v.detach().clone() for k, v in sd.items()}
+        cfg = OM.cfg_for(size, keep_rate=[kr])
+
+        def run():
+            return OM.forward(method, sd, x, cfg)
     for _ in range(warmup):
-        OM.forward(method, sd, x, cfg)
+        run()
     t0 = time.perf_counter()
     for _ in range(steps):
-        OM.forward(method, sd, x, cfg)
+        run()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return sample_batch / dt, dt * 1e3, torch.get_num_threads()
+    return sample_batch / dt, dt * 1e3, torch.get_num_threads(), kind
 
 
 def run_reference(a):
@@ -240,15 +279,19 @@ def run_reference(a):
     if rank != 0:
         return
     method, size, kr, batch, amp = WORKLOADS[a.workload]
-    sample = min(batch, a.cpu_batch)
-    ips, ms, cores = cpu_reference_run(method, size, kr, amp, sample, a.steps, max(a.warmup, 1))
+    if a.batch:
+        batch = a.batch
+    sample = min(batch, a.cpu_batch) if a.cpu_batch else batch
+    ips, ms, cores, kind = cpu_reference_run(method, size, kr, amp, sample, a.steps, max(min(a.warmup, 2), 1))
     line = {
         "impl": "reference", "metric": "images_per_s", "value": round(ips, 2), "unit": "images/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": a.workload, "per_gpu_batch": batch, "reduction_loc": [3, 6, 9], "keep_rate": kr,
-                   "note": "oracle port of the reference model on host cores; each step = one forward over the sample"},
-        "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
+        "config": {"workload": a.workload, "model": f"{method}_{size}_patch16_224", "per_gpu_batch": batch,
+                   "keep_rate": kr, "reduction_loc": [3, 6, 9],
+                   "note": ("unmodified reference model (baseline/_ref)" if kind == "reference" else "oracle port of the reference model")
+                           + f" on the host cores, fp32 (the GPU arm runs bf16 autocast), {sample} images per step"},
+        "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": kind,
                          "sample": f"{sample} images/step x {a.steps} steps, fp32, torch CPU threads={cores}"},
         "e2e": {"value": round(ips, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -256,11 +299,132 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------ tokred arm
+DECISION_KEYS = ("Kept_Tokens", "Assignment_Maps")
+
+
+def pack_decisions(viz):
+    """every stage's kept-token / assignment indices of this rank's shard as ONE int32 tensor [B, total] (device)."""
+    cols = []
+    for key in DECISION_KEYS:
+        for i in sorted(viz.get(key, {})):
+            t = viz[key][i]
+            cols.append(t.reshape(t.shape[0], -1).to(torch.int32))
+    return torch.cat(cols, dim=1) if cols else None
+
+
+class Runner:
+    """one workload on this rank: model, synthetic shard, forward (+ the NCCL exchange when world > 1)."""
+
+    def __init__(self, wl_key, batch, dev, rank, world):
+        import contextlib
+        import io
+        from tokenreduction_b200 import create_model
+        import torch.distributed as dist
+        self.dist, self.world, self.dev = dist, world, dev
+        method, size, kr, _, amp = WORKLOADS[wl_key]
+        self.method, self.size, self.kr, self.amp, self.batch = method, size, kr, amp, batch
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            # viz_mode + tokred_device_viz: the per-stage decisions come back as DEVICE tensors (no copy, no sync)
+            model = create_model(f"{method}_{size}_patch16_224", pretrained=False, num_classes=1000, drop_rate=0.0,
+                                 drop_path_rate=0.0, drop_block_rate=None, img_size=224,
+                                 args=model_args(kr, viz_mode=world > 1, tokred_device_viz=True))
+        self.model = model.eval().to(dev)
+        gen = torch.Generator().manual_seed(1 + rank)
+        self.host_images = torch.randn(batch, 3, 224, 224, generator=gen).pin_memory()
+        self.images = self.host_images.to(dev)
+        self.host_logits = torch.empty(batch, 1000, dtype=torch.float32).pin_memory()
+        self.g_logits = torch.empty(world * batch, 1000, device=dev) if world > 1 else None
+        self.g_dec = None
+        self.dec_cols = 0
+
+    def forward(self, x):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+            out = self.model(x)
+        if self.world == 1:
+            return out.float()
+        y, viz = out
+        y = y.float()
+        # the path's only exchange: logits and kept / assignment indices of every shard (two all_gathers, KBs-MBs)
+        self.dist.all_gather_into_tensor(self.g_logits, y)
+        dec = pack_decisions(viz)
+        if dec is not None:
+            if self.g_dec is None or self.g_dec.shape[1] != dec.shape[1]:
+                self.g_dec = torch.empty(self.world * dec.shape[0], dec.shape[1], dtype=torch.int32, device=self.dev)
+                self.dec_cols = dec.shape[1]
+            self.dist.all_gather_into_tensor(self.g_dec, dec.contiguous())
+        return y
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure(self, steps, warmup, timeline=False, e2e=True):
+        """-> dict(ms, ms_e2e, launches, kernels timeline).  Timed region 1: inputs resident in HBM.  Timed region 2: end
+        to end through the public API -- every step copies ITS batch from pinned host memory and reads ITS logits back;
+        the copy of step i+1 runs on a second stream into the other of two device buffers while step i computes."""
+        from tokenreduction_b200 import _lib
+        for _ in range(max(warmup, 3)):
+            self.forward(self.images)
+        self.barrier()
+        if timeline:
+            _lib.TIMELINE = []
+        launches0 = _lib.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        for _ in range(steps):
+            self.forward(self.images)
+        ev1.record()
+        self.barrier()
+        res = {"ms": ev0.elapsed_time(ev1), "launches": _lib.launch_count() - launches0, "timeline": None, "ms_e2e": None}
+        if timeline:
+            res["timeline"], _lib.TIMELINE = _lib.TIMELINE, None
+        if not e2e:
+            return res
+        cur = torch.cuda.current_stream()
+        copy_stream = torch.cuda.Stream()
+        bufs = [torch.empty_like(self.images), torch.empty_like(self.images)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]      # H2D into buffer i finished
+        freed = [None, None]                                  # forward that read buffer i finished
+
+        def stage(i, after=None):
+            with torch.cuda.stream(copy_stream):
+                if after is not None:
+                    copy_stream.wait_event(after)
+                if freed[i % 2] is not None:
+                    copy_stream.wait_event(freed[i % 2])
+                bufs[i % 2].copy_(self.host_images, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_steps(n, start_event=None):
+            stage(0, start_event)
+            for i in range(n):
+                if i + 1 < n:
+                    stage(i + 1)
+                cur.wait_event(ready[i % 2])
+                y = self.forward(bufs[i % 2])
+                freed[i % 2] = torch.cuda.Event()
+                freed[i % 2].record(cur)
+                self.host_logits.copy_(y, non_blocking=True)
+                cur.synchronize()                              # the caller reads the logits every step
+
+        e2e_steps(2)
+        self.barrier()
+        freed[0] = freed[1] = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_steps(steps, e0)
+        e1.record()
+        self.barrier()
+        res["ms_e2e"] = e0.elapsed_time(e1)
+        return res
+
+
 def run_tokred(a):
     import torch.distributed as dist
-    from tokenreduction_b200 import _lib, create_model
-    import contextlib
-    import io
+    from tokenreduction_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -274,101 +438,59 @@ def run_tokred(a):
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
+    def max_over_ranks(*vals):
+        if world == 1:
+            return vals
+        t = torch.tensor([float("nan") if v is None else v for v in vals], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(v) for v in t)
+
     method, size, kr, batch, amp = WORKLOADS[a.workload]
     if a.batch:
         batch = a.batch
-    torch.manual_seed(0)
-    with contextlib.redirect_stdout(io.StringIO()):
-        model = create_model(f"{method}_{size}_patch16_224", pretrained=False, num_classes=1000, drop_rate=0.0,
-                             drop_path_rate=0.0, drop_block_rate=None, img_size=224, args=model_args(kr))
-    model = model.eval().to(dev)
-    gen = torch.Generator().manual_seed(1 + rank)
-    host_images = torch.randn(batch, 3, 224, 224, generator=gen).pin_memory()
-    images = host_images.to(dev)
-    host_logits = torch.empty(batch, 1000, dtype=torch.float32).pin_memory()
-    gathered = [torch.empty(batch, 1000, device=dev) for _ in range(world)] if world > 1 else None
-
-    def forward(x):
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-            y = model(x).float()
-        if world > 1:                      # the path's only exchange: gather the logits of every shard
-            dist.all_gather(gathered, y)
-        return y
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(a.warmup, 3)):
-        forward(images)
-    barrier()
-
     peaks, peak_kind = measured_peaks()
+    run = Runner(a.workload, batch, dev, rank, world)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-
-    # ---- timed region 1: inputs resident in HBM (value); every tokred launch bracketed by events on its stream
-    _lib.TIMELINE = []
-    launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(a.steps):
-        forward(images)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count() - launches0
-    timeline, _lib.TIMELINE = _lib.TIMELINE, None
-    kernels = summarise_timeline(timeline, a.steps, peaks["hbm_gbs"])
-
-    # ---- timed region 2: end to end through the public API (pinned host -> device, forward, logits -> host).
-    # Every step copies ITS batch from pinned host memory and reads ITS logits back; the copy of step i+1 runs on a
-    # second stream into the other of two device buffers while step i computes (what a serving loop does).
-    cur = torch.cuda.current_stream()
-    copy_stream = torch.cuda.Stream()
-    bufs = [torch.empty_like(images), torch.empty_like(images)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]      # H2D into buffer i finished
-    freed = [None, None]                                  # forward that read buffer i finished
-
-    def stage(i, after=None):
-        with torch.cuda.stream(copy_stream):
-            if after is not None:
-                copy_stream.wait_event(after)
-            if freed[i % 2] is not None:
-                copy_stream.wait_event(freed[i % 2])
-            bufs[i % 2].copy_(host_images, non_blocking=True)
-            ready[i % 2].record(copy_stream)
-
-    def e2e_steps(n, start_event=None):
-        stage(0, start_event)
-        for i in range(n):
-            if i + 1 < n:
-                stage(i + 1)
-            cur.wait_event(ready[i % 2])
-            y = forward(bufs[i % 2])
-            freed[i % 2] = torch.cuda.Event()
-            freed[i % 2].record(cur)
-            host_logits.copy_(y, non_blocking=True)
-            cur.synchronize()                              # the caller reads the logits every step
-
-    e2e_steps(2)
-    barrier()
-    freed = [None, None]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_steps(a.steps, e0)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    res = run.measure(a.steps, a.warmup, timeline=True)
     clock_rec = clocks.stop() if rank == 0 else None
+    ms, ms_e2e = max_over_ranks(res["ms"], res["ms_e2e"])
+    kernels = summarise_timeline(res["timeline"], a.steps, peaks["hbm_gbs"])
+    launches = res["launches"]
+    dec_cols = run.dec_cols
+    h2d = run.host_images.numel() * 4 * world
+    d2h = run.host_logits.numel() * 4 * world
+    del run
+    torch.cuda.empty_cache()
 
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- every other BASELINE config, same method, shorter (they are reported in "workloads", not as the headline)
+    extras = []
+    if not a.headline_only:
+        xsteps, xwarm = max(3, min(a.steps, 6)), 3
+        for label, cfg_no, key, bsz, scaling in extra_workloads(world):
+            try:
+                r = Runner(key, bsz, dev, rank, world)
+                rr = r.measure(xsteps, xwarm, timeline=True)
+                xms, xms_e2e = max_over_ranks(rr["ms"], rr["ms_e2e"])
+                ks = summarise_timeline(rr["timeline"], xsteps, peaks["hbm_gbs"])
+                top = ks[0] if ks else None
+                m_, s_, kr_, _, amp_ = WORKLOADS[key]
+                extras.append({
+                    "workload": label, "baseline_config": cfg_no, "model": f"{m_}_{s_}_patch16_224", "keep_rate": kr_,
+                    "dtype": "bf16" if amp_ else "f32", "per_gpu_batch": bsz, "global_batch": bsz * world, "scaling": scaling,
+                    "value": round(bsz * world * xsteps / (xms * 1e-3), 1), "unit": "images/s",
+                    "ms_per_step": round(xms / xsteps, 3), "e2e": round(bsz * world * xsteps / (xms_e2e * 1e-3), 1),
+                    "gpu_launches_per_step": rr["launches"] / xsteps,
+                    "top_kernel": None if not top else {"kernel": top["kernel"], "avg_us": top["avg_us"], "alg_mb": top["alg_mb"],
+                                                        "alg_gbs": top["alg_gbs"], "frac_hbm": top["frac_hbm"]},
+                    "kernels": [{k: v for k, v in kk.items() if k in ("kernel", "launches_per_step", "avg_us", "frac_hbm")} for kk in ks],
+                    "tokred_share_of_step": round(sum(k["avg_us"] * k["launches_per_step"] for k in ks) / (xms / xsteps * 1e3), 4),
+                })
+                del r
+            except Exception as e:      # one failing workload must not cost the headline line
+                extras.append({"workload": label, "baseline_config": cfg_no, "failed": f"{type(e).__name__}: {e}"[:300]})
+            torch.cuda.empty_cache()
 
     if rank == 0:
         total = batch * world
@@ -378,13 +500,15 @@ def run_tokred(a):
         if top and os.path.exists(tpath):
             with open(tpath) as fh:
                 traffic = json.load(fh).get(a.workload, {}).get(top["kernel"])
+            if isinstance(traffic, dict):      # {"bytes": ..., "grid": ..., "capture": ...} written by tools/ncu_traffic.py
+                traffic = traffic.get("bytes")
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
-            sample = min(batch, a.cpu_batch)
-            ips, cms, cores = cpu_reference_run(method, size, kr, amp, sample, a.cpu_steps, 1)
-            cpu = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": f"{sample} images/step x {a.cpu_steps} steps of the same model (oracle port, fp32), "
-                             f"{cms:.0f} ms/step"}
+            sample = min(batch, a.cpu_batch) if a.cpu_batch else batch
+            ips, cms, cores, kind = cpu_reference_run(method, size, kr, amp, sample, a.cpu_steps, 1)
+            cpu = {"value": round(ips, 2), "unit": "images/s", "cores": cores, "kind": kind,
+                   "sample": f"{sample} images/step x {a.cpu_steps} steps of the same model "
+                             f"({'unmodified reference, baseline/_ref' if kind == 'reference' else 'oracle port'}, fp32), {cms:.0f} ms/step"}
         line = {
             "metric": "images_per_s", "value": round(total * a.steps / (ms * 1e-3), 1), "unit": "images/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 3),
@@ -394,10 +518,12 @@ def run_tokred(a):
                        "global_batch": total, "keep_rate": kr, "reduction_loc": [3, 6, 9], "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2 (batch of fp32 images = %.0f MB)" % (batch * 3 * 224 * 224 * 4 / 1e6),
                        "timing": "CUDA events, max over ranks",
+                       "exchange": "none (1 GPU)" if world == 1 else
+                                   f"per step: NCCL all_gather of logits [B,1000] f32 + kept/assignment indices [B,{dec_cols}] i32",
                        "e2e_pipeline": "per step: H2D of the batch (pinned, copy stream, 2 device buffers; overlaps the "
                                        "previous step's forward) + forward + D2H of the logits + stream sync"},
             "e2e": {"value": round(total * a.steps / (ms_e2e * 1e-3), 1), "unit": "images/s",
-                    "h2d_bytes_per_step": host_images.numel() * 4 * world, "d2h_bytes_per_step": host_logits.numel() * 4 * world},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clock_rec,
             "roofline": None if not top else {
@@ -406,6 +532,7 @@ def run_tokred(a):
                 "avg_us": top["avg_us"], "alg_mb_per_launch": top["alg_mb"]},
             "kernels": kernels,
             "tokred_share_of_step": round(sum(k["avg_us"] * k["launches_per_step"] for k in kernels) / (ms / a.steps * 1e3), 4),
+            "workloads": extras,
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -422,8 +549,9 @@ def main():
     ap.add_argument("--impl", default="tokred", choices=["tokred", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
-    ap.add_argument("--cpu-batch", type=int, default=32, help="images per step of the CPU baseline sample")
+    ap.add_argument("--cpu-batch", type=int, default=0, help="images per step of the CPU arm (0 = the GPU arm's per-GPU batch)")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs (workloads array)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

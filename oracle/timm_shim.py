@@ -15,7 +15,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("TOKRED_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root() -> str:
+    """TOKRED_REFERENCE_ROOT, else the read-only mount of the build container, else the git-ignored staging copy
+    baseline/_ref that __graft_entry__.build() makes there (it travels to the GPU box; the mount does not)."""
+    cands = [os.environ.get("TOKRED_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "models")) and os.path.isfile(os.path.join(c, "models_act.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 _model_entrypoints = {}
 

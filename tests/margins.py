@@ -37,12 +37,21 @@ def topk_set_margin(scores: torch.Tensor, k: int, rel: float) -> torch.Tensor:
     return (s[:, k - 1] - s[:, k]) > rel * s[:, k - 1].abs().clamp_min(1e-300)
 
 
+def _per_image(v, b):
+    """scalar or [B] bound -> float64 [B,1]."""
+    t = torch.as_tensor(v, dtype=torch.float64).cpu().reshape(-1)
+    return (t.expand(b) if t.numel() == 1 else t).reshape(b, 1).clone()
+
+
 # ------------------------------------------------------------------------------------------------ DPC-KNN
-def dpcknn_decidable(d_scaled: torch.Tensor, noise_u: torch.Tensor, cluster_num: int, knn: int, eps_d: float = 0.0):
+def dpcknn_decidable(d_scaled: torch.Tensor, noise_u: torch.Tensor, cluster_num: int, knn: int, eps_d: float = 0.0,
+                     eps_diag: float = 0.0):
     """models/dpcknn.py:56-98 re-evaluated in float64 on the fp32 distance matrix ``d_scaled`` (= cdist / sqrt(C)).
 
-    eps_d = bound on |D_impl - d_scaled| when the implementation under test computed its own distances (0 when it
-    was handed this very matrix).  Error model of an fp32 evaluation:
+    eps_d = bound on the OFF-DIAGONAL |D_impl - d_scaled| when the implementation under test computed its own
+    distances (0 when it was handed this very matrix); eps_diag = bound on the self distances of either side (the
+    matmul form of cdist leaves up to ~1e-2 of cancellation noise on the diagonal where the exact value is 0, SURVEY
+    A.7 -- the self distance is one of the knn neighbours).  Error model of an fp32 evaluation:
       density  rho = exp(-mean(knn smallest d^2)) + 1e-6 U :  |err| <= 4 ulp(1) + 2 rho d_knn eps_d
       parent distance delta = an entry of D                 :  |err| <= eps_d
       score    = delta * rho                                :  |err| <= delta err_rho + rho eps_d + 2 ulp(score)
@@ -53,16 +62,19 @@ def dpcknn_decidable(d_scaled: torch.Tensor, noise_u: torch.Tensor, cluster_num:
     d = d_scaled.double().cpu()
     u = noise_u.double().cpu()
     b, p, _ = d.shape
+    has_eps = bool(torch.as_tensor(eps_d).max() > 0)
+    eps_d = _per_image(eps_d, b)                                       # [B,1]: a scalar or one bound per image
+    eps_diag = _per_image(eps_diag, b)
     near = torch.topk(d, k=knn, dim=-1, largest=False).values
     rho = (-(near ** 2).mean(dim=-1)).exp() + u * float(torch.tensor(1e-6, dtype=torch.float32))
-    err_rho = 4 * 2 * U32 + 2.0 * rho * near[..., -1] * eps_d
+    err_rho = 4 * 2 * U32 + 2.0 * rho * near[..., -1] * eps_d + rho * eps_diag ** 2 / knn
     denser = rho[:, None, :] > rho[:, :, None]                           # [b,i,j]: j denser than i
     d_max = d.flatten(1).max(dim=-1).values
     delta = torch.where(denser, d, d_max[:, None, None].expand_as(d)).min(dim=-1).values
     # (1) ambiguous density pairs that matter
     amb = (rho[:, None, :] - rho[:, :, None]).abs() <= (err_rho[:, None, :] + err_rho[:, :, None])
     amb &= ~torch.eye(p, dtype=torch.bool)[None]
-    matters = d <= torch.maximum(delta[:, :, None], delta[:, None, :]) + 2 * eps_d
+    matters = d <= torch.maximum(delta[:, :, None], delta[:, None, :]) + 2 * eps_d[:, :, None]
     ok = ~(amb & matters).flatten(1).any(dim=1)
     # (2) centre order
     score = delta * rho
@@ -75,7 +87,7 @@ def dpcknn_decidable(d_scaled: torch.Tensor, noise_u: torch.Tensor, cluster_num:
     # (3) assignment
     d_c = torch.gather(d, 1, index_down.unsqueeze(-1).expand(-1, -1, p))   # [b,K,p]
     idx_cluster = d_c.argmin(dim=1)
-    if eps_d > 0 and cluster_num > 1:
+    if has_eps and cluster_num > 1:
         two = torch.topk(d_c, 2, dim=1, largest=False).values
         is_centre = torch.zeros(b, p, dtype=torch.bool).scatter_(1, index_down, True)
         ok &= (((two[:, 1] - two[:, 0]) > 2 * eps_d) | is_centre).all(dim=1)
@@ -85,7 +97,7 @@ def dpcknn_decidable(d_scaled: torch.Tensor, noise_u: torch.Tensor, cluster_num:
 
 # ------------------------------------------------------------------------------------------------ K-Medoids
 def kmedoids_decidable(d: torch.Tensor, token_weight: torch.Tensor, cluster_num: int, iters: int, eps_d: float = 0.0,
-                       rel_s: float = 2e-5, rel_w: float = 0.0):
+                       rel_s: float = 2e-5, rel_w: float = 0.0, eps_diag: float = 0.0):
     """models/kmedoids.py:62-85 re-evaluated in float64 on the fp32 distance matrix ``d`` along the float64 trajectory.
 
     Scores S_i = w_i sum_j D_ij are sums of P fp32 terms: two summation orders differ by up to ~P u relative
@@ -96,8 +108,11 @@ def kmedoids_decidable(d: torch.Tensor, token_weight: torch.Tensor, cluster_num:
     d = d.double().cpu()
     w = token_weight.double().cpu().reshape(d.shape[0], -1)
     b, p, _ = d.shape
+    has_eps = bool(torch.as_tensor(eps_d).max() > 0)
+    eps_d = _per_image(eps_d, b)
+    eps_diag = _per_image(eps_diag, b)
     s = w * d.sum(dim=-1)
-    err_s = rel_s * s + p * w * eps_d
+    err_s = rel_s * s + p * w * eps_d + w * eps_diag
     ok = torch.ones(b, dtype=torch.bool)
     order = torch.sort(w, dim=-1, descending=True, stable=True).indices
     centre = order[:, :cluster_num].clone()
@@ -110,7 +125,7 @@ def kmedoids_decidable(d: torch.Tensor, token_weight: torch.Tensor, cluster_num:
         dc = torch.gather(d, 2, centre.unsqueeze(1).expand(-1, p, -1))     # [b,p,K]  D[i, c_k]
         a = dc.argmin(dim=-1)
         good = torch.ones(b, dtype=torch.bool)
-        if eps_d > 0 and cluster_num > 1:
+        if has_eps and cluster_num > 1:
             two = torch.topk(dc, 2, dim=-1, largest=False).values
             good = ((two[..., 1] - two[..., 0]) > 2 * eps_d).all(dim=1)
         return a, good
@@ -143,29 +158,38 @@ def _bf16_boundary_distance(s: torch.Tensor) -> torch.Tensor:
     return ulp / 2 - (s - r).abs()
 
 
-def tome_bf16_decidable(metric: torch.Tensor, r: int, class_token: bool = True, delta: float = 3e-7):
-    """bf16-autocast matching (models/tome.py:258-277 with a bf16 matmul): the similarity is an fp32 accumulation of
-    exact bf16 x bf16 products rounded ONCE to bf16.  Two accumulation orders (cuBLAS / CPU / tcgen05, whose fp32
-    accumulator truncates) differ by a few fp32 ulps (delta = 3e-7 ~ 5 ulps at |s| <= 0.5) BEFORE that rounding, so
-    an entry can land on either side of a bf16 rounding boundary only if its exact value is within delta of one.
+def tome_bf16_decidable(metric: torch.Tensor, r: int, class_token: bool = True, delta: float = 3e-7, rel_op: float = 2.5e-7):
+    """bf16-autocast matching (models/tome.py:258-277 with a bf16 matmul).  Two correct implementations can disagree
+    on the bf16 value of a similarity for exactly two reasons:
+      (a) the fp32 accumulation of the exact bf16 x bf16 products runs in another order (cuBLAS / CPU / tcgen05, whose
+          fp32 accumulator truncates): a few fp32 ulps (delta = 3e-7 ~ 5 ulps at |s| <= 0.5) BEFORE the one rounding to
+          bf16 -- the entry flips only if its exact value is within delta of a bf16 rounding boundary;
+      (b) the normalised operand m / |m| is rounded to bf16 after an fp32 norm whose summation order differs (ATen CPU
+          vs ATen CUDA vs the kernel's 8-lane partial sums): the quotient differs by ~2 fp32 ulps (rel_op), which flips
+          the bf16 rounding of an operand element sitting on a boundary -> that token's similarities move by up to
+          ulp_bf16(element) * |partner element| (measured: 8e-5 on a 0.31 score, image 15 of the B=256 test).
     All exact bf16 ties are resolved identically by both sides (lowest index), so an image is decidable iff no entry
-    that can influence a row maximum (bf16 value within one bf16 ulp of its row's maximum) is within delta of a
-    rounding boundary.
+    that can influence a row maximum (bf16 value within one bf16 ulp of its row's maximum) can change its bf16 value
+    under (a) + (b).
     -> (decidable [B] bool, scores_bf16 [B,a,b] as float64 with the CLS row at -inf)."""
-    m = metric.float().cpu()
-    m = m / m.norm(dim=-1, keepdim=True)
-    mb = m.to(torch.bfloat16).double()
-    s = mb[:, ::2] @ mb[:, 1::2].transpose(1, 2)               # exact products, float64 sum = exact similarity
+    m = metric.float().cpu().double()
+    x = m / m.norm(dim=-1, keepdim=True)                        # exact (float64) normalised operands
+    xb = x.float().to(torch.bfloat16).double()
+    two = torch.tensor(2.0, dtype=torch.float64)
+    ulp_op = torch.pow(two, torch.floor(torch.log2(xb.abs().clamp_min(2.0 ** -126))) - 7)
+    risky_op = (_bf16_boundary_distance(x) < rel_op * x.abs()).double() * ulp_op       # possible operand shift
+    a_, b_ = xb[:, ::2], xb[:, 1::2]
+    s = a_ @ b_.transpose(1, 2)                                 # exact products, float64 sum = exact similarity
+    shift = risky_op[:, ::2] @ b_.abs().transpose(1, 2) + a_.abs() @ risky_op[:, 1::2].transpose(1, 2)
     sb = s.float().to(torch.bfloat16).double()
-    near_boundary = _bf16_boundary_distance(s) < delta
+    unstable = _bf16_boundary_distance(s) < delta + shift
     row_max = sb.max(dim=-1, keepdim=True).values
-    expo = torch.floor(torch.log2(row_max.abs().clamp_min(2.0 ** -126)))
-    ulp = torch.pow(torch.tensor(2.0, dtype=torch.float64), expo - 7)
+    ulp = torch.pow(two, torch.floor(torch.log2(row_max.abs().clamp_min(2.0 ** -126))) - 7)
     relevant = sb >= row_max - ulp
     if class_token:
         relevant[:, 0] = False
         sb[:, 0] = -math.inf
-    ok = ~(relevant & near_boundary).flatten(1).any(dim=1)
+    ok = ~(relevant & unstable).flatten(1).any(dim=1)
     return ok, sb
 
 

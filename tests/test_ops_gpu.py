@@ -312,7 +312,17 @@ def inv_sqrt_c(c):
     return float(torch.tensor(1.0) / torch.tensor(float(c) ** 0.5, dtype=torch.float32))
 
 
-def _check_dpcknn(T, x, noise, k, exact, min_own=0.7, min_e2e=0.3):
+def dist_discrepancy(d_a, d_b):
+    """per image: (max off-diagonal |d_a - d_b|, max self distance of either) -- the two error sources of
+    margins.*_decidable, as [B] tensors."""
+    b, p, _ = d_a.shape
+    eye = torch.eye(p, dtype=torch.bool, device=d_a.device)
+    eps = (d_a - d_b).abs().masked_fill(eye, 0.0).flatten(1).max(dim=1).values * 1.01 + 1e-9
+    diag = torch.maximum(d_a.diagonal(dim1=1, dim2=2).abs().max(dim=1).values, d_b.diagonal(dim1=1, dim2=2).abs().max(dim=1).values)
+    return eps.cpu(), diag.cpu()
+
+
+def _check_dpcknn(T, x, noise, k, exact, min_own=0.7, min_e2e=0.0):
     """Margin-aware protocol (margins.dpcknn_decidable):
     (1) decision logic: against the oracle fed the kernel's OWN scaled distance matrix, every image whose float64
         margins exceed the fp32 evaluation error must match exactly (100 %);
@@ -331,19 +341,20 @@ def _check_dpcknn(T, x, noise, k, exact, min_own=0.7, min_e2e=0.3):
         f"own-D: {int((~same[ok]).sum())} decidable images differ from the oracle ({int((~same64[ok]).sum())} from float64)"
     # end to end against the reference pipeline's distances
     d_ref = O.pairwise_dist(x) / (c ** 0.5)
-    eps = float((d_own - d_ref).abs().max()) * 1.01 + 1e-9
+    eps, eps_diag = dist_discrepancy(d_own, d_ref)
     ic_ref2, id_ref2 = O.dpcknn_cluster(x, k, 5, noise)
-    ok2, _, _ = MG.dpcknn_decidable(d_ref, noise, k, 5, eps_d=eps)
+    ok2, _, _ = MG.dpcknn_decidable(d_ref, noise, k, 5, eps_d=eps, eps_diag=eps_diag)
     same2 = ((index_down == id_ref2).all(dim=1) & (idx_cluster == ic_ref2).all(dim=1)).cpu()
     frac2 = float(ok2.float().mean())
-    assert frac2 >= min_e2e, f"only {frac2:.2f} of the images are decidable end to end (eps_d = {eps:.2e})"
+    assert frac2 >= min_e2e, f"only {frac2:.2f} of the images are decidable end to end (eps_d <= {float(eps.max()):.2e})"
     assert bool(same2[ok2].all()), f"end to end: {int((~same2[ok2]).sum())} decidable images differ from the reference pipeline"
-    assert (idx_cluster == ic_ref2).float().mean() > 0.9
+    # the error model is a worst-case bound: far more images agree than it can certify -- keep an empirical floor too
+    assert float(same2.float().mean()) >= 0.9 and (idx_cluster == ic_ref2).float().mean() > 0.98
     own = torch.gather(idx_cluster, 1, index_down)
     assert torch.equal(own, torch.arange(k, device=DEV).expand(b, -1))
     assert int(idx_cluster.min()) >= 0 and int(idx_cluster.max()) < k
     print(f"dpcknn P={p} K={k} C={c} B={b} exact={exact}: own-D decidable {frac:.3f} (identical overall "
-          f"{float(same.float().mean()):.3f}); end to end eps_d={eps:.1e} decidable {frac2:.3f} (identical overall "
+          f"{float(same.float().mean()):.3f}); end to end eps_d<={float(eps.max()):.1e} decidable {frac2:.3f} (identical overall "
           f"{float(same2.float().mean()):.3f})")
 
 
@@ -362,7 +373,7 @@ def test_dpcknn_cluster_at_bench_batch(T, p, k):
     b, c = 256, 384
     x = torch.randn(b, p, c, generator=g(2300 + p)).to(DEV)
     noise = torch.rand(b, p, generator=g(2600 + p)).to(DEV)
-    _check_dpcknn(T, x, noise, k, False, min_own=0.6, min_e2e=0.2)
+    _check_dpcknn(T, x, noise, k, False, min_own=0.6, min_e2e=0.3)
 
 
 @pytest.mark.parametrize("p,k,c,with_w", [(196, 49, 384, True), (49, 12, 384, True), (12, 3, 384, False), (196, 49, 100, True),
@@ -393,7 +404,7 @@ def test_attn_colsum(T, h, n):
     assert_close_rel(out, ref, 1e-6, "token weights")
 
 
-def _check_kmedoids(T, x, tw, k, iters, exact, min_own=0.7, min_e2e=0.5):
+def _check_kmedoids(T, x, tw, k, iters, exact, min_own=0.7, min_e2e=0.0):
     """same protocol as _check_dpcknn (margins.kmedoids_decidable follows the float64 trajectory of the iterations)."""
     b, p, c = x.shape
     centres, cidx, assign = T.kmedoids_fit(x, tw, k, iters, exact)
@@ -407,17 +418,18 @@ def _check_kmedoids(T, x, tw, k, iters, exact, min_own=0.7, min_e2e=0.5):
     assert bool(same[ok].all()) and bool(same64[ok].all()), \
         f"own-D: {int((~same[ok]).sum())} decidable images differ from the oracle ({int((~same64[ok]).sum())} from float64)"
     d_ref = O.pairwise_dist(x)
-    eps = float((d_own - d_ref).abs().max()) * 1.01 + 1e-9
+    eps, eps_diag = dist_discrepancy(d_own, d_ref)
     _, ci_ref2, as_ref2 = O.kmedoids_fit(x, k, iters, tw)
-    ok2, _, _ = MG.kmedoids_decidable(d_ref, tw, k, iters, eps_d=eps)
+    ok2, _, _ = MG.kmedoids_decidable(d_ref, tw, k, iters, eps_d=eps, eps_diag=eps_diag)
     same2 = ((cidx == ci_ref2).all(dim=1) & (assign == as_ref2).all(dim=1)).cpu()
     frac2 = float(ok2.float().mean())
-    assert frac2 >= min_e2e, f"only {frac2:.2f} of the images are decidable end to end (eps_d = {eps:.2e})"
+    assert frac2 >= min_e2e, f"only {frac2:.2f} of the images are decidable end to end (eps_d <= {float(eps.max()):.2e})"
     assert bool(same2[ok2].all()), f"end to end: {int((~same2[ok2]).sum())} decidable images differ from the reference pipeline"
+    assert float(same2.float().mean()) >= 0.9
     assert torch.equal(centres, torch.gather(x, 1, cidx.unsqueeze(-1).expand(-1, -1, c))), "centres are medoid rows verbatim"
     assert int(assign.min()) >= 0 and int(assign.max()) < k
     print(f"kmedoids P={p} K={k} C={c} B={b} exact={exact}: own-D decidable {frac:.3f} (identical overall "
-          f"{float(same.float().mean()):.3f}); end to end eps_d={eps:.1e} decidable {frac2:.3f} (identical overall "
+          f"{float(same.float().mean()):.3f}); end to end eps_d<={float(eps.max()):.1e} decidable {frac2:.3f} (identical overall "
           f"{float(same2.float().mean()):.3f})")
 
 
@@ -436,7 +448,7 @@ def test_kmedoids_fit_at_bench_batch(T, p, k):
     b, c = 256, 384
     x = torch.randn(b, p, c, generator=g(3300 + p)).to(DEV)
     tw = (5.5 + tie_free_scores(b, p, 3600 + p)).unsqueeze(-1).to(DEV)
-    _check_kmedoids(T, x, tw, k, 3, False, min_own=0.6, min_e2e=0.4)
+    _check_kmedoids(T, x, tw, k, 3, False, min_own=0.6, min_e2e=0.5)
 
 
 # ------------------------------------------------------------------------------------------------ soft merges
@@ -727,6 +739,22 @@ def ats_cdf64(v, attn, mask):
     return torch.where(mask[:, 1:], cdf, cdf + 0.1)
 
 
+def check_ats_candidates(ids, m, cdf64, steps, n, tol=2e-6):
+    """Margin-aware ATS check.  The reference measures |step - cdf| with cdist's matmul expansion (s^2 + c^2 - 2sc in
+    fp32), so the pick between two nearly equidistant CDF entries is decided by cancellation noise (~1e-7 on d^2) and
+    by the fp32 summation order of the CDF itself (torch.cumsum on CUDA is a parallel scan; the CPU reference scans
+    sequentially).  With a float64 CDF: every step must have one of its near-minimal candidates (d^2 within tol of the
+    minimum) among the kernel's ids, and every id must be such a candidate of some step."""
+    d2 = (steps.double().cpu()[None, :, None] - cdf64[:, None, :]) ** 2          # [B, steps, P]
+    cand = d2 <= d2.min(dim=-1, keepdim=True).values + tol
+    for i in range(ids.shape[0]):
+        got = torch.zeros(n - 1, dtype=torch.bool)
+        body_i = ids[i, 1:m + 1].cpu()
+        got[body_i[body_i > 0] - 1] = True
+        assert bool((cand[i] & got[None, :]).any(dim=-1).all()), f"image {i}: a step has no candidate among the ids"
+        assert bool(cand[i].any(dim=0)[got].all()), f"image {i}: an id is not a near-minimal candidate of any step"
+
+
 def spread_attn(b, h, n, seed):
     """attention whose CLS row is far from uniform, so the inverse-CDF picks are well separated."""
     return torch.softmax(6 * torch.randn(b, h, n, n, generator=g(seed)), dim=-1)
@@ -746,21 +774,7 @@ def test_ats_sample(T, n, count, h, dh, vdtype):
     na_ref, nm_ref, ids_ref = O.ats_sample(v, attn, mask, count)
     m = int(max_count.item())
     assert abs(m + 1 - ids_ref.shape[1]) <= 2
-    # Margin-aware check.  The reference measures |step - cdf| with cdist's matmul expansion (s^2 + c^2 - 2sc in
-    # fp32), so the pick between two nearly equidistant CDF entries is decided by cancellation noise (~1e-7 on
-    # d^2) and by the fp32 summation order of the CDF itself (torch.cumsum on CUDA is a parallel scan; the CPU
-    # reference scans sequentially).  With a float64 CDF: every step must have one of its near-minimal candidates
-    # (d^2 within TOL of the minimum) among the kernel's ids, and every id must be such a candidate of some step.
-    TOL = 2e-6
-    cdf64 = ats_cdf64(v, attn, mask)
-    d2 = (steps.double().cpu()[None, :, None] - cdf64[:, None, :]) ** 2          # [B, steps, P]
-    cand = d2 <= d2.min(dim=-1, keepdim=True).values + TOL
-    for i in range(b):
-        got = torch.zeros(n - 1, dtype=torch.bool)
-        body_i = ids[i, 1:m + 1].cpu()
-        got[body_i[body_i > 0] - 1] = True
-        assert bool((cand[i] & got[None, :]).any(dim=-1).all()), f"image {i}: a step has no candidate among the ids"
-        assert bool(cand[i].any(dim=0)[got].all()), f"image {i}: an id is not a near-minimal candidate of any step"
+    check_ats_candidates(ids, m, ats_cdf64(v, attn, mask), steps, n)
     agree = 0
     for i in range(b):
         a, r = set(ids[i, :m + 1].tolist()), set(ids_ref[i].tolist())
@@ -967,29 +981,31 @@ def test_tome_distill_token_and_no_class_token(T):
 
 def test_ats_more_steps_than_tokens(T):
     """after the first ATS stage N = 1 + max #unique shrinks with peaked attention while the
-    per-stage sample_count stays fixed, so n_steps > N - 1 is normal (the reference runs fine).  Checked against the
-    oracle through two chained stages with sharply peaked attention at B=1."""
+    per-stage sample_count stays fixed, so n_steps > N - 1 is normal (the reference runs fine).  Two chained stages
+    with sharply peaked attention at B=1, each checked against the float64 candidate sets and the oracle's width."""
     h, dh, n = 6, 64, 197
-    attn = torch.softmax(40 * torch.randn(1, h, n, n, generator=g(950)), dim=-1)
+    attn = torch.softmax(10 * torch.randn(1, h, n, n, generator=g(950)), dim=-1)
     v = torch.randn(1, h, n, dh, generator=g(951))
     mask = torch.ones(1, n, dtype=torch.bool)
-    na1, m1, ids1 = O.ats_sample(v, attn, mask, 138)
-    n2 = ids1.shape[1]
-    assert n2 - 1 < 96, f"stage 1 kept {n2 - 1} tokens: the input is not peaked enough for this test"
-    steps1 = O.ats_sample_steps(138).to(DEV)
-    ids, mo, mc = T.ats_sample(v.to(DEV), attn.to(DEV), mask.to(DEV), steps1)
-    assert int(mc.item()) + 1 == n2
-    # stage 2: N = n2 tokens, sample_count 97 -> 96 steps > N - 1
-    attn2 = torch.softmax(40 * torch.randn(1, h, n2, n2, generator=g(952)), dim=-1)
+    _, m1_ref, ids1_ref = O.ats_sample(v, attn, mask, 138)
+    assert ids1_ref.shape[1] - 1 < 96, "stage 1 is not peaked enough for this test"
+    steps1 = O.ats_sample_steps(138)
+    ids, mo, mc = T.ats_sample(v.to(DEV), attn.to(DEV), mask.to(DEV), steps1.to(DEV))
+    m = int(mc.item())
+    check_ats_candidates(ids, m, ats_cdf64(v, attn, mask), steps1, n)
+    assert abs(m + 1 - ids1_ref.shape[1]) <= 2
+    # stage 2: N = m + 1 tokens (what the product model feeds on), sample_count 97 -> 96 steps > N - 1
+    n2 = m + 1
+    m1 = mo[:, :n2].cpu()
+    attn2 = torch.softmax(10 * torch.randn(1, h, n2, n2, generator=g(952)), dim=-1)
     v2 = torch.randn(1, h, n2, dh, generator=g(953))
-    cdf64 = ats_cdf64(v2, attn2, m1)
     steps2 = O.ats_sample_steps(97)
     assert steps2.numel() > n2 - 1
     _, m2_ref, ids2_ref = O.ats_sample(v2, attn2, m1, 97)
     ids2, mo2, mc2 = T.ats_sample(v2.to(DEV), attn2.to(DEV), m1.to(DEV), steps2.to(DEV))
-    m = int(mc2.item())
-    assert ids2.shape[1] == steps2.numel() + 1 and m <= n2 - 1
-    if bool(MG.ats_decidable(cdf64, steps2).all()):
-        assert torch.equal(ids2[:, :m + 1].cpu(), ids2_ref) and torch.equal(mo2[:, :m + 1].cpu(), m2_ref)
-    assert bool((ids2[:, m + 1:] == 0).all()) and not bool(mo2[:, m + 1:].any())
-    assert int(ids2.max()) < n2
+    m2 = int(mc2.item())
+    assert ids2.shape[1] == steps2.numel() + 1 and m2 <= n2 - 1
+    check_ats_candidates(ids2, m2, ats_cdf64(v2, attn2, m1), steps2, n2)
+    assert abs(m2 + 1 - ids2_ref.shape[1]) <= 2
+    assert bool((ids2[:, m2 + 1:] == 0).all()) and not bool(mo2[:, m2 + 1:].any())
+    assert int(ids2.max()) < n2 and bool(mo2[:, :m2 + 1].all())

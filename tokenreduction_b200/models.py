@@ -29,9 +29,19 @@ def _np(t):
     return _Pending(t.detach())
 
 
-def _finalize_viz(viz):
+def _finalize_viz(viz, keep_on_device=False):
     """every pending tensor -> pinned host memory with async copies, ONE stream synchronisation, then numpy arrays
-    (the types validate.py:199-229 consumes)."""
+    (the types validate.py:199-229 consumes).  keep_on_device (args.tokred_device_viz): hand the device tensors out
+    instead -- no copy, no synchronisation; a multi-GPU caller all_gathers them (bench.py)."""
+    if keep_on_device:
+        def unwrap(d):
+            for k, v in d.items():
+                if isinstance(v, dict):
+                    unwrap(v)
+                elif isinstance(v, _Pending):
+                    d[k] = v.t
+        unwrap(viz)
+        return viz
     pend = []
 
     def walk(d):
@@ -91,7 +101,7 @@ class _ReducedViT(VisionTransformer):
     def _ret(self, x, viz_data=None):
         if self.training or not self.viz_mode:
             return x
-        return x, _finalize_viz(viz_data)
+        return x, _finalize_viz(viz_data, getattr(self, "device_viz", False))
 
 
 # =============================================================================================== Top-K / EViT
@@ -125,6 +135,7 @@ class TopKVisionTransformer(_ReducedViT):
         self.pruning_loc = pruning_loc
         self.token_ratio = token_ratio
         self.viz_mode = getattr(args, "viz_mode", False)
+        self.device_viz = bool(getattr(args, "tokred_device_viz", False))
         self.apply(self._init_weights)
 
     def get_new_module_names(self):
@@ -186,6 +197,7 @@ class ToMeVisionTransformer(_ReducedViT):
         self.token_ratio = token_ratio
         self.prop_attn = True
         self.viz_mode = getattr(args, "viz_mode", False)
+        self.device_viz = bool(getattr(args, "tokred_device_viz", False))
         self.apply(self._init_weights)
 
     def get_new_module_names(self):
@@ -221,6 +233,7 @@ class _ClusterLayerViT(_ReducedViT):
         self.cluster_layers = nn.ModuleList([make_layer(c) for c in self.cluster_count])
         self.blocks = nn.ModuleList([*self.blocks])
         self.viz_mode = getattr(args, "viz_mode", False)
+        self.device_viz = bool(getattr(args, "tokred_device_viz", False))
         self.apply(self._init_weights)
 
     def get_new_module_names(self):
@@ -454,6 +467,7 @@ class ATSVisionTransformer(_ReducedViT):
             if blk.attn.ats_sample_count:
                 blk.attn.ats.static_width = static
         self.viz_mode = getattr(args, "viz_mode", False)
+        self.device_viz = bool(getattr(args, "tokred_device_viz", False))
         self.apply(self._init_weights)
 
     def get_new_module_names(self):
@@ -509,6 +523,7 @@ class DynamicVisionTransformer(_ReducedViT):
         self.pruning_loc = pruning_loc
         self.token_ratio = token_ratio
         self.viz_mode = getattr(args, "viz_mode", False)
+        self.device_viz = bool(getattr(args, "tokred_device_viz", False))
         self.apply(self._init_weights)
 
     def get_new_module_names(self):
