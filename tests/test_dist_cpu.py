@@ -62,5 +62,5 @@ def test_reference_arm_runs_on_rank0_only(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] in ("reference", "port") and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0

@@ -46,17 +46,21 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, stamps: bool = False) -> str:
+    """stamps=True builds the bring-up variant libtokred_sm100a_dbg.so (-DTOKRED_STAMPS: clock64 phase stamps, see
+    csrc/common.cuh and tools/diag/); the release library contains no stamp code."""
     os.makedirs(OBJ_DIR, exist_ok=True)
-    stamp = os.path.join(OBJ_DIR, "stamp.txt")
+    lib_path = LIB_PATH.replace(".so", "_dbg.so") if stamps else LIB_PATH
+    extra = (["-DTOKRED_STAMPS"] + os.environ.get("TOKRED_DBG_FLAGS", "").split()) if stamps else []
+    stamp = os.path.join(OBJ_DIR, "stamp_dbg.txt" if stamps else "stamp.txt")
     digest = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return LIB_PATH
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return lib_path
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ("_dbg.o" if stamps else ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -66,14 +70,14 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as fh:
         fh.write(digest)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, stamps="--stamps" in sys.argv))

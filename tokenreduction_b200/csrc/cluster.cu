@@ -1,97 +1,62 @@
 // Clustering kernels: DPC-KNN (cluster + merge), K-Medoids (token weights + fit).
 // Reference: models/dpcknn.py:44-140, models/kmedoids.py:62-85,240.
 //
-// dpcknn_cluster / kmedoids_fit: ONE persistent CTA per image.  The P x P distance matrix (P <= 196 patches)
-// never leaves the SM: X is streamed through a [P][32] shared-memory tile, the Gram matrix is accumulated in
-// registers (13x7 outputs per thread, LDS.128 operands) and written to shared memory as
-// D_ij = sqrt(max(|xi|^2 + |xj|^2 - 2 xi.xj, 1e-30)) — the matmul expansion torch.cdist uses for P > 25
-// (direct differences for P <= 25), so that diag(D) and cancellation error behave like the reference
-// (SURVEY.md A.7).  D is bit-symmetric by construction, so every later pass reads COLUMNS (conflict-free).
-// All the reference's [B,P,P] intermediates (3 for DPC-KNN, K*iters clones for K-Medoids = 895 launches)
-// collapse into shared-memory passes of this one kernel; global traffic is x in, two index vectors out.
+// dpcknn_cluster / kmedoids_fit / pairwise_dist keep the P x P distance matrix of an image (P <= 208 patches) in the
+// shared memory of one CTA, so all the reference's [B,P,P] intermediates (3 for DPC-KNN, K*iters clones for
+// K-Medoids = 895 launches) collapse into shared-memory passes; global traffic is x in, two index vectors out.
+// D_ij = sqrt(max(|xi|^2 + |xj|^2 - 2 xi.xj, 1e-30)) is the matmul expansion torch.cdist uses for P > 25 (direct
+// differences for P <= 25), so diag(D) and cancellation error behave like the reference.  D is
+// bit-symmetric by construction, so every later pass reads COLUMNS (conflict-free with the odd row stride).
+//
+// Three Gram engines feed the same epilogues:
+//   * dist_pipe.cuh  (default, P > 25): persistent warp-specialised tcgen05 pipeline, 3 x fp16-split MMAs, the
+//     epilogue of image i overlaps the staging + MMAs of image i+1;
+//   * FFMA           (exact_fp32 = 1): 13x7 register tiles, true fp32 products (gemm_nt.cuh), one CTA per image;
+//   * direct         (P <= 25): staged rows, sqrt(sum (xi - xj)^2) like ATen's non-matmul path.
 #include <math_constants.h>
 
+#include "dist_pipe.cuh"
 #include "gemm_nt.cuh"
-#include "umma.cuh"
 
 namespace tokred {
 namespace {
 
 constexpr int kThreads = kGemmThreads;      // FFMA variants (gemm_nt.cuh is written for 256 threads)
 constexpr int kWarps = kThreads / 32;
-constexpr int kTcThreads = 512;              // tensor-core variants: no FFMA register tile -> 16 warps per CTA
-constexpr int kMaxP = 208;    // P*P + staging must fit 227 KB of shared memory
-constexpr int KT = 32;        // tf32 path: contraction columns per stage
+constexpr int kLightThreads = 512;           // direct-difference variants (P <= 25): no FFMA register tile
+constexpr int kMaxP = pipe::kMaxP;           // P*P + staging must fit 227 KB of shared memory
 
-// Shared-memory plan of the distance kernels.  D has an odd row stride so that both row-per-thread stores (the
-// TMEM epilogue) and column reads (every later pass) are bank-conflict free.  On the tensor-core path the two
-// operand stages alias D's region: D is only written after the last MMA has completed.
+struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+struct BackSync { __device__ __forceinline__ void operator()() const { pipe::bar_sync(pipe::BAR_BACK, pipe::kBack); } };
+
+// ------------------------------------------------------------------------------------------ legacy (one CTA / image)
 struct DistCtx {
   float* D; int DS;
   float* xt;                 // FFMA path: [P][XS] staging tile
-  unsigned char* stage;      // tensor-core path: 2 stages x {hi, lo} canonical tf32 tiles
   float* sq;                 // [P]
   float* extra;              // kernel-specific vectors
-  uint64_t* bars;            // [2]
-  uint32_t* tmem_slot;
-  uint32_t tmem_base, tmem_cols;
-  int use_tc;
 };
-
-__host__ __device__ inline size_t dist_stage_bytes(int P) { return (size_t)((P + 127) / 128) * 16 * 1024 * 2; }   // hi + lo
-__host__ __device__ inline size_t dist_region0_bytes(int P, int use_tc) {
+__host__ __device__ inline size_t dist_region0_bytes(int P) {
   size_t d = ((size_t)P * (P | 1) * 4 + 15) & ~(size_t)15;
   if (P <= 25) d += (size_t)P * 257 * 4 + 16;      // direct path: staged rows [P][256+1]
-  const size_t st = use_tc ? 2 * dist_stage_bytes(P) : 0;
-  return d > st ? d : st;
+  return d;
 }
-__host__ __device__ inline size_t dist_smem_bytes(int P, int extra_floats, int use_tc) {
-  size_t n = dist_region0_bytes(P, use_tc);
-  if (!use_tc) n += (size_t)P * XS * 4;
+__host__ __device__ inline size_t dist_smem_bytes(int P, int extra_floats, int light) {
+  size_t n = dist_region0_bytes(P);
+  if (!light) n += (size_t)P * XS * 4;
   n += (((size_t)P + extra_floats) * 4 + 15) & ~(size_t)15;
   return n + 32;
 }
-
-// carve the dynamic shared memory, and (tensor-core path) allocate TMEM + init the mbarriers.  All threads call.
-__device__ __forceinline__ DistCtx dist_setup(float* smem, int P, int extra_floats, int use_tc) {
+__device__ __forceinline__ DistCtx dist_setup(float* smem, int P, int light) {
   DistCtx cx;
-  cx.use_tc = use_tc;
   cx.D = smem;
   cx.DS = P | 1;
-  cx.stage = reinterpret_cast<unsigned char*>(smem);
-  float* after = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(smem) + dist_region0_bytes(P, use_tc));
+  float* after = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(smem) + dist_region0_bytes(P));
   cx.xt = after;
-  if (!use_tc) after += P * XS;
+  if (!light) after += P * XS;
   cx.sq = after;
   cx.extra = after + P;
-  cx.bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(after) + ((((size_t)P + extra_floats) * 4 + 15) & ~(size_t)15));
-  cx.tmem_slot = reinterpret_cast<uint32_t*>(cx.bars + 2);
-  cx.tmem_base = 0;
-  const int Np = (P + 15) & ~15;
-  cx.tmem_cols = P > 128 ? 512u : umma::tmem_cols_pow2((uint32_t)Np);
-  if (use_tc) {
-    if ((threadIdx.x >> 5) == 0) umma::tmem_alloc(cx.tmem_slot, cx.tmem_cols);
-    if (threadIdx.x == 0) { umma::mbar_init(&cx.bars[0], 1); umma::mbar_init(&cx.bars[1], 1); umma::fence_mbar_init(); }
-    umma::tc_fence_before_sync();
-    __syncthreads();
-    umma::tc_fence_after_sync();
-    cx.tmem_base = *cx.tmem_slot;
-  }
   return cx;
-}
-__device__ __forceinline__ void dist_teardown(const DistCtx& cx) {
-  if (cx.use_tc) {
-    umma::tc_fence_before_sync();
-    __syncthreads();
-    if ((threadIdx.x >> 5) == 0) umma::tmem_dealloc(cx.tmem_base, cx.tmem_cols);
-  }
-}
-
-// round-to-nearest tf32, returned in an fp32 container (low 13 mantissa bits zero)
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
 }
 
 __device__ __forceinline__ void row_sqnorms(const float* __restrict__ xb, int P, int C, float* sq) {
@@ -113,120 +78,9 @@ __device__ __forceinline__ void row_sqnorms(const float* __restrict__ xb, int P,
   }
 }
 
-// Gram matrix on tcgen05 with 3xTF32 error compensation: x = hi + lo (hi = tf32(x), lo = x - hi exactly),
-// G ~= hi.hi^T + hi.lo^T + lo.hi^T accumulated in one fp32 TMEM accumulator — the same accuracy class as the fp32
-// matmul torch.cdist runs (plain tf32 would be 1e-3 and flip neighbour decisions).  Both MMA operands are the SAME
-// shared-memory tile (A = rows of an M tile, B = rows 0..Np-1), written by the threads in the canonical K-major
-// layout (4 tf32 per 16-byte core row); two stages alias the D region.
-__device__ void pairdist_tc(const float* __restrict__ xb, int P, int C, DistCtx& cx, float post_scale) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  row_sqnorms(xb, P, C, cx.sq);
-  const int n_mt = (P + 127) / 128, Np = (P + 15) & ~15;
-  const size_t stage_bytes = dist_stage_bytes(P), half = stage_bytes / 2;
-  const uint32_t sbo = (KT / 4) * 128;      // 1024
-  const uint32_t idesc = umma::instr_desc(umma::FMT_TF32, 128, (uint32_t)Np);
-  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0);
-  const int nchunk = (C + KT - 1) / KT;
-  const int ng = ((P + 7) / 8) * 64;        // (8 rows) x (8 core columns of 4 floats) per row group
-  // software pipeline: the loads of chunk c+1 are issued right after the barrier of chunk c and stay in registers while
-  // the MMAs of chunk c run; split + store happen one iteration later
-  constexpr int GMAX = 8;                   // float4 groups per thread: (208/8)*64 / 256 threads = 6.5
-  float4 v[GMAX];
-  auto load_chunk = [&](int c) {
-    const int k0 = c * KT;
-#pragma unroll
-    for (int u = 0; u < GMAX; ++u) {
-      const int gI = tid + u * nthreads;
-      const int row = (gI & 7) + ((gI >> 6) << 3), k = k0 + ((gI >> 3) & 7) * 4;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gI < ng && row < P) {
-        const float* g = xb + (long long)row * C + k;
-        if (vec && k + 3 < C) v[u] = *reinterpret_cast<const float4*>(g);
-        else { if (k < C) v[u].x = g[0]; if (k + 1 < C) v[u].y = g[1]; if (k + 2 < C) v[u].z = g[2]; if (k + 3 < C) v[u].w = g[3]; }
-      }
-    }
-  };
-  load_chunk(0);
-  for (int c = 0; c < nchunk; ++c) {
-    const int st = c & 1;
-    unsigned char* hi = cx.stage + (size_t)st * stage_bytes;
-    unsigned char* lo = hi + half;
-    if (c >= 2) umma::mbar_wait(&cx.bars[st], (uint32_t)(((c - 2) >> 1) & 1));
-#pragma unroll
-    for (int u = 0; u < GMAX; ++u) {
-      const int gI = tid + u * nthreads;
-      const int row = (gI & 7) + ((gI >> 6) << 3), core = (gI >> 3) & 7;
-      if (gI < ng) {
-        float4 h, l;
-        h.x = to_tf32(v[u].x); h.y = to_tf32(v[u].y); h.z = to_tf32(v[u].z); h.w = to_tf32(v[u].w);
-        // the remainder is exact in fp32; round it to tf32 ourselves (the MMA would TRUNCATE it: a biased error)
-        l.x = to_tf32(v[u].x - h.x); l.y = to_tf32(v[u].y - h.y); l.z = to_tf32(v[u].z - h.z); l.w = to_tf32(v[u].w - h.w);
-        const uint32_t off = (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 16u + (uint32_t)core * 128u;
-        *reinterpret_cast<float4*>(hi + off) = h;
-        *reinterpret_cast<float4*>(lo + off) = l;
-      }
-    }
-    umma::fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      umma::tc_fence_after_sync();
-      const uint32_t h0 = umma::smem_u32(hi), l0 = umma::smem_u32(lo);
-      for (int mt = 0; mt < n_mt; ++mt)
-        for (int ks = 0; ks < KT / 8; ++ks) {
-          const uint32_t ao = (uint32_t)mt * 16u * sbo + (uint32_t)ks * 256u, bo = (uint32_t)ks * 256u;
-          const uint64_t a_hi = umma::smem_desc_kmajor(h0 + ao, 128, sbo), a_lo = umma::smem_desc_kmajor(l0 + ao, 128, sbo);
-          const uint64_t b_hi = umma::smem_desc_kmajor(h0 + bo, 128, sbo), b_lo = umma::smem_desc_kmajor(l0 + bo, 128, sbo);
-          const uint32_t acc = cx.tmem_base + (uint32_t)mt * 256u;
-          umma::mma_tf32(acc, a_hi, b_hi, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-          umma::mma_tf32(acc, a_hi, b_lo, idesc, 1u);
-          umma::mma_tf32(acc, a_lo, b_hi, idesc, 1u);
-        }
-      umma::mma_commit(&cx.bars[st]);
-    }
-    if (c + 1 < nchunk) load_chunk(c + 1);
-  }
-  {
-    const int last = nchunk - 1;
-    umma::mbar_wait(&cx.bars[last & 1], (uint32_t)((last >> 1) & 1));
-    if (nchunk >= 2) umma::mbar_wait(&cx.bars[(last - 1) & 1], (uint32_t)(((last - 1) >> 1) & 1));
-  }
-  umma::tc_fence_after_sync();
-  // accumulator row i -> D row i (thread = row; odd row stride => conflict-free).  Warp w owns TMEM lane quarter
-  // w % 4; the (w / 4) index enumerates (M tile, column part) pairs so that 8 or 16 warps all take part.
-  {
-    const int q = warp & 3, slot = warp >> 2, nslots = nwarps >> 2;
-    const int parts = nslots / n_mt > 0 ? nslots / n_mt : 1;            // column parts per M tile
-    for (int s = slot; s < n_mt * parts; s += nslots) {
-      const int mt = s / parts, part = s % parts;
-      const int cbeg = ((Np / 16) * part / parts) * 16, cend = ((Np / 16) * (part + 1) / parts) * 16;
-      const int i = mt * 128 + q * 32 + lane;
-      const float sqi = i < P ? cx.sq[i] : 0.f;
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        uint32_t v[16];
-        umma::tmem_ld16(umma::tmem_addr(cx.tmem_base, (uint32_t)(q * 32), (uint32_t)(mt * 256 + c0)), v);
-        umma::tmem_ld_wait();
-        if (i < P) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + j < P) {
-              // diagonal: g_ii == |x_i|^2 exactly in exact arithmetic; use it (ATen's diagonal is clamp-level noise too)
-              const float d2 = (c0 + j == i) ? 0.f : (sqi + cx.sq[c0 + j]) - 2.0f * __uint_as_float(v[j]);
-              cx.D[i * cx.DS + c0 + j] = sqrtf(fmaxf(d2, 1e-30f)) * post_scale;
-            }
-        }
-      }
-    }
-  }
-  umma::tc_fence_before_sync();
-  __syncthreads();
-  // G_ij and G_ji add the same products in a different order: mirror the upper triangle so D is bit-symmetric
-  for (int i = warp; i < P; i += nwarps)
-    for (int j = i + 1 + lane; j < P; j += 32) cx.D[j * cx.DS + i] = cx.D[i * cx.DS + j];
-  __syncthreads();
-}
-
 // Fills cx.D (shared) with the pairwise distances of the P rows of xb (global, [P][C]) times post_scale.
-template <bool TC>
+// LIGHT = true: direct differences only (P <= 25, 512 threads); LIGHT = false: FFMA Gram (or direct when P <= 25).
+template <bool LIGHT>
 __device__ __forceinline__ void pairdist_to_smem(const float* __restrict__ xb, int P, int C, DistCtx& cx, float post_scale) {
   const int tid = threadIdx.x;
   float* D = cx.D;
@@ -235,7 +89,7 @@ __device__ __forceinline__ void pairdist_to_smem(const float* __restrict__ xb, i
     // direct form (ATen's non-matmul cdist path): sqrt(sum (xi - xj)^2).  The <= 25 rows are staged through shared
     // memory in 256-column chunks (the D region is free until the end; pair sums live in registers).
     constexpr int CH = 256;
-    float* xs = D + (((P * DS + 3) & ~3));          // [P][CH+1] after the (tiny) D matrix, inside region 0 / tile space
+    float* xs = D + (((P * DS + 3) & ~3));          // [P][CH+1] after the (tiny) D matrix, inside region 0
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;               // up to 3 pairs per thread (P*P <= 625 <= 3*256)
     const int nthr = (int)blockDim.x;
     for (int k0 = 0; k0 < C; k0 += CH) {
@@ -264,102 +118,86 @@ __device__ __forceinline__ void pairdist_to_smem(const float* __restrict__ xb, i
     __syncthreads();
     return;
   }
-  if constexpr (TC) {
-    pairdist_tc(xb, P, C, cx, post_scale);      // light kernels are only launched with use_tc = 1 when P > 25
-    return;
-  } else {
-  row_sqnorms(xb, P, C, cx.sq);
-  const bool vec_ok = stage_vec_ok(xb, C);
-  float* xt = cx.xt;
-  const float* sq = cx.sq;
-  gemm_nt(P, P, C, xt, xt,
-          [&](int k0) { stage_rows(xb, P, C, C, k0, xt, vec_ok, [](int, int, float v) { return v; }); },
-          [&](int i, int j, float g) {
-            const float d2 = (sq[i] + sq[j]) - 2.0f * g;
-            D[i * DS + j] = sqrtf(fmaxf(d2, 1e-30f)) * post_scale;
-          });
+  if constexpr (!LIGHT) {
+    row_sqnorms(xb, P, C, cx.sq);
+    const bool vec_ok = stage_vec_ok(xb, C);
+    float* xt = cx.xt;
+    const float* sq = cx.sq;
+    gemm_nt(P, P, C, xt, xt,
+            [&](int k0) { stage_rows(xb, P, C, C, k0, xt, vec_ok, [](int, int, float v) { return v; }); },
+            [&](int i, int j, float g) {
+              const float d2 = (sq[i] + sq[j]) - 2.0f * g;
+              D[i * DS + j] = sqrtf(fmaxf(d2, 1e-30f)) * post_scale;
+            });
   }
 }
 
-// ------------------------------------------------------------------------------------------ plain cdist(x, x)
-// Every distance kernel exists in two variants: TC = true (tcgen05 Gram, 512 threads, no FFMA register tile) and
-// TC = false (exact fp32 FFMA Gram, 256 threads).
-template <bool TC>
-__global__ void __launch_bounds__(TC ? kTcThreads : kThreads, 1)
-pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale, float* __restrict__ out, int use_tc) {
-  constexpr int NT = TC ? kTcThreads : kThreads;
-  extern __shared__ __align__(128) float smem[];
-  DistCtx cx = dist_setup(smem, P, 0, use_tc);
-  pairdist_to_smem<TC>(x + (long long)blockIdx.x * P * C, P, C, cx, post_scale);
-  float* ob = out + (long long)blockIdx.x * P * P;
-  for (int i = threadIdx.x >> 5; i < P; i += NT / 32)
-    for (int j = threadIdx.x & 31; j < P; j += 32) ob[i * P + j] = cx.D[i * cx.DS + j];
-  dist_teardown(cx);
+// ------------------------------------------------------------------------------------------ epilogues
+// Run by a group of NT threads (a whole CTA, or the BACK group of the pipeline) on a finished D in shared memory;
+// `tid` is the index inside the group, `sync` its barrier.
+
+template <int KS, int NT>
+__device__ __forceinline__ void knn_density(const float* D, int DS, int P, int knn, const float* __restrict__ noise_b, float* rho,
+                                            int tid, float& lmax) {
+  for (int base = 0; base < 2 * P; base += NT) {
+    const int it = base + tid;
+    const bool act = it < 2 * P;
+    const int i = act ? it >> 1 : 0, h = it & 1;
+    const int j0 = h ? (P + 1) / 2 : 0, j1 = act ? (h ? P : (P + 1) / 2) : 0;
+    float nb[KS];
+#pragma unroll
+    for (int t = 0; t < KS; ++t) nb[t] = CUDART_INF_F;
+#pragma unroll 8
+    for (int j = j0; j < j1; ++j) {
+      const float cur = D[j * DS + i];
+      lmax = fmaxf(lmax, cur);
+      // sorted insert without a dependency chain: new[t] = min(old[t], max(old[t-1], cur)), highest slot first
+#pragma unroll
+      for (int t = KS - 1; t > 0; --t) nb[t] = fminf(nb[t], fmaxf(nb[t - 1], cur));
+      nb[0] = fminf(nb[0], cur);
+    }
+    float pv[KS];
+#pragma unroll
+    for (int t = 0; t < KS; ++t) pv[t] = __shfl_xor_sync(0xffffffffu, nb[t], 1);
+    if (act && h == 0) {
+#pragma unroll
+      for (int q = 0; q < KS; ++q) {
+        const float cur = pv[q];
+#pragma unroll
+        for (int t = KS - 1; t > 0; --t) nb[t] = fminf(nb[t], fmaxf(nb[t - 1], cur));
+        nb[0] = fminf(nb[0], cur);
+      }
+      float sumsq = 0.f;
+#pragma unroll
+      for (int t = 0; t < KS; ++t)
+        if (t < knn) sumsq += nb[t] * nb[t];
+      rho[i] = expf(-(sumsq * (1.0f / (float)knn))) + noise_b[i] * 1e-6f;
+    }
+  }
 }
 
-// ------------------------------------------------------------------------------------------ DPC-KNN cluster
-template <bool TC>
-__global__ void __launch_bounds__(TC ? kTcThreads : kThreads, 1)
-dpcknn_cluster_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ noise_u, int P, int C, int K, int knn,
-                      float inv_sqrt_c, int64_t* __restrict__ idx_cluster, int64_t* __restrict__ index_down, int use_tc) {
-  constexpr int NT = TC ? kTcThreads : kThreads;
-  extern __shared__ __align__(128) float smem[];
-  DistCtx cx = dist_setup(smem, P, 2 * P + K + kTcThreads / 32, use_tc);
-  float* D = cx.D;
-  const int DS = cx.DS;
-  float* rho = cx.extra;
+// DPC-KNN (models/dpcknn.py:62-98).  extra: rho[P], score[P], centre[K] (int), red[NT/32].
+__host__ __device__ constexpr int dpc_extra_floats(int P, int K) { return 2 * P + K + 16; }
+template <int NT, class Sync>
+__device__ __forceinline__ void dpc_epilogue(const float* D, int DS, int P, int K, int knn, const float* __restrict__ noise_b,
+                                             float* extra, int tid, Sync sync, int64_t* __restrict__ idx_cluster_b,
+                                             int64_t* __restrict__ index_down_b, int img = 0) {
+  float* rho = extra;
   float* score = rho + P;
-  int* centre = reinterpret_cast<int*>(score + P);   // [K]
-  float* red = reinterpret_cast<float*>(centre + K);  // [NT / 32]
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  pairdist_to_smem<TC>(x + (long long)b * xbs, P, C, cx, inv_sqrt_c);
-  dist_teardown(cx);
+  int* centre = reinterpret_cast<int*>(score + P);    // [K]
+  float* red = reinterpret_cast<float*>(centre + K);   // [NT / 32]
+  const int warp = tid >> 5, lane = tid & 31;
 
   // local density from the knn nearest (self included): exp(-mean(d^2)) + 1e-6 * U
   float lmax = 0.f;
   if (knn <= 8) {
-    // Two threads (adjacent lanes) per token, one per half of its column: each keeps the 8 smallest of its rows
-    // sorted in registers (strict < keeps the lower row first on ties), then the even lane inserts the odd lane's
-    // list -- rows above its own, in order -- so the result equals the single ascending scan.  The scan is serial
-    // per column and was 19 % of the kernel's stall samples with 196 of 512 threads active.
-    for (int base = 0; base < 2 * P; base += NT) {
-      const int it = base + tid;
-      const bool act = it < 2 * P;
-      const int i = act ? it >> 1 : 0, h = it & 1;
-      const int j0 = h ? (P + 1) / 2 : 0, j1 = act ? (h ? P : (P + 1) / 2) : 0;
-      float nb[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) nb[t] = CUDART_INF_F;
-      for (int j = j0; j < j1; ++j) {
-        float cur = D[j * DS + i];
-        lmax = fmaxf(lmax, cur);
-        if (cur < nb[7]) {
-#pragma unroll
-          for (int t = 0; t < 8; ++t)
-            if (cur < nb[t]) { const float tmp = nb[t]; nb[t] = cur; cur = tmp; }
-        }
-      }
-      float pv[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) pv[t] = __shfl_xor_sync(0xffffffffu, nb[t], 1);
-      if (act && h == 0) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float cur = pv[q];
-          if (cur < nb[7]) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-              if (cur < nb[t]) { const float tmp = nb[t]; nb[t] = cur; cur = tmp; }
-          }
-        }
-        float sumsq = 0.f;
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-          if (t < knn) sumsq += nb[t] * nb[t];
-        rho[i] = expf(-(sumsq * (1.0f / (float)knn))) + noise_u[(long long)b * P + i] * 1e-6f;
-      }
-    }
+    // Two threads (adjacent lanes) per token, one per half of its column: each keeps its KS smallest values sorted in
+    // registers with a BRANCH-FREE min/max insertion (2 FMNMX per slot; the sum of squares only needs the multiset of
+    // the knn smallest values, so ties need no index), then the even lane inserts the odd lane's list.  The first
+    // version took a divergent branch into an 8-step compare-swap chain: some lane of the warp needs it on almost
+    // every row, so every row paid for it (7.3 M warp instructions, 16-20 us of a 40 us epilogue in the stamps).
+    if (knn <= 5) knn_density<5, NT>(D, DS, P, knn, noise_b, rho, tid, lmax);
+    else knn_density<8, NT>(D, DS, P, knn, noise_b, rho, tid, lmax);
   } else {
     for (int i = tid; i < P; i += NT) {
       float sumsq = 0.f;
@@ -377,12 +215,13 @@ dpcknn_cluster_kernel(const float* __restrict__ x, long long xbs, const float* _
         prev_v = best; prev_j = bj;
       }
       for (int j = 0; j < P; ++j) lmax = fmaxf(lmax, D[j * DS + i]);
-      rho[i] = expf(-(sumsq * (1.0f / (float)knn))) + noise_u[(long long)b * P + i] * 1e-6f;
+      rho[i] = expf(-(sumsq * (1.0f / (float)knn))) + noise_b[i] * 1e-6f;
     }
   }
   lmax = warp_max(lmax);
   if (lane == 0) red[warp] = lmax;
-  __syncthreads();
+  sync();
+  TOKRED_STAMP(tid == 0, img, 11);
   float dmax = red[0];
 #pragma unroll
   for (int w = 1; w < NT / 32; ++w) dmax = fmaxf(dmax, red[w]);
@@ -390,55 +229,54 @@ dpcknn_cluster_kernel(const float* __restrict__ x, long long xbs, const float* _
   // distance to the nearest denser token (or the global max), centre score
   for (int i = tid; i < P; i += NT) {
     const float ri = rho[i];
-    float best = dmax;
-    for (int j = 0; j < P; ++j) {
-      const float v = rho[j] > ri ? D[j * DS + i] : dmax;
-      best = fminf(best, v);
+    float b0 = dmax, b1 = dmax, b2 = dmax, b3 = dmax;      // four independent minima: the fmin chain was the critical path
+    int j = 0;
+    for (; j + 3 < P; j += 4) {
+      b0 = fminf(b0, rho[j] > ri ? D[j * DS + i] : dmax);
+      b1 = fminf(b1, rho[j + 1] > ri ? D[(j + 1) * DS + i] : dmax);
+      b2 = fminf(b2, rho[j + 2] > ri ? D[(j + 2) * DS + i] : dmax);
+      b3 = fminf(b3, rho[j + 3] > ri ? D[(j + 3) * DS + i] : dmax);
     }
-    score[i] = best * ri;
+    for (; j < P; ++j) b0 = fminf(b0, rho[j] > ri ? D[j * DS + i] : dmax);
+    score[i] = fminf(fminf(b0, b1), fminf(b2, b3)) * ri;
   }
-  __syncthreads();
+  sync();
+  TOKRED_STAMP(tid == 0, img, 12);
   for (int i = tid; i < P; i += NT) {
     const int rk = rank_desc(score, P, i);
-    if (rk < K) { centre[rk] = i; index_down[(long long)b * K + rk] = i; }
+    if (rk < K) { centre[rk] = i; index_down_b[rk] = i; }
   }
-  __syncthreads();
+  sync();
+  TOKRED_STAMP(tid == 0, img, 13);
   // nearest centre (lowest k on ties); centres belong to their own cluster
   for (int i = tid; i < P; i += NT) {
     float best = CUDART_INF_F;
-    int bk = 0;
+    int bk = 0, own = -1;
+#pragma unroll 4
     for (int k = 0; k < K; ++k) {
-      const float v = D[centre[k] * DS + i];
+      const int ck = centre[k];
+      const float v = D[ck * DS + i];
       if (v < best) { best = v; bk = k; }
+      if (ck == i) own = k;
     }
-    for (int k = 0; k < K; ++k)
-      if (centre[k] == i) bk = k;
-    idx_cluster[(long long)b * P + i] = bk;
+    idx_cluster_b[i] = own >= 0 ? own : bk;
   }
 }
 
-// ------------------------------------------------------------------------------------------ K-Medoids fit
-template <bool TC>
-__global__ void __launch_bounds__(TC ? kTcThreads : kThreads, 1)
-kmedoids_fit_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ token_weight, int P, int C, int K, int iters,
-                    float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment,
-                    int use_tc) {
-  constexpr int NT = TC ? kTcThreads : kThreads;
-  extern __shared__ __align__(128) float smem[];
-  DistCtx cx = dist_setup(smem, P, 3 * P + K, use_tc);
-  float* D = cx.D;
-  const int DS = cx.DS;
-  float* w = cx.extra;
+// K-Medoids (models/kmedoids.py:62-85).  extra: w[P], S[P], assign[P] (int), centre[K] (int).
+__host__ __device__ constexpr int kmed_extra_floats(int P, int K) { return 3 * P + K; }
+template <int NT, class Sync>
+__device__ __forceinline__ void kmed_epilogue(const float* D, int DS, int P, int C, int K, int iters, const float* __restrict__ tw_b,
+                                              const float* __restrict__ xb, float* extra, int tid, Sync sync,
+                                              float* __restrict__ centres_b, int64_t* __restrict__ cidx_b,
+                                              int64_t* __restrict__ assign_b) {
+  float* w = extra;
   float* S = w + P;
   int* assign = reinterpret_cast<int*>(S + P);   // [P]
   int* centre = assign + P;                       // [K]
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* xb = x + (long long)b * xbs;
-
-  for (int i = tid; i < P; i += NT) w[i] = token_weight[(long long)b * P + i];
-  pairdist_to_smem<TC>(xb, P, C, cx, 1.0f);
-  dist_teardown(cx);
-
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < P; i += NT) w[i] = tw_b[i];
+  sync();
   // S_i = sum_j (D_ij * w_i); initial centres = top-K token weights (descending, lowest index on ties)
   for (int i = tid; i < P; i += NT) {
     const float wi = w[i];
@@ -448,7 +286,7 @@ kmedoids_fit_kernel(const float* __restrict__ x, long long xbs, const float* __r
     const int rk = rank_desc(w, P, i);
     if (rk < K) centre[rk] = i;
   }
-  __syncthreads();
+  sync();
   const float big = 1.0e6f * (float)P;     // P masked columns of 1e6 sum exactly in fp32
   for (int it = 0; it <= iters; ++it) {
     for (int i = tid; i < P; i += NT) {
@@ -460,7 +298,7 @@ kmedoids_fit_kernel(const float* __restrict__ x, long long xbs, const float* __r
       }
       assign[i] = bk;
     }
-    __syncthreads();
+    sync();
     if (it == iters) break;
     for (int k = tid; k < K; k += NT) {
       float best = CUDART_INF_F;
@@ -471,19 +309,101 @@ kmedoids_fit_kernel(const float* __restrict__ x, long long xbs, const float* __r
       }
       centre[k] = bi;
     }
-    __syncthreads();
+    sync();
   }
-  for (int i = tid; i < P; i += NT) assignment[(long long)b * P + i] = assign[i];
-  for (int k = tid; k < K; k += NT) cluster_idx[(long long)b * K + k] = centre[k];
+  for (int i = tid; i < P; i += NT) assign_b[i] = assign[i];
+  for (int k = tid; k < K; k += NT) cidx_b[k] = centre[k];
   // medoid rows verbatim
-  float* cb = centres + (long long)b * K * C;
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15u) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(cb) & 15u) == 0);
+                   ((reinterpret_cast<uintptr_t>(centres_b) & 15u) == 0);
   for (int k = warp; k < K; k += NT / 32) {
     const float* src = xb + (long long)centre[k] * C;
-    if (vec) warp_copy_row16(cb + (long long)k * C, src, C * 4, lane);
-    else warp_copy_row_elems(cb + (long long)k * C, src, C, lane);
+    if (vec) warp_copy_row16(centres_b + (long long)k * C, src, C * 4, lane);
+    else warp_copy_row_elems(centres_b + (long long)k * C, src, C, lane);
   }
+}
+
+// ------------------------------------------------------------------------------------------ legacy kernels
+template <bool LIGHT>
+__global__ void __launch_bounds__(LIGHT ? kLightThreads : kThreads, 1)
+pairwise_dist_kernel(const float* __restrict__ x, int P, int C, float post_scale, float* __restrict__ out) {
+  constexpr int NT = LIGHT ? kLightThreads : kThreads;
+  extern __shared__ __align__(128) float smem[];
+  DistCtx cx = dist_setup(smem, P, LIGHT);
+  pairdist_to_smem<LIGHT>(x + (long long)blockIdx.x * P * C, P, C, cx, post_scale);
+  float* ob = out + (long long)blockIdx.x * P * P;
+  for (int i = threadIdx.x >> 5; i < P; i += NT / 32)
+    for (int j = threadIdx.x & 31; j < P; j += 32) ob[i * P + j] = cx.D[i * cx.DS + j];
+}
+
+template <bool LIGHT>
+__global__ void __launch_bounds__(LIGHT ? kLightThreads : kThreads, 1)
+dpcknn_cluster_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ noise_u, int P, int C, int K, int knn,
+                      float inv_sqrt_c, int64_t* __restrict__ idx_cluster, int64_t* __restrict__ index_down) {
+  constexpr int NT = LIGHT ? kLightThreads : kThreads;
+  extern __shared__ __align__(128) float smem[];
+  DistCtx cx = dist_setup(smem, P, LIGHT);
+  const int b = blockIdx.x;
+  pairdist_to_smem<LIGHT>(x + (long long)b * xbs, P, C, cx, inv_sqrt_c);
+  __syncthreads();
+  dpc_epilogue<NT>(cx.D, cx.DS, P, K, knn, noise_u + (long long)b * P, cx.extra, (int)threadIdx.x, BlockSync(),
+                   idx_cluster + (long long)b * P, index_down + (long long)b * K);
+}
+
+template <bool LIGHT>
+__global__ void __launch_bounds__(LIGHT ? kLightThreads : kThreads, 1)
+kmedoids_fit_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ token_weight, int P, int C, int K, int iters,
+                    float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment) {
+  constexpr int NT = LIGHT ? kLightThreads : kThreads;
+  extern __shared__ __align__(128) float smem[];
+  DistCtx cx = dist_setup(smem, P, LIGHT);
+  const int b = blockIdx.x;
+  const float* xb = x + (long long)b * xbs;
+  pairdist_to_smem<LIGHT>(xb, P, C, cx, 1.0f);
+  __syncthreads();
+  kmed_epilogue<NT>(cx.D, cx.DS, P, C, K, iters, token_weight + (long long)b * P, xb, cx.extra, (int)threadIdx.x, BlockSync(),
+                    centres + (long long)b * K * C, cluster_idx + (long long)b * K, assignment + (long long)b * P);
+}
+
+// ------------------------------------------------------------------------------------------ pipelined kernels
+struct PipeParams {
+  const float* x; long long xbs; int B, P, C; float post_scale;
+  const float* noise; int K, knn; int64_t* idx_cluster; int64_t* index_down;                    // DPC-KNN
+  const float* tw; int iters; float* centres; int64_t* cidx; int64_t* assign;                   // K-Medoids
+  float* out;                                                                                   // plain cdist
+};
+enum { EPI_PLAIN = 0, EPI_DPC = 1, EPI_KMED = 2 };
+
+template <int EPI>
+__global__ void __launch_bounds__(pipe::kThreads, 1) dist_pipe_kernel(const PipeParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int extra = EPI == EPI_DPC ? dpc_extra_floats(p.P, p.K) : (EPI == EPI_KMED ? kmed_extra_floats(p.P, p.K) : 0);
+  pipe::Ctx cx = pipe::setup(smem_raw, p.B, p.P, p.C, extra);
+  if ((int)threadIdx.x < pipe::kLoad) {
+    pipe::loader_run(p.x, p.xbs, cx);
+  } else if ((int)threadIdx.x < pipe::kFront) {
+    pipe::mma_run(cx);
+  } else {
+    const int bt = (int)threadIdx.x - pipe::kFront;
+    for (int it = 0; it < cx.n_img; ++it) {
+      const long long b = (long long)blockIdx.x + (long long)it * gridDim.x;
+      pipe::back_drain(cx, it, p.post_scale);
+      if constexpr (EPI == EPI_PLAIN) {
+        float* ob = p.out + b * p.P * p.P;
+        for (int i = bt >> 5; i < p.P; i += pipe::kBack / 32)
+          for (int j = bt & 31; j < p.P; j += 32) ob[i * p.P + j] = cx.D[i * cx.DS + j];
+      } else if constexpr (EPI == EPI_DPC) {
+        dpc_epilogue<pipe::kBack>(cx.D, cx.DS, p.P, p.K, p.knn, p.noise + b * p.P, cx.extra, bt, BackSync(),
+                                  p.idx_cluster + b * p.P, p.index_down + b * p.K, it);
+      } else {
+        kmed_epilogue<pipe::kBack>(cx.D, cx.DS, p.P, p.C, p.K, p.iters, p.tw + b * p.P, p.x + b * p.xbs, cx.extra, bt, BackSync(),
+                                   p.centres + b * (long long)p.K * p.C, p.cidx + b * p.K, p.assign + b * p.P);
+      }
+      pipe::bar_sync(pipe::BAR_BACK, pipe::kBack);       // D and the epilogue vectors are free for the next image
+      TOKRED_STAMP(bt == 0, it, 14);
+    }
+  }
+  pipe::teardown(cx);
 }
 
 // ------------------------------------------------------------------------------------------ DPC-KNN merge
@@ -705,11 +625,19 @@ attn_colsum_kernel(const T* __restrict__ attn, int H, int N, int nt, int Tg, int
 }  // namespace tokred
 
 using namespace tokred;
+TOKRED_STAMP_SETTER(cluster)
 
 // tensor cores for every P that takes ATen's matmul form (P > 25), unless the caller asks for the exact-fp32 FFMA path
-static int pick_tc(int P, int exact_fp32) { return (P > 25 && !exact_fp32) ? 1 : 0; }
-// the light 512-thread kernels (no FFMA register tile) also serve the direct-difference path of P <= 25
-static int pick_light(int P, int use_tc) { return (use_tc || P <= 25) ? 1 : 0; }
+static int pick_pipe(int P, int exact_fp32) { return (P > 25 && !exact_fp32) ? 1 : 0; }
+
+template <int EPI>
+static int launch_pipe(const PipeParams& p, int extra_floats, const char* what, cudaStream_t st) {
+  const size_t smem = pipe::smem_bytes(p.P, extra_floats);
+  if (int e = allow_smem(dist_pipe_kernel<EPI>, smem, what)) return e;
+  const int grid = p.B < kNumSMs ? p.B : kNumSMs;       // persistent: one CTA per SM walks its images
+  dist_pipe_kernel<EPI><<<grid, pipe::kThreads, smem, st>>>(p);
+  return finish_launch(what);
+}
 
 extern "C" int tokred_pairwise_dist(const float* x, int B, int P, int C, float post_scale, int exact_fp32, float* out,
                                     void* stream) {
@@ -718,15 +646,20 @@ extern "C" int tokred_pairwise_dist(const float* x, int B, int P, int C, float p
   TOKRED_REQUIRE(x && out, "%s: null tensor", what);
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 1, "%s: bad shape B=%d P=%d C=%d", what, B, P, C);
   if (P > kMaxP) { set_error("%s: P=%d > %d patches is not supported (distance matrix is kept in shared memory)", what, P, kMaxP); return TOKRED_ERR_UNSUPPORTED; }
-  if (B == 0) return TOKRED_OK;
-  const int use_tc = pick_tc(P, exact_fp32);
-  const size_t smem = dist_smem_bytes(P, 0, use_tc);
-  if (pick_light(P, use_tc)) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pick_pipe(P, exact_fp32)) {
+    PipeParams p{};
+    p.x = x; p.xbs = (long long)P * C; p.B = B; p.P = P; p.C = C; p.post_scale = post_scale; p.out = out;
+    return launch_pipe<EPI_PLAIN>(p, 0, what, st);
+  }
+  const int light = P <= 25;
+  const size_t smem = dist_smem_bytes(P, 0, light);
+  if (light) {
     if (int e = allow_smem(pairwise_dist_kernel<true>, smem, what)) return e;
-    pairwise_dist_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out, use_tc);
+    pairwise_dist_kernel<true><<<B, kLightThreads, smem, st>>>(x, P, C, post_scale, out);
   } else {
     if (int e = allow_smem(pairwise_dist_kernel<false>, smem, what)) return e;
-    pairwise_dist_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, P, C, post_scale, out, 0);
+    pairwise_dist_kernel<false><<<B, kThreads, smem, st>>>(x, P, C, post_scale, out);
   }
   return finish_launch(what);
 }
@@ -740,20 +673,24 @@ extern "C" int tokred_dpcknn_cluster(const float* x, int64_t x_batch_stride, con
   TOKRED_REQUIRE(K >= 1 && K <= P, "%s: cluster_num=%d outside [1, P=%d]", what, K, P);
   TOKRED_REQUIRE(knn >= 1 && knn <= P, "%s: k=%d outside [1, P=%d]", what, knn, P);
   if (P > kMaxP) { set_error("%s: P=%d > %d patches is not supported (distance matrix is kept in shared memory)", what, P, kMaxP); return TOKRED_ERR_UNSUPPORTED; }
-  if (B == 0) return TOKRED_OK;
   TOKRED_REQUIRE(x_batch_stride == 0 || x_batch_stride >= (int64_t)P * C, "%s: x_batch_stride=%lld < P*C", what, (long long)x_batch_stride);
   const long long xbs = x_batch_stride ? (long long)x_batch_stride : (long long)P * C;
-  const int use_tc = pick_tc(P, exact_fp32);
-  const size_t smem = dist_smem_bytes(P, 2 * P + K + kTcThreads / 32, use_tc);
   const float inv = 1.0f / (float)sqrt((double)C);     // CUDA tensor / python-scalar = multiply by fp32 reciprocal
-  if (pick_light(P, use_tc)) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pick_pipe(P, exact_fp32)) {
+    PipeParams p{};
+    p.x = x; p.xbs = xbs; p.B = B; p.P = P; p.C = C; p.post_scale = inv;
+    p.noise = noise_u; p.K = K; p.knn = knn; p.idx_cluster = idx_cluster; p.index_down = index_down;
+    return launch_pipe<EPI_DPC>(p, dpc_extra_floats(P, K), what, st);
+  }
+  const int light = P <= 25;
+  const size_t smem = dist_smem_bytes(P, dpc_extra_floats(P, K), light);
+  if (light) {
     if (int e = allow_smem(dpcknn_cluster_kernel<true>, smem, what)) return e;
-    dpcknn_cluster_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, xbs, noise_u, P, C, K, knn, inv, idx_cluster,
-                                                                              index_down, use_tc);
+    dpcknn_cluster_kernel<true><<<B, kLightThreads, smem, st>>>(x, xbs, noise_u, P, C, K, knn, inv, idx_cluster, index_down);
   } else {
     if (int e = allow_smem(dpcknn_cluster_kernel<false>, smem, what)) return e;
-    dpcknn_cluster_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, xbs, noise_u, P, C, K, knn, inv, idx_cluster,
-                                                                             index_down, 0);
+    dpcknn_cluster_kernel<false><<<B, kThreads, smem, st>>>(x, xbs, noise_u, P, C, K, knn, inv, idx_cluster, index_down);
   }
   return finish_launch(what);
 }
@@ -767,19 +704,23 @@ extern "C" int tokred_kmedoids_fit(const float* x, int64_t x_batch_stride, const
   TOKRED_REQUIRE(K >= 1 && K <= P, "%s: cluster_num=%d outside [1, P=%d]", what, K, P);
   TOKRED_REQUIRE(iters >= 0, "%s: iters=%d < 0", what, iters);
   if (P > kMaxP) { set_error("%s: P=%d > %d patches is not supported (distance matrix is kept in shared memory)", what, P, kMaxP); return TOKRED_ERR_UNSUPPORTED; }
-  if (B == 0) return TOKRED_OK;
   TOKRED_REQUIRE(x_batch_stride == 0 || x_batch_stride >= (int64_t)P * C, "%s: x_batch_stride=%lld < P*C", what, (long long)x_batch_stride);
   const long long xbs = x_batch_stride ? (long long)x_batch_stride : (long long)P * C;
-  const int use_tc = pick_tc(P, exact_fp32);
-  const size_t smem = dist_smem_bytes(P, 3 * P + K, use_tc);
-  if (pick_light(P, use_tc)) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pick_pipe(P, exact_fp32)) {
+    PipeParams p{};
+    p.x = x; p.xbs = xbs; p.B = B; p.P = P; p.C = C; p.post_scale = 1.0f;
+    p.tw = token_weight; p.K = K; p.iters = iters; p.centres = centres; p.cidx = cluster_idx; p.assign = assignment;
+    return launch_pipe<EPI_KMED>(p, kmed_extra_floats(P, K), what, st);
+  }
+  const int light = P <= 25;
+  const size_t smem = dist_smem_bytes(P, kmed_extra_floats(P, K), light);
+  if (light) {
     if (int e = allow_smem(kmedoids_fit_kernel<true>, smem, what)) return e;
-    kmedoids_fit_kernel<true><<<B, kTcThreads, smem, (cudaStream_t)stream>>>(x, xbs, token_weight, P, C, K, iters, centres,
-                                                                            cluster_idx, assignment, use_tc);
+    kmedoids_fit_kernel<true><<<B, kLightThreads, smem, st>>>(x, xbs, token_weight, P, C, K, iters, centres, cluster_idx, assignment);
   } else {
     if (int e = allow_smem(kmedoids_fit_kernel<false>, smem, what)) return e;
-    kmedoids_fit_kernel<false><<<B, kThreads, smem, (cudaStream_t)stream>>>(x, xbs, token_weight, P, C, K, iters, centres,
-                                                                           cluster_idx, assignment, 0);
+    kmedoids_fit_kernel<false><<<B, kThreads, smem, st>>>(x, xbs, token_weight, P, C, K, iters, centres, cluster_idx, assignment);
   }
   return finish_launch(what);
 }

@@ -146,15 +146,40 @@ __device__ __forceinline__ int rank_desc(const float* keys, int n, int i) {
   if (ki != ki) {
     for (int j = 0; j < i; ++j) { const float kj = keys[j]; r += (kj != kj); }
   } else {
-    for (int j = 0; j < n; ++j) {
-      const float kj = keys[j];
-      r += !(kj <= ki) || (kj == ki && j < i);      // !(kj <= ki): kj > ki, or kj is NaN
+    int r1 = 0, r2 = 0, r3 = 0, j = 0;            // four counters: the add chain was the critical path
+    for (; j + 3 < n; j += 4) {
+      const float k0 = keys[j], k1 = keys[j + 1], k2 = keys[j + 2], k3 = keys[j + 3];
+      r += !(k0 <= ki) || (k0 == ki && j < i);     // !(kj <= ki): kj > ki, or kj is NaN
+      r1 += !(k1 <= ki) || (k1 == ki && j + 1 < i);
+      r2 += !(k2 <= ki) || (k2 == ki && j + 2 < i);
+      r3 += !(k3 <= ki) || (k3 == ki && j + 3 < i);
     }
+    for (; j < n; ++j) { const float kj = keys[j]; r += !(kj <= ki) || (kj == ki && j < i); }
+    r += r1 + r2 + r3;
   }
   return r;
 }
 
 __device__ __forceinline__ int clamp_idx(long long v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : (int)v); }
+
+// Phase stamps for kernel bring-up (tools/diag/*): compiled ONLY into the debug library (python -m
+// tokenreduction_b200.build --stamps -> libtokred_sm100a_dbg.so); the release build contains no stamp code at all.
+#ifdef TOKRED_STAMPS
+static __device__ unsigned long long* g_tokred_stamps = nullptr;      // one per translation unit: [CTA][8 images][32 slots]
+__device__ __forceinline__ void tokred_stamp(int img, int slot) {
+  if (g_tokred_stamps) g_tokred_stamps[((size_t)blockIdx.x * 8 + (img & 7)) * 32 + slot] = (unsigned long long)clock64();
+}
+#define TOKRED_STAMP(cond, img, slot) do { if (cond) ::tokred::tokred_stamp((img), (slot)); } while (0)
+// each .cu that stamps exports tokred_debug_set_stamps_<unit>(device buffer or NULL)
+#define TOKRED_STAMP_SETTER(unit)                                                                            \
+  extern "C" __attribute__((visibility("default"))) int tokred_debug_set_stamps_##unit(void* device_buffer) { \
+    unsigned long long* p = (unsigned long long*)device_buffer;                                              \
+    return (int)cudaMemcpyToSymbol(::tokred::g_tokred_stamps, &p, sizeof(p));                                \
+  }
+#else
+#define TOKRED_STAMP(cond, img, slot) do { } while (0)
+#define TOKRED_STAMP_SETTER(unit)
+#endif
 
 #endif  // __CUDACC__
 }  // namespace tokred

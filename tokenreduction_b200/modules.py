@@ -40,6 +40,14 @@ def _f16_to_bf16(t: Tensor) -> Tensor:
     return t.float() if t.dtype == torch.float16 else t
 
 
+def _amp_out(t: Tensor) -> Tensor:
+    """a reduced-precision op output in the dtype the reference's autocast matmul would have produced (fp16 under fp16
+    autocast; the kernels emit bf16)."""
+    if t.dtype == torch.bfloat16 and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16:
+        return t.half()
+    return t
+
+
 def _train_guard(mod: nn.Module) -> None:
     if mod.training and torch.is_grad_enabled():
         raise NotImplementedError(
@@ -415,7 +423,8 @@ class Sinkhorn(nn.Module):
         _train_guard(self)
         with torch.no_grad():                       # the reference overwrites its parameter (:73-76); idempotent
             self.v.copy_(F.normalize(self.v.clone(), p=2, dim=-1))
-        return ops.sinkhorn_merge(x, self.v.detach(), self.eps, self.iters, _lowp(), True)
+        out, w = ops.sinkhorn_merge(x, self.v.detach(), self.eps, self.iters, _lowp(), True)
+        return _amp_out(out), w
 
 
 # =============================================================================================== PatchMerger
@@ -430,8 +439,9 @@ class PatchMerger(nn.Module):
 
     def forward(self, x):
         _train_guard(self)
-        return ops.patchmerger(x, self.norm.weight.detach(), self.norm.bias.detach(), self.queries.detach(), self.scale,
-                               self.norm.eps, _lowp(), True)
+        out, attn = ops.patchmerger(x, self.norm.weight.detach(), self.norm.bias.detach(), self.queries.detach(), self.scale,
+                                    self.norm.eps, _lowp(), True)
+        return _amp_out(out), attn
 
 
 # =============================================================================================== SiT
@@ -447,7 +457,8 @@ class TokenSlimmingModule(nn.Module):
 
     def forward(self, x):
         _train_guard(self)
-        return ops.sit_merge(x, self.weight(x), self.scale.detach(), _lowp(), True)
+        out, w = ops.sit_merge(x, self.weight(x), self.scale.detach(), _lowp(), True)
+        return _amp_out(out), w
 
 
 # =============================================================================================== ATS

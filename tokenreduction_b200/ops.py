@@ -63,6 +63,17 @@ def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _up(*ts):
+    """fp16 boundary (the reference's eval default is fp16 autocast, validate.py:52-54): half tensors enter the kernels as
+    fp32 -- an exact conversion -- everything else passes through."""
+    return tuple(t.float() if (t is not None and t.dtype == torch.float16) else t for t in ts)
+
+
+def _down(out: Tensor, like: Tensor) -> Tensor:
+    """floating outputs go back to fp16 when the tensor they derive from was fp16."""
+    return out.half() if (like.dtype == torch.float16 and out.is_floating_point()) else out
+
+
 def _rows(x: Tensor) -> Tuple[Tensor, int]:
     """[B,P,C] token tensor for the entry points that take x_batch_stride: a view whose rows are dense and C apart
     (x[:, 1:] of a contiguous [B,N,C] tensor -- what the cluster / soft-merge layers receive) is passed in place with
@@ -118,12 +129,16 @@ def _(x, attn, k):
 
 def topk_gather(x: Tensor, scores: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     """models/topk.py:62 + :89-93 (also DynamicViT keep, models/dyvit.py:231-236): (x_out [B,k+1,C], idx [B,k])."""
-    return torch.ops.tokred.topk_gather(x, scores, k)
+    xf, sf = _up(x, scores)
+    out, idx = torch.ops.tokred.topk_gather(xf, sf, k)
+    return _down(out, x), idx
 
 
 def topk_gather_attn(x: Tensor, attn: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     """Same, with the head-mean of the CLS attention row computed in-kernel (no [B,P] round trip)."""
-    return torch.ops.tokred.topk_gather_attn(x, attn, k)
+    xf, af = _up(x, attn)
+    out, idx = torch.ops.tokred.topk_gather_attn(xf, af, k)
+    return _down(out, x), idx
 
 
 # ----------------------------------------------------------------------------------------------- EViT
@@ -176,11 +191,15 @@ def _(x, attn, k):
 
 def evit_select_fuse(x: Tensor, scores: Tensor, k: int):
     """models/evit.py:84 + :111-123: (x_out [B,k+2,C], idx [B,k+1] with trailing -1, compl [B,P-k])."""
-    return torch.ops.tokred.evit_select_fuse(x, scores, k)
+    xf, sf = _up(x, scores)
+    out, idx, compl = torch.ops.tokred.evit_select_fuse(xf, sf, k)
+    return _down(out, x), idx, compl
 
 
 def evit_select_fuse_attn(x: Tensor, attn: Tensor, k: int):
-    return torch.ops.tokred.evit_select_fuse_attn(x, attn, k)
+    xf, af = _up(x, attn)
+    out, idx, compl = torch.ops.tokred.evit_select_fuse_attn(xf, af, k)
+    return _down(out, x), idx, compl
 
 
 # ----------------------------------------------------------------------------------------------- ToMe
@@ -251,14 +270,16 @@ def tome_match(metric: Tensor, r: int, class_token: bool = True, lowp: bool = Fa
     """models/tome.py:258-277: (unm_idx [B,a-r], src_idx [B,r], dst_idx [B,r]) int64.
     lowp=True reproduces the bf16 autocast matmul (on tcgen05 tensor cores; tensor_cores=False keeps the same
     rounding on the FFMA path, used as a cross-check).  distill_token protects odd token 0 as a destination (:265-266)."""
-    return torch.ops.tokred.tome_match(metric, r, class_token, lowp, tensor_cores, distill_token)
+    return torch.ops.tokred.tome_match(_up(metric)[0], r, class_token, lowp, tensor_cores, distill_token)
 
 
 def tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor, want_map: bool = True,
                divide: bool = True):
     """models/tome.py:279-289,309-323 + Block_ToMe :91-99: (x_out [B,N-r,C], size_out [B,N-r,1], map [B,N-1] f32).
     divide=False returns the bare merge closure's sums instead of the size-weighted mean."""
-    return torch.ops.tokred.tome_merge(x, size, unm, src, dst, want_map, divide)
+    xf, sf = _up(x, size)
+    out, size_out, rci = torch.ops.tokred.tome_merge(xf, sf, unm, src, dst, want_map, divide)
+    return _down(out, x), _down(size_out, x), rci
 
 
 # ----------------------------------------------------------------------------------------------- distances
@@ -281,7 +302,7 @@ def _(x, post_scale, exact_fp32):
 def pairwise_dist(x: Tensor, post_scale: float = 1.0, exact_fp32: bool = False) -> Tensor:
     """torch.cdist(x, x) * post_scale with ATen's formula selection (models/dpcknn.py:59, models/kmedoids.py:68).
     Default: Gram on tcgen05 with 3xTF32 compensation; exact_fp32=True: FFMA."""
-    return torch.ops.tokred.pairwise_dist(x, post_scale, exact_fp32)
+    return torch.ops.tokred.pairwise_dist(_up(x)[0], post_scale, exact_fp32)
 
 
 # ----------------------------------------------------------------------------------------------- DPC-KNN
@@ -336,12 +357,14 @@ def _(x, idx_token, agg_weight, idx_cluster, token_weight, cluster_num):
 
 def dpcknn_cluster(x: Tensor, noise_u: Tensor, cluster_num: int, knn: int = 5, exact_fp32: bool = False):
     """models/dpcknn.py:44-100: (idx_cluster [B,P], index_down [B,K]) int64; noise_u = torch.rand(B,P)."""
-    return torch.ops.tokred.dpcknn_cluster(x, noise_u, cluster_num, knn, exact_fp32)
+    return torch.ops.tokred.dpcknn_cluster(_up(x)[0], noise_u, cluster_num, knn, exact_fp32)
 
 
 def dpcknn_merge(x, idx_token, agg_weight, idx_cluster, token_weight, cluster_num):
     """models/dpcknn.py:103-140: (x_merged [B,K,C], idx_token_new [B,T], agg_weight_new [B,T,1])."""
-    return torch.ops.tokred.dpcknn_merge(x, idx_token, agg_weight, idx_cluster, token_weight, cluster_num)
+    xf, aw, tw = _up(x, agg_weight, token_weight)
+    merged, idx_new, agg_new = torch.ops.tokred.dpcknn_merge(xf, idx_token, aw, idx_cluster, tw, cluster_num)
+    return _down(merged, x), idx_new, _down(agg_new, agg_weight)
 
 
 # ----------------------------------------------------------------------------------------------- K-Medoids
@@ -389,12 +412,14 @@ def _(x, token_weight, cluster_num, iters, exact_fp32):
 
 def attn_colsum(attn: Tensor, num_tokens: int = 1) -> Tensor:
     """models/kmedoids.py:240: token weights [B,P,1] = sum over heads and query rows of attention columns."""
-    return torch.ops.tokred.attn_colsum(attn, num_tokens)
+    return torch.ops.tokred.attn_colsum(_up(attn)[0], num_tokens)
 
 
 def kmedoids_fit(x: Tensor, token_weight: Tensor, cluster_num: int, iters: int, exact_fp32: bool = False):
     """models/kmedoids.py:62-85: (centres [B,K,C], cluster_idx [B,K], assignment [B,P])."""
-    return torch.ops.tokred.kmedoids_fit(x, token_weight, cluster_num, iters, exact_fp32)
+    xf, tw = _up(x, token_weight)
+    centres, cidx, assign = torch.ops.tokred.kmedoids_fit(xf, tw, cluster_num, iters, exact_fp32)
+    return _down(centres, x), cidx, assign
 
 
 # ----------------------------------------------------------------------------------------------- soft merges
@@ -510,18 +535,19 @@ def _(x, logits, scale, lowp, tensor_cores):
 
 def sinkhorn_merge(x: Tensor, v_hat: Tensor, eps: float, iters: int, lowp: bool = False, tensor_cores: bool = True):
     """models/sinkhorn.py:66-86: (out [B,K,C], weights [B,K,P]); v_hat = F.normalize(v)."""
-    return torch.ops.tokred.sinkhorn_merge(x, v_hat, eps, iters, lowp, tensor_cores)
+    return torch.ops.tokred.sinkhorn_merge(_up(x)[0], _up(v_hat)[0], eps, iters, lowp, tensor_cores)
 
 
 def patchmerger(x, ln_weight, ln_bias, queries, scale: float = 1.0, ln_eps: float = 1e-5, lowp: bool = False,
                 tensor_cores: bool = True):
     """models/patchmerger.py:35-39: (out [B,K,C], attn [B,K,P])."""
-    return torch.ops.tokred.patchmerger(x, ln_weight, ln_bias, queries, scale, ln_eps, lowp, tensor_cores)
+    return torch.ops.tokred.patchmerger(_up(x)[0], ln_weight, ln_bias, queries, scale, ln_eps, lowp, tensor_cores)
 
 
 def sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool = False, tensor_cores: bool = True):
     """models/sit.py:37-40: (out [B,K,C], weight [B,K,P])."""
-    return torch.ops.tokred.sit_merge(x, logits, scale, lowp, tensor_cores)
+    xf, lf = _up(x, logits)
+    return torch.ops.tokred.sit_merge(xf, lf, scale, lowp, tensor_cores)
 
 
 # ----------------------------------------------------------------------------------------------- ATS
@@ -582,12 +608,13 @@ def _(src, ids, m):
 
 def ats_sample(v: Tensor, attn: Tensor, mask: Tensor, steps: Tensor, eps: float = 1e-6):
     """models/ats.py:52-82: (ids [B,n_steps+1] zero-padded sorted unique, mask [B,n_steps+1], max_count int32[1])."""
-    return torch.ops.tokred.ats_sample(v, attn, mask, steps, eps)
+    vf, af = _up(v, attn)
+    return torch.ops.tokred.ats_sample(vf, af, mask, steps, eps)
 
 
 def gather_rows(src: Tensor, ids: Tensor, m: Optional[int] = None) -> Tensor:
     """out[b,(g,)j,:] = src[b,(g,)ids[b,j],:] for j < m (models/ats.py:84-87, :156-157)."""
-    return torch.ops.tokred.gather_rows(src, ids, ids.shape[1] if m is None else m)
+    return _down(torch.ops.tokred.gather_rows(_up(src)[0], ids, ids.shape[1] if m is None else m), src)
 
 
 # ----------------------------------------------------------------------------------------------- DynamicViT
@@ -612,4 +639,6 @@ def _(h, policy, eps):
 
 def dyvit_pool_concat(h: Tensor, policy: Tensor, eps: float = 1e-6) -> Tensor:
     """models/dyvit.py:114-118: [local half | masked mean of the global half + eps]."""
-    return torch.ops.tokred.dyvit_pool_concat(h, policy, eps)
+    hf, pf = _up(h, policy)
+    out = torch.ops.tokred.dyvit_pool_concat(hf, pf, eps)
+    return out.to(torch.promote_types(h.dtype, policy.dtype))      # torch.cat's promotion (models/dyvit.py:118)
