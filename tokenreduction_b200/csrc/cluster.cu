@@ -226,45 +226,68 @@ __device__ __forceinline__ void dpc_epilogue(const float* D, int DS, int P, int 
 #pragma unroll
   for (int w = 1; w < NT / 32; ++w) dmax = fmaxf(dmax, red[w]);
 
+  // The three passes below give every token to TWO adjacent lanes (one half of the scan each, combined with one
+  // shuffle): 2P tasks keep all warps of the group busy and halve the serial scan length.
   // distance to the nearest denser token (or the global max), centre score
-  for (int i = tid; i < P; i += NT) {
+  for (int base = 0; base < 2 * P; base += NT) {
+    const int it = base + tid;
+    const bool act = it < 2 * P;
+    const int i = act ? it >> 1 : 0, h = it & 1;
+    const int j0 = h ? (P + 1) / 2 : 0, j1 = act ? (h ? P : (P + 1) / 2) : 0;
     const float ri = rho[i];
     float b0 = dmax, b1 = dmax, b2 = dmax, b3 = dmax;      // four independent minima: the fmin chain was the critical path
-    int j = 0;
-    for (; j + 3 < P; j += 4) {
+    int j = j0;
+    for (; j + 3 < j1; j += 4) {
       b0 = fminf(b0, rho[j] > ri ? D[j * DS + i] : dmax);
       b1 = fminf(b1, rho[j + 1] > ri ? D[(j + 1) * DS + i] : dmax);
       b2 = fminf(b2, rho[j + 2] > ri ? D[(j + 2) * DS + i] : dmax);
       b3 = fminf(b3, rho[j + 3] > ri ? D[(j + 3) * DS + i] : dmax);
     }
-    for (; j < P; ++j) b0 = fminf(b0, rho[j] > ri ? D[j * DS + i] : dmax);
-    score[i] = fminf(fminf(b0, b1), fminf(b2, b3)) * ri;
+    for (; j < j1; ++j) b0 = fminf(b0, rho[j] > ri ? D[j * DS + i] : dmax);
+    float best = fminf(fminf(b0, b1), fminf(b2, b3));
+    best = fminf(best, __shfl_xor_sync(0xffffffffu, best, 1));
+    if (act && h == 0) score[i] = best * ri;
   }
   sync();
   TOKRED_STAMP(tid == 0, img, 12);
-  for (int i = tid; i < P; i += NT) {
-    const int rk = rank_desc(score, P, i);
-    if (rk < K) { centre[rk] = i; index_down_b[rk] = i; }
+  for (int base = 0; base < 2 * P; base += NT) {
+    const int it = base + tid;
+    const bool act = it < 2 * P;
+    const int i = act ? it >> 1 : 0, h = it & 1;
+    int rk = rank_desc_range(score, h ? (P + 1) / 2 : 0, act ? (h ? P : (P + 1) / 2) : 0, i);
+    rk += __shfl_xor_sync(0xffffffffu, rk, 1);
+    if (act && h == 0 && rk < K) { centre[rk] = i; index_down_b[rk] = i; }
   }
   sync();
   TOKRED_STAMP(tid == 0, img, 13);
   // nearest centre (lowest k on ties); centres belong to their own cluster
-  for (int i = tid; i < P; i += NT) {
+  for (int base = 0; base < 2 * P; base += NT) {
+    const int it = base + tid;
+    const bool act = it < 2 * P;
+    const int i = act ? it >> 1 : 0, h = it & 1;
+    const int k0 = h ? (K + 1) / 2 : 0, k1 = act ? (h ? K : (K + 1) / 2) : 0;
     float best = CUDART_INF_F;
-    int bk = 0, own = -1;
+    int bk = 0x7fffffff, own = -1;
 #pragma unroll 4
-    for (int k = 0; k < K; ++k) {
+    for (int k = k0; k < k1; ++k) {
       const int ck = centre[k];
       const float v = D[ck * DS + i];
       if (v < best) { best = v; bk = k; }
       if (ck == i) own = k;
     }
-    idx_cluster_b[i] = own >= 0 ? own : bk;
+    const float ob = __shfl_xor_sync(0xffffffffu, best, 1);
+    const int ok = __shfl_xor_sync(0xffffffffu, bk, 1), oo = __shfl_xor_sync(0xffffffffu, own, 1);
+    if (act && h == 0) {
+      if (ob < best || bk == 0x7fffffff) bk = ok;             // the upper half only wins when strictly nearer
+      if (bk == 0x7fffffff) bk = 0;
+      own = own >= 0 ? own : oo;
+      idx_cluster_b[i] = own >= 0 ? own : bk;
+    }
   }
 }
 
-// K-Medoids (models/kmedoids.py:62-85).  extra: w[P], S[P], assign[P] (int), centre[K] (int).
-__host__ __device__ constexpr int kmed_extra_floats(int P, int K) { return 3 * P + K; }
+// K-Medoids (models/kmedoids.py:62-85).  extra: w[P], S[P], assign[P] (int), centre[K] (int), best_key[K] (u64).
+__host__ __device__ constexpr int kmed_extra_floats(int P, int K) { return 3 * P + K + 2 + 2 * K + 2; }
 template <int NT, class Sync>
 __device__ __forceinline__ void kmed_epilogue(const float* D, int DS, int P, int C, int K, int iters, const float* __restrict__ tw_b,
                                               const float* __restrict__ xb, float* extra, int tid, Sync sync,
@@ -287,28 +310,38 @@ __device__ __forceinline__ void kmed_epilogue(const float* D, int DS, int P, int
     if (rk < K) centre[rk] = i;
   }
   sync();
-  const float big = 1.0e6f * (float)P;     // P masked columns of 1e6 sum exactly in fp32
+  // Medoid update: c_k = argmin_{i: assign_i = k} S_i with the lowest i on ties, empty cluster -> token 0 (every
+  // masked row sums to P * 1e6 > any S).  One shared-memory atomicMin per token on the key (S bits, i):
+  // S > 0, so the fp32 bit pattern orders like the value -- replaces K serial scans of P by 49 threads.
+  unsigned long long* best_key =                                                                  // [K], 8-byte aligned
+      reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(centre + K) + 7) & ~(uintptr_t)7);
   for (int it = 0; it <= iters; ++it) {
-    for (int i = tid; i < P; i += NT) {
+    for (int base = 0; base < 2 * P; base += NT) {          // two adjacent lanes per token, half of the centres each
+      const int t2 = base + tid;
+      const bool act = t2 < 2 * P;
+      const int i = act ? t2 >> 1 : 0, h = t2 & 1;
+      const int k0 = h ? (K + 1) / 2 : 0, k1 = act ? (h ? K : (K + 1) / 2) : 0;
       float best = CUDART_INF_F;
-      int bk = 0;
-      for (int k = 0; k < K; ++k) {
+      int bk = 0x7fffffff;
+#pragma unroll 4
+      for (int k = k0; k < k1; ++k) {
         const float v = D[centre[k] * DS + i];
         if (v < best) { best = v; bk = k; }
       }
-      assign[i] = bk;
+      const float ob = __shfl_xor_sync(0xffffffffu, best, 1);
+      const int ok = __shfl_xor_sync(0xffffffffu, bk, 1);
+      if (act && h == 0) {
+        if (ob < best || bk == 0x7fffffff) bk = ok;
+        assign[i] = bk == 0x7fffffff ? 0 : bk;
+      }
     }
+    for (int k = tid; k < K; k += NT) best_key[k] = ~0ull;
     sync();
     if (it == iters) break;
-    for (int k = tid; k < K; k += NT) {
-      float best = CUDART_INF_F;
-      int bi = 0;
-      for (int i = 0; i < P; ++i) {
-        const float v = assign[i] == k ? S[i] : big;
-        if (v < best) { best = v; bi = i; }
-      }
-      centre[k] = bi;
-    }
+    for (int i = tid; i < P; i += NT)
+      atomicMin(&best_key[assign[i]], ((unsigned long long)__float_as_uint(S[i]) << 32) | (unsigned)i);
+    sync();
+    for (int k = tid; k < K; k += NT) centre[k] = best_key[k] == ~0ull ? 0 : (int)(best_key[k] & 0xffffffffu);
     sync();
   }
   for (int i = tid; i < P; i += NT) assign_b[i] = assign[i];

@@ -160,6 +160,25 @@ __device__ __forceinline__ int rank_desc(const float* keys, int n, int i) {
   return r;
 }
 
+// the same count restricted to keys [j0, j1): two lanes split a rank and add their halves
+__device__ __forceinline__ int rank_desc_range(const float* keys, int j0, int j1, int i) {
+  const float ki = keys[i];
+  int r = 0, r1 = 0, r2 = 0, r3 = 0, j = j0;
+  if (ki != ki) {
+    for (; j < j1 && j < i; ++j) { const float kj = keys[j]; r += (kj != kj); }
+    return r;
+  }
+  for (; j + 3 < j1; j += 4) {
+    const float k0 = keys[j], k1 = keys[j + 1], k2 = keys[j + 2], k3 = keys[j + 3];
+    r += !(k0 <= ki) || (k0 == ki && j < i);
+    r1 += !(k1 <= ki) || (k1 == ki && j + 1 < i);
+    r2 += !(k2 <= ki) || (k2 == ki && j + 2 < i);
+    r3 += !(k3 <= ki) || (k3 == ki && j + 3 < i);
+  }
+  for (; j < j1; ++j) { const float kj = keys[j]; r += !(kj <= ki) || (kj == ki && j < i); }
+  return r + r1 + r2 + r3;
+}
+
 __device__ __forceinline__ int clamp_idx(long long v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : (int)v); }
 
 // Phase stamps for kernel bring-up (tools/diag/*): compiled ONLY into the debug library (python -m

@@ -1,8 +1,7 @@
 // Persistent, warp-specialised pairwise-distance pipeline for the clustering kernels (DPC-KNN, K-Medoids, cdist).
 //
 //   grid = min(B, 148) CTAs of 512 threads, each CTA walks images b = blockIdx.x, blockIdx.x + gridDim.x, ...
-//   LOADER warps 0-13:  stream the image's token rows HBM -> L2 (prefetch.global.L2, six 32-column chunks ahead) ->
-//        registers (two chunks ahead), split every
+//   LOADER warps 0-13:  stream the image's token rows HBM -> registers (two 32-column chunks ahead), split every
 //        fp32 value x into two fp16 terms h = fp16(x), l = fp16(x - h) (|x - h - l| <= 2^-22 |x|) and write them as
 //        canonical K-major UMMA tiles into a 2-stage shared-memory ring (stage_full mbarrier, no CTA barrier).
 //   MMA warp 14:  one lane issues, per 16-column k-step, three tcgen05.mma kind::f16 (h.h^T, h.l^T, l.h^T) into ONE
@@ -37,11 +36,17 @@
 namespace tokred {
 namespace pipe {
 
-// 14 loader warps + 1 MMA warp + 8 BACK warps = 736 threads at <= 88 registers: every phase of this kernel is
-// latency-bound (ncu: 1.4 warp instructions per cycle per SM with 16 warps), so more, lighter warps beat few heavy ones
+// 14 loader warps + 1 MMA warp + 8 BACK warps = 736 threads at 80 registers.
+// Measured (tools/diag/pipe_stamps.py, B=256 P=196 C=384): a chunk takes ~1.2 us end to end whatever the data size
+// (P=49 too): ~0.5 us stage + arrive of the FIRST loader warp, up to 1 us until the LAST one arrives (the loaders are
+// issue-bound: ~20 instructions per float once address arithmetic and predicates are counted), 0.8 us for one lane to
+// issue 12 MMAs + 2 commits, 0.55 us MMA execution.  Not the bottleneck (measured, so they are not retried blind):
+// more bytes in flight (3 register buffers: slower), L2 prefetches (bulk, per line, 512 B per row: no change), an L2
+// warm-up by the idle BACK group (no change), a third of the MMAs (no change), 7 vs 14 loader warps (no change).
 constexpr int kLoad = 448;              // loader threads (warps 0-13); warp 14 issues the MMAs
 constexpr int kItems = 2;               // (row, core column) items per loader thread and chunk: 2 x 448 >= 208 rows x 4
-constexpr int kFront = kLoad + 32, kBack = 256, kThreads = kFront + kBack;
+constexpr int kBackWarps = 8;           // (10 loader + 13 BACK warps measured slower: the front went from 14 to 22 us per image)
+constexpr int kFront = kLoad + 32, kBack = kBackWarps * 32, kThreads = kFront + kBack;
 constexpr int KC = 32;                  // contraction columns per stage (4 core columns of 8 halves)
 constexpr int kStages = 2;
 constexpr int kMaxP = 208;
@@ -108,28 +113,8 @@ struct FrontNorms {
 #endif
 };
 
-// A chunk touches one 128-byte line of every row (row stride 1.5-3 KB): scattered 128-byte DRAM reads, which this
-// part serves at about half its streaming rate (stamps: 1.05 us per chunk = 3.4 TB/s chip-wide with 8 MB in flight;
-// more loads in flight only queued longer).  So the loaders ask the L2 for FOUR adjacent lines of every row at once
-// (prefetch.global.L2, 512 contiguous bytes per row: DRAM page hits, no registers, no shared memory) one group of
-// four chunks ahead; the chunk loads then hit L2.  gidx = first chunk of the group to request.
-constexpr int kPrefetch = 4;
-__device__ __forceinline__ void front_prefetch(const float* __restrict__ x, long long xbs, int gidx, const Ctx& cx) {
-  const int total = cx.n_img * cx.nchunk;
-  if (gidx >= total) return;
-  const int img = gidx / cx.nchunk, c = gidx - img * cx.nchunk;
-  const float* xb = x + (long long)(blockIdx.x + (long long)img * gridDim.x) * xbs;
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int t = threadIdx.x + kLoad * u;
-    const int row = t >> 2, k = (c + (t & 3)) * KC;
-    if (row < cx.P && k < cx.C) asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + (long long)row * cx.C + k));
-  }
-}
-
 __device__ __forceinline__ void front_load(const float* __restrict__ x, long long xbs, int gidx, const Ctx& cx, bool vec, FrontRegs& r) {
   const int total = cx.n_img * cx.nchunk;
-  if (gidx % kPrefetch == 0) front_prefetch(x, xbs, gidx + kPrefetch, cx);     // chunk groups never straddle images when nchunk % 4 == 0
   if (gidx >= total) return;
   const int img = gidx / cx.nchunk, c = gidx - img * cx.nchunk;
   const float* xb = x + (long long)(blockIdx.x + (long long)img * gridDim.x) * xbs;
@@ -169,6 +154,7 @@ __device__ __forceinline__ void front_stage(int gidx, const Ctx& cx, const Front
   if (gidx >= 2) mbar_wait_warp(&cx.bars[s], (uint32_t)(((gidx >> 1) - 1) & 1));       // the MMAs that read this stage are done
 #ifdef TOKRED_STAMPS
   const long long c1 = clock64();
+  TOKRED_STAMP(tid == 0 && img_of == 0 && c_of < 32, 4, c_of);
   {   // first touch of the prefetched registers: time until the chunk's loads have landed
     float probe = r.v[0][0].x + r.v[1][1].w + r.v[1][0].y + r.v[0][1].z;
     asm volatile("" ::"f"(probe));
@@ -214,6 +200,7 @@ __device__ __forceinline__ void front_stage(int gidx, const Ctx& cx, const Front
   mbar_arrive(&cx.bars[5 + s]);                               // stage_full: this thread's part of chunk gidx is in place
 #ifdef TOKRED_STAMPS
   const long long c3 = clock64();
+  TOKRED_STAMP(tid == 0 && img_of == 0 && c_of < 32, 5, c_of);
   nm.t_free += c1 - c0; nm.t_data += c2 - c1; nm.t_conv += c3 - c2;
   if (tid == 0 && g_tokred_stamps && gidx == cx.n_img * cx.nchunk - 1) {
     unsigned long long* o = g_tokred_stamps + ((size_t)blockIdx.x * 8 + 7) * 32;
@@ -232,6 +219,7 @@ __device__ __forceinline__ void mma_run(const Ctx& cx) {
     mbar_wait_warp(&cx.bars[5 + s], (uint32_t)((g >> 1) & 1));
     if (c == 0 && img > 0) mbar_wait_warp(&cx.bars[3], (uint32_t)((img - 1) & 1));     // accumulator drained by the BACK group
     umma::tc_fence_after_sync();
+    TOKRED_STAMP(lane == 0 && img == 0 && c < 32, 2, c);
     if (lane == 0) {
       const unsigned char* hi = cx.stages + (size_t)s * stage_bytes(cx.P);
       const uint32_t h0 = umma::smem_u32(hi), l0 = h0 + (uint32_t)(stage_bytes(cx.P) / 2);
@@ -241,24 +229,21 @@ __device__ __forceinline__ void mma_run(const Ctx& cx) {
         const uint32_t acc = (c > 0 || ks > 0) ? 1u : 0u;
         const uint64_t ah = umma::smem_desc_kmajor(h0 + o, 128, kSBO), al = umma::smem_desc_kmajor(l0 + o, 128, kSBO);
         umma::mma_bf16(cx.tmem_base, ah, ah, idesc1, acc);       // kind::f16 with fp16 operands (format in idesc)
-#if !defined(TOKRED_EXP) || TOKRED_EXP != 1
         umma::mma_bf16(cx.tmem_base, ah, al, idesc1, 1u);
         umma::mma_bf16(cx.tmem_base, al, ah, idesc1, 1u);
-#endif
         if (cx.N2 > 0) {      // rows 128.. x columns 128.. (upper triangle of the second M tile)
           const uint32_t o2 = o + 16u * kSBO;
           const uint64_t bh = umma::smem_desc_kmajor(h0 + o2, 128, kSBO), bl = umma::smem_desc_kmajor(l0 + o2, 128, kSBO);
           umma::mma_bf16(cx.tmem_base + (uint32_t)cx.Np, bh, bh, idesc2, acc);
-#if !defined(TOKRED_EXP) || TOKRED_EXP != 1
           umma::mma_bf16(cx.tmem_base + (uint32_t)cx.Np, bh, bl, idesc2, 1u);
           umma::mma_bf16(cx.tmem_base + (uint32_t)cx.Np, bl, bh, idesc2, 1u);
-#endif
         }
       }
       umma::mma_commit(&cx.bars[s]);
       if (c == cx.nchunk - 1) umma::mma_commit(&cx.bars[2]);
       TOKRED_STAMP(c == 0, img, 1);
       TOKRED_STAMP(c == cx.nchunk - 1, img, 2);
+      TOKRED_STAMP(img == 0 && c < 32, 3, c);
     }
     __syncwarp();
   }
@@ -269,7 +254,6 @@ __device__ __forceinline__ void loader_run(const float* __restrict__ x, long lon
   const int total = cx.n_img * cx.nchunk;
   FrontRegs ra, rb;
   FrontNorms nm;
-  front_prefetch(x, xbs, 0, cx);          // columns 0..127 of every row; later groups are requested from front_load
   front_load(x, xbs, 0, cx, vec, ra);
   front_load(x, xbs, 1, cx, vec, rb);
   for (int g = 0; g < total; g += 2) {
@@ -318,8 +302,10 @@ __device__ __forceinline__ void drain16(float* D, int DS, int P, int i, int j0, 
 
 // bt = thread index inside the BACK group (0..255).  Fills cx.D for the image whose accumulator is complete.
 __device__ __forceinline__ void back_drain(const Ctx& cx, int it, float post_scale) {
-  // a warp may only touch the TMEM lane quarter (warp index in the CTA) % 4; the two warps of a quarter split the columns
+  // a warp may only touch the TMEM lane quarter (warp index in the CTA) % 4; the BACK warps of a quarter take turns
+  // on PAIRS of 16-column chunks: `half` = this warp's turn, `nq` = warps in its quarter
   const int bt = threadIdx.x - kFront, bw = bt >> 5, lane = bt & 31, q = (threadIdx.x >> 5) & 3, half = bw >> 2;
+  const int nq = (kBackWarps - (bw & 3) + 3) >> 2;
   const int P = cx.P, Np = cx.Np, N2 = cx.N2, DS = cx.DS;
   float* D = cx.D;
   TOKRED_STAMP(bt == 0, it, 8);
@@ -335,7 +321,7 @@ __device__ __forceinline__ void back_drain(const Ctx& cx, int it, float post_sca
     const int i = q * 32 + lane;
     const float gi = i < P ? gd[i] : 0.f;
     const int nch = Np / 16, first = (q * 32) / 16;           // chunks below `first` hold only j <= i for every lane
-    for (int ch = first + 2 * half; ch < nch; ch += 4) {
+    for (int ch = first + 2 * half; ch < nch; ch += 2 * nq) {
       const bool two = ch + 1 < nch;
       uint32_t va[16], vb[16];
       umma::tmem_ld16(umma::tmem_addr(cx.tmem_base, (uint32_t)(q * 32), (uint32_t)(ch * 16)), va);
@@ -349,7 +335,7 @@ __device__ __forceinline__ void back_drain(const Ctx& cx, int it, float post_sca
     const int i = 128 + q * 32 + lane;
     const float gi = i < P ? gd[i] : 0.f;
     const int nch = N2 / 16, first = (q * 32) / 16;
-    for (int ch = first + 2 * half; ch < nch; ch += 4) {
+    for (int ch = first + 2 * half; ch < nch; ch += 2 * nq) {
       const bool two = ch + 1 < nch;
       uint32_t va[16], vb[16];
       umma::tmem_ld16(umma::tmem_addr(cx.tmem_base, (uint32_t)(q * 32), (uint32_t)(Np + ch * 16)), va);

@@ -28,3 +28,7 @@ for cta in (0, 1, 120, 147):
         if int(s[cta, img, 0]) == 0: continue
         print("  image", img, " | ".join(f"{names[i]} {(int(s[cta, img, i]) - t0) / 1.9e3:7.2f}us" for i in sorted(names) if int(s[cta, img, i])))
     print("  loader thread 0 totals over all chunks: wait stage_free %.2fus, wait loads %.2fus, norms+convert+STS+arrive %.2fus" % tuple(int(s[cta, 7, i]) / 1.9e3 for i in range(3)))
+    if cta == 120:
+        for c in range(12):
+            print("   chunk %2d: loader0 stage_free seen %6.2f  loader0 staged+arrived %6.2f | MMA warp stage_full seen %6.2f  MMAs issued+committed %6.2f" % (
+                c, *[(int(s[cta, k, c]) - t0) / 1.9e3 for k in (4, 5, 2, 3)]))
