@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TOKRED_ABI_VERSION 2   /* 2: x_batch_stride on a6-a9, a12, a13 */
+#define TOKRED_ABI_VERSION 3   /* 2: x_batch_stride on a6-a9, a12, a13; 3: tokred_attention (f1) */
 #define TOKRED_API __attribute__((visibility("default")))
 
 enum { TOKRED_F32 = 0, TOKRED_BF16 = 1 };
@@ -179,6 +179,20 @@ TOKRED_API int tokred_gather_rows(const void* src, int dtype, const int64_t* ids
  *   the reference's cat promotes)                                                                       */
 TOKRED_API int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float* policy, int B, int P, int C, float eps,
                              void* out, int out_dtype, void* stream);
+
+/* ---- f1 / f2: attention that emits only what the reduction operators read ---------------------------
+ * models/topk.py:44-52,59-61; evit.py:66-87; tome.py:44-58 (proportional attention :48-49); kmedoids.py:105-112;
+ * ats.py:115-127; dyvit.py:53-69 (eval branch); the stock timm block.  bf16-autocast semantics: S = q k^T rounded to
+ * bf16, * scale rounded to bf16, (+ key_bias in fp32), softmax in fp32, probabilities rounded to bf16, out = P v
+ * rounded to bf16.  The [B,H,N,N] probabilities are never written.
+ *   qkv      [B,N,3,H,head_dim] bf16 -- the qkv Linear's output, consumed in place (topk.py:45)
+ *   key_bias [B,N] fp32 or NULL: added to every row of the scaled logits (ToMe: log(size), tome.py:48-49)
+ *   out      [B,N,H*head_dim] bf16 = (attn @ v).transpose(1,2).reshape(B,N,C)   (topk.py:51)
+ *   cls_row  [B,H,N] fp32 or NULL: attn[b,h,0,:] (fp32 probabilities before the bf16 rounding; topk.py:60,
+ *            ats.py:57)
+ * head_dim must be 64 and N <= 256 (TOKRED_ERR_UNSUPPORTED otherwise: the caller keeps its ATen sequence).  */
+TOKRED_API int tokred_attention(const void* qkv, int B, int N, int H, int head_dim, float scale, const float* key_bias,
+                     void* out, float* cls_row, void* stream);
 
 #ifdef __cplusplus
 }

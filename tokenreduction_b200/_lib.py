@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libtokred_sm100a.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 F32, BF16 = 0, 1
 
@@ -35,6 +35,7 @@ SIGNATURES = {
     "tokred_ats_sample": [_P, c_int, c_int64, c_int64, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P],
     "tokred_gather_rows": [_P, c_int, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "tokred_dyvit_pool_concat": [_P, c_int, _P, c_int, c_int, c_int, c_float, _P, c_int, _P],
+    "tokred_attention": [_P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P],
 }
 EXPORTS = ["tokred_abi_version", "tokred_last_error", "tokred_launch_count", *SIGNATURES]
 

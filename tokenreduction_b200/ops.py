@@ -19,7 +19,7 @@ from ._lib import BF16, F32, TokredError
 __all__ = [
     "topk_gather", "topk_gather_attn", "evit_select_fuse", "evit_select_fuse_attn", "tome_effective_r", "tome_match",
     "tome_merge", "pairwise_dist", "dpcknn_cluster", "dpcknn_merge", "attn_colsum", "kmedoids_fit", "sinkhorn_merge", "patchmerger",
-    "sit_merge", "ats_sample", "gather_rows", "dyvit_pool_concat",
+    "sit_merge", "ats_sample", "gather_rows", "dyvit_pool_concat", "attention", "attention_supported",
 ]
 
 
@@ -642,3 +642,44 @@ def dyvit_pool_concat(h: Tensor, policy: Tensor, eps: float = 1e-6) -> Tensor:
     hf, pf = _up(h, policy)
     out = torch.ops.tokred.dyvit_pool_concat(hf, pf, eps)
     return out.to(torch.promote_types(h.dtype, policy.dtype))      # torch.cat's promotion (models/dyvit.py:118)
+
+
+# ----------------------------------------------------------------------------------------------- f1: attention producer
+def attention_supported(qkv: Tensor, num_heads: int) -> bool:
+    """shapes the fused attention kernel covers: bf16 qkv [B,N,3C] on CUDA, head dim 64, N <= 256."""
+    return (qkv.is_cuda and qkv.dtype == torch.bfloat16 and qkv.dim() == 3 and qkv.shape[1] <= 256
+            and qkv.shape[2] == 3 * 64 * num_heads)
+
+
+@torch.library.custom_op("tokred::attention", mutates_args=(), device_types="cuda")
+def _attention(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Tensor], want_cls: bool) -> Tuple[Tensor, Tensor]:
+    _need_cuda("attention", qkv, key_bias)
+    if qkv.dim() != 3 or qkv.dtype != torch.bfloat16 or qkv.shape[2] % (3 * num_heads) != 0:
+        raise TokredError(f"attention: qkv {tuple(qkv.shape)} {qkv.dtype}; expected bf16 [B,N,3*H*Dh]")
+    b, n, c3 = qkv.shape
+    c = c3 // 3
+    qkv = _c(qkv)
+    if key_bias is not None:
+        if key_bias.numel() != b * n:
+            raise TokredError(f"attention: key_bias {tuple(key_bias.shape)} does not match qkv {tuple(qkv.shape)}")
+        key_bias = _c(key_bias.to(torch.float32))
+    out = torch.empty((b, n, c), dtype=torch.bfloat16, device=qkv.device)
+    cls = torch.empty((b, num_heads, n) if want_cls else (0,), dtype=torch.float32, device=qkv.device)
+    _lib.call("tokred_attention", _ptr(qkv), b, n, num_heads, c // num_heads, float(scale), _ptr(key_bias), _ptr(out),
+              _ptr(cls) if want_cls else None, _stream())
+    return out, cls
+
+
+@_attention.register_fake
+def _(qkv, num_heads, scale, key_bias, want_cls):
+    b, n, c3 = qkv.shape
+    return (qkv.new_empty((b, n, c3 // 3)),
+            qkv.new_empty((b, num_heads, n) if want_cls else (0,), dtype=torch.float32))
+
+
+def attention(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Tensor] = None, want_cls: bool = False):
+    """softmax(q k^T * scale [+ key_bias]) v with bf16-autocast roundings (models/topk.py:44-52; tome.py:44-58) from the
+    qkv Linear's output [B,N,3C] -> (x [B,N,C] bf16 ready for proj, cls_row [B,H,N] fp32 | None).  The [B,H,N,N]
+    probabilities are never materialised; cls_row is attn[:, :, 0, :] (models/topk.py:60)."""
+    out, cls = torch.ops.tokred.attention(qkv, num_heads, scale, key_bias, want_cls)
+    return out, (cls if want_cls else None)
