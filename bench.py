@@ -206,6 +206,15 @@ def algorithmic_bytes(name: str, a: tuple) -> float:
     if name == "tokred_gather_rows":
         m = g["M"]
         return g["B"] * (2 * g["G"] * m * g["W"] * esz(g["dtype"]) + 8 * m)
+    if name == "tokred_attention":
+        n, hh, m = g["N"], g["H"], (g["M"] if g["q_ids"] else g["N"])
+        c = hh * g["head_dim"]
+        per = m * c * 2 + n * c * 2                      # q rows, k
+        if g["out"]:
+            per += n * c * 2 + m * c * 2                 # v, out
+        per += (4 * n if g["key_bias"] else 0) + (n if g["mask"] else 0) + (8 * m if g["q_ids"] else 0)
+        per += (4 * hh * n if g["cls_row"] else 0) + (4 * hh * n if g["colsum"] else 0)
+        return g["B"] * per
     if name == "tokred_dyvit_pool_concat":
         p, c = g["P"], g["C"]
         return g["B"] * (p * c * esz(g["h_dtype"]) + p * 4 + p * c * esz(g["out_dtype"]))

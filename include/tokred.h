@@ -160,13 +160,16 @@ TOKRED_API int tokred_sit_merge(const void* x, int x_dtype, int64_t x_batch_stri
 /* ---- a10 ATS -----------------------------------------------------------------------------------------
  * models/ats.py:52-82: significance score, inverse-CDF sampling, per-image sorted unique ids.
  *   v [B,H,N,Dh] v_dtype with element strides (v_stride_b, v_stride_h, v_stride_n, 1) — the qkv view of
- *   :112-113 is consumed in place; attn [B,H,N,N] fp32, mask [B,N] uint8, steps [n_steps] fp32 (= sample_steps, :48)
+ *   :112-113 is consumed in place; attn fp32: only the CLS rows attn[b,h,0,:] are read, at b*H*attn_head_stride +
+ *   h*attn_head_stride (N*N, or 0, for a [B,H,N,N] tensor; N for the [B,H,N] cls_row output of tokred_attention);
+ *   mask [B,N] uint8, steps [n_steps] fp32 (= sample_steps, :48)
  *   ids_out  [B,n_steps+1] int64: 0, sorted unique sampled tokens, 0-padding
  *   mask_out [B,n_steps+1] uint8: 1, ids != 0
  *   max_count [1] int32: max_b #unique (caller zeroes it before the call; device atomicMax)             */
 TOKRED_API int tokred_ats_sample(const void* v, int v_dtype, int64_t v_stride_b, int64_t v_stride_h, int64_t v_stride_n,
-                      const float* attn, const uint8_t* mask, const float* steps, int B, int H, int N, int Dh,
-                      int n_steps, float eps, int64_t* ids_out, uint8_t* mask_out, int32_t* max_count, void* stream);
+                      const float* attn, int64_t attn_head_stride, const uint8_t* mask, const float* steps, int B, int H,
+                      int N, int Dh, int n_steps, float eps, int64_t* ids_out, uint8_t* mask_out, int32_t* max_count,
+                      void* stream);
 
 /* models/ats.py:27-41,84-87 (attention rows) and :156-157 (residual tokens): out[b,g,m,:] = src[b,g,ids[b,m],:]
  *   src [B,G,N,W] dtype, ids [B,ids_stride] int64 (first M used) -> out [B,G,M,W]                         */
@@ -181,18 +184,26 @@ TOKRED_API int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float*
                              void* out, int out_dtype, void* stream);
 
 /* ---- f1 / f2: attention that emits only what the reduction operators read ---------------------------
- * models/topk.py:44-52,59-61; evit.py:66-87; tome.py:44-58 (proportional attention :48-49); kmedoids.py:105-112;
- * ats.py:115-127; dyvit.py:53-69 (eval branch); the stock timm block.  bf16-autocast semantics: S = q k^T rounded to
- * bf16, * scale rounded to bf16, (+ key_bias in fp32), softmax in fp32, probabilities rounded to bf16, out = P v
- * rounded to bf16.  The [B,H,N,N] probabilities are never written.
+ * models/topk.py:44-52,59-61; evit.py:66-87; tome.py:44-58 (proportional attention :48-49); kmedoids.py:105-112,240;
+ * ats.py:115-127,84-87; dyvit.py:53-69 (eval branch); the stock timm block.  bf16-autocast semantics: S = q k^T rounded
+ * to bf16, * scale rounded to bf16, (+ key_bias in fp32), masked_fill, softmax in fp32, probabilities rounded to bf16,
+ * out = P v rounded to bf16.  The [B,H,N,N] probabilities are never written.
  *   qkv      [B,N,3,H,head_dim] bf16 -- the qkv Linear's output, consumed in place (topk.py:45)
  *   key_bias [B,N] fp32 or NULL: added to every row of the scaled logits (ToMe: log(size), tome.py:48-49)
- *   out      [B,N,H*head_dim] bf16 = (attn @ v).transpose(1,2).reshape(B,N,C)   (topk.py:51)
- *   cls_row  [B,H,N] fp32 or NULL: attn[b,h,0,:] (fp32 probabilities before the bf16 rounding; topk.py:60,
- *            ats.py:57)
- * head_dim must be 64 and N <= 256 (TOKRED_ERR_UNSUPPORTED otherwise: the caller keeps its ATen sequence).  */
+ *   mask     [B,N] uint8 or NULL (ATS, ats.py:118-121): logits with mask[i]*mask[j] == 0 are filled with -max
+ *            (a masked query row therefore comes out uniform, as in the reference)
+ *   q_ids    [B,ids_stride] int64 or NULL: query row m of the output is token q_ids[b,m] (first M used) -- the ATS
+ *            row gather attn[:, :, ids, :] (ats.py:84-87) applied to the queries, so only M rows are computed
+ *   out      [B,M,H*head_dim] bf16 = (attn @ v).transpose(1,2).reshape(B,M,C) (topk.py:51), M = N without q_ids;
+ *            NULL = scores only (v is not read, P.v is skipped)
+ *   cls_row  [B,H,N] fp32 or NULL: probabilities of query row 0 -- attn[b,h,0,:] (topk.py:60, ats.py:57), fp32
+ *            values before the bf16 rounding
+ *   colsum   [B,H,N] fp32 or NULL: sum over the query rows of attn[b,h,:,j] (K-Medoids token weights are the sum of
+ *            this over heads, kmedoids.py:240); combined in a fixed order: deterministic
+ * head_dim must be 64 and N, M <= 256 (TOKRED_ERR_UNSUPPORTED otherwise: the caller keeps its ATen sequence).  */
 TOKRED_API int tokred_attention(const void* qkv, int B, int N, int H, int head_dim, float scale, const float* key_bias,
-                     void* out, float* cls_row, void* stream);
+                     const uint8_t* mask, const int64_t* q_ids, int64_t ids_stride, int M, void* out, float* cls_row,
+                     float* colsum, void* stream);
 
 #ifdef __cplusplus
 }

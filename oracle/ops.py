@@ -336,3 +336,30 @@ def dyvit_pool_concat(h: Tensor, policy: Tensor, eps: float = 1e-6) -> Tensor:
 def dyvit_keep(x: Tensor, score: Tensor, k: int) -> Tuple[Tensor, Tensor]:
     """models/dyvit.py:231-236 + :340-356 — same selection/gather as Top-K with predictor scores."""
     return topk_gather(x, score, k)
+
+
+# ----------------------------------------------------------------------------------------------- f1: attention producer
+def attention_autocast(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Tensor] = None,
+                       mask: Optional[Tensor] = None, q_ids: Optional[Tensor] = None):
+    """The reference's attention under CUDA bf16 autocast with every dtype written out, device
+    independent: models/topk.py:44-52 (qkv split, q k^T * scale, softmax, attn @ v, transpose/reshape), tome.py:48-49
+    (+ log size: pass key_bias = size.log()), ats.py:118-121 (masked_fill with -finfo.max), ats.py:84-87 (row gather).
+    autocast runs the two matmuls in bf16 (fp32 accumulation, bf16 result), ``* scale`` on the bf16 tensor, the softmax
+    in fp32, and casts the fp32 probabilities to bf16 for attn @ v.
+    qkv [B,N,3*H*Dh] bf16 -> (out [B,M,H*Dh] bf16, attn [B,H,M,N] fp32 probabilities, attn_full_cls [B,H,N] fp32)."""
+    b, n, c3 = qkv.shape
+    c = c3 // 3
+    qkv = qkv.to(torch.bfloat16)
+    q, k, v = qkv.reshape(b, n, 3, num_heads, c // num_heads).permute(2, 0, 3, 1, 4)
+    dots = (q @ k.transpose(-2, -1)) * scale                            # bf16 matmul, bf16 * python float -> bf16
+    if key_bias is not None:
+        dots = dots + key_bias.float()[:, None, None, :]                # bf16 + fp32 -> fp32 (tome.py:49)
+    if mask is not None:
+        m2 = mask.unsqueeze(1).unsqueeze(3) * mask.unsqueeze(1).unsqueeze(2)
+        dots = dots.masked_fill(~m2, -torch.finfo(dots.dtype).max)     # ats.py:118-121
+    attn = dots.float().softmax(dim=-1)                                 # autocast: softmax in fp32
+    cls = attn[:, :, 0, :].clone()
+    if q_ids is not None:                                               # ats.py:84-87
+        attn = torch.gather(attn, 2, q_ids[:, None, :, None].expand(b, num_heads, q_ids.shape[1], n))
+    out = (attn.to(torch.bfloat16) @ v).transpose(1, 2).reshape(b, attn.shape[2], c)
+    return out, attn, cls

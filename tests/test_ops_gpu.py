@@ -1011,3 +1011,131 @@ def test_ats_more_steps_than_tokens(T):
     assert abs(m2 + 1 - ids2_ref.shape[1]) <= 2
     assert bool((ids2[:, m2 + 1:] == 0).all()) and not bool(mo2[:, m2 + 1:].any())
     assert int(ids2.max()) < n2 and bool(mo2[:, :m2 + 1].all())
+
+
+# ================================================================================================ f1: attention producer
+def _attn_inputs(b, n, h, seed, spread=1.5):
+    return (torch.randn(b, n, 3 * h * 64, generator=g(seed)) * spread).bfloat16()
+
+
+def _attn_inputs_exact(b, n, h, seed):
+    """margin-controlled inputs: q, k entries in {-1, -.5, 0, .5, 1} make every dot product a multiple of
+    1/4 of magnitude <= 64 -- exactly representable in bf16 -- so S = q k^T is free of rounding in ANY implementation and
+    no accumulation-order difference can flip a bf16 rounding of the logits.  v is ordinary."""
+    x = torch.randn(b, n, 3, h, 64, generator=g(seed))
+    x[:, :, :2] = torch.randint(-2, 3, (b, n, 2, h, 64), generator=g(seed + 1)).float() * 0.5
+    return x.reshape(b, n, 3 * h * 64).bfloat16()
+
+
+def _check_attention(T, qkv, h, scale, bias=None, mask=None, ids=None, check_sets_k=None, exact=True):
+    """fused attention vs the written-out autocast sequence (oracle, CPU).
+    out: <= 1e-2 of the output scale (the bf16 bar) and overwhelmingly bit-identical.
+    CLS rows / column sums are fp32 quantities recomputed with another evaluation order (ex2.approx, column-split
+    sums): 1e-5 of the largest entry on margin-controlled inputs.  On random inputs the fp32 accumulation order of the
+    64-term dot products differs between the CPU GEMM and the tensor core, which flips the bf16 rounding of a logit
+    about once per 2^16 elements (a 0.8 % change of that row's probabilities): there the fp32 side outputs must meet
+    1e-5 on >= 99.5 % of their entries and stay within one flipped logit everywhere."""
+    dev = lambda t: None if t is None else t.to(DEV)
+    out, cls, cs = T.attention(dev(qkv), h, scale, dev(bias), dev(mask), dev(ids), True, True, True)
+    out_r, attn_r, cls_r = O.attention_autocast(qkv, h, scale, bias, mask, ids)
+    out, cls, cs = out.cpu().float(), cls.cpu(), cs.cpu()
+    out_r = out_r.float()
+    assert out.shape == out_r.shape and torch.isfinite(out).all()
+    err = (out - out_r).abs().max() / out_r.abs().max()
+    assert float(err) <= RTOL16, f"attention out: {float(err):.2e} of the output scale"
+    same = float((out == out_r).float().mean())
+    assert same > 0.97, f"attention out: only {same:.3f} of the bf16 outputs are bit-identical"
+    cs_r = attn_r.sum(2)
+    for what, got, want in (("cls_row", cls, cls_r), ("colsum", cs, cs_r)):
+        e = (got - want).abs() / want.abs().max()
+        if exact:
+            assert float(e.max()) <= RTOL32, f"{what}: {float(e.max()):.2e}"
+        else:
+            assert float((e <= RTOL32).float().mean()) >= 0.995 and float(e.max()) <= 5e-2, \
+                f"{what}: {float((e <= RTOL32).float().mean()):.4f} of entries within 1e-5, worst {float(e.max()):.2e}"
+    # scores-only mode (v never read) must give the same CLS rows
+    _, cls2, _ = T.attention(dev(qkv), h, scale, dev(bias), dev(mask), None, False, True, False)
+    assert torch.equal(cls2.cpu(), cls)
+    if check_sets_k:
+        # Top-K / EViT consumer (models/topk.py:60-62): the kept SET from the fused scores equals the reference's on
+        # every image whose k / k+1 boundary is wider than the score tolerance (set-wise criterion, SURVEY §8c.1)
+        s, s_r = cls[:, :, 1:].mean(1), cls_r[:, :, 1:].mean(1)
+        dec = MG.topk_set_margin(s_r, check_sets_k, 4 * RTOL32)
+        kept = torch.zeros_like(s, dtype=torch.bool).scatter_(1, s.topk(check_sets_k, dim=1).indices, True)
+        kept_r = torch.zeros_like(s, dtype=torch.bool).scatter_(1, s_r.topk(check_sets_k, dim=1).indices, True)
+        eq = (kept == kept_r).all(dim=1)
+        assert bool(eq[dec].all()), "kept set differs on an image with a decidable boundary"
+        assert float(dec.float().mean()) > 0.6, "margin check would be vacuous"
+    return same
+
+
+@pytest.mark.parametrize("b,n,h", [(3, 197, 6), (2, 138, 6), (2, 97, 12), (2, 68, 6), (2, 198, 3), (1, 256, 2), (2, 129, 2),
+                                   (2, 128, 2), (2, 50, 6), (3, 26, 12), (2, 13, 6), (2, 16, 1), (2, 2, 1), (1, 1, 2)])
+def test_attention_plain(T, b, n, h):
+    k = max(1, int(0.7 * (n - 1))) if n > 20 else None
+    _check_attention(T, _attn_inputs_exact(b, n, h, 900 + n), h, 0.125, check_sets_k=k)
+    _check_attention(T, _attn_inputs(b, n, h, 900 + n), h, 0.125, exact=False)
+
+
+def test_attention_non_power_of_two_scale_and_peaked_logits(T):
+    """scale not a power of two: the scaled logits round to bf16 a second time (ROUND2 path; 0.1 * multiples of 1/4 is
+    not margin-controlled any more: random-input criterion); large logits: the max-subtraction must keep the
+    exponentials finite."""
+    _check_attention(T, _attn_inputs(2, 197, 6, 950), 6, 0.1, exact=False)
+    _check_attention(T, _attn_inputs(2, 138, 6, 951, spread=6.0), 6, 0.125, exact=False)
+    _check_attention(T, _attn_inputs_exact(2, 138, 6, 952) * 4, 6, 0.125)        # logits up to +-32, still exact
+
+
+@pytest.mark.parametrize("n,h", [(197, 6), (138, 6), (97, 12), (68, 3)])
+def test_attention_tome_proportional_bias(T, n, h):
+    """models/tome.py:48-49: + log(size), sizes 1..8 as after three merge stages."""
+    size = torch.randint(1, 9, (3, n), generator=g(961 + n)).float()
+    _check_attention(T, _attn_inputs_exact(3, n, h, 960 + n), h, 0.125, bias=size.log())
+    _check_attention(T, _attn_inputs(3, n, h, 960 + n), h, 0.125, bias=size.log(), exact=False)
+
+
+def test_attention_ats_mask_and_row_gather(T):
+    """models/ats.py:118-121 (pairwise mask, masked rows come out uniform) and :84-87 (row gather = query gather),
+    ids sorted unique with 0-padding as ats_sample emits them."""
+    b, n, h, m = 4, 177, 12, 143
+    mask = torch.rand(b, n, generator=g(971)) > 0.25
+    mask[:, 0] = True
+    mask[1] = True                                   # one image without masked tokens
+    ids = torch.zeros(b, m, dtype=torch.int64)
+    for i in range(b):
+        u = torch.randperm(n - 1, generator=g(972 + i))[: m - 1 - 7 * i].add(1).sort().values
+        ids[i, 1:1 + u.numel()] = u
+    for qkv, exact in ((_attn_inputs_exact(b, n, h, 970), True), (_attn_inputs(b, n, h, 970), False)):
+        _check_attention(T, qkv, h, 0.125, mask=mask, exact=exact)
+        _check_attention(T, qkv, h, 0.125, mask=mask, ids=ids, exact=exact)
+        _check_attention(T, qkv, h, 0.125, ids=ids[:, :97], exact=exact)
+
+
+def test_attention_at_bench_batch(T):
+    """the grid bench.py launches (B=256 DeiT-S: 1536 CTAs, > 5 waves of two resident CTAs per SM), per-image check:
+    an inter-CTA hazard (TMEM reuse, barrier phase) would show up as a few wrong images."""
+    b, n, h = 256, 197, 6
+    qkv = _attn_inputs_exact(b, n, h, 980)
+    out, cls, cs = T.attention(qkv.to(DEV), h, 0.125, None, None, None, True, True, True)
+    out_r, attn_r, cls_r = O.attention_autocast(qkv, h, 0.125)
+    out, out_r = out.cpu().float(), out_r.float()
+    per_img = (out - out_r).abs().flatten(1).max(dim=1).values / out_r.abs().flatten(1).max(dim=1).values
+    assert float(per_img.max()) <= RTOL16, f"worst image {int(per_img.argmax())}: {float(per_img.max()):.2e}"
+    assert float((out == out_r).float().mean()) > 0.97
+    assert float((cls.cpu() - cls_r).abs().max() / cls_r.abs().max()) <= RTOL32
+    assert float((cs.cpu() - attn_r.sum(2)).abs().max() / attn_r.sum(2).abs().max()) <= RTOL32
+    # deterministic: the column sums are combined in a fixed order
+    out2, cls2, cs2 = T.attention(qkv.to(DEV), h, 0.125, None, None, None, True, True, True)
+    assert torch.equal(out2.cpu().float(), out) and torch.equal(cls2, cls) and torch.equal(cs2, cs)
+
+
+def test_attention_rejects_what_it_does_not_cover(T):
+    from tokenreduction_b200._lib import TokredError
+    with pytest.raises(TokredError):
+        T.attention(torch.zeros(1, 300, 3 * 64, dtype=torch.bfloat16, device=DEV), 1, 0.125)     # N > 256
+    with pytest.raises(TokredError):
+        T.attention(torch.zeros(1, 8, 3 * 32, dtype=torch.bfloat16, device=DEV), 1, 0.125)       # head dim 32
+    with pytest.raises(TokredError):
+        T.attention(torch.zeros(1, 8, 3 * 64, dtype=torch.float32, device=DEV), 1, 0.125)        # not bf16
+    with pytest.raises((TokredError, NotImplementedError)):
+        T.attention(torch.zeros(1, 8, 3 * 64, dtype=torch.bfloat16), 1, 0.125)                   # CPU tensor: no fallback

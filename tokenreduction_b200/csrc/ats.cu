@@ -20,8 +20,8 @@ constexpr int kWarps = kThreads / 32;
 template <typename TV>
 __global__ void __launch_bounds__(kThreads)
 ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long long vs_n,
-                  const float* __restrict__ attn, const uint8_t* __restrict__ mask, const float* __restrict__ steps,
-                  int H, int N, int Dh, int n_steps, float eps, int use_mm, int64_t* __restrict__ ids_out,
+                  const float* __restrict__ attn, long long ahs, const uint8_t* __restrict__ mask,
+                  const float* __restrict__ steps, int H, int N, int Dh, int n_steps, float eps, int use_mm, int64_t* __restrict__ ids_out,
                   uint8_t* __restrict__ mask_out, int32_t* __restrict__ max_count) {
   extern __shared__ float smem[];
   const int P = N - 1, b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -34,7 +34,7 @@ ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long
   // significance per (head, patch): one THREAD per pair — the 64-element value row is one or two 128-byte lines,
   // read with 16-byte loads that are all independent (the first version used a warp per pair with a shuffle
   // reduction: 294 dependent global-latency round trips per warp, 370 us at B=128)
-  const float* ab = attn + (long long)b * H * N * N;
+  const float* ab = attn + (long long)b * H * ahs;    // ahs: element stride between the heads' CLS rows
   {
     constexpr int VE = 16 / sizeof(TV);
     const bool vec = (Dh % VE == 0) && (vs_n % VE == 0) && (vs_h % VE == 0) && (vs_b % VE == 0) &&
@@ -57,7 +57,7 @@ ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long
 #pragma unroll
             for (int w = 0; w < 8; ++w)
               if (w < nv) r[u][w] = *reinterpret_cast<const int4*>(row + w * VE);
-            a[u] = ab[((long long)h * N) * N + 1 + p];
+            a[u] = ab[(long long)h * ahs + 1 + p];
           }
         }
 #pragma unroll
@@ -97,7 +97,7 @@ ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long
       } else {
         for (int d = 0; d < Dh; ++d) { const float x = to_f32(row[d]); s = fmaf(x, x, s); }
       }
-      hp[e] = ab[((long long)h * N) * N + 1 + p] * sqrtf(s);
+      hp[e] = ab[(long long)h * ahs + 1 + p] * sqrtf(s);
     }
   }
   for (int t = tid; t < N; t += kThreads) hit[t] = 0;
@@ -186,7 +186,8 @@ ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long
 using namespace tokred;
 
 extern "C" int tokred_ats_sample(const void* v, int v_dtype, int64_t v_stride_b, int64_t v_stride_h,
-                                 int64_t v_stride_n, const float* attn, const uint8_t* mask, const float* steps, int B,
+                                 int64_t v_stride_n, const float* attn, int64_t attn_head_stride, const uint8_t* mask,
+                                 const float* steps, int B,
                                  int H, int N, int Dh, int n_steps, float eps, int64_t* ids_out, uint8_t* mask_out,
                                  int32_t* max_count, void* stream) {
   const char* what = "tokred_ats_sample";
@@ -199,19 +200,21 @@ extern "C" int tokred_ats_sample(const void* v, int v_dtype, int64_t v_stride_b,
   // and the id / mask rows are n_steps + 1 wide, so nothing in the kernel needs an upper bound.
   TOKRED_REQUIRE(n_steps >= 1 && n_steps <= 65535, "%s: n_steps=%d outside [1, 65535]", what, n_steps);
   if (B == 0) return TOKRED_OK;
+  const long long ahs = attn_head_stride > 0 ? attn_head_stride : (long long)N * N;
+  TOKRED_REQUIRE(ahs >= N, "%s: attn_head_stride %lld < N", what, ahs);
   const int P = N - 1;
   const size_t smem = ((size_t)H * P + P + kWarps + N + 1) * 4;
   const int use_mm = (n_steps > 25 || P > 25) ? 1 : 0;     // ATen: matmul expansion when either side has > 25 points
   cudaStream_t st = (cudaStream_t)stream;
   if (v_dtype == TOKRED_F32) {
     if (int e = allow_smem(ats_sample_kernel<float>, smem, what)) return e;
-    ats_sample_kernel<float><<<B, kThreads, smem, st>>>((const float*)v, v_stride_b, v_stride_h, v_stride_n, attn, mask,
+    ats_sample_kernel<float><<<B, kThreads, smem, st>>>((const float*)v, v_stride_b, v_stride_h, v_stride_n, attn, ahs, mask,
                                                         steps, H, N, Dh, n_steps, eps, use_mm, ids_out, mask_out,
                                                         max_count);
   } else {
     if (int e = allow_smem(ats_sample_kernel<__nv_bfloat16>, smem, what)) return e;
     ats_sample_kernel<__nv_bfloat16><<<B, kThreads, smem, st>>>((const __nv_bfloat16*)v, v_stride_b, v_stride_h,
-                                                                v_stride_n, attn, mask, steps, H, N, Dh, n_steps, eps,
+                                                                v_stride_n, attn, ahs, mask, steps, H, N, Dh, n_steps, eps,
                                                                 use_mm, ids_out, mask_out, max_count);
   }
   return finish_launch(what);

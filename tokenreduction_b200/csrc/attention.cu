@@ -5,22 +5,26 @@
 // kmedoids.py:105-112, ats.py:115-127, dyvit.py:53-69 eval branch and the stock timm block):
 //     attn = (q @ k^T) * scale            bf16 matmul, bf16 result, bf16 product
 //     attn = attn + log(size)             (ToMe proportional attention, tome.py:48-49; fp32 from here on)
+//     attn = masked_fill(~(m_i m_j))      (ATS, ats.py:118-121)
 //     attn = attn.softmax(-1)             fp32 (autocast runs softmax in fp32)
+//     attn = attn[:, :, ids, :]           (ATS row gather, ats.py:84-87 -- here the QUERY rows are gathered instead)
 //     x    = (attn @ v)                   probabilities rounded to bf16, bf16 matmul
-// and emits, on request, the only parts of `attn` the reduction operators read: the CLS row of every head
-// (Top-K / EViT / ATS scores) -- the [B,H,N,N] tensor is never written.
+// and emits, on request, the only parts of `attn` the reduction operators read: the CLS row of every head (Top-K /
+// EViT / ATS scores) and the per-head column sums (K-Medoids token weights) -- the [B,H,N,N] tensor is never written.
 //
-// One CTA per (image, head), 128 threads, two CTAs per SM (<= 79 KB shared memory, <= 256 TMEM columns each), so one
+// One CTA per (image, head), 256 threads, two CTAs per SM (<= 81 KB shared memory, <= 256 TMEM columns each), so one
 // CTA's loads overlap the other's softmax without any explicit pipeline:
 //   load   q, k, v head slices (128-byte rows, row stride 3C) -> shared memory with 16-byte cp.async straight into the
 //          canonical no-swizzle UMMA core-matrix layout (8 consecutive lanes = 8 consecutive rows = one contiguous 128-byte
 //          core matrix: conflict-free); pad rows are zero-filled by the copy itself (src-size 0)
 //   S      = Q_tile K^T      tcgen05.mma kind::f16 (bf16), M = 128, N = ceil16(N), K = 64, accumulator in TMEM cols [0, Np)
-//   softmax thread = accumulator row (tcgen05.ld 32x32b): pass A max, pass B exp2 + sum (e written back IN PLACE as
-//          fp32), pass C normalise -> bf16 pairs written back IN PLACE to TMEM cols [0, Np/2) (writes trail the reads)
+//   softmax thread = accumulator row (tcgen05.ld 32x32b); the two warps that share a TMEM lane quarter split the columns
+//          for pass A (max) and pass B (exp2 + sum, e written back IN PLACE as fp32) and exchange the partials through
+//          shared memory; pass C (normalise -> bf16 pairs written back IN PLACE to TMEM cols [0, Np/2), writes trailing
+//          the reads) belongs to one warp of the pair, which therefore takes the smaller share of the columns
 //   O      = P V             tcgen05.mma with the A operand read FROM TMEM (P never touches shared memory), B = the v tile
 //          used MN-major (no transpose), accumulator in TMEM cols [o_col, o_col + 64) (dead part of the S region)
-//   store  thread = output row: 64 fp32 -> bf16 -> 128 contiguous bytes of out[b, row, h*64 ..]
+//   store  thread = output row: 32 fp32 -> bf16 -> 64 contiguous bytes of out[b, row, h*64 ..]
 // Rounding points are the reference's: S to bf16, (S*scale) to bf16, P to bf16, O to bf16; everything else fp32.
 #include <cmath>
 
@@ -30,15 +34,19 @@
 namespace tokred {
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct AttnParams {
   const __nv_bfloat16* qkv;     // [B, N, 3, H, 64]
   const float* key_bias;        // [B, N] or null
-  __nv_bfloat16* out;           // [B, N, H*64]
-  float* cls_row;               // [B, H, N] or null
-  int B, N, H;
+  const uint8_t* mask;          // [B, N] or null
+  const int64_t* q_ids;         // [B, ids_stride] or null: query row m reads token q_ids[b, m]
+  long long ids_stride;
+  __nv_bfloat16* out;           // [B, M, H*64] or null (scores only)
+  float* cls_row;               // [B, H, N] or null: probabilities of query row 0
+  float* colsum;                // [B, H, N] or null: sum over query rows
+  int B, N, H, M;               // M query rows (= N without q_ids)
   float scale;
 };
 
@@ -55,9 +63,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
+                                         uint32_t r5, uint32_t r6, uint32_t r7) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2),
+               "r"(r3), "r"(r4), "r"(r5), "r"(r6), "r"(r7)
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -81,11 +90,45 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
   return d;
 }
+__device__ __forceinline__ void pair_sync(int quarter) {      // the two warps of one TMEM lane quarter
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
+}
+
+// the TMEM load is asynchronous: tying the destination registers to the wait keeps every use behind it
+__device__ __forceinline__ void ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+// f(r, c) over the 16-column chunks [c0, c1) of one accumulator row, the load of chunk c+1 in flight while chunk c is
+// processed (two register sets, loop unrolled by two so they never move)
+template <typename F>
+__device__ __forceinline__ void for_chunks(uint32_t trow, int c0, int c1, F&& f) {
+  if (c0 >= c1) return;
+  uint32_t ra[16], rb[16];
+  umma::tmem_ld16(trow + c0 * 16, ra);
+  int c = c0;
+  while (true) {
+    ld_wait16(ra);
+    if (c + 1 < c1) umma::tmem_ld16(trow + (c + 1) * 16, rb);
+    f(ra, c);
+    if (++c >= c1) break;
+    ld_wait16(rb);
+    if (c + 1 < c1) umma::tmem_ld16(trow + (c + 1) * 16, ra);
+    f(rb, c);
+    if (++c >= c1) break;
+  }
+}
+__device__ __forceinline__ float bf16r(float v) { return __uint_as_float(pack_bf16x2(v, 0.f) << 16); }
 
 // logits of 16 accumulator columns starting at col0, with the reference's roundings: bf16(acc) * scale (rounded again
-// unless scale is a power of two, where the product is exact), + bias in fp32
-template <bool BIAS, bool ROUND2>
-__device__ __forceinline__ void logits16(const uint32_t (&r)[16], float (&x)[16], float scale, const float* bias, int col0) {
+// unless scale is a power of two, where the product is exact), + bias in fp32 (-inf at masked keys); a masked query
+// row is all-equal in the reference (every entry filled with -max) -> uniform probabilities: logits 0
+template <bool BIAS, bool ROUND2, bool MASK>
+__device__ __forceinline__ void logits16(const uint32_t (&r)[16], float (&x)[16], float scale, const float* bias, int col0,
+                                         bool row_masked) {
 #pragma unroll
   for (int i = 0; i < 16; i += 2) {
     const uint32_t pk = pack_bf16x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
@@ -105,49 +148,128 @@ __device__ __forceinline__ void logits16(const uint32_t (&r)[16], float (&x)[16]
       x[i] += bv.x; x[i + 1] += bv.y; x[i + 2] += bv.z; x[i + 3] += bv.w;
     }
   }
+  if (MASK) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = row_masked ? 0.f : x[i];
+  }
+}
+// exponent arguments (base 2) of 16 columns: without bias and with a power-of-two scale the scaling folds into one FFMA
+template <bool BIAS, bool ROUND2, bool MASK>
+__device__ __forceinline__ void exp_args16(const uint32_t (&r)[16], float (&x)[16], float scale, const float* bias, int col0,
+                                           bool row_masked, float mneg) {
+  if (!BIAS && !ROUND2) {
+    const float sl2 = scale * kLog2e;
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const uint32_t pk = pack_bf16x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+      x[i] = fmaf(__uint_as_float(pk << 16), sl2, mneg);
+      x[i + 1] = fmaf(__uint_as_float(pk & 0xffff0000u), sl2, mneg);
+    }
+  } else {
+    logits16<BIAS, ROUND2, MASK>(r, x, scale, bias, col0, row_masked);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], kLog2e, mneg);
+  }
 }
 
-template <bool BIAS, bool ROUND2>
-__global__ void __launch_bounds__(kThreads) attention_kernel(const AttnParams p) {
+// column sums of a 32 x 16 block held one row per lane: 16 shuffles; lane l ends with the sum of column l >> 1
+__device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
+  float w8[8], w4[4], w2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? v[i] : v[i + 8], keep = b4 ? v[i + 8] : v[i];
+    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? w8[i] : w8[i + 4], keep = b3 ? w8[i + 4] : w8[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? w4[i] : w4[i + 2], keep = b2 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? w2[0] : w2[1], keep = b1 ? w2[1] : w2[0];
+  float s = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  return s;
+}
+
+// one 8-row group of a [rows x 64] bf16 head slice -> canonical K-major core matrices: lane -> row = lane % 8,
+// 16-byte chunks 2*(lane/8) and 2*(lane/8)+1 (8 consecutive lanes fill one contiguous 128-byte core matrix)
+__device__ __forceinline__ void load_group(uint32_t dst_lane, const unsigned char* src_lane, bool ok) {
+  cp_async16(dst_lane, src_lane, ok ? 16u : 0u);
+  cp_async16(dst_lane + 128, src_lane + 16, ok ? 16u : 0u);
+}
+
+template <bool BIAS, bool ROUND2, bool MASK, bool COLSUM>
+__global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = p.N, H = p.H, C = H * 64;
-  const int Np = (N + 15) & ~15;                 // keys: UMMA N of S, UMMA K of P.V
-  const int gq = (N + 7) >> 3, gk = Np >> 3;     // 8-row groups of the Q / K,V tiles
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int q = warp & 3, half = warp >> 2;          // TMEM lane quarter; 0 = "lower" warp of the pair, 1 = "upper"
+  const int N = p.N, H = p.H, C = H * 64, M = p.M;
+  const int Np = (N + 15) & ~15;                     // keys: UMMA N of S, UMMA K of P.V
+  const int gq = (M + 7) >> 3, gk = Np >> 3;         // 8-row groups of the Q / K,V tiles
+  const int ntiles = (M + 127) >> 7;
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const bool want_out = p.out != nullptr;
 
   unsigned char* Qs = smem;
   unsigned char* Ks = Qs + (size_t)gq * 1024;
   unsigned char* Vs = Ks + (size_t)gk * 1024;
   // the S MMA always reads 128 A rows: the operand area spans at least ntiles*16 row groups past Qs
-  const int ggrp = max(gq + 2 * gk, ((N + 127) >> 7) * 16);
-  float* bias_s = reinterpret_cast<float*>(smem + (size_t)ggrp * 1024);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(bias_s + Np);
+  const int ggrp = max(gq + 2 * gk, ntiles * 16);
+  float* bias_s = reinterpret_cast<float*>(smem + (size_t)ggrp * 1024);      // [Np]
+  float* red_max = bias_s + Np;                                               // [2][128]
+  float* red_sum = red_max + 256;                                             // [2][128]
+  float* colpart = red_sum + 256;                                             // [8][Np] (COLSUM)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(colpart + (COLSUM ? 8 * Np : 0));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const uint32_t ncols = Np <= 128 ? 128u : 256u;
   const uint32_t o_col = Np <= 128 ? 64u : 128u;
+  TOKRED_STAMP(tid == 0, 0, 0);
   if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
   if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_mbar_init(); }
 
-  // ---- loads: job = (matrix, 8-row group); lane -> row = lane % 8, 16-byte chunks 2*(lane/8), 2*(lane/8)+1
+  // ---- loads
+  const int64_t* ids = p.q_ids ? p.q_ids + (size_t)b * p.ids_stride : nullptr;
   {
-    const __nv_bfloat16* base = p.qkv + (size_t)b * N * 3 * C + (size_t)h * 64;
-    const int r8 = lane & 7, cp = lane >> 3;
-    const int njobs = gq + 2 * gk;
-    for (int j = warp; j < njobs; j += kThreads / 32) {
-      int m, g;
-      if (j < gq) { m = 0; g = j; } else if (j < gq + gk) { m = 1; g = j - gq; } else { m = 2; g = j - gq - gk; }
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(p.qkv + (size_t)b * N * 3 * C + (size_t)h * 64);
+    const size_t row_bytes = (size_t)3 * C * 2;
+    const int r8 = lane & 7;
+    const uint32_t lane_dst = (uint32_t)(r8 * 16 + (lane >> 3) * 256);
+    const unsigned char* lane_src = base + (lane >> 3) * 32;
+    // K and V: rows [0, N), zero-filled up to Np
+    const uint32_t k0 = umma::smem_u32(Ks) + lane_dst, v0 = umma::smem_u32(Vs) + lane_dst;
+    for (int g = warp; g < gk; g += kThreads / 32) {
       const int row = g * 8 + r8;
       const bool ok = row < N;
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(base + ((size_t)(ok ? row : 0) * 3 + m) * C) + cp * 32;
-      unsigned char* tile = (m == 0 ? Qs : m == 1 ? Ks : Vs) + (size_t)g * 1024 + r8 * 16 + cp * 256;
-      const uint32_t dst = umma::smem_u32(tile);
-      cp_async16(dst, src, ok ? 16u : 0u);
-      cp_async16(dst + 128, src + 16, ok ? 16u : 0u);
+      const unsigned char* src = lane_src + (size_t)(ok ? row : 0) * row_bytes;
+      load_group(k0 + g * 1024, src + C * 2, ok);
+      if (want_out) load_group(v0 + g * 1024, src + C * 4, ok);
+    }
+    const uint32_t q0 = umma::smem_u32(Qs) + lane_dst;
+    for (int g = warp; g < gq; g += kThreads / 32) {
+      const int row = g * 8 + r8;
+      const bool ok = row < M;
+      int srow = ok ? row : 0;
+      if (ids && ok) srow = clamp_idx(ids[row], N);
+      load_group(q0 + g * 1024, lane_src + (size_t)srow * row_bytes, ok);
     }
     if (BIAS)
-      for (int j = tid; j < Np; j += kThreads) bias_s[j] = j < N ? p.key_bias[(size_t)b * N + j] : 0.f;
+      for (int j = tid; j < Np; j += kThreads) {
+        float bv = 0.f;
+        if (j < N) {
+          if (p.key_bias) bv = p.key_bias[(size_t)b * N + j];
+          if (MASK && !p.mask[(size_t)b * N + j]) bv = -INFINITY;
+        }
+        bias_s[j] = bv;
+      }
+    if (COLSUM)
+      for (int j = tid; j < 8 * Np; j += kThreads) colpart[j] = 0.f;
     cp_async_wait_all();
   }
   umma::fence_proxy_async_smem();
@@ -155,13 +277,20 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(const AttnParams p)
   __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  TOKRED_STAMP(tid == 0, 0, 1);
 
   const uint32_t idesc_s = umma::instr_desc(umma::FMT_BF16, 128, (uint32_t)Np);
   const uint32_t idesc_o = umma::instr_desc(umma::FMT_BF16, 128, 64) | (1u << 16);      // B operand (v) MN-major
   const float scale = p.scale;
   uint32_t phase = 0;
-  const int ntiles = (N + 127) >> 7;
   const int nch = Np >> 4;
+  // Column split of passes A and B between the two warps of a quarter; pass C (cheap, and its in-place writes must trail
+  // its reads) is the lower warp's alone, so the lower warp takes fewer columns: 87 a + 27 nch = 87 (nch - a).
+  const int nlo = (nch * 11 + 16) >> 5;
+  const int c_beg = half ? nlo : 0, c_end = half ? nch : nlo;
+  const int c_full = (c_end == nch && (N & 15)) ? c_end - 1 : c_end;      // [c_beg, c_full) full chunks, then the ragged one
+  const uint32_t trow = umma::tmem_addr(tmem, (uint32_t)(q * 32), 0);
+  const int rl = q * 32 + lane;                            // row inside the tile
 
   for (int t = 0; t < ntiles; ++t) {
     // ---- S = Q_t K^T (rows past the Q tile read the K tile behind it: finite garbage in accumulator rows nobody reads)
@@ -172,70 +301,117 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(const AttnParams p)
         umma::mma_bf16(tmem, umma::smem_desc_kmajor(a0 + ks * 256, 128, 1024), umma::smem_desc_kmajor(b0 + ks * 256, 128, 1024),
                        idesc_s, ks > 0 ? 1u : 0u);
       umma::mma_commit(bar);
+      umma::mbar_wait(bar, phase);       // one thread polls; everybody else parks at the barrier below
     }
-    umma::mbar_wait(bar, phase);
     phase ^= 1u;
+    __syncthreads();
     umma::tc_fence_after_sync();
+    TOKRED_STAMP(tid == 0, t, 2);
 
-    const int row = t * 128 + warp * 32 + lane;
-    const bool active = t * 128 + warp * 32 < N;           // warp-uniform
-    const uint32_t trow = umma::tmem_addr(tmem, (uint32_t)(warp * 32), 0);
+    const int row = t * 128 + rl;                          // query row
+    const bool active = t * 128 + q * 32 < M;              // uniform over the warp pair of a quarter
     if (active) {
-      uint32_t r[16];
-      float x[16];
-      // pass A: row maximum
-      float mx = -INFINITY;
-      for (int c = 0; c < nch; ++c) {
-        umma::tmem_ld16(trow + c * 16, r);
-        umma::tmem_ld_wait();
-        logits16<BIAS, ROUND2>(r, x, scale, bias_s, c * 16);
-        if (c * 16 + 16 <= N) {
+      bool row_masked = false;
+      if (MASK && row < M) row_masked = !p.mask[(size_t)b * N + (ids ? clamp_idx(ids[row], N) : row)];
+      // pass A: row maximum over this warp's columns.  Without a bias the roundings and the (positive) scale are
+      // monotone, so the maximum is taken over the raw accumulators and rounded once.
+      float m0 = -INFINITY, m1 = -INFINITY;
+      auto pass_a = [&](uint32_t (&r)[16], int c, bool ragged) {
+        float x[16];
+        if (BIAS) logits16<BIAS, ROUND2, MASK>(r, x, scale, bias_s, c * 16, row_masked);
+        else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, x[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (c * 16 + i < N) mx = fmaxf(mx, x[i]);
+          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
         }
+        if (ragged) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (c * 16 + i >= N) x[i] = -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          m0 = fmaxf(m0, fmaxf(x[i], x[i + 1]));
+          m1 = fmaxf(m1, fmaxf(x[i + 2], x[i + 3]));
+        }
+      };
+      for_chunks(trow, c_beg, c_full, [&](uint32_t (&r)[16], int c) { pass_a(r, c, false); });
+      if (c_full < c_end) {
+        uint32_t r[16];
+        umma::tmem_ld16(trow + c_full * 16, r);
+        ld_wait16(r);
+        pass_a(r, c_full, true);
       }
+      float mw = fmaxf(m0, m1);
+      if (!BIAS) {
+        mw = bf16r(mw) * scale;
+        if (ROUND2) mw = bf16r(mw);
+      }
+      red_max[half * 128 + rl] = mw;
+      TOKRED_STAMP(tid == 128, t, 3);
+      TOKRED_STAMP(tid == 0, t, 8);
+      pair_sync(q);
+      const float mx = fmaxf(red_max[rl], red_max[128 + rl]);
       // pass B: e = exp(x - max) (kept in place as fp32), row sum
       const float mneg = -mx * kLog2e;
-      float sum = 0.f;
-      for (int c = 0; c < nch; ++c) {
-        umma::tmem_ld16(trow + c * 16, r);
-        umma::tmem_ld_wait();
-        logits16<BIAS, ROUND2>(r, x, scale, bias_s, c * 16);
-        const bool full = c * 16 + 16 <= N;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      auto pass_b = [&](uint32_t (&r)[16], int c, bool ragged) {
+        float x[16];
+        exp_args16<BIAS, ROUND2, MASK>(r, x, scale, bias_s, c * 16, row_masked, mneg);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float e = ex2(fmaf(x[i], kLog2e, mneg));
-          if (!full && c * 16 + i >= N) e = 0.f;
-          sum += e;
-          r[i] = __float_as_uint(e);
-        }
-        tmem_st16(trow + c * 16, r);
-      }
-      tmem_st_wait();
-      // pass C: p = e / sum -> bf16 pairs in place (column j holds keys 2j, 2j+1); CLS row to global in fp32
-      const float inv = 1.0f / sum;
-      float* cls = (p.cls_row && row == 0) ? p.cls_row + ((size_t)b * H + h) * N : nullptr;
-      for (int c = 0; c < nch; ++c) {
-        umma::tmem_ld16(trow + c * 16, r);
-        umma::tmem_ld_wait();
-        uint32_t pk[8];
+        for (int i = 0; i < 16; ++i) x[i] = ex2(x[i]);
+        if (ragged) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]) * inv;
-        if (cls) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (c * 16 + i < N) cls[c * 16 + i] = x[i];
+          for (int i = 0; i < 16; ++i) if (c * 16 + i >= N) x[i] = 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
-        tmem_st8(trow + c * 8, pk);
+        for (int i = 0; i < 16; i += 4) { s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3]; }
+        uint32_t e[16];                  // a separate array: writing into r would keep the values alive for the next wait
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = __float_as_uint(x[i]);
+        tmem_st16(trow + c * 16, e);
+      };
+      for_chunks(trow, c_beg, c_full, [&](uint32_t (&r)[16], int c) { pass_b(r, c, false); });
+      if (c_full < c_end) {
+        uint32_t r[16];
+        umma::tmem_ld16(trow + c_full * 16, r);
+        ld_wait16(r);
+        pass_b(r, c_full, true);
       }
+      red_sum[half * 128 + rl] = (s0 + s1) + (s2 + s3);
       tmem_st_wait();
+      TOKRED_STAMP(tid == 128, t, 4);
+      TOKRED_STAMP(tid == 0, t, 9);
+      pair_sync(q);
+      // pass C (lower warp): p = e / sum -> bf16 pairs in place (column j holds keys 2j, 2j+1; the writes trail the
+      // reads); side outputs in fp32
+      if (!half) {
+        const float inv = 1.0f / (red_sum[rl] + red_sum[128 + rl]);
+        float* cls = (p.cls_row && row == 0) ? p.cls_row + ((size_t)b * H + h) * N : nullptr;
+        for_chunks(trow, 0, nch, [&](uint32_t (&r)[16], int c) {
+          float x[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]) * inv;
+          if (cls) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c * 16 + i < N) cls[c * 16 + i] = x[i];
+          }
+          if (COLSUM) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = row < M ? x[i] : 0.f;
+            const float cs = colsum16(v, lane);
+            if (!(lane & 1)) colpart[(size_t)(t * 4 + q) * Np + c * 16 + (lane >> 1)] = cs;
+          }
+          tmem_st8(trow + c * 8, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                   pack_bf16x2(x[6], x[7]), pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]),
+                   pack_bf16x2(x[14], x[15]));
+        });
+        tmem_st_wait();
+        TOKRED_STAMP(tid == 0, t, 5);
+      }
     }
     umma::tc_fence_before_sync();
     __syncthreads();
+    if (!want_out) continue;             // scores only (uniform): nothing reads the accumulator again
 
     // ---- O = P V : A from TMEM, B = v tile MN-major (LBO field = stride between 8-token groups, SBO field = 8-channel cores)
     if (tid == 0) {
@@ -244,68 +420,102 @@ __global__ void __launch_bounds__(kThreads) attention_kernel(const AttnParams p)
       for (int ks = 0; ks < nch; ++ks)
         mma_bf16_ts(tmem + o_col, tmem + ks * 8, umma::smem_desc_kmajor(v0 + ks * 2048, 1024, 128), idesc_o, ks > 0 ? 1u : 0u);
       umma::mma_commit(bar);
+      umma::mbar_wait(bar, phase);
     }
-    umma::mbar_wait(bar, phase);
     phase ^= 1u;
+    __syncthreads();
     umma::tc_fence_after_sync();
+    TOKRED_STAMP(tid == 0, t, 6);
     if (active) {                                          // whole warp: the TMEM loads are .sync.aligned
-      __nv_bfloat16* dst = p.out + ((size_t)b * N + (row < N ? row : 0)) * C + h * 64;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[16];
-        umma::tmem_ld16(trow + o_col + c * 16, r);
-        umma::tmem_ld_wait();
-        uint32_t w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-        if (row < N)
-          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + c * 16), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                       "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-                       : "memory");
+      __nv_bfloat16* dst = p.out + ((size_t)b * M + (row < M ? row : 0)) * C + h * 64 + half * 32;
+      uint32_t ra[16], rb[16];
+      umma::tmem_ld16(trow + o_col + half * 32, ra);
+      umma::tmem_ld16(trow + o_col + half * 32 + 16, rb);
+      ld_wait16(ra);
+      ld_wait16(rb);
+      if (row < M) {
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(pack_bf16x2(__uint_as_float(ra[0]), __uint_as_float(ra[1]))),
+                     "r"(pack_bf16x2(__uint_as_float(ra[2]), __uint_as_float(ra[3]))), "r"(pack_bf16x2(__uint_as_float(ra[4]), __uint_as_float(ra[5]))),
+                     "r"(pack_bf16x2(__uint_as_float(ra[6]), __uint_as_float(ra[7]))), "r"(pack_bf16x2(__uint_as_float(ra[8]), __uint_as_float(ra[9]))),
+                     "r"(pack_bf16x2(__uint_as_float(ra[10]), __uint_as_float(ra[11]))), "r"(pack_bf16x2(__uint_as_float(ra[12]), __uint_as_float(ra[13]))),
+                     "r"(pack_bf16x2(__uint_as_float(ra[14]), __uint_as_float(ra[15])))
+                     : "memory");
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 16), "r"(pack_bf16x2(__uint_as_float(rb[0]), __uint_as_float(rb[1]))),
+                     "r"(pack_bf16x2(__uint_as_float(rb[2]), __uint_as_float(rb[3]))), "r"(pack_bf16x2(__uint_as_float(rb[4]), __uint_as_float(rb[5]))),
+                     "r"(pack_bf16x2(__uint_as_float(rb[6]), __uint_as_float(rb[7]))), "r"(pack_bf16x2(__uint_as_float(rb[8]), __uint_as_float(rb[9]))),
+                     "r"(pack_bf16x2(__uint_as_float(rb[10]), __uint_as_float(rb[11]))), "r"(pack_bf16x2(__uint_as_float(rb[12]), __uint_as_float(rb[13]))),
+                     "r"(pack_bf16x2(__uint_as_float(rb[14]), __uint_as_float(rb[15])))
+                     : "memory");
       }
     }
     umma::tc_fence_before_sync();
     __syncthreads();
+    TOKRED_STAMP(tid == 0, t, 7);
+  }
+  if (COLSUM) {
+    // fixed-order combine of the (tile, quarter) partials: deterministic
+    float* dst = p.colsum + ((size_t)b * H + h) * N;
+    for (int j = tid; j < N; j += kThreads) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += colpart[(size_t)k * Np + j];
+      dst[j] = s;
+    }
   }
   if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
-size_t attn_smem_bytes(int N) {
+size_t attn_smem_bytes(int N, int M, bool colsum) {
   const int Np = (N + 15) & ~15;
-  const int groups = (N + 7) / 8 + 2 * (Np / 8), mma_rows = ((N + 127) / 128) * 16;
-  return (size_t)(groups > mma_rows ? groups : mma_rows) * 1024 + (size_t)Np * 4 + 64;
+  const int groups = (M + 7) / 8 + 2 * (Np / 8), mma_rows = ((M + 127) / 128) * 16;
+  return (size_t)(groups > mma_rows ? groups : mma_rows) * 1024 + (size_t)Np * 4 + 2048 + (colsum ? (size_t)8 * Np * 4 : 0) + 64;
 }
 
 }  // namespace
 }  // namespace tokred
 
 using namespace tokred;
+TOKRED_STAMP_SETTER(attention)
 
 extern "C" int tokred_attention(const void* qkv, int B, int N, int H, int head_dim, float scale, const float* key_bias,
-                                void* out, float* cls_row, void* stream) {
-  TOKRED_REQUIRE(qkv && out, "attention: null pointer");
+                                const uint8_t* mask, const int64_t* q_ids, int64_t ids_stride, int M, void* out,
+                                float* cls_row, float* colsum, void* stream) {
+  TOKRED_REQUIRE(qkv, "attention: null qkv");
+  TOKRED_REQUIRE(out || cls_row || colsum, "attention: no output requested");
   TOKRED_REQUIRE(B >= 1 && H >= 1 && N >= 1, "attention: B=%d N=%d H=%d", B, N, H);
-  if (head_dim != 64 || N > 256) {
-    set_error("attention: head_dim=%d N=%d outside the fused kernel's range (head_dim 64, N <= 256)", head_dim, N);
+  TOKRED_REQUIRE(scale > 0.f && std::isfinite(scale), "attention: scale %g must be positive", (double)scale);
+  if (!q_ids) M = N;
+  TOKRED_REQUIRE(M >= 1 && (!q_ids || ids_stride >= M), "attention: M=%d ids_stride=%lld", M, (long long)ids_stride);
+  if (head_dim != 64 || N > 256 || M > 256) {
+    set_error("attention: head_dim=%d N=%d M=%d outside the fused kernel's range (head_dim 64, N <= 256)", head_dim, N, M);
     return TOKRED_ERR_UNSUPPORTED;
   }
   TOKRED_REQUIRE((long long)B * H <= 0x7fffffffLL, "attention: B*H too large");
   TOKRED_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0,
                  "attention: qkv must be 16-byte and out 32-byte aligned");
   AttnParams prm{};
-  prm.qkv = (const __nv_bfloat16*)qkv; prm.key_bias = key_bias; prm.out = (__nv_bfloat16*)out; prm.cls_row = cls_row;
-  prm.B = B; prm.N = N; prm.H = H; prm.scale = scale;
+  prm.qkv = (const __nv_bfloat16*)qkv; prm.key_bias = key_bias; prm.mask = mask; prm.q_ids = q_ids; prm.ids_stride = ids_stride;
+  prm.out = (__nv_bfloat16*)out; prm.cls_row = cls_row; prm.colsum = colsum;
+  prm.B = B; prm.N = N; prm.H = H; prm.M = M; prm.scale = scale;
   int ex = 0;
-  const bool pow2 = std::frexp(scale, &ex) == 0.5f;
-  const size_t smem = attn_smem_bytes(N);
+  const bool r2 = std::frexp(scale, &ex) != 0.5f;          // not a power of two: the scaled logits round to bf16 again
+  const bool cs = colsum != nullptr;
+  const size_t smem = attn_smem_bytes(N, M, cs);
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(BIAS, R2)                                                                          \
-  do {                                                                                            \
-    if (int e = allow_smem(attention_kernel<BIAS, R2>, smem, "attention")) return e;             \
-    attention_kernel<BIAS, R2><<<B * H, kThreads, smem, st>>>(prm);                               \
+#define LAUNCH(BIAS, R2, MASK, CS)                                                                  \
+  do {                                                                                              \
+    if (int e = allow_smem(attention_kernel<BIAS, R2, MASK, CS>, smem, "attention")) return e;     \
+    attention_kernel<BIAS, R2, MASK, CS><<<B * H, kThreads, smem, st>>>(prm);                       \
   } while (0)
-  if (key_bias) { if (pow2) LAUNCH(true, false); else LAUNCH(true, true); }
-  else          { if (pow2) LAUNCH(false, false); else LAUNCH(false, true); }
+#define PICK(BIAS, MASK)                                                                            \
+  do {                                                                                              \
+    if (r2) { if (cs) LAUNCH(BIAS, true, MASK, true); else LAUNCH(BIAS, true, MASK, false); }       \
+    else    { if (cs) LAUNCH(BIAS, false, MASK, true); else LAUNCH(BIAS, false, MASK, false); }     \
+  } while (0)
+  if (mask) PICK(true, true);
+  else if (key_bias) PICK(true, false);
+  else PICK(false, false);
+#undef PICK
 #undef LAUNCH
   return finish_launch("attention");
 }

@@ -307,6 +307,10 @@ class KMedoidsVisionTransformer(_ClusterLayerViT):
             for i in range(depth)])
         self.fused_token_weights = bool(getattr(args, "tokred_fused_scores", False))
         self._setup(args, lambda c: M.KMedoids(c, self.cluster_iters, self.equal_weight))
+        # only the block in front of a cluster layer has its probabilities read, and only their column sums
+        # (models/kmedoids.py:240): under bf16 autocast no block materialises [B,H,N,N] (modules.AttentionWithProbs)
+        for i, blk in enumerate(self.blocks):
+            blk.attn.probs_mode = "colsum" if (i + 1) in self.cluster_loc else "none"
 
     def forward(self, x):
         x = self.patch_embed(x)
@@ -320,7 +324,9 @@ class KMedoidsVisionTransformer(_ClusterLayerViT):
         for i, blk in enumerate(self.blocks):
             if i in self.cluster_loc:
                 global_tokens = x[:, :self.num_tokens]
-                if self.fused_token_weights:
+                if attn.dim() == 3:      # per-head column sums [B,H,N] from the fused attention (deterministic order)
+                    token_weights = attn.sum(1)[:, self.num_tokens:].unsqueeze(2)
+                elif self.fused_token_weights:
                     token_weights = ops.attn_colsum(attn, self.num_tokens)          # one pass over [B,H,N,N]
                 else:   # the reference's two torch.sum launches: bit-identical decision input
                     token_weights = torch.sum(torch.sum(attn, dim=1), dim=1)[:, self.num_tokens:].unsqueeze(2)

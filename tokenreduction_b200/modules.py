@@ -12,6 +12,7 @@ validate.py default) converts at the op boundary, see ``_lowp``.
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -55,6 +56,26 @@ def _train_guard(mod: nn.Module) -> None:
             "call .eval() and run under torch.no_grad()")
 
 
+FUSED_ATTENTION = os.environ.get("TOKRED_FUSED_ATTENTION", "1") != "0"
+
+
+def fused_attention_ok(mod: nn.Module, x: Tensor, num_heads: int) -> bool:
+    """True where the fused attention producer (ops.attention) reproduces the module's ATen sequence:
+    bf16 autocast (or bf16 tensors) in inference, head dim 64, N <= 256.  fp32 models, fp16 autocast, training with
+    attention dropout and other shapes keep the reference's own sequence."""
+    if not (FUSED_ATTENTION and x.is_cuda and x.dim() == 3 and x.shape[1] <= 256 and x.shape[2] == 64 * num_heads):
+        return False
+    if torch.is_autocast_enabled("cuda"):
+        if torch.get_autocast_dtype("cuda") != torch.bfloat16:
+            return False
+    elif x.dtype != torch.bfloat16:
+        return False
+    drop = getattr(mod, "attn_drop", None)
+    if mod.training and (torch.is_grad_enabled() or (drop is not None and drop.p > 0)):
+        return False
+    return True
+
+
 class _AttentionBase(nn.Module):
     """qkv / proj layout shared by every reference attention variant (e.g. models/topk.py:27-52)."""
 
@@ -77,6 +98,17 @@ class _AttentionBase(nn.Module):
         x = (attn @ v).transpose(1, 2).reshape(b, n, -1)
         return self.proj_drop(self.proj(x))
 
+    def _fused(self, x) -> bool:
+        return fused_attention_ok(self, x, self.num_heads)
+
+    def _attend_fused(self, x, key_bias=None, mask=None, q_ids=None, want_cls=False, want_colsum=False):
+        """qkv Linear -> ONE attention launch (no [B,H,N,N] tensor) -> proj.  Returns (x, cls_row, colsum, qkv)."""
+        qkv = self.qkv(x)
+        if qkv.dtype != torch.bfloat16:
+            qkv = qkv.to(torch.bfloat16)
+        out, cls, colsum = ops.attention(qkv, self.num_heads, self.scale, key_bias, mask, q_ids, True, want_cls, want_colsum)
+        return self.proj_drop(self.proj(out)), cls, colsum, qkv
+
 
 # =============================================================================================== Top-K
 class Attention_TopK(_AttentionBase):
@@ -90,6 +122,14 @@ class Attention_TopK(_AttentionBase):
 
     def forward(self, x):
         n = x.shape[1]
+        if self._fused(x):
+            left_tokens = int(self.keep_rate * self.init_n)
+            reduce = self.keep_rate < 1 and left_tokens != n - 1
+            x, cls_row, _, _ = self._attend_fused(x, want_cls=reduce)
+            if not reduce:
+                return x, None, None
+            assert left_tokens >= 1
+            return x, cls_row[:, :, 1:].mean(dim=1), left_tokens      # = attn[:, :, 0, 1:].mean(1), models/topk.py:60
         q, k, v = self._qkv(x)
         attn = self.attn_drop(((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1))
         x = self._out(attn, v)
@@ -264,7 +304,15 @@ def _reduced_cluster_idx(source: Tensor, cls_token: bool) -> Tensor:
 class Attention_ToMe(_AttentionBase):
     """models/tome.py:29-59.  forward(x, size) -> (x, metric = k.mean(1))."""
 
+    need_metric = True      # Block_ToMe switches the key mean off in blocks that do not merge (r == 0)
+
     def forward(self, x, size=None):
+        if self._fused(x):
+            b, n, c = x.shape
+            bias = None if size is None else size.log()[..., 0]               # proportional attention, :48-49
+            x, _, _, qkv = self._attend_fused(x, key_bias=bias)
+            metric = qkv.view(b, n, 3, self.num_heads, c // self.num_heads)[:, :, 1].mean(2) if self.need_metric else None
+            return x, metric                                                   # = k.mean(1), :58
         q, k, v = self._qkv(x)
         attn = (q @ k.transpose(-2, -1)) * self.scale
         if size is not None:
@@ -287,6 +335,7 @@ class Block_ToMe(nn.Module):
         self.r = r
         self.cls_token = cls_token
         self.dist_token = dist_token
+        self.attn.need_metric = r > 0
 
     def forward(self, x, attn_size=None):
         x_attn, metric = self.attn(self.norm1(x), attn_size)
@@ -384,7 +433,15 @@ class KMedoids(nn.Module):
 class AttentionWithProbs(_AttentionBase):
     """models/kmedoids.py:88-112.  forward(x) -> (x, attn)."""
 
+    # "full": the reference's materialised probabilities (default; the block-level signature of the reference).
+    # "colsum" / "none": set by KMedoidsVisionTransformer for the blocks whose probabilities feed the next cluster
+    # layer / nobody: forward returns (x, column sums [B,H,N] | None) and [B,H,N,N] is never written.
+    probs_mode = "full"
+
     def forward(self, x):
+        if self.probs_mode != "full" and self._fused(x):
+            x, _, colsum, _ = self._attend_fused(x, want_colsum=self.probs_mode == "colsum")
+            return x, colsum
         q, k, v = self._qkv(x)
         attn = self.attn_drop(((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1))
         return self._out(attn, v), attn
@@ -489,7 +546,8 @@ class AdaptiveTokenSampling(nn.Module):
         self.static_width = static_width
         self._steps_dev = None
 
-    def forward(self, x, attn, mask):
+    def sample(self, x, attn, mask):
+        """ids / new mask only.  ``attn`` may be the [B,H,N,N] probabilities or just their CLS rows [B,H,N]."""
         _train_guard(self)
         if self._steps_dev is None or self._steps_dev.device != attn.device:
             self._steps_dev = self.sample_steps.to(attn.device)
@@ -497,6 +555,10 @@ class AdaptiveTokenSampling(nn.Module):
         if not self.static_width:
             m = int(max_count.item()) + 1
             ids, new_mask = ids[:, :m], new_mask[:, :m]
+        return ids, new_mask
+
+    def forward(self, x, attn, mask):
+        ids, new_mask = self.sample(x, attn, mask)
         new_attn = ops.gather_rows(attn, ids, ids.shape[1])
         return new_attn, new_mask, ids
 
@@ -512,6 +574,21 @@ class ATSAttention(_AttentionBase):
             self.ats = AdaptiveTokenSampling(ats_sample_count)
 
     def forward(self, x, mask):
+        if self._fused(x):
+            # scores first (CLS rows only: v is not read), then the attention of the SAMPLED query rows only -- the
+            # row gather attn[:, :, ids, :] of models/ats.py:84-87 commutes with the row-wise softmax
+            b, n, c = x.shape
+            qkv = self.qkv(x)
+            qkv = qkv if qkv.dtype == torch.bfloat16 else qkv.to(torch.bfloat16)
+            sample_ids = None
+            old_mask = mask
+            if self.ats_sample_count:
+                _, cls_row, _ = ops.attention(qkv, self.num_heads, self.scale, None, old_mask, None, False, True, False)
+                v = qkv.view(b, n, 3, self.num_heads, c // self.num_heads)[:, :, 2].permute(0, 2, 1, 3)
+                full = old_mask if old_mask is not None else torch.ones(b, n, dtype=torch.bool, device=x.device)
+                sample_ids, mask = self.ats.sample(v, cls_row, full)
+            out, _, _ = ops.attention(qkv, self.num_heads, self.scale, None, old_mask, sample_ids, True, False, False)
+            return self.proj_drop(self.proj(out)), mask, sample_ids
         q, k, v = self._qkv(x)
         dots = (q @ k.transpose(-2, -1)) * self.scale
         if mask is not None:
@@ -585,6 +662,8 @@ class Policy_Attention(_AttentionBase):
     def forward(self, x, policy=None):
         if policy is not None:
             raise NotImplementedError("Policy_Attention: softmax_with_policy is the training path (out of scope)")
+        if self._fused(x):
+            return self._attend_fused(x)[0]
         q, k, v = self._qkv(x)
         attn = ((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1)
         return self._out(attn, v)

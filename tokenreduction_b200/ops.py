@@ -555,7 +555,7 @@ def sit_merge(x: Tensor, logits: Tensor, scale: Tensor, lowp: bool = False, tens
 def _ats_sample(v: Tensor, attn: Tensor, mask: Tensor, steps: Tensor, eps: float) -> Tuple[Tensor, Tensor, Tensor]:
     _need_cuda("ats_sample", v, attn, mask, steps)
     b, h, n, dh = v.shape
-    if attn.shape != (b, h, n, n) or mask.shape != (b, n):
+    if attn.shape not in ((b, h, n, n), (b, h, n)) or mask.shape != (b, n):          # [B,H,N] = CLS rows only
         raise TokredError("ats_sample: attn/mask shapes do not match v")
     if v.stride(3) != 1:
         v = v.contiguous()
@@ -566,8 +566,8 @@ def _ats_sample(v: Tensor, attn: Tensor, mask: Tensor, steps: Tensor, eps: float
     ids = torch.empty((b, ns + 1), dtype=torch.int64, device=v.device)
     mask_out = torch.empty((b, ns + 1), dtype=torch.bool, device=v.device)
     max_count = torch.zeros((1,), dtype=torch.int32, device=v.device)
-    _lib.call("tokred_ats_sample", _ptr(v), _dt(v), v.stride(0), v.stride(1), v.stride(2), _ptr(attn), _ptr(mask8),
-              _ptr(steps), b, h, n, dh, ns, float(eps),
+    _lib.call("tokred_ats_sample", _ptr(v), _dt(v), v.stride(0), v.stride(1), v.stride(2), _ptr(attn),
+              n * n if attn.dim() == 4 else n, _ptr(mask8), _ptr(steps), b, h, n, dh, ns, float(eps),
               _ptr(ids), mask_out.data_ptr(), _ptr(max_count), _stream())
     return ids, mask_out, max_count
 
@@ -652,8 +652,9 @@ def attention_supported(qkv: Tensor, num_heads: int) -> bool:
 
 
 @torch.library.custom_op("tokred::attention", mutates_args=(), device_types="cuda")
-def _attention(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Tensor], want_cls: bool) -> Tuple[Tensor, Tensor]:
-    _need_cuda("attention", qkv, key_bias)
+def _attention(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Tensor], mask: Optional[Tensor],
+               q_ids: Optional[Tensor], want_out: bool, want_cls: bool, want_colsum: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("attention", qkv, key_bias, mask, q_ids)
     if qkv.dim() != 3 or qkv.dtype != torch.bfloat16 or qkv.shape[2] % (3 * num_heads) != 0:
         raise TokredError(f"attention: qkv {tuple(qkv.shape)} {qkv.dtype}; expected bf16 [B,N,3*H*Dh]")
     b, n, c3 = qkv.shape
@@ -663,23 +664,40 @@ def _attention(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Ten
         if key_bias.numel() != b * n:
             raise TokredError(f"attention: key_bias {tuple(key_bias.shape)} does not match qkv {tuple(qkv.shape)}")
         key_bias = _c(key_bias.to(torch.float32))
-    out = torch.empty((b, n, c), dtype=torch.bfloat16, device=qkv.device)
-    cls = torch.empty((b, num_heads, n) if want_cls else (0,), dtype=torch.float32, device=qkv.device)
-    _lib.call("tokred_attention", _ptr(qkv), b, n, num_heads, c // num_heads, float(scale), _ptr(key_bias), _ptr(out),
-              _ptr(cls) if want_cls else None, _stream())
-    return out, cls
+    if mask is not None:
+        if mask.shape != (b, n):
+            raise TokredError(f"attention: mask {tuple(mask.shape)} does not match qkv {tuple(qkv.shape)}")
+        mask = _c(mask.to(torch.bool)).view(torch.uint8)
+    m, ids_stride = n, 0
+    if q_ids is not None:
+        if q_ids.dim() != 2 or q_ids.shape[0] != b or q_ids.dtype != torch.int64:
+            raise TokredError(f"attention: q_ids {tuple(q_ids.shape)} {q_ids.dtype}; expected int64 [B,M]")
+        q_ids = _c(q_ids)
+        m, ids_stride = q_ids.shape[1], q_ids.shape[1]
+    dev = qkv.device
+    out = torch.empty((b, m, c) if want_out else (0,), dtype=torch.bfloat16, device=dev)
+    cls = torch.empty((b, num_heads, n) if want_cls else (0,), dtype=torch.float32, device=dev)
+    colsum = torch.empty((b, num_heads, n) if want_colsum else (0,), dtype=torch.float32, device=dev)
+    _lib.call("tokred_attention", _ptr(qkv), b, n, num_heads, c // num_heads, float(scale), _ptr(key_bias), _ptr(mask),
+              _ptr(q_ids), ids_stride, m, _ptr(out) if want_out else None, _ptr(cls) if want_cls else None,
+              _ptr(colsum) if want_colsum else None, _stream())
+    return out, cls, colsum
 
 
 @_attention.register_fake
-def _(qkv, num_heads, scale, key_bias, want_cls):
+def _(qkv, num_heads, scale, key_bias, mask, q_ids, want_out, want_cls, want_colsum):
     b, n, c3 = qkv.shape
-    return (qkv.new_empty((b, n, c3 // 3)),
-            qkv.new_empty((b, num_heads, n) if want_cls else (0,), dtype=torch.float32))
+    m = n if q_ids is None else q_ids.shape[1]
+    f32 = lambda on: qkv.new_empty((b, num_heads, n) if on else (0,), dtype=torch.float32)
+    return qkv.new_empty((b, m, c3 // 3) if want_out else (0,)), f32(want_cls), f32(want_colsum)
 
 
-def attention(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Tensor] = None, want_cls: bool = False):
-    """softmax(q k^T * scale [+ key_bias]) v with bf16-autocast roundings (models/topk.py:44-52; tome.py:44-58) from the
-    qkv Linear's output [B,N,3C] -> (x [B,N,C] bf16 ready for proj, cls_row [B,H,N] fp32 | None).  The [B,H,N,N]
-    probabilities are never materialised; cls_row is attn[:, :, 0, :] (models/topk.py:60)."""
-    out, cls = torch.ops.tokred.attention(qkv, num_heads, scale, key_bias, want_cls)
-    return out, (cls if want_cls else None)
+def attention(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+              q_ids: Optional[Tensor] = None, want_out: bool = True, want_cls: bool = False, want_colsum: bool = False):
+    """softmax(q k^T * scale [+ key_bias] [masked]) v with bf16-autocast roundings (models/topk.py:44-52; tome.py:44-58;
+    ats.py:115-127) from the qkv Linear's output [B,N,3C] -> (x [B,M,C] bf16 ready for proj | None, cls_row [B,H,N]
+    fp32 | None, colsum [B,H,N] fp32 | None).  The [B,H,N,N] probabilities are never materialised: cls_row is
+    attn[:, :, 0, :] (models/topk.py:60), colsum is attn.sum(2) (models/kmedoids.py:240 sums it over heads), q_ids
+    [B,M] selects the query rows to compute (the ATS row gather, models/ats.py:84-87)."""
+    out, cls, colsum = torch.ops.tokred.attention(qkv, num_heads, scale, key_bias, mask, q_ids, want_out, want_cls, want_colsum)
+    return (out if want_out else None), (cls if want_cls else None), (colsum if want_colsum else None)

@@ -122,6 +122,11 @@ class Attention(nn.Module):
         return self.proj_drop(self.proj(x))
 
     def forward(self, x):
+        from . import modules, ops
+        if modules.fused_attention_ok(self, x, self.num_heads):        # no [B,H,N,N] tensor
+            qkv = self.qkv(x)
+            qkv = qkv if qkv.dtype == torch.bfloat16 else qkv.to(torch.bfloat16)
+            return self.proj_drop(self.proj(ops.attention(qkv, self.num_heads, self.scale)[0]))
         q, k, v = self.qkv_heads(x)
         attn = self.attn_drop(self.attend(q, k).softmax(dim=-1))
         return self.project(attn, v)
