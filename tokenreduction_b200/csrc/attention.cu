@@ -12,8 +12,9 @@
 // and emits, on request, the only parts of `attn` the reduction operators read: the CLS row of every head (Top-K /
 // EViT / ATS scores) and the per-head column sums (K-Medoids token weights) -- the [B,H,N,N] tensor is never written.
 //
-// One CTA per (image, head), 256 threads, two CTAs per SM (<= 81 KB shared memory, <= 256 TMEM columns each), so one
-// CTA's loads overlap the other's softmax without any explicit pipeline:
+// Work item = (image, head); persistent CTAs of 256 threads, two per SM (<= 108 KB shared memory, <= 256 TMEM columns
+// each): the two CTAs of an SM drift into different phases, so one's MMA / barrier waits are filled by the other's
+// softmax, and each CTA prefetches its next item's q, k, v during the last query tile of the current one:
 //   load   q, k, v head slices (128-byte rows, row stride 3C) -> shared memory with 16-byte cp.async straight into the
 //          canonical no-swizzle UMMA core-matrix layout (8 consecutive lanes = 8 consecutive rows = one contiguous 128-byte
 //          core matrix: conflict-free); pad rows are zero-filled by the copy itself (src-size 0)
@@ -213,16 +214,18 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
   const int Np = (N + 15) & ~15;                     // keys: UMMA N of S, UMMA K of P.V
   const int gq = (M + 7) >> 3, gk = Np >> 3;         // 8-row groups of the Q / K,V tiles
   const int ntiles = (M + 127) >> 7;
-  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const bool want_out = p.out != nullptr;
+  const int nitems = p.B * H;
 
+  // Q | K | V[0] | V[1]: the CTA is persistent; while it works on the last query tile of an item, the next item's q, k
+  // (their area is dead once the last S MMA has completed) and v (other buffer) are already on their way
   unsigned char* Qs = smem;
   unsigned char* Ks = Qs + (size_t)gq * 1024;
   unsigned char* Vs = Ks + (size_t)gk * 1024;
   // the S MMA always reads 128 A rows: the operand area spans at least ntiles*16 row groups past Qs
-  const int ggrp = max(gq + 2 * gk, ntiles * 16);
-  float* bias_s = reinterpret_cast<float*>(smem + (size_t)ggrp * 1024);      // [Np]
-  float* red_max = bias_s + Np;                                               // [2][128]
+  const int ggrp = max(gq + 3 * gk, ntiles * 16);
+  float* bias_s = reinterpret_cast<float*>(smem + (size_t)ggrp * 1024);      // [2][Np]
+  float* red_max = bias_s + 2 * Np;                                           // [2][128]
   float* red_sum = red_max + 256;                                             // [2][128]
   float* colpart = red_sum + 256;                                             // [8][Np] (COLSUM)
   uint64_t* bar = reinterpret_cast<uint64_t*>(colpart + (COLSUM ? 8 * Np : 0));
@@ -234,25 +237,25 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
   if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
   if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_mbar_init(); }
 
-  // ---- loads
-  const int64_t* ids = p.q_ids ? p.q_ids + (size_t)b * p.ids_stride : nullptr;
-  {
-    const unsigned char* base = reinterpret_cast<const unsigned char*>(p.qkv + (size_t)b * N * 3 * C + (size_t)h * 64);
-    const size_t row_bytes = (size_t)3 * C * 2;
-    const int r8 = lane & 7;
-    const uint32_t lane_dst = (uint32_t)(r8 * 16 + (lane >> 3) * 256);
-    const unsigned char* lane_src = base + (lane >> 3) * 32;
+  // ---- loads of one item into (Qs, Ks, V[buf], bias[buf]); asynchronous (cp.async), completed by cp_async_wait_all
+  const int r8 = lane & 7;
+  const uint32_t lane_dst = (uint32_t)(r8 * 16 + (lane >> 3) * 256);
+  const size_t row_bytes = (size_t)3 * C * 2;
+  auto issue_loads = [&](int item, int buf, int wi, int nw) {      // warp wi of nw issuing warps
+    const int b = item / H, h = item - b * H;
+    const unsigned char* lane_src = reinterpret_cast<const unsigned char*>(p.qkv + (size_t)b * N * 3 * C + (size_t)h * 64) + (lane >> 3) * 32;
     // K and V: rows [0, N), zero-filled up to Np
-    const uint32_t k0 = umma::smem_u32(Ks) + lane_dst, v0 = umma::smem_u32(Vs) + lane_dst;
-    for (int g = warp; g < gk; g += kThreads / 32) {
+    const uint32_t k0 = umma::smem_u32(Ks) + lane_dst, v0 = umma::smem_u32(Vs) + (uint32_t)buf * (uint32_t)gk * 1024u + lane_dst;
+    for (int g = wi; g < gk; g += nw) {
       const int row = g * 8 + r8;
       const bool ok = row < N;
       const unsigned char* src = lane_src + (size_t)(ok ? row : 0) * row_bytes;
       load_group(k0 + g * 1024, src + C * 2, ok);
       if (want_out) load_group(v0 + g * 1024, src + C * 4, ok);
     }
+    const int64_t* ids = p.q_ids ? p.q_ids + (size_t)b * p.ids_stride : nullptr;
     const uint32_t q0 = umma::smem_u32(Qs) + lane_dst;
-    for (int g = warp; g < gq; g += kThreads / 32) {
+    for (int g = wi; g < gq; g += nw) {
       const int row = g * 8 + r8;
       const bool ok = row < M;
       int srow = ok ? row : 0;
@@ -260,18 +263,20 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
       load_group(q0 + g * 1024, lane_src + (size_t)srow * row_bytes, ok);
     }
     if (BIAS)
-      for (int j = tid; j < Np; j += kThreads) {
+      for (int j = wi * 32 + lane; j < Np; j += nw * 32) {
         float bv = 0.f;
         if (j < N) {
           if (p.key_bias) bv = p.key_bias[(size_t)b * N + j];
           if (MASK && !p.mask[(size_t)b * N + j]) bv = -INFINITY;
         }
-        bias_s[j] = bv;
+        bias_s[buf * Np + j] = bv;
       }
-    if (COLSUM)
-      for (int j = tid; j < 8 * Np; j += kThreads) colpart[j] = 0.f;
-    cp_async_wait_all();
-  }
+  };
+  int item = blockIdx.x;
+  if (item < nitems) issue_loads(item, 0, warp, kThreads / 32);
+  if (COLSUM)
+    for (int j = tid; j < 8 * Np; j += kThreads) colpart[j] = 0.f;
+  cp_async_wait_all();
   umma::fence_proxy_async_smem();
   umma::tc_fence_before_sync();
   __syncthreads();
@@ -286,189 +291,213 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
   const int nch = Np >> 4;
   // Column split of passes A and B between the two warps of a quarter; pass C (cheap, and its in-place writes must trail
   // its reads) is the lower warp's alone, so the lower warp takes fewer columns: 87 a + 27 nch = 87 (nch - a).
+  // (Splitting pass C too, with the upper warp parking its packed half in registers until the lower warp has read, was
+  // measured slower: 128 registers no longer hold it and the spills queue behind the prefetch in the load/store unit.)
   const int nlo = (nch * 11 + 16) >> 5;
   const int c_beg = half ? nlo : 0, c_end = half ? nch : nlo;
-  const int c_full = (c_end == nch && (N & 15)) ? c_end - 1 : c_end;      // [c_beg, c_full) full chunks, then the ragged one
+  const int c_full = (c_end == nch && c_end > c_beg && (N & 15)) ? c_end - 1 : c_end;      // [c_beg, c_full) full chunks, then the ragged one
   const uint32_t trow = umma::tmem_addr(tmem, (uint32_t)(q * 32), 0);
   const int rl = q * 32 + lane;                            // row inside the tile
 
-  for (int t = 0; t < ntiles; ++t) {
-    // ---- S = Q_t K^T (rows past the Q tile read the K tile behind it: finite garbage in accumulator rows nobody reads)
-    if (tid == 0) {
-      const uint32_t a0 = umma::smem_u32(Qs) + (uint32_t)t * 16u * 1024u, b0 = umma::smem_u32(Ks);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma::mma_bf16(tmem, umma::smem_desc_kmajor(a0 + ks * 256, 128, 1024), umma::smem_desc_kmajor(b0 + ks * 256, 128, 1024),
-                       idesc_s, ks > 0 ? 1u : 0u);
-      umma::mma_commit(bar);
-      umma::mbar_wait(bar, phase);       // one thread polls; everybody else parks at the barrier below
-    }
-    phase ^= 1u;
-    __syncthreads();
-    umma::tc_fence_after_sync();
-    TOKRED_STAMP(tid == 0, t, 2);
+  for (int it = 0; item < nitems; ++it, item += gridDim.x) {
+    const int buf = it & 1;
+    const int b = item / H, h = item - b * H;
+    const int64_t* ids = p.q_ids ? p.q_ids + (size_t)b * p.ids_stride : nullptr;
+    const float* bias_i = bias_s + buf * Np;
+    const uint32_t v_i = umma::smem_u32(Vs) + (uint32_t)buf * (uint32_t)gk * 1024u;
 
-    const int row = t * 128 + rl;                          // query row
-    const bool active = t * 128 + q * 32 < M;              // uniform over the warp pair of a quarter
-    if (active) {
-      bool row_masked = false;
-      if (MASK && row < M) row_masked = !p.mask[(size_t)b * N + (ids ? clamp_idx(ids[row], N) : row)];
-      // pass A: row maximum over this warp's columns.  Without a bias the roundings and the (positive) scale are
-      // monotone, so the maximum is taken over the raw accumulators and rounded once.
-      float m0 = -INFINITY, m1 = -INFINITY;
-      auto pass_a = [&](uint32_t (&r)[16], int c, bool ragged) {
-        float x[16];
-        if (BIAS) logits16<BIAS, ROUND2, MASK>(r, x, scale, bias_s, c * 16, row_masked);
-        else {
+    for (int t = 0; t < ntiles; ++t) {
+      // ---- S = Q_t K^T (rows past the Q tile read what lies behind it: finite garbage in accumulator rows nobody reads)
+      if (tid == 0) {
+        const uint32_t a0 = umma::smem_u32(Qs) + (uint32_t)t * 16u * 1024u, b0 = umma::smem_u32(Ks);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
-        }
-        if (ragged) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (c * 16 + i >= N) x[i] = -INFINITY;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          m0 = fmaxf(m0, fmaxf(x[i], x[i + 1]));
-          m1 = fmaxf(m1, fmaxf(x[i + 2], x[i + 3]));
-        }
-      };
-      for_chunks(trow, c_beg, c_full, [&](uint32_t (&r)[16], int c) { pass_a(r, c, false); });
-      if (c_full < c_end) {
-        uint32_t r[16];
-        umma::tmem_ld16(trow + c_full * 16, r);
-        ld_wait16(r);
-        pass_a(r, c_full, true);
+        for (int ks = 0; ks < 4; ++ks)
+          umma::mma_bf16(tmem, umma::smem_desc_kmajor(a0 + ks * 256, 128, 1024), umma::smem_desc_kmajor(b0 + ks * 256, 128, 1024),
+                         idesc_s, ks > 0 ? 1u : 0u);
+        umma::mma_commit(bar);
+        umma::mbar_wait(bar, phase);       // one thread polls; everybody else parks at the barrier below
       }
-      float mw = fmaxf(m0, m1);
-      if (!BIAS) {
-        mw = bf16r(mw) * scale;
-        if (ROUND2) mw = bf16r(mw);
-      }
-      red_max[half * 128 + rl] = mw;
-      TOKRED_STAMP(tid == 128, t, 3);
-      TOKRED_STAMP(tid == 0, t, 8);
-      pair_sync(q);
-      const float mx = fmaxf(red_max[rl], red_max[128 + rl]);
-      // pass B: e = exp(x - max) (kept in place as fp32), row sum
-      const float mneg = -mx * kLog2e;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      auto pass_b = [&](uint32_t (&r)[16], int c, bool ragged) {
-        float x[16];
-        exp_args16<BIAS, ROUND2, MASK>(r, x, scale, bias_s, c * 16, row_masked, mneg);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = ex2(x[i]);
-        if (ragged) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) if (c * 16 + i >= N) x[i] = 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) { s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3]; }
-        uint32_t e[16];                  // a separate array: writing into r would keep the values alive for the next wait
-#pragma unroll
-        for (int i = 0; i < 16; ++i) e[i] = __float_as_uint(x[i]);
-        tmem_st16(trow + c * 16, e);
-      };
-      for_chunks(trow, c_beg, c_full, [&](uint32_t (&r)[16], int c) { pass_b(r, c, false); });
-      if (c_full < c_end) {
-        uint32_t r[16];
-        umma::tmem_ld16(trow + c_full * 16, r);
-        ld_wait16(r);
-        pass_b(r, c_full, true);
-      }
-      red_sum[half * 128 + rl] = (s0 + s1) + (s2 + s3);
-      tmem_st_wait();
-      TOKRED_STAMP(tid == 128, t, 4);
-      TOKRED_STAMP(tid == 0, t, 9);
-      pair_sync(q);
-      // pass C (lower warp): p = e / sum -> bf16 pairs in place (column j holds keys 2j, 2j+1; the writes trail the
-      // reads); side outputs in fp32
-      if (!half) {
-        const float inv = 1.0f / (red_sum[rl] + red_sum[128 + rl]);
-        float* cls = (p.cls_row && row == 0) ? p.cls_row + ((size_t)b * H + h) * N : nullptr;
-        for_chunks(trow, 0, nch, [&](uint32_t (&r)[16], int c) {
-          float x[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]) * inv;
-          if (cls) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (c * 16 + i < N) cls[c * 16 + i] = x[i];
-          }
-          if (COLSUM) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = row < M ? x[i] : 0.f;
-            const float cs = colsum16(v, lane);
-            if (!(lane & 1)) colpart[(size_t)(t * 4 + q) * Np + c * 16 + (lane >> 1)] = cs;
-          }
-          tmem_st8(trow + c * 8, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
-                   pack_bf16x2(x[6], x[7]), pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]),
-                   pack_bf16x2(x[14], x[15]));
-        });
-        tmem_st_wait();
-        TOKRED_STAMP(tid == 0, t, 5);
-      }
-    }
-    umma::tc_fence_before_sync();
-    __syncthreads();
-    if (!want_out) continue;             // scores only (uniform): nothing reads the accumulator again
-
-    // ---- O = P V : A from TMEM, B = v tile MN-major (LBO field = stride between 8-token groups, SBO field = 8-channel cores)
-    if (tid == 0) {
+      phase ^= 1u;
+      __syncthreads();
       umma::tc_fence_after_sync();
-      const uint32_t v0 = umma::smem_u32(Vs);
-      for (int ks = 0; ks < nch; ++ks)
-        mma_bf16_ts(tmem + o_col, tmem + ks * 8, umma::smem_desc_kmajor(v0 + ks * 2048, 1024, 128), idesc_o, ks > 0 ? 1u : 0u);
-      umma::mma_commit(bar);
-      umma::mbar_wait(bar, phase);
+      TOKRED_STAMP(tid == 0 && it == 0, t, 2);
+      const int row = t * 128 + rl;                          // query row
+      const bool active = t * 128 + q * 32 < M;              // uniform over the warp pair of a quarter
+      // The last S MMA of this item has completed: q and k are dead, the other v buffer was last read an item ago ->
+      // prefetch the next item.  Issuing 75 KB of cp.async stalls the issuing warp on the load/store queue for about as
+      // long as the copy takes, so the warps of the quarters that hold no query row of this tile (N = 197: rows 128..196
+      // leave quarter 3 idle) do it; only when every quarter is busy do all warps share it.
+      if (t == ntiles - 1 && item + (int)gridDim.x < nitems) {
+        const int aq = min(4, (M - t * 128 + 31) >> 5);      // quarters with query rows in this tile
+        if (aq == 4) issue_loads(item + gridDim.x, buf ^ 1, warp, kThreads / 32);
+        else if (!active) issue_loads(item + gridDim.x, buf ^ 1, (q - aq) * 2 + half, (4 - aq) * 2);
+      }
+      if (active) {
+        bool row_masked = false;
+        if (MASK && row < M) row_masked = !p.mask[(size_t)b * N + (ids ? clamp_idx(ids[row], N) : row)];
+        // pass A: row maximum over this warp's columns.  Without a bias the roundings and the (positive) scale are
+        // monotone, so the maximum is taken over the raw accumulators and rounded once.
+        float m0 = -INFINITY, m1 = -INFINITY;
+        auto pass_a = [&](uint32_t (&r)[16], int c, bool ragged) {
+          float x[16];
+          if (BIAS) logits16<BIAS, ROUND2, MASK>(r, x, scale, bias_i, c * 16, row_masked);
+          else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]);
+          }
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c * 16 + i >= N) x[i] = -INFINITY;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            m0 = fmaxf(m0, fmaxf(x[i], x[i + 1]));
+            m1 = fmaxf(m1, fmaxf(x[i + 2], x[i + 3]));
+          }
+        };
+        for_chunks(trow, c_beg, c_full, [&](uint32_t (&r)[16], int c) { pass_a(r, c, false); });
+        if (c_full < c_end) {
+          uint32_t r[16];
+          umma::tmem_ld16(trow + c_full * 16, r);
+          ld_wait16(r);
+          pass_a(r, c_full, true);
+        }
+        float mw = fmaxf(m0, m1);
+        if (!BIAS) {
+          mw = bf16r(mw) * scale;
+          if (ROUND2) mw = bf16r(mw);
+        }
+        red_max[half * 128 + rl] = mw;
+        TOKRED_STAMP(tid == 128 && it == 0, t, 3);
+        TOKRED_STAMP(tid == 0 && it == 0, t, 8);
+        pair_sync(q);
+        const float mx = fmaxf(red_max[rl], red_max[128 + rl]);
+        // pass B: e = exp(x - max) (kept in place as fp32), row sum
+        const float mneg = -mx * kLog2e;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        auto pass_b = [&](uint32_t (&r)[16], int c, bool ragged) {
+          float x[16];
+          exp_args16<BIAS, ROUND2, MASK>(r, x, scale, bias_i, c * 16, row_masked, mneg);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = ex2(x[i]);
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c * 16 + i >= N) x[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) { s0 += x[i]; s1 += x[i + 1]; s2 += x[i + 2]; s3 += x[i + 3]; }
+          uint32_t e[16];                  // a separate array: writing into r would keep the values alive for the next wait
+#pragma unroll
+          for (int i = 0; i < 16; ++i) e[i] = __float_as_uint(x[i]);
+          tmem_st16(trow + c * 16, e);
+        };
+        for_chunks(trow, c_beg, c_full, [&](uint32_t (&r)[16], int c) { pass_b(r, c, false); });
+        if (c_full < c_end) {
+          uint32_t r[16];
+          umma::tmem_ld16(trow + c_full * 16, r);
+          ld_wait16(r);
+          pass_b(r, c_full, true);
+        }
+        red_sum[half * 128 + rl] = (s0 + s1) + (s2 + s3);
+        tmem_st_wait();
+        TOKRED_STAMP(tid == 128 && it == 0, t, 4);
+        TOKRED_STAMP(tid == 0 && it == 0, t, 9);
+        pair_sync(q);
+        // pass C (lower warp): p = e / sum -> bf16 pairs in place (column j holds keys 2j, 2j+1; the writes trail the
+        // reads); side outputs in fp32
+        if (!half) {
+          const float inv = 1.0f / (red_sum[rl] + red_sum[128 + rl]);
+          float* cls = (p.cls_row && row == 0) ? p.cls_row + ((size_t)b * H + h) * N : nullptr;
+          for_chunks(trow, 0, nch, [&](uint32_t (&r)[16], int c) {
+            float x[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(r[i]) * inv;
+            if (cls) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) if (c * 16 + i < N) cls[c * 16 + i] = x[i];
+            }
+            if (COLSUM) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = row < M ? x[i] : 0.f;
+              const float cs = colsum16(v, lane);
+              if (!(lane & 1)) colpart[(size_t)(t * 4 + q) * Np + c * 16 + (lane >> 1)] = cs;
+            }
+            tmem_st8(trow + c * 8, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
+                     pack_bf16x2(x[6], x[7]), pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]),
+                     pack_bf16x2(x[14], x[15]));
+          });
+          tmem_st_wait();
+          TOKRED_STAMP(tid == 0 && it == 0, t, 5);
+        }
+      }
+      umma::tc_fence_before_sync();
+      __syncthreads();
+      if (!want_out) continue;             // scores only (uniform): nothing reads the accumulator again
+
+      // ---- O = P V : A from TMEM, B = v tile MN-major (LBO field = stride between 8-token groups, SBO field = 8-channel cores)
+      if (tid == 0) {
+        umma::tc_fence_after_sync();
+        for (int ks = 0; ks < nch; ++ks)
+          mma_bf16_ts(tmem + o_col, tmem + ks * 8, umma::smem_desc_kmajor(v_i + ks * 2048, 1024, 128), idesc_o, ks > 0 ? 1u : 0u);
+        umma::mma_commit(bar);
+        umma::mbar_wait(bar, phase);
+      }
+      phase ^= 1u;
+      __syncthreads();
+      umma::tc_fence_after_sync();
+      TOKRED_STAMP(tid == 0 && it == 0, t, 6);
+      if (active) {                                          // whole warp: the TMEM loads are .sync.aligned
+        __nv_bfloat16* dst = p.out + ((size_t)b * M + (row < M ? row : 0)) * C + h * 64 + half * 32;
+        uint32_t ra[16], rb[16];
+        umma::tmem_ld16(trow + o_col + half * 32, ra);
+        umma::tmem_ld16(trow + o_col + half * 32 + 16, rb);
+        ld_wait16(ra);
+        ld_wait16(rb);
+        if (row < M) {
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(pack_bf16x2(__uint_as_float(ra[0]), __uint_as_float(ra[1]))),
+                       "r"(pack_bf16x2(__uint_as_float(ra[2]), __uint_as_float(ra[3]))), "r"(pack_bf16x2(__uint_as_float(ra[4]), __uint_as_float(ra[5]))),
+                       "r"(pack_bf16x2(__uint_as_float(ra[6]), __uint_as_float(ra[7]))), "r"(pack_bf16x2(__uint_as_float(ra[8]), __uint_as_float(ra[9]))),
+                       "r"(pack_bf16x2(__uint_as_float(ra[10]), __uint_as_float(ra[11]))), "r"(pack_bf16x2(__uint_as_float(ra[12]), __uint_as_float(ra[13]))),
+                       "r"(pack_bf16x2(__uint_as_float(ra[14]), __uint_as_float(ra[15])))
+                       : "memory");
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 16), "r"(pack_bf16x2(__uint_as_float(rb[0]), __uint_as_float(rb[1]))),
+                       "r"(pack_bf16x2(__uint_as_float(rb[2]), __uint_as_float(rb[3]))), "r"(pack_bf16x2(__uint_as_float(rb[4]), __uint_as_float(rb[5]))),
+                       "r"(pack_bf16x2(__uint_as_float(rb[6]), __uint_as_float(rb[7]))), "r"(pack_bf16x2(__uint_as_float(rb[8]), __uint_as_float(rb[9]))),
+                       "r"(pack_bf16x2(__uint_as_float(rb[10]), __uint_as_float(rb[11]))), "r"(pack_bf16x2(__uint_as_float(rb[12]), __uint_as_float(rb[13]))),
+                       "r"(pack_bf16x2(__uint_as_float(rb[14]), __uint_as_float(rb[15])))
+                       : "memory");
+        }
+      }
+      umma::tc_fence_before_sync();
+      __syncthreads();
+      TOKRED_STAMP(tid == 0 && it == 0, t, 7);
     }
-    phase ^= 1u;
-    __syncthreads();
-    umma::tc_fence_after_sync();
-    TOKRED_STAMP(tid == 0, t, 6);
-    if (active) {                                          // whole warp: the TMEM loads are .sync.aligned
-      __nv_bfloat16* dst = p.out + ((size_t)b * M + (row < M ? row : 0)) * C + h * 64 + half * 32;
-      uint32_t ra[16], rb[16];
-      umma::tmem_ld16(trow + o_col + half * 32, ra);
-      umma::tmem_ld16(trow + o_col + half * 32 + 16, rb);
-      ld_wait16(ra);
-      ld_wait16(rb);
-      if (row < M) {
-        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(pack_bf16x2(__uint_as_float(ra[0]), __uint_as_float(ra[1]))),
-                     "r"(pack_bf16x2(__uint_as_float(ra[2]), __uint_as_float(ra[3]))), "r"(pack_bf16x2(__uint_as_float(ra[4]), __uint_as_float(ra[5]))),
-                     "r"(pack_bf16x2(__uint_as_float(ra[6]), __uint_as_float(ra[7]))), "r"(pack_bf16x2(__uint_as_float(ra[8]), __uint_as_float(ra[9]))),
-                     "r"(pack_bf16x2(__uint_as_float(ra[10]), __uint_as_float(ra[11]))), "r"(pack_bf16x2(__uint_as_float(ra[12]), __uint_as_float(ra[13]))),
-                     "r"(pack_bf16x2(__uint_as_float(ra[14]), __uint_as_float(ra[15])))
-                     : "memory");
-        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 16), "r"(pack_bf16x2(__uint_as_float(rb[0]), __uint_as_float(rb[1]))),
-                     "r"(pack_bf16x2(__uint_as_float(rb[2]), __uint_as_float(rb[3]))), "r"(pack_bf16x2(__uint_as_float(rb[4]), __uint_as_float(rb[5]))),
-                     "r"(pack_bf16x2(__uint_as_float(rb[6]), __uint_as_float(rb[7]))), "r"(pack_bf16x2(__uint_as_float(rb[8]), __uint_as_float(rb[9]))),
-                     "r"(pack_bf16x2(__uint_as_float(rb[10]), __uint_as_float(rb[11]))), "r"(pack_bf16x2(__uint_as_float(rb[12]), __uint_as_float(rb[13]))),
-                     "r"(pack_bf16x2(__uint_as_float(rb[14]), __uint_as_float(rb[15])))
-                     : "memory");
+    if (COLSUM) {
+      // fixed-order combine of the (tile, quarter) partials: deterministic
+      float* dst = p.colsum + ((size_t)b * H + h) * N;
+      for (int j = tid; j < N; j += kThreads) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s += colpart[(size_t)k * Np + j]; colpart[(size_t)k * Np + j] = 0.f; }
+        dst[j] = s;
       }
     }
+    // the next item's operands (issued during the last tile) have landed
+    cp_async_wait_all();
+    umma::fence_proxy_async_smem();
     umma::tc_fence_before_sync();
     __syncthreads();
-    TOKRED_STAMP(tid == 0, t, 7);
-  }
-  if (COLSUM) {
-    // fixed-order combine of the (tile, quarter) partials: deterministic
-    float* dst = p.colsum + ((size_t)b * H + h) * N;
-    for (int j = tid; j < N; j += kThreads) {
-      float s = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s += colpart[(size_t)k * Np + j];
-      dst[j] = s;
-    }
+    umma::tc_fence_after_sync();
+    TOKRED_STAMP(tid == 0 && it < 8, it, 10);
   }
   if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
 size_t attn_smem_bytes(int N, int M, bool colsum) {
   const int Np = (N + 15) & ~15;
-  const int groups = (M + 7) / 8 + 2 * (Np / 8), mma_rows = ((M + 127) / 128) * 16;
-  return (size_t)(groups > mma_rows ? groups : mma_rows) * 1024 + (size_t)Np * 4 + 2048 + (colsum ? (size_t)8 * Np * 4 : 0) + 64;
+  const int groups = (M + 7) / 8 + 3 * (Np / 8), mma_rows = ((M + 127) / 128) * 16;
+  return (size_t)(groups > mma_rows ? groups : mma_rows) * 1024 + (size_t)2 * Np * 4 + 2048 + (colsum ? (size_t)8 * Np * 4 : 0) + 64;
 }
 
 }  // namespace
@@ -501,11 +530,13 @@ extern "C" int tokred_attention(const void* qkv, int B, int N, int H, int head_d
   const bool r2 = std::frexp(scale, &ex) != 0.5f;          // not a power of two: the scaled logits round to bf16 again
   const bool cs = colsum != nullptr;
   const size_t smem = attn_smem_bytes(N, M, cs);
+  // persistent CTAs, two per SM (108 KB of shared memory and <= 256 TMEM columns each)
+  const int grid = B * H < 2 * kNumSMs ? B * H : 2 * kNumSMs;
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(BIAS, R2, MASK, CS)                                                                  \
   do {                                                                                              \
     if (int e = allow_smem(attention_kernel<BIAS, R2, MASK, CS>, smem, "attention")) return e;     \
-    attention_kernel<BIAS, R2, MASK, CS><<<B * H, kThreads, smem, st>>>(prm);                       \
+    attention_kernel<BIAS, R2, MASK, CS><<<grid, kThreads, smem, st>>>(prm);                       \
   } while (0)
 #define PICK(BIAS, MASK)                                                                            \
   do {                                                                                              \

@@ -10,7 +10,7 @@ B, N, H = 256, int(sys.argv[1]) if len(sys.argv) > 1 else 197, 6
 qkv = torch.randn(B, N, 3 * H * 64, device="cuda").bfloat16()
 for _ in range(3):
     T.attention(qkv, H, 0.125)
-ncta = B * H
+ncta = min(B * H, 2 * 148)
 st = torch.zeros(ncta * 8 * 32, dtype=torch.int64, device="cuda")
 lib.tokred_debug_set_stamps_attention.argtypes = [ctypes.c_void_p]
 assert lib.tokred_debug_set_stamps_attention(st.data_ptr()) == 0
@@ -24,6 +24,10 @@ for tile in range(2):
     rel = (s[:, tile, :10] - t0) / 1.9e3
     rel[s[:, tile, :10] == 0] = float("nan")
     print(f"tile {tile}: mean us since CTA start: " + " | ".join(f"{names[i]} {rel[:, i].nanmean().item():6.2f}" for i in range(10)))
-    for cta in (0, 5, 700, 1500):
+    for cta in (0, 5, 150, 295):
         print(f"   CTA {cta}: " + " ".join(f"{rel[cta, i].item():6.2f}" for i in range(10)))
-print("CTA duration mean %.2f us; first CTA start -> last CTA end %.2f us" % (((s[:, 1, 7] - s[:, 0, 0]) / 1.9e3).mean().item(), (s[:, 1, 7].max() - s[:, 0, 0].min()).item() / 1.9e3))
+ends = (s[:, :8, 10] - t0) / 1.9e3
+ends[s[:, :8, 10] == 0] = float("nan")
+print("item end times (us since CTA start), mean over CTAs:", " ".join(f"{ends[:, i].nanmean().item():6.2f}" for i in range(8)))
+for cta in (0, 5, 150, 295):
+    print(f"   CTA {cta}: " + " ".join(f"{ends[cta, i].item():6.2f}" for i in range(8)))
