@@ -164,7 +164,7 @@ def algorithmic_bytes(name: str, a: tuple) -> float:
         n, r = g["N"], g["r"]
         na = (n + 1) // 2
         re_ = min(r, (n - 1) // 2)
-        return g["B"] * (n * g["D"] * esz(g["metric_dtype"]) + 8 * (na - re_) + 16 * re_)
+        return g["B"] * (n * g["D"] * max(1, g["heads"]) * esz(g["metric_dtype"]) + 8 * (na - re_) + 16 * re_)
     if name == "tokred_tome_merge":
         n, c, r, e = g["N"], g["C"], g["r"], esz(g["x_dtype"])
         na = (n + 1) // 2
@@ -332,6 +332,7 @@ class Runner:
         self.dist, self.world, self.dev = dist, world, dev
         method, size, kr, _, amp = WORKLOADS[wl_key]
         self.method, self.size, self.kr, self.amp, self.batch = method, size, kr, amp, batch
+        torch.backends.cudnn.benchmark = True      # the reference's own evaluation setting (validate.py:32,63)
         torch.manual_seed(0)
         with contextlib.redirect_stdout(io.StringIO()):
             # viz_mode + tokred_device_viz: the per-stage decisions come back as DEVICE tensors (no copy, no sync)

@@ -65,7 +65,10 @@ TOKRED_API int tokred_evit_select_fuse(const void* x, int x_dtype, const void* s
  * models/tome.py:230-277 bipartite_soft_matching (cosine similarity of even vs odd tokens, per-row argmax,
  * descending edge order, CLS protected).  r is clamped to (N - protected)/2 like :252-253; the caller sizes
  * the outputs with tokred_tome_effective_r().
- *   metric [B,N,D] metric_dtype (= k.mean(1), models/tome.py:58)
+ *   metric [B,N,D] metric_dtype (= k.mean(1), models/tome.py:58); or, heads > 1: the per-head keys themselves,
+ *   metric[b,n,h,:] at ((b*N+n)*token_stride + h*D) -- the k slice of the qkv Linear's output (tome.py:33-35) -- and the
+ *   head mean of :58 is taken in-kernel (fp32 sum * 1/heads, rounded to bf16 like ATen's mean); bf16, D = 64,
+ *   score_lowp = 1 only.  heads <= 1 and token_stride = 0: plain dense metric.
  *   NaN metric rows (zero norm) order like ATen: NaN is the largest key, so all index slots are always written.
  *   score_lowp: 0 = fp32 similarity (FFMA); 1 = operands and similarity rounded to bf16 (what CUDA autocast
  *   does) on tcgen05 tensor cores; 3 = same rounding on the FFMA path (cross-check of the tensor-core path)
@@ -74,8 +77,9 @@ TOKRED_API int tokred_evit_select_fuse(const void* x, int x_dtype, const void* s
  *   The distilled output row order of :286-287 is a fixed permutation applied by the caller.
  *   unm_idx [B,a-r] (ascending when class_token), src_idx [B,r], dst_idx [B,r] int64; a = ceil(N/2)      */
 TOKRED_API int tokred_tome_effective_r(int N, int r, int class_token);
-TOKRED_API int tokred_tome_match(const void* metric, int metric_dtype, int B, int N, int D, int r, int class_token,
-                      int score_lowp, int64_t* unm_idx, int64_t* src_idx, int64_t* dst_idx, void* stream);
+TOKRED_API int tokred_tome_match(const void* metric, int metric_dtype, int heads, int64_t token_stride, int B, int N, int D,
+                      int r, int class_token, int score_lowp, int64_t* unm_idx, int64_t* src_idx, int64_t* dst_idx,
+                      void* stream);
 
 /* ---- a4/a5 ToMe merge --------------------------------------------------------------------------------
  * models/tome.py:279-289 (merge closure), :309-323 (merge_wavg), :326-337 + Block_ToMe :91-99 (source map).

@@ -1139,3 +1139,22 @@ def test_attention_rejects_what_it_does_not_cover(T):
         T.attention(torch.zeros(1, 8, 3 * 64, dtype=torch.float32, device=DEV), 1, 0.125)        # not bf16
     with pytest.raises((TokredError, NotImplementedError)):
         T.attention(torch.zeros(1, 8, 3 * 64, dtype=torch.bfloat16), 1, 0.125)                   # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("b,n,h,r", [(256, 197, 6, 59), (64, 138, 6, 41), (32, 97, 12, 29), (8, 68, 3, 20), (4, 198, 6, 60), (3, 11, 2, 4)])
+def test_tome_match_from_qkv_keys(T, b, n, h, r):
+    """f1 for ToMe: the matching kernel takes `metric = k.mean(1)` (models/tome.py:58) straight from the qkv Linear's
+    output.  The in-kernel head mean rounds where ATen's mean rounds, so the three index lists are BIT-IDENTICAL to
+    matching on the materialised torch mean (whose parity with the oracle is test_tome_match_bf16_*)."""
+    qkv = torch.randn(b, n, 3 * h * 64, generator=g(1200 + n)).bfloat16().to(DEV)
+    metric = qkv.view(b, n, 3, h, 64)[:, :, 1].mean(2)
+    assert metric.dtype == torch.bfloat16
+    want = T.tome_match(metric.contiguous(), r, True, True, True)
+    got = T.tome_match_qkv(qkv, h, r, True)
+    for a, w in zip(got, want):
+        assert torch.equal(a, w)
+    # and against the oracle on the same metric: decidable images (bf16 score ties excluded) must match exactly
+    unm_r, src_r, dst_r, _ = O.tome_match(metric.cpu(), r, True, lowp=torch.bfloat16)
+    dec = MG.tome_bf16_decidable(metric.cpu(), r)[0]
+    same = (got[1].cpu() == src_r).all(1) & (got[2].cpu() == dst_r).all(1) & (got[0].cpu() == unm_r).all(1)
+    assert bool(same[dec].all()), f"{int((~same[dec]).sum())} decidable images differ from the oracle"

@@ -173,6 +173,7 @@ tome_match_kernel(const TM* __restrict__ metric, int N, int D, int r, int class_
 // accumulator, and the epilogue reads it with tcgen05.ld 32x32b — thread i owns accumulator row i, which is exactly
 // what the per-row (max, argmax) needs: no similarity matrix in shared memory, no cross-thread reduction.
 constexpr int kTcThreads = 256;
+constexpr int kTc2Threads = 512;
 
 template <typename TM>
 __global__ void __launch_bounds__(kTcThreads)
@@ -307,6 +308,184 @@ tome_match_tc_kernel(const TM* __restrict__ metric, int N, int D, int r, int cla
         for (int q = 0; q < i; ++q) pos += !merged[q];
         unm_idx[(long long)b * n_unm + pos] = i;
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ match, tensor cores, v2
+// bf16 metric with D = 64 (every DeiT), optionally given as the per-head keys themselves: metric[b,n,h,:] at
+// ((b*N + n) * token_stride + h*64) -- the k slice of the qkv Linear's output, so that `metric = k.mean(1)`
+// (models/tome.py:58) costs neither a launch nor an HBM round trip: the head mean is taken here in fp32 and rounded to
+// bf16 exactly where ATen's mean rounds.  Against the first tensor-core kernel: no raw staging copy, 32 contiguous
+// bytes per lane straight from global memory, one conflict-free 16-byte store per K-chunk into the UMMA layout instead
+// of sixty-four 2-byte stores per row (721k shared-memory bank conflicts in the round-1 profile), ballot-based
+// compaction of the unmerged list.
+template <bool HEADS>
+__global__ void __launch_bounds__(kTc2Threads)
+tome_match_tc2_kernel(const __nv_bfloat16* __restrict__ metric, long long token_stride, int heads, int N, int r, int class_token,
+                      int64_t* __restrict__ unm_idx, int64_t* __restrict__ src_idx, int64_t* __restrict__ dst_idx) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int na = (N + 1) / 2, nb = N / 2;
+  const int Np = (nb + 15) & ~15;
+  unsigned char* opA = smem_raw;                               // 128 rows (even tokens), canonical K-major bf16, 128 B per row
+  unsigned char* opB = opA + 16 * 1024;                        // Np rows (odd tokens)
+  float* node_max = reinterpret_cast<float*>(opB + (Np / 8) * 1024);
+  int* node_idx = reinterpret_cast<int*>(node_max + 128);
+  int* wcount = node_idx + 128;                                // [4]
+  unsigned char* merged = reinterpret_cast<unsigned char*>(wcount + 4);   // [128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(merged + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __nv_bfloat16* mb = metric + (long long)b * N * token_stride;
+  const uint32_t ncols = umma::tmem_cols_pow2((uint32_t)Np);
+  const bool dist_token = (class_token & 2) != 0;      // protection flags, see tome_match_kernel
+  class_token &= 1;
+
+  if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
+  if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_mbar_init(); }
+
+  // m / ||m|| in fp32, rounded to bf16 (what the autocast matmul does to its operands), into the UMMA layout.
+  // job = 8 rows of one operand; lane -> row = lane % 8, K-chunks 2*(lane/8), 2*(lane/8)+1 (16 elements).
+  {
+    const int r8 = lane & 7, cp = lane >> 3;
+    const float inv_h = 1.0f / (float)heads;
+    const int njobs = 16 + Np / 8;
+    for (int j = warp; j < njobs; j += kTc2Threads / 32) {
+      const bool isA = j < 16;
+      const int g = isA ? j : j - 16;
+      const int i = g * 8 + r8;
+      const bool live = i < (isA ? na : nb);
+      float v[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = 0.f;
+      if (live) {
+        const __nv_bfloat16* row = mb + (long long)(2 * i + (isA ? 0 : 1)) * token_stride + cp * 16;
+        if (HEADS) {
+          for (int h0 = 0; h0 < heads; h0 += 6) {      // six heads = twelve independent 16-byte loads in flight per lane
+            int4 a[6], c[6];
+#pragma unroll
+            for (int u = 0; u < 6; ++u)
+              if (h0 + u < heads) { a[u] = ld_stream16(row + (h0 + u) * 64); c[u] = ld_stream16(row + (h0 + u) * 64 + 8); }
+#pragma unroll
+            for (int u = 0; u < 6; ++u)
+              if (h0 + u < heads) {
+                const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a[u]);
+                const __nv_bfloat16* pc = reinterpret_cast<const __nv_bfloat16*>(&c[u]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { v[e] += __bfloat162float(pa[e]); v[8 + e] += __bfloat162float(pc[e]); }
+              }
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = bf16_round(v[e] * inv_h);        // ATen mean: fp32 sum * (1/H), one rounding
+        } else {
+          const int4 a = ld_stream16(row), c = ld_stream16(row + 8);
+          const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a);
+          const __nv_bfloat16* pc = reinterpret_cast<const __nv_bfloat16*>(&c);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { v[e] = __bfloat162float(pa[e]); v[8 + e] = __bfloat162float(pc[e]); }
+        }
+      }
+      float ss = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) ss = fmaf(v[e], v[e], ss);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+      const float nrm = sqrtf(ss);
+      __nv_bfloat162 o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        o[e] = live ? __floats2bfloat162_rn(v[2 * e] / nrm, v[2 * e + 1] / nrm) : __floats2bfloat162_rn(0.f, 0.f);
+      unsigned char* dst = (isA ? opA : opB) + (size_t)g * 1024 + r8 * 16 + cp * 256;
+      *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(&o[0]);
+      *reinterpret_cast<int4*>(dst + 128) = *reinterpret_cast<const int4*>(&o[4]);
+    }
+  }
+  umma::fence_proxy_async_smem();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (tid == 0) {
+    const uint32_t idesc = umma::instr_desc(umma::FMT_BF16, 128, (uint32_t)Np);
+    const uint32_t a0 = umma::smem_u32(opA), b0 = umma::smem_u32(opB);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+      umma::mma_bf16(tmem_base, umma::smem_desc_kmajor(a0 + ks * 256, 128, 1024), umma::smem_desc_kmajor(b0 + ks * 256, 128, 1024),
+                     idesc, ks > 0 ? 1u : 0u);
+    umma::mma_commit(bar);
+    umma::mbar_wait(bar, 0);
+  }
+  __syncthreads();
+  umma::tc_fence_after_sync();
+
+  // per-row (max, argmax) straight from TMEM: lane quarter q = warp % 4 holds rows 32q..32q+31; warps q and q+4
+  // split the columns (a warp may only touch its own lane quarter).  Lowest column wins ties; CLS row protected.
+  {
+    const int i = (warp & 3) * 32 + lane;
+    const int half = ((Np / 16 + 1) / 2) * 16;
+    const int cbeg = warp < 4 ? 0 : half, cend = warp < 4 ? half : (warp < 8 ? Np : 0);     // warps 8.. idle here
+    float best = -CUDART_INF_F;
+    int bj = 0x7fffffff;
+    for (int c0 = cbeg; c0 < cend; c0 += 16) {
+      uint32_t v[16];
+      umma::tmem_ld16(umma::tmem_addr(tmem_base, (uint32_t)((warp & 3) * 32), (uint32_t)c0), v);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float sc = (dist_token && c0 + j == 0) ? -CUDART_INF_F : bf16_round(__uint_as_float(v[j]));
+        if (c0 + j < nb && (nan_gt(sc, best) || bj == 0x7fffffff)) { best = sc; bj = c0 + j; }
+      }
+    }
+    if (warp >= 4 && warp < 8) { node_max[i] = best; node_idx[i] = bj; }
+    __syncthreads();
+    if (warp < 4) {
+      const float ob = node_max[i];
+      const int oj = node_idx[i];
+      if (oj != 0x7fffffff && (nan_gt(ob, best) || bj == 0x7fffffff)) { best = ob; bj = oj; }   // ties keep the lower column
+      if (bj == 0x7fffffff) bj = 0;
+      if (class_token && i == 0) { best = -CUDART_INF_F; bj = 0; }
+    }
+    __syncthreads();
+    if (warp < 4) { node_max[i] = best; node_idx[i] = bj; }
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base, ncols);
+
+  // edge order: four lanes per even token split the rank count (all 512 threads busy)
+  const int n_unm = na - r;
+  {
+    const int i = tid >> 2, part = tid & 3;
+    int rk = 0;
+    if (i < na) rk = rank_desc_range(node_max, na * part / 4, na * (part + 1) / 4, i);
+    rk += __shfl_xor_sync(0xffffffffu, rk, 1);
+    rk += __shfl_xor_sync(0xffffffffu, rk, 2);
+    if (i < na && part == 0) {
+      merged[i] = rk < r;
+      if (rk < r) {
+        src_idx[(long long)b * r + rk] = i;
+        dst_idx[(long long)b * r + rk] = node_idx[i];
+      } else if (!class_token) {
+        unm_idx[(long long)b * n_unm + (rk - r)] = i;
+      }
+    }
+  }
+  if (class_token) {          // unmerged even tokens in ascending order (models/tome.py:272): ballot compaction
+    __syncthreads();
+    bool keep = false;
+    unsigned bal = 0;
+    if (warp < 4) {
+      keep = tid < na && !merged[tid];
+      bal = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) wcount[warp] = __popc(bal);
+    }
+    __syncthreads();
+    if (warp < 4 && keep) {
+      int pos = __popc(bal & ((1u << lane) - 1u));
+      for (int w = 0; w < warp; ++w) pos += wcount[w];
+      unm_idx[(long long)b * n_unm + pos] = tid;
     }
   }
 }
@@ -484,8 +663,9 @@ extern "C" int tokred_tome_effective_r(int N, int r, int class_token) {
   return e > 0 ? e : 0;
 }
 
-extern "C" int tokred_tome_match(const void* metric, int metric_dtype, int B, int N, int D, int r, int class_token,
-                                 int score_lowp, int64_t* unm_idx, int64_t* src_idx, int64_t* dst_idx, void* stream) {
+extern "C" int tokred_tome_match(const void* metric, int metric_dtype, int heads, int64_t token_stride, int B, int N, int D, int r,
+                                 int class_token, int score_lowp, int64_t* unm_idx, int64_t* src_idx, int64_t* dst_idx,
+                                 void* stream) {
   const char* what = "tokred_tome_match";
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(metric && unm_idx && src_idx && dst_idx, "%s: null tensor", what);
@@ -496,8 +676,30 @@ extern "C" int tokred_tome_match(const void* metric, int metric_dtype, int B, in
   if (B == 0) return TOKRED_OK;
   const int na = (N + 1) / 2, nb = N / 2;
   cudaStream_t st = (cudaStream_t)stream;
+  if (heads < 1) heads = 1;
+  if (token_stride <= 0) token_stride = (int64_t)heads * D;
+  TOKRED_REQUIRE(token_stride >= (int64_t)heads * D, "%s: token_stride %lld < heads*D", what, (long long)token_stride);
   // tensor-core path: bf16-rounded similarity (autocast), one 128-row M tile, N <= 256 columns
   const int Dp = (D + 15) & ~15, Np = (nb + 15) & ~15;
+  if (score_lowp == 1 && metric_dtype == TOKRED_BF16 && D == 64 && na <= 128 && Np <= 256 && aligned16(metric) &&
+      token_stride % 8 == 0) {
+    const size_t smem2 = (size_t)(16 + Np / 8) * 1024 + 128 * 4 + 128 * 4 + 16 + 128 + 16;
+    if (heads > 1) {
+      if (int e = allow_smem(tome_match_tc2_kernel<true>, smem2, what)) return e;
+      tome_match_tc2_kernel<true><<<B, kTc2Threads, smem2, st>>>((const __nv_bfloat16*)metric, token_stride, heads, N, re,
+                                                                class_token, unm_idx, src_idx, dst_idx);
+    } else {
+      if (int e = allow_smem(tome_match_tc2_kernel<false>, smem2, what)) return e;
+      tome_match_tc2_kernel<false><<<B, kTc2Threads, smem2, st>>>((const __nv_bfloat16*)metric, token_stride, 1, N, re,
+                                                                 class_token, unm_idx, src_idx, dst_idx);
+    }
+    return finish_launch(what);
+  }
+  if (heads != 1 || token_stride != D) {
+    set_error("%s: per-head / strided metric (heads=%d, token_stride=%lld) needs the bf16 tensor-core path (bf16, D=64, score_lowp=1)",
+              what, heads, (long long)token_stride);
+    return TOKRED_ERR_UNSUPPORTED;
+  }
   const size_t tc_smem = (size_t)(16 + Np / 8) * (Dp / 8) * 128 + (((size_t)N * D * dtype_size(metric_dtype) + 15) & ~(size_t)15) +
                          128 * 4 + 128 * 4 + 128 + 16;
   if (score_lowp && (score_lowp & 2) == 0 && na <= 128 && Np <= 256 && tc_smem <= 200 * 1024) {

@@ -301,18 +301,32 @@ def _reduced_cluster_idx(source: Tensor, cls_token: bool) -> Tensor:
     return (rci - 2)[:, 1:] if cls_token else rci - 1
 
 
+class KeyMean:
+    """``k.mean(1)`` (models/tome.py:58) not yet taken: the qkv Linear's output and the head count.  ops.tome_match_qkv
+    consumes it in place (head mean in-kernel); ``tensor()`` materialises the reference's [B,N,64] metric."""
+
+    def __init__(self, qkv: Tensor, num_heads: int):
+        self.qkv, self.num_heads = qkv, num_heads
+
+    def tensor(self) -> Tensor:
+        b, n, c3 = self.qkv.shape
+        return self.qkv.view(b, n, 3, self.num_heads, c3 // (3 * self.num_heads))[:, :, 1].mean(2)
+
+
 class Attention_ToMe(_AttentionBase):
     """models/tome.py:29-59.  forward(x, size) -> (x, metric = k.mean(1))."""
 
     need_metric = True      # Block_ToMe switches the key mean off in blocks that do not merge (r == 0)
+    lazy_metric = False     # Block_ToMe: hand over the keys themselves (KeyMean) -- the match kernel takes the head mean
 
     def forward(self, x, size=None):
         if self._fused(x):
-            b, n, c = x.shape
             bias = None if size is None else size.log()[..., 0]               # proportional attention, :48-49
             x, _, _, qkv = self._attend_fused(x, key_bias=bias)
-            metric = qkv.view(b, n, 3, self.num_heads, c // self.num_heads)[:, :, 1].mean(2) if self.need_metric else None
-            return x, metric                                                   # = k.mean(1), :58
+            if not self.need_metric:
+                return x, None
+            km = KeyMean(qkv, self.num_heads)
+            return x, (km if self.lazy_metric else km.tensor())               # = k.mean(1), :58
         q, k, v = self._qkv(x)
         attn = (q @ k.transpose(-2, -1)) * self.scale
         if size is not None:
@@ -336,6 +350,7 @@ class Block_ToMe(nn.Module):
         self.cls_token = cls_token
         self.dist_token = dist_token
         self.attn.need_metric = r > 0
+        self.attn.lazy_metric = True
 
     def forward(self, x, attn_size=None):
         x_attn, metric = self.attn(self.norm1(x), attn_size)
@@ -344,7 +359,16 @@ class Block_ToMe(nn.Module):
         if self.r > 0:
             _train_guard(self)
             re = ops.tome_effective_r(x.shape[1], self.r, self.cls_token, self.dist_token)
-            if re > 0 and self.cls_token and not self.dist_token:
+            if re > 0 and self.cls_token and not self.dist_token and isinstance(metric, KeyMean):
+                # keys straight from the qkv output: head mean + matching in ONE launch, no [B,N,64] metric tensor
+                unm, src, dst = ops.tome_match_qkv(metric.qkv, metric.num_heads, self.r, True)
+                x, attn_size, reduced_cluster_idx = ops.tome_merge(x, attn_size, unm, src, dst, True, True)
+                metric = None
+            elif isinstance(metric, KeyMean):
+                metric = metric.tensor()
+            if metric is None:
+                pass
+            elif re > 0 and self.cls_token and not self.dist_token:
                 lowp = _lowp() or metric.dtype in (torch.bfloat16, torch.float16)
                 unm, src, dst = ops.tome_match(_f16_to_bf16(metric), self.r, True, lowp, True)
                 # merged tokens, new sizes and the source map from ONE launch (the reference pushes a [B,t,t]

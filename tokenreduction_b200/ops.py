@@ -18,7 +18,7 @@ from ._lib import BF16, F32, TokredError
 
 __all__ = [
     "topk_gather", "topk_gather_attn", "evit_select_fuse", "evit_select_fuse_attn", "tome_effective_r", "tome_match",
-    "tome_merge", "pairwise_dist", "dpcknn_cluster", "dpcknn_merge", "attn_colsum", "kmedoids_fit", "sinkhorn_merge", "patchmerger",
+    "tome_match_qkv", "tome_merge", "pairwise_dist", "dpcknn_cluster", "dpcknn_merge", "attn_colsum", "kmedoids_fit", "sinkhorn_merge", "patchmerger",
     "sit_merge", "ats_sample", "gather_rows", "dyvit_pool_concat", "attention", "attention_supported",
 ]
 
@@ -222,9 +222,39 @@ def _tome_match(metric: Tensor, r: int, class_token: bool, lowp: bool, tensor_co
     src = torch.empty((b, re), dtype=torch.int64, device=metric.device)
     dst = torch.empty((b, re), dtype=torch.int64, device=metric.device)
     mode = (1 if tensor_cores else 3) if lowp else 0
-    _lib.call("tokred_tome_match", _ptr(metric), _dt(metric), b, n, d, r, int(class_token) | (2 if distill_token else 0),
+    _lib.call("tokred_tome_match", _ptr(metric), _dt(metric), 1, 0, b, n, d, r, int(class_token) | (2 if distill_token else 0),
               mode, _ptr(unm), _ptr(src), _ptr(dst), _stream())
     return unm, src, dst
+
+
+@torch.library.custom_op("tokred::tome_match_qkv", mutates_args=(), device_types="cuda")
+def _tome_match_qkv(qkv: Tensor, num_heads: int, r: int, class_token: bool, distill_token: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("tome_match_qkv", qkv)
+    if qkv.dim() != 3 or qkv.dtype != torch.bfloat16 or qkv.shape[2] != 3 * 64 * num_heads:
+        raise TokredError(f"tome_match_qkv: qkv {tuple(qkv.shape)} {qkv.dtype}; expected bf16 [B,N,3*H*64]")
+    b, n, c3 = qkv.shape
+    c = c3 // 3
+    re = tome_effective_r(n, r, class_token, distill_token)
+    if re <= 0:
+        raise TokredError(f"tome_match_qkv: effective r = {re}; nothing to merge (caller must skip, models/tome.py:255)")
+    qkv = _c(qkv)
+    na = (n + 1) // 2
+    unm = torch.empty((b, na - re), dtype=torch.int64, device=qkv.device)
+    src = torch.empty((b, re), dtype=torch.int64, device=qkv.device)
+    dst = torch.empty((b, re), dtype=torch.int64, device=qkv.device)
+    # the k slice of token 0 starts C elements into the row; consecutive tokens are 3C apart
+    _lib.call("tokred_tome_match", qkv.data_ptr() + 2 * c, BF16, num_heads, c3, b, n, 64, r,
+              int(class_token) | (2 if distill_token else 0), 1, _ptr(unm), _ptr(src), _ptr(dst), _stream())
+    return unm, src, dst
+
+
+@_tome_match_qkv.register_fake
+def _(qkv, num_heads, r, class_token, distill_token=False):
+    b, n, _ = qkv.shape
+    re = tome_effective_r(n, r, class_token, distill_token)
+    na = (n + 1) // 2
+    mk = lambda m: qkv.new_empty((b, m), dtype=torch.int64)
+    return mk(na - re), mk(re), mk(re)
 
 
 @_tome_match.register_fake
@@ -271,6 +301,13 @@ def tome_match(metric: Tensor, r: int, class_token: bool = True, lowp: bool = Fa
     lowp=True reproduces the bf16 autocast matmul (on tcgen05 tensor cores; tensor_cores=False keeps the same
     rounding on the FFMA path, used as a cross-check).  distill_token protects odd token 0 as a destination (:265-266)."""
     return torch.ops.tokred.tome_match(_up(metric)[0], r, class_token, lowp, tensor_cores, distill_token)
+
+
+def tome_match_qkv(qkv: Tensor, num_heads: int, r: int, class_token: bool = True, distill_token: bool = False):
+    """bipartite matching on ``metric = k.mean(1)`` (models/tome.py:58, :258-277) taken straight from the qkv Linear's
+    bf16 output [B,N,3C]: the head mean is computed in-kernel (fp32 sum * 1/H, rounded to bf16 like ATen's mean), so the
+    metric tensor is never materialised.  bf16-autocast semantics (= tome_match(..., lowp=True))."""
+    return torch.ops.tokred.tome_match_qkv(qkv, num_heads, r, class_token, distill_token)
 
 
 def tome_merge(x: Tensor, size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor, want_map: bool = True,

@@ -71,6 +71,10 @@ def cases():
             m, x, size = rnd(b, n, 64, dtype=torch.bfloat16), rnd(b, n, 384), torch.ones(b, n, 1, device=DEV)
             unm, src, dst = T.tome_match(m, r, True, True)
             return lambda: T.tome_merge(x, size, unm, src, dst, True, True)
+        def mk_match_qkv(b=b, n=n, r=r):
+            qkv = rnd(b, n, 3 * 384, dtype=torch.bfloat16)
+            return lambda: T.tome_match_qkv(qkv, 6, r, True)
+        add(f"tome_match S B={b} N={n} r={r} from qkv keys (head mean in-kernel) tcgen05", mk_match_qkv)
         add(f"tome_match S B={b} N={n} r={r} lowp tcgen05", lambda f=mk_match: f("tc"))
         add(f"tome_match S B={b} N={n} r={r} lowp ffma", lambda f=mk_match: f("ffma"))
         add(f"tome_match S B={b} N={n} r={r} fp32", lambda f=mk_match: f("fp32"))
