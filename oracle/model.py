@@ -254,3 +254,52 @@ def forward(method: str, sd: Dict[str, Tensor], images: Tensor, cfg: Cfg, amp: b
 def cfg_for(size: str, **kw) -> Cfg:
     dims = {"tiny": (192, 3), "small": (384, 6), "base": (768, 12)}[size]
     return Cfg(embed_dim=dims[0], num_heads=dims[1], **kw)
+
+
+# ------------------------------------------------------------------------------------------------ f4: training paths
+def softmax_with_policy(attn: Tensor, policy: Tensor, eps: float = 1e-6) -> Tensor:
+    """models/dyvit.py:39-51."""
+    b, n, _ = policy.shape
+    pol = policy.reshape(b, 1, 1, n)
+    eye = torch.eye(n, dtype=pol.dtype, device=pol.device).view(1, 1, n, n)
+    pol = pol + (1.0 - pol) * eye
+    mx = attn.max(dim=-1, keepdim=True)[0]
+    a = (attn - mx).to(torch.float32).exp() * pol.to(torch.float32)
+    a = (a + eps / n) / (a.sum(dim=-1, keepdim=True) + eps)
+    return a.type_as(mx)
+
+
+def dyvit_train_forward(sd: Dict[str, Tensor], images: Tensor, cfg: Cfg):
+    """DynamicViT training forward, models/dyvit.py:205-229 + :251-261 (dyvit_distillation=False): differentiable with
+    respect to every tensor in ``sd`` that requires grad.  Returns (logits, [hard keep decisions per stage])."""
+    heads, loc = cfg.num_heads, list(cfg.reduction_loc)
+    x = _embed(sd, images, cfg)
+    b = x.shape[0]
+    n0 = cfg.num_patches
+    prev = torch.ones(b, n0, 1, dtype=x.dtype, device=x.device)
+    policy = torch.ones(b, n0 + 1, 1, dtype=x.dtype, device=x.device)
+    out_pred = []
+
+    def block(x, i, policy):
+        q, k, v = _qkv(_ln(x, sd, f"blocks.{i}.norm1"), sd, i, heads)
+        dots = (q @ k.transpose(-2, -1)) * ((x.shape[-1] // heads) ** -0.5)
+        attn = softmax_with_policy(dots, policy)
+        return _mlp(x + _proj(attn, v, sd, i), sd, i)
+
+    for i in range(cfg.depth):
+        if i in loc:
+            j = loc.index(i)
+            pre = f"score_predictor.{j}"
+            h = F.gelu(_lin(_ln(x[:, 1:], sd, pre + ".in_conv.0", 1e-5), sd, pre + ".in_conv.1"))
+            feat = O.dyvit_pool_concat(h, prev)
+            h = F.gelu(_lin(feat, sd, pre + ".out_conv.0"))
+            h = F.gelu(_lin(h, sd, pre + ".out_conv.2"))
+            score = F.log_softmax(_lin(h, sd, pre + ".out_conv.4"), dim=-1).reshape(b, -1, 2)
+            hard = F.gumbel_softmax(score, hard=True)[:, :, 0:1] * prev                 # :216
+            out_pred.append(hard.reshape(b, n0))
+            policy = torch.cat([torch.ones(b, 1, 1, dtype=hard.dtype, device=hard.device), hard], dim=1)
+            x = block(x, i, policy)
+            prev = hard
+        else:
+            x = block(x, i, policy)
+    return _head(x, sd), out_pred

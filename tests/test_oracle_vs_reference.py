@@ -220,3 +220,36 @@ def test_model_tiny_vs_reference(ref, name):
     torch.manual_seed(5)
     y = OM.forward(name, sd, x, OM.cfg_for("tiny", keep_rate=[_KR[name]]))
     assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-5), float((y - y_ref).abs().max())
+
+
+def test_dyvit_training_path_vs_reference(ref):
+    """f4 pin: oracle.model.dyvit_train_forward == the UNMODIFIED reference model in train() mode (gumbel keep decisions,
+    softmax_with_policy, models/dyvit.py:205-229) -- logits, per-stage hard decisions and parameter gradients, with the
+    same generator state on both sides so that F.gumbel_softmax draws the same noise."""
+    from timm.models import create_model
+    args = argparse.Namespace(keep_rate=[0.5], reduction_loc=[3, 6, 9], distillation_type="none", k_neighbors=5,
+                              cluster_iters=3, sinkhorn_eps=1.0, equal_weight=False, dyvit_distill=False)
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = create_model("dyvit_tiny_patch16_224", pretrained=False, num_classes=16, drop_rate=0.0,
+                             drop_path_rate=0.0, drop_block_rate=None, img_size=224, args=args).train()
+    with torch.no_grad():          # spread the predictor so that keep / drop decisions are not all ties
+        for n_, p_ in model.named_parameters():
+            if n_.startswith("score_predictor") and p_.dim() >= 2:
+                p_.mul_(4.0)
+    x = torch.randn(2, 3, 224, 224, generator=g(78))
+    names = ["score_predictor.0.in_conv.1.weight", "score_predictor.2.out_conv.4.weight", "blocks.4.attn.qkv.weight",
+             "blocks.0.mlp.fc1.weight", "patch_embed.proj.weight"]
+    torch.manual_seed(6)
+    y_ref, dec_ref = model(x)
+    (y_ref.square().sum() + sum(d.sum() for d in dec_ref)).backward()
+    g_ref = {n: dict(model.named_parameters())[n].grad.clone() for n in names}
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    torch.manual_seed(6)
+    y, dec = OM.dyvit_train_forward(sd, x, OM.cfg_for("tiny", keep_rate=[0.5]))
+    (y.square().sum() + sum(d.sum() for d in dec)).backward()
+    assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-5), float((y - y_ref).abs().max())
+    for a, b_ in zip(dec, dec_ref):
+        assert torch.equal(a, b_)
+    for n in names:
+        assert torch.allclose(sd[n].grad, g_ref[n], rtol=1e-3, atol=1e-6), (n, float((sd[n].grad - g_ref[n]).abs().max()))

@@ -502,7 +502,8 @@ class ATSVisionTransformer(_ReducedViT):
 
 # =============================================================================================== DynamicViT
 class DynamicVisionTransformer(_ReducedViT):
-    """models/dyvit.py:122-268 — inference (eval) path; the gumbel/policy training path is out of scope."""
+    """models/dyvit.py:122-268.  eval: keep top-k tokens (one select+gather launch per stage); training: gumbel-softmax
+    keep decisions as a policy mask through softmax_with_policy (:205-229), differentiable end to end."""
 
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12,
                  num_heads=12, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, representation_size=None, distilled=False,
@@ -538,10 +539,38 @@ class DynamicVisionTransformer(_ReducedViT):
     def get_reduction_count(self):
         return self.pruning_loc
 
+    def _forward_train(self, x):
+        """models/dyvit.py:205-229,251-261: nothing is removed; the hard gumbel decisions mask the attention."""
+        import torch.nn.functional as F
+        b = x.shape[0]
+        x = self.embed(x)
+        p_count = 0
+        out_pred_prob = []
+        init_n = self.num_patches
+        prev_decision = torch.ones(b, init_n, 1, dtype=x.dtype, device=x.device)
+        policy = torch.ones(b, init_n + 1, 1, dtype=x.dtype, device=x.device)
+        for i, blk in enumerate(self.blocks):
+            if i in self.pruning_loc:
+                pred_score = self.score_predictor[p_count](x[:, 1:], prev_decision).reshape(b, -1, 2)
+                hard_keep_decision = F.gumbel_softmax(pred_score, hard=True)[:, :, 0:1] * prev_decision
+                out_pred_prob.append(hard_keep_decision.reshape(b, init_n))
+                cls_policy = torch.ones(b, 1, 1, dtype=hard_keep_decision.dtype, device=hard_keep_decision.device)
+                policy = torch.cat([cls_policy, hard_keep_decision], dim=1)
+                x = blk(x, policy=policy)
+                prev_decision = hard_keep_decision
+                p_count += 1
+            else:
+                x = blk(x, policy)
+        x = self.norm(x)
+        features = x[:, 1:]
+        x = self.head(self.pre_logits(x[:, 0]))
+        if self.dyvit_distillation:
+            return x, features, prev_decision.detach(), out_pred_prob
+        return x, out_pred_prob
+
     def forward(self, x):
         if self.training:
-            raise NotImplementedError("DynamicVisionTransformer: only the eval keep path is accelerated "
-                                      "(models/dyvit.py:230-238); call .eval()")
+            return self._forward_train(x)
         b = x.shape[0]
         x = self.embed(x)
         p_count = 0

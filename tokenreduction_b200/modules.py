@@ -49,10 +49,12 @@ def _amp_out(t: Tensor) -> Tensor:
     return t
 
 
-def _train_guard(mod: nn.Module) -> None:
-    if mod.training and torch.is_grad_enabled():
+def _train_guard(mod: nn.Module, differentiable: bool = False) -> None:
+    """Top-K / EViT / ToMe / DynamicViT ops carry autograd formulas (ops.py) and may sit in a training
+    graph; the cluster layers, soft merges and ATS are inference-only and refuse."""
+    if mod.training and torch.is_grad_enabled() and not differentiable:
         raise NotImplementedError(
-            f"{type(mod).__name__}: the tokred reduction kernels are inference-only (no autograd formula); "
+            f"{type(mod).__name__}: this tokred reduction kernel is inference-only (no autograd formula); "
             "call .eval() and run under torch.no_grad()")
 
 
@@ -161,7 +163,7 @@ class Block_TopK(nn.Module):
         x = x + self.drop_path(tmp)
         idx = None
         if cls_attn is not None:
-            _train_guard(self)
+            _train_guard(self, True)
             x, idx = ops.topk_gather(x, cls_attn, left_tokens)          # select + gather + cat in one launch
         x = x + self.drop_path(self.mlp(self.norm2(x)))
         return x, x.shape[1] - 1, idx
@@ -198,7 +200,7 @@ class Block_EVIT(nn.Module):
         x = x + self.drop_path(tmp)
         idx = compl = None
         if cls_attn is not None:
-            _train_guard(self)
+            _train_guard(self, True)
             x, idx, compl = ops.evit_select_fuse(x, cls_attn, left_tokens)
         x = x + self.drop_path(self.mlp(self.norm2(x)))
         return x, x.shape[1] - 1, idx, compl
@@ -241,7 +243,8 @@ def bipartite_soft_matching(metric: Tensor, r: int, class_token: bool = False,
     if r <= 0:
         return do_nothing, do_nothing
     lowp = _lowp() or metric.dtype in (torch.bfloat16, torch.float16)
-    unm_idx, src_idx, dst_idx = ops.tome_match(_f16_to_bf16(metric), r, class_token, lowp, True, distill_token)
+    with torch.no_grad():                                                 # models/tome.py:258
+        unm_idx, src_idx, dst_idx = ops.tome_match(_f16_to_bf16(metric), r, class_token, lowp, True, distill_token)
     merge = _ToMeMerge(unm_idx, src_idx, dst_idx, t, class_token, distill_token)
 
     def unmerge(x: Tensor) -> Tensor:
@@ -357,7 +360,7 @@ class Block_ToMe(nn.Module):
         x = x + self.drop_path(x_attn)
         reduced_cluster_idx = None
         if self.r > 0:
-            _train_guard(self)
+            _train_guard(self, True)
             re = ops.tome_effective_r(x.shape[1], self.r, self.cls_token, self.dist_token)
             if re > 0 and self.cls_token and not self.dist_token and isinstance(metric, KeyMean):
                 # keys straight from the qkv output: head mean + matching in ONE launch, no [B,N,64] metric tensor
@@ -370,7 +373,8 @@ class Block_ToMe(nn.Module):
                 pass
             elif re > 0 and self.cls_token and not self.dist_token:
                 lowp = _lowp() or metric.dtype in (torch.bfloat16, torch.float16)
-                unm, src, dst = ops.tome_match(_f16_to_bf16(metric), self.r, True, lowp, True)
+                with torch.no_grad():                                     # models/tome.py:258
+                    unm, src, dst = ops.tome_match(_f16_to_bf16(metric), self.r, True, lowp, True)
                 # merged tokens, new sizes and the source map from ONE launch (the reference pushes a [B,t,t]
                 # identity through the merge to get the map, models/tome.py:91-99)
                 x, attn_size, reduced_cluster_idx = ops.tome_merge(x, attn_size, unm, src, dst, True, True)
@@ -683,13 +687,25 @@ class Policy_Attention(_AttentionBase):
         if qk_scale is not None:
             self.scale = qk_scale
 
+    @staticmethod
+    def softmax_with_policy(attn, policy, eps=1e-6):
+        """models/dyvit.py:39-51 (training): dropped keys are masked out of every row but their own diagonal entry."""
+        b, n, _ = policy.size()
+        attn_policy = policy.reshape(b, 1, 1, n)
+        eye = torch.eye(n, dtype=attn_policy.dtype, device=attn_policy.device).view(1, 1, n, n)
+        attn_policy = attn_policy + (1.0 - attn_policy) * eye
+        max_att = torch.max(attn, dim=-1, keepdim=True)[0]
+        attn = attn - max_att
+        attn = attn.to(torch.float32).exp_() * attn_policy.to(torch.float32)
+        attn = (attn + eps / n) / (attn.sum(dim=-1, keepdim=True) + eps)
+        return attn.type_as(max_att)
+
     def forward(self, x, policy=None):
-        if policy is not None:
-            raise NotImplementedError("Policy_Attention: softmax_with_policy is the training path (out of scope)")
-        if self._fused(x):
+        if policy is None and self._fused(x):
             return self._attend_fused(x)[0]
         q, k, v = self._qkv(x)
-        attn = ((q @ k.transpose(-2, -1)) * self.scale).softmax(dim=-1)
+        attn = (q @ k.transpose(-2, -1)) * self.scale
+        attn = attn.softmax(dim=-1) if policy is None else self.softmax_with_policy(attn, policy)
         return self._out(attn, v)
 
 

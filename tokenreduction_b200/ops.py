@@ -738,3 +738,124 @@ def attention(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Tens
     [B,M] selects the query rows to compute (the ATS row gather, models/ats.py:84-87)."""
     out, cls, colsum = torch.ops.tokred.attention(qkv, num_heads, scale, key_bias, mask, q_ids, want_out, want_cls, want_colsum)
     return (out if want_out else None), (cls if want_cls else None), (colsum if want_colsum else None)
+
+
+# ----------------------------------------------------------------------------------------------- f4: autograd formulas
+# SURVEY §8f row 4.  The reference fine-tunes its reduced models with the reduction operators inside the autograd graph
+# (train.py; the discrete selections themselves carry no gradient: topk / argsort / argmax indices).  The forward of
+# every op below stays the tokred kernel; the backward is the adjoint of the gather / merge written with ATen ops
+# (training throughput is not a metric of this path, SURVEY §8f).  Index outputs are non-differentiable.
+def _bwd_topk_gather(ctx, g_out, g_idx):
+    (idx,) = ctx.saved_tensors
+    b, n, c = ctx.x_shape
+    gx = g_out.new_zeros((b, n, c))
+    gx[:, 0] = g_out[:, 0]
+    gx.scatter_(1, (idx + 1).unsqueeze(-1).expand(-1, -1, c), g_out[:, 1:])        # kept indices are distinct
+    return gx, None, None
+
+
+def _setup_topk_gather(ctx, inputs, output):
+    x, scores, k = inputs
+    ctx.x_shape = tuple(x.shape)
+    ctx.save_for_backward(output[1])
+
+
+_topk_gather.register_autograd(_bwd_topk_gather, setup_context=_setup_topk_gather)
+
+
+def _bwd_evit(ctx, g_out, g_idx, g_compl):
+    x, scores, idx, compl = ctx.saved_tensors
+    b, n, c = x.shape
+    k = idx.shape[1] - 1
+    kept = idx[:, :k]
+    gx = g_out.new_zeros((b, n, c))
+    gx[:, 0] = g_out[:, 0]
+    gx.scatter_(1, (kept + 1).unsqueeze(-1).expand(-1, -1, c), g_out[:, 1:k + 1])
+    g_extra = g_out[:, k + 1:k + 2]                                                # [B,1,C]: fused token = sum s_p x_p
+    s_c = torch.gather(scores.to(g_out.dtype), 1, compl).unsqueeze(-1)             # [B,P-k,1]
+    gx.scatter_(1, (compl + 1).unsqueeze(-1).expand(-1, -1, c), s_c * g_extra)
+    x_c = torch.gather(x, 1, (compl + 1).unsqueeze(-1).expand(-1, -1, c))
+    gs = torch.zeros_like(scores, dtype=g_out.dtype).scatter_(1, compl, (x_c * g_extra).sum(-1))
+    return gx, gs.to(scores.dtype), None
+
+
+def _setup_evit(ctx, inputs, output):
+    x, scores, k = inputs
+    ctx.save_for_backward(x, scores, output[1], output[2])
+
+
+_evit_select_fuse.register_autograd(_bwd_evit, setup_context=_setup_evit)
+
+
+def _bwd_gather_rows(ctx, g_out):
+    (ids,) = ctx.saved_tensors
+    shape, m = ctx.src_shape, ctx.m
+    gs = g_out.new_zeros(shape)
+    ix = ids[:, :m]
+    if len(shape) == 3:
+        gs.scatter_add_(1, ix.unsqueeze(-1).expand(-1, -1, shape[2]), g_out)     # ids may repeat (ATS 0-padding)
+    else:
+        gs.scatter_add_(2, ix[:, None, :, None].expand(-1, shape[1], -1, shape[3]), g_out)
+    return gs, None, None
+
+
+def _setup_gather_rows(ctx, inputs, output):
+    src, ids, m = inputs
+    ctx.src_shape, ctx.m = tuple(src.shape), m
+    ctx.save_for_backward(ids)
+
+
+_gather_rows.register_autograd(_bwd_gather_rows, setup_context=_setup_gather_rows)
+
+
+def _tome_rows(unm, src, dst, n):
+    """[B,n] output row of every input token (models/tome.py:279-289 order: unmerged even tokens, then all odd tokens)."""
+    b, u = unm.shape
+    rows = torch.empty(b, n, dtype=torch.long, device=unm.device)
+    rows[:, 1::2] = u + torch.arange(n // 2, device=unm.device)
+    rows.scatter_(1, 2 * unm, torch.arange(u, device=unm.device).expand(b, -1))
+    rows.scatter_(1, 2 * src, u + dst)
+    return rows
+
+
+def _bwd_tome_merge(ctx, g_out, g_size, g_map):
+    size, size_out, unm, src, dst = ctx.saved_tensors
+    b, n, c = ctx.x_shape
+    rows = _tome_rows(unm, src, dst, n)
+    g = g_out / size_out if ctx.divide else g_out                                 # out = merge(x * size) / size_out
+    gx = torch.gather(g, 1, rows.unsqueeze(-1).expand(-1, -1, c))
+    if ctx.has_size:
+        gx = gx * size.reshape(b, n, 1)
+    # sizes are integer token counts (sums of ones): no parameter reaches them, so they carry no gradient
+    return gx, None, None, None, None, None, None
+
+
+def _setup_tome_merge(ctx, inputs, output):
+    x, size, unm, src, dst, want_map, divide = inputs
+    ctx.x_shape, ctx.divide, ctx.has_size = tuple(x.shape), bool(divide), size is not None
+    ctx.save_for_backward(size if size is not None else x.new_empty(0), output[1], unm, src, dst)
+
+
+_tome_merge.register_autograd(_bwd_tome_merge, setup_context=_setup_tome_merge)
+
+
+def _bwd_dyvit_pool(ctx, g_out):
+    h, policy = ctx.saved_tensors
+    b, p, c = h.shape
+    half = c // 2
+    pol = policy.reshape(b, p, 1).to(g_out.dtype)
+    s = pol.sum(dim=1, keepdim=True)                                               # [B,1,1]
+    gsum = g_out[:, :, half:].sum(dim=1, keepdim=True)                             # every row received the same pooled vector
+    hf = h[:, :, half:].to(g_out.dtype)
+    gh = torch.cat([g_out[:, :, :half], (pol / s) * gsum], dim=-1).to(h.dtype)
+    gbar = (hf * pol).sum(dim=1, keepdim=True) / s
+    gp = ((hf - gbar) * gsum).sum(dim=-1) / s[:, :, 0]                             # [B,P]
+    return gh, gp.reshape(policy.shape).to(policy.dtype), None
+
+
+def _setup_dyvit_pool(ctx, inputs, output):
+    h, policy, eps = inputs
+    ctx.save_for_backward(h, policy)
+
+
+_dyvit_pool_concat.register_autograd(_bwd_dyvit_pool, setup_context=_setup_dyvit_pool)
