@@ -347,10 +347,23 @@ class Runner:
         self.g_logits = torch.empty(world * batch, 1000, device=dev) if world > 1 else None
         self.g_dec = None
         self.dec_cols = 0
+        self.graphs = {}
 
-    def forward(self, x):
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
-            out = self.model(x)
+    def graphed(self, buf):
+        """one CUDA graph of the forward reading `buf` in place (tokenreduction_b200.graph: a step = one launch)."""
+        from tokenreduction_b200.graph import GraphedForward
+        g = self.graphs.get(buf.data_ptr())
+        if g is None:
+            g = GraphedForward(self.model, buf, torch.bfloat16 if self.amp else None, static_input=buf)
+            self.graphs[buf.data_ptr()] = g
+        return g
+
+    def forward(self, x, graph=False):
+        if graph:
+            out = self.graphed(x)(x)
+        else:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+                out = self.model(x)
         if self.world == 1:
             return out.float()
         y, viz = out
@@ -370,7 +383,7 @@ class Runner:
             self.dist.barrier()
         torch.cuda.synchronize()
 
-    def measure(self, steps, warmup, timeline=False, e2e=True):
+    def measure(self, steps, warmup, timeline=False, e2e=True, graph=True):
         """-> dict(ms, ms_e2e, launches, kernels timeline).  Timed region 1: inputs resident in HBM.  Timed region 2: end
         to end through the public API -- every step copies ITS batch from pinned host memory and reads ITS logits back;
         the copy of step i+1 runs on a second stream into the other of two device buffers while step i computes."""
@@ -378,19 +391,32 @@ class Runner:
         for _ in range(max(warmup, 3)):
             self.forward(self.images)
         self.barrier()
+        # per-kernel timeline: a separate, untimed eager pass with an event pair around every tokred launch (the event
+        # records cost host time, so they stay out of the timed region); also counts the launches of one step
+        res = {"timeline": None, "ms_e2e": None}
+        tl_steps = min(steps, 3)
         if timeline:
             _lib.TIMELINE = []
         launches0 = _lib.launch_count()
+        for _ in range(tl_steps):
+            self.forward(self.images)
+        self.barrier()
+        res["launches"] = (_lib.launch_count() - launches0) * steps // tl_steps
+        res["timeline_steps"] = tl_steps
+        if timeline:
+            res["timeline"], _lib.TIMELINE = _lib.TIMELINE, None
+        if graph:
+            for _ in range(2):
+                self.forward(self.images, True)      # capture + first replays
+            self.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         ev0.record()
         for _ in range(steps):
-            self.forward(self.images)
+            self.forward(self.images, graph)
         ev1.record()
         self.barrier()
-        res = {"ms": ev0.elapsed_time(ev1), "launches": _lib.launch_count() - launches0, "timeline": None, "ms_e2e": None}
-        if timeline:
-            res["timeline"], _lib.TIMELINE = _lib.TIMELINE, None
+        res["ms"] = ev0.elapsed_time(ev1)
         if not e2e:
             return res
         cur = torch.cuda.current_stream()
@@ -414,7 +440,7 @@ class Runner:
                 if i + 1 < n:
                     stage(i + 1)
                 cur.wait_event(ready[i % 2])
-                y = self.forward(bufs[i % 2])
+                y = self.forward(bufs[i % 2], graph)
                 freed[i % 2] = torch.cuda.Event()
                 freed[i % 2].record(cur)
                 self.host_logits.copy_(y, non_blocking=True)
@@ -463,10 +489,10 @@ def run_tokred(a):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    res = run.measure(a.steps, a.warmup, timeline=True)
+    res = run.measure(a.steps, a.warmup, timeline=True, graph=not a.no_graph)
     clock_rec = clocks.stop() if rank == 0 else None
     ms, ms_e2e = max_over_ranks(res["ms"], res["ms_e2e"])
-    kernels = summarise_timeline(res["timeline"], a.steps, peaks["hbm_gbs"])
+    kernels = summarise_timeline(res["timeline"], res["timeline_steps"], peaks["hbm_gbs"])
     launches = res["launches"]
     dec_cols = run.dec_cols
     h2d = run.host_images.numel() * 4 * world
@@ -481,9 +507,9 @@ def run_tokred(a):
         for label, cfg_no, key, bsz, scaling in extra_workloads(world):
             try:
                 r = Runner(key, bsz, dev, rank, world)
-                rr = r.measure(xsteps, xwarm, timeline=True)
+                rr = r.measure(xsteps, xwarm, timeline=True, graph=not a.no_graph)
                 xms, xms_e2e = max_over_ranks(rr["ms"], rr["ms_e2e"])
-                ks = summarise_timeline(rr["timeline"], xsteps, peaks["hbm_gbs"])
+                ks = summarise_timeline(rr["timeline"], rr["timeline_steps"], peaks["hbm_gbs"])
                 top = ks[0] if ks else None
                 m_, s_, kr_, _, amp_ = WORKLOADS[key]
                 extras.append({
@@ -528,6 +554,9 @@ def run_tokred(a):
                        "global_batch": total, "keep_rate": kr, "reduction_loc": [3, 6, 9], "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2 (batch of fp32 images = %.0f MB)" % (batch * 3 * 224 * 224 * 4 / 1e6),
                        "timing": "CUDA events, max over ranks",
+                       "execution": "eager (one Python-issued launch per kernel)" if a.no_graph else
+                                    "one CUDA graph replay per step (tokenreduction_b200.graph.GraphedForward); the per-kernel "
+                                    "timeline is a separate untimed eager pass",
                        "exchange": "none (1 GPU)" if world == 1 else
                                    f"per step: NCCL all_gather of logits [B,1000] f32 + kept/assignment indices [B,{dec_cols}] i32",
                        "e2e_pipeline": "per step: H2D of the batch (pinned, copy stream, 2 device buffers; overlaps the "
@@ -563,6 +592,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs (workloads array)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying one CUDA graph per step")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -209,6 +209,16 @@ TOKRED_API int tokred_attention(const void* qkv, int B, int N, int H, int head_d
                      const uint8_t* mask, const int64_t* q_ids, int64_t ids_stride, int M, void* out, float* cls_row,
                      float* colsum, void* stream);
 
+/* ---- callers either side of the attention producer: residual add + LayerNorm + bf16 cast in one pass ----------
+ * e.g. models/topk.py:87 (x = x + drop_path(tmp)) + :94 (norm2(x)) + the autocast cast in front of the next Linear.
+ *   x       [rows,C] fp32 residual stream
+ *   branch  [rows,C] branch_dtype (bf16 under autocast) or NULL: x_out = x + branch (fp32); NULL: plain LayerNorm of x
+ *   gamma, beta [C] fp32, eps: the LayerNorm's affine parameters
+ *   x_out   [rows,C] fp32 (required with branch; may alias x), y [rows,C] bf16 = LayerNorm(x_out) rounded once
+ * C must be a multiple of 128 up to 1024 (TOKRED_ERR_UNSUPPORTED otherwise).                               */
+TOKRED_API int tokred_add_layernorm(const float* x, const void* branch, int branch_dtype, const float* gamma, const float* beta,
+                         float eps, int64_t rows, int C, float* x_out, void* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1158,3 +1158,21 @@ def test_tome_match_from_qkv_keys(T, b, n, h, r):
     dec = MG.tome_bf16_decidable(metric.cpu(), r)[0]
     same = (got[1].cpu() == src_r).all(1) & (got[2].cpu() == dst_r).all(1) & (got[0].cpu() == unm_r).all(1)
     assert bool(same[dec].all()), f"{int((~same[dec]).sum())} decidable images differ from the oracle"
+
+
+@pytest.mark.parametrize("rows,c,bdt", [(197 * 7, 384, torch.bfloat16), (138 * 5, 768, torch.bfloat16), (999, 128, torch.float32),
+                                        (64, 1024, torch.bfloat16), (3, 384, None)])
+def test_add_layernorm(T, rows, c, bdt):
+    """residual add + LayerNorm + bf16 cast in one pass against the reference's three ATen calls under autocast
+    (x + branch in fp32, layer_norm in fp32, cast to bf16): the new residual row is bit-identical (same fp32 add), the
+    normalised row is the same fp32 LayerNorm rounded once (reduction order differs: rare last-bit bf16 flips)."""
+    x = torch.randn(rows, c, generator=g(1300)) * 2 + 0.3
+    br = None if bdt is None else torch.randn(rows, c, generator=g(1301)).to(bdt)
+    w, b = torch.randn(c, generator=g(1302)), torch.randn(c, generator=g(1303))
+    xo, y = T.add_layernorm(x.to(DEV), None if br is None else br.to(DEV), w.to(DEV), b.to(DEV), 1e-6)
+    x_ref = x if br is None else x + br.float()
+    y_ref = torch.nn.functional.layer_norm(x_ref, (c,), w, b, 1e-6)
+    assert torch.equal(xo.cpu(), x_ref)
+    yb, yr = y.cpu().float(), y_ref.bfloat16().float()
+    assert float((yb == yr).float().mean()) > 0.995
+    assert float(((yb - y_ref).abs() / y_ref.abs().clamp_min(1.0)).max()) <= 2 ** -8      # within one bf16 rounding of the fp32 result

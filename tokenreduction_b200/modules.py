@@ -78,6 +78,29 @@ def fused_attention_ok(mod: nn.Module, x: Tensor, num_heads: int) -> bool:
     return True
 
 
+def _norm_fusable(norm: nn.Module, x: Tensor) -> bool:
+    return (FUSED_ATTENTION and isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+            and x.is_cuda and x.dtype == torch.float32 and x.shape[-1] % 128 == 0 and x.shape[-1] <= 1024
+            and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+            and not (norm.training and torch.is_grad_enabled()))
+
+
+def norm_lowp(norm: nn.Module, x: Tensor) -> Tensor:
+    """``norm(x)`` as the next autocast Linear consumes it: under bf16 autocast one kernel computes the fp32 LayerNorm
+    and rounds it to bf16 (the reference: layer_norm in fp32, then a separate cast)."""
+    if _norm_fusable(norm, x):
+        return ops.add_layernorm(x, None, norm.weight, norm.bias, norm.eps)[1]
+    return norm(x)
+
+
+def add_norm(x: Tensor, branch: Tensor, norm: nn.Module) -> Tuple[Tensor, Tensor]:
+    """(x + branch, norm(x + branch)) -- e.g. models/topk.py:87 + :94 -- in one pass under bf16 autocast."""
+    if _norm_fusable(norm, x) and branch.shape == x.shape and branch.is_cuda:
+        return ops.add_layernorm(x, branch, norm.weight, norm.bias, norm.eps)
+    x = x + branch
+    return x, norm(x)
+
+
 class _AttentionBase(nn.Module):
     """qkv / proj layout shared by every reference attention variant (e.g. models/topk.py:27-52)."""
 
@@ -159,13 +182,16 @@ class Block_TopK(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x):
-        tmp, cls_attn, left_tokens = self.attn(self.norm1(x))
-        x = x + self.drop_path(tmp)
+        tmp, cls_attn, left_tokens = self.attn(norm_lowp(self.norm1, x))
         idx = None
         if cls_attn is not None:
             _train_guard(self, True)
+            x = x + self.drop_path(tmp)
             x, idx = ops.topk_gather(x, cls_attn, left_tokens)          # select + gather + cat in one launch
-        x = x + self.drop_path(self.mlp(self.norm2(x)))
+            y = norm_lowp(self.norm2, x)
+        else:
+            x, y = add_norm(x, self.drop_path(tmp), self.norm2)
+        x = x + self.drop_path(self.mlp(y))
         return x, x.shape[1] - 1, idx
 
 
@@ -196,13 +222,16 @@ class Block_EVIT(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x):
-        tmp, cls_attn, left_tokens = self.attn(self.norm1(x))
-        x = x + self.drop_path(tmp)
+        tmp, cls_attn, left_tokens = self.attn(norm_lowp(self.norm1, x))
         idx = compl = None
         if cls_attn is not None:
             _train_guard(self, True)
+            x = x + self.drop_path(tmp)
             x, idx, compl = ops.evit_select_fuse(x, cls_attn, left_tokens)
-        x = x + self.drop_path(self.mlp(self.norm2(x)))
+            y = norm_lowp(self.norm2, x)
+        else:
+            x, y = add_norm(x, self.drop_path(tmp), self.norm2)
+        x = x + self.drop_path(self.mlp(y))
         return x, x.shape[1] - 1, idx, compl
 
 
@@ -356,9 +385,12 @@ class Block_ToMe(nn.Module):
         self.attn.lazy_metric = True
 
     def forward(self, x, attn_size=None):
-        x_attn, metric = self.attn(self.norm1(x), attn_size)
-        x = x + self.drop_path(x_attn)
+        x_attn, metric = self.attn(norm_lowp(self.norm1, x), attn_size)
         reduced_cluster_idx = None
+        if self.r <= 0:
+            x, y = add_norm(x, self.drop_path(x_attn), self.norm2)
+            return x + self.drop_path(self.mlp(y)), attn_size, reduced_cluster_idx
+        x = x + self.drop_path(x_attn)
         if self.r > 0:
             _train_guard(self, True)
             re = ops.tome_effective_r(x.shape[1], self.r, self.cls_token, self.dist_token)
@@ -384,7 +416,7 @@ class Block_ToMe(nn.Module):
                 merge, _ = bipartite_soft_matching(metric, self.r, self.cls_token, self.dist_token)
                 reduced_cluster_idx = _reduced_cluster_idx(merge_source(merge, x, None), self.cls_token)
                 x, attn_size = merge_wavg(merge, x, attn_size)
-        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        x = x + self.drop_path(self.mlp(norm_lowp(self.norm2, x)))
         return x, attn_size, reduced_cluster_idx
 
 
@@ -488,9 +520,9 @@ class BlockWithProbs(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x):
-        x_attn, attn = self.attn(self.norm1(x))
-        x = x + self.drop_path(x_attn)
-        x = x + self.drop_path(self.mlp(self.norm2(x)))
+        x_attn, attn = self.attn(norm_lowp(self.norm1, x))
+        x, y = add_norm(x, self.drop_path(x_attn), self.norm2)
+        x = x + self.drop_path(self.mlp(y))
         return x, attn
 
 
@@ -644,11 +676,11 @@ class ATSBlock(nn.Module):
         self.drop_path2 = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
     def forward(self, x, mask):
-        x_tmp, mask, sample_ids = self.attn(self.norm1(x), mask)
+        x_tmp, mask, sample_ids = self.attn(norm_lowp(self.norm1, x), mask)
         if sample_ids is not None:
             x = ops.gather_rows(x, sample_ids)
-        x = x + self.drop_path1(x_tmp)
-        x = x + self.drop_path2(self.mlp(self.norm2(x)))
+        x, y = add_norm(x, self.drop_path1(x_tmp), self.norm2)
+        x = x + self.drop_path2(self.mlp(y))
         return x, mask, sample_ids
 
 
@@ -723,5 +755,5 @@ class Block_DyVIT(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x, policy=None):
-        x = x + self.drop_path(self.attn(self.norm1(x), policy=policy))
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        x, y = add_norm(x, self.drop_path(self.attn(norm_lowp(self.norm1, x), policy=policy)), self.norm2)
+        return x + self.drop_path(self.mlp(y))

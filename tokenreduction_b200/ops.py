@@ -19,7 +19,7 @@ from ._lib import BF16, F32, TokredError
 __all__ = [
     "topk_gather", "topk_gather_attn", "evit_select_fuse", "evit_select_fuse_attn", "tome_effective_r", "tome_match",
     "tome_match_qkv", "tome_merge", "pairwise_dist", "dpcknn_cluster", "dpcknn_merge", "attn_colsum", "kmedoids_fit", "sinkhorn_merge", "patchmerger",
-    "sit_merge", "ats_sample", "gather_rows", "dyvit_pool_concat", "attention", "attention_supported",
+    "sit_merge", "ats_sample", "gather_rows", "dyvit_pool_concat", "attention", "attention_supported", "add_layernorm",
 ]
 
 
@@ -738,6 +738,41 @@ def attention(qkv: Tensor, num_heads: int, scale: float, key_bias: Optional[Tens
     [B,M] selects the query rows to compute (the ATS row gather, models/ats.py:84-87)."""
     out, cls, colsum = torch.ops.tokred.attention(qkv, num_heads, scale, key_bias, mask, q_ids, want_out, want_cls, want_colsum)
     return (out if want_out else None), (cls if want_cls else None), (colsum if want_colsum else None)
+
+
+# ----------------------------------------------------------------------------------------------- residual + LayerNorm
+@torch.library.custom_op("tokred::add_layernorm", mutates_args=(), device_types="cuda")
+def _add_layernorm(x: Tensor, branch: Optional[Tensor], weight: Tensor, bias: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+    _need_cuda("add_layernorm", x, branch, weight, bias)
+    if x.dtype != torch.float32 or x.shape[-1] != weight.numel():
+        raise TokredError(f"add_layernorm: x {tuple(x.shape)} {x.dtype}; expected fp32 [..., {weight.numel()}]")
+    x = _c(x)
+    c = x.shape[-1]
+    rows = x.numel() // c
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if branch is not None:
+        if branch.shape != x.shape:
+            raise TokredError("add_layernorm: branch shape differs from x")
+        branch = _c(branch if branch.dtype in (torch.float32, torch.bfloat16) else branch.float())
+        x_out = torch.empty_like(x)
+    else:
+        x_out = x.new_empty((0,))
+    _lib.call("tokred_add_layernorm", _ptr(x), _ptr(branch), _dt(branch) if branch is not None else 0, _ptr(_c(weight.float())),
+              _ptr(_c(bias.float())), float(eps), rows, c, _ptr(x_out) if branch is not None else None, _ptr(y), _stream())
+    return x_out, y
+
+
+@_add_layernorm.register_fake
+def _(x, branch, weight, bias, eps):
+    return (torch.empty_like(x) if branch is not None else x.new_empty((0,))), x.new_empty(x.shape, dtype=torch.bfloat16)
+
+
+def add_layernorm(x: Tensor, branch: Optional[Tensor], weight: Tensor, bias: Tensor, eps: float):
+    """x_new = x + branch (fp32 residual stream); y = LayerNorm(x_new) rounded to bf16 (what the next autocast Linear
+    would cast it to) -- one pass instead of add / layer_norm / cast (e.g. models/topk.py:87,94).  branch=None: plain
+    LayerNorm of x.  Returns (x_new | x, y)."""
+    x_out, y = torch.ops.tokred.add_layernorm(x, branch, weight, bias, eps)
+    return (x_out if branch is not None else x), y
 
 
 # ----------------------------------------------------------------------------------------------- f4: autograd formulas

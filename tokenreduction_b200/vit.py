@@ -160,8 +160,9 @@ class Block(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x):
-        x = x + self.drop_path(self.attn(self.norm1(x)))
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        from . import modules
+        x, y = modules.add_norm(x, self.drop_path(self.attn(modules.norm_lowp(self.norm1, x))), self.norm2)
+        return x + self.drop_path(self.mlp(y))
 
 
 def _init_vit_weights(module: nn.Module, name: str = "", head_bias: float = 0.0, jax_impl: bool = False):
