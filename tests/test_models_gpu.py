@@ -335,3 +335,20 @@ def test_batch_shard_equivalence():
         full = model(x)
         parts = torch.cat([model(x[:4]), model(x[4:])])
     assert torch.allclose(full, parts, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["tome", "topk", "kmedoids", "ats", "sinkhorn"])
+def test_cuda_graph_replay_equals_eager(name):
+    """tokenreduction_b200.graph.GraphedForward: the whole bf16 forward (every tokred entry point only enqueues on the
+    current stream) captured into one CUDA graph reproduces the eager forward bit for bit, also on a second input."""
+    from tokenreduction_b200 import create_model
+    from tokenreduction_b200.graph import GraphedForward
+    torch.manual_seed(0)
+    model = quiet(create_model, f"{name}_small_patch16_224", num_classes=100, args=margs(KR[name])).eval().cuda()
+    xs = [torch.randn(8, 3, 224, 224, generator=torch.Generator().manual_seed(s)).cuda() for s in (3, 4)]
+    run = GraphedForward(model, xs[0], torch.bfloat16)
+    for x in xs:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            want = model(x).clone()
+        got = run(x)
+        assert torch.equal(got, want)
