@@ -206,6 +206,11 @@ def algorithmic_bytes(name: str, a: tuple) -> float:
     if name == "tokred_gather_rows":
         m = g["M"]
         return g["B"] * (2 * g["G"] * m * g["W"] * esz(g["dtype"]) + 8 * m)
+    if name == "tokred_add_layernorm":
+        per = g["C"] * (4 + 2)                                   # x read, y written
+        if g["branch"]:
+            per += g["C"] * (esz(g["branch_dtype"]) + 4)          # branch read, new residual row written
+        return g["rows"] * per + 8 * g["C"]
     if name == "tokred_attention":
         n, hh, m = g["N"], g["H"], (g["M"] if g["q_ids"] else g["N"])
         c = hh * g["head_dim"]

@@ -403,10 +403,22 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
         TOKRED_STAMP(tid == 128 && it == 0, t, 4);
         TOKRED_STAMP(tid == 0 && it == 0, t, 9);
         pair_sync(q);
+        const float inv = 1.0f / (red_sum[rl] + red_sum[128 + rl]);
+        if (COLSUM) {
+          // column sums of the fp32 probabilities: both warps of the quarter work on their own columns (the butterfly
+          // would triple pass C, which only the lower warp can run), before pass C starts overwriting e
+          for_chunks(trow, c_beg, c_end, [&](uint32_t (&r)[16], int c) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = row < M ? __uint_as_float(r[i]) * inv : 0.f;
+            const float cs = colsum16(v, lane);
+            if (!(lane & 1)) colpart[(size_t)(t * 4 + q) * Np + c * 16 + (lane >> 1)] = cs;
+          });
+          pair_sync(q);
+        }
         // pass C (lower warp): p = e / sum -> bf16 pairs in place (column j holds keys 2j, 2j+1; the writes trail the
-        // reads); side outputs in fp32
+        // reads); the CLS row goes out in fp32
         if (!half) {
-          const float inv = 1.0f / (red_sum[rl] + red_sum[128 + rl]);
           float* cls = (p.cls_row && row == 0) ? p.cls_row + ((size_t)b * H + h) * N : nullptr;
           for_chunks(trow, 0, nch, [&](uint32_t (&r)[16], int c) {
             float x[16];
@@ -415,13 +427,6 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
             if (cls) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) if (c * 16 + i < N) cls[c * 16 + i] = x[i];
-            }
-            if (COLSUM) {
-              float v[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = row < M ? x[i] : 0.f;
-              const float cs = colsum16(v, lane);
-              if (!(lane & 1)) colpart[(size_t)(t * 4 + q) * Np + c * 16 + (lane >> 1)] = cs;
             }
             tmem_st8(trow + c * 8, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]),
                      pack_bf16x2(x[6], x[7]), pack_bf16x2(x[8], x[9]), pack_bf16x2(x[10], x[11]), pack_bf16x2(x[12], x[13]),
@@ -513,7 +518,7 @@ extern "C" int tokred_attention(const void* qkv, int B, int N, int H, int head_d
   TOKRED_REQUIRE(out || cls_row || colsum, "attention: no output requested");
   TOKRED_REQUIRE(B >= 1 && H >= 1 && N >= 1, "attention: B=%d N=%d H=%d", B, N, H);
   TOKRED_REQUIRE(scale > 0.f && std::isfinite(scale), "attention: scale %g must be positive", (double)scale);
-  if (!q_ids) M = N;
+  if (!q_ids) M = (out || colsum) ? N : 1;        // CLS rows only: query row 0 is all that is needed
   TOKRED_REQUIRE(M >= 1 && (!q_ids || ids_stride >= M), "attention: M=%d ids_stride=%lld", M, (long long)ids_stride);
   if (head_dim != 64 || N > 256 || M > 256) {
     set_error("attention: head_dim=%d N=%d M=%d outside the fused kernel's range (head_dim 64, N <= 256)", head_dim, N, M);

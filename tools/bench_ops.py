@@ -166,6 +166,43 @@ def cases():
             add(f"{tag}ats_sample B B={b} N={n} count={count}", lambda f=mk_ats: f("sample"))
             add(f"{tag}ats gather attn rows B B={b} N={n} M={count}", lambda f=mk_ats: f("rows"))
             add(f"{tag}ats gather tokens B B={b} N={n} M={count}", lambda f=mk_ats: f("tokens"))
+    # f1: attention producer (no [B,H,N,N] tensor) at the stage sizes of configs 2 (DeiT-S, B=256) and 3/5 (DeiT-B)
+    for b, h, sizes in ((256, 6, (197, 138, 97, 68)), (128, 12, (197,)), (1024, 12, (197, 100, 51))):
+        for n in sizes:
+            def mk_attn(b=b, h=h, n=n, side=False):
+                qkv = rnd(b, n, 3 * h * 64, dtype=torch.bfloat16)
+                return lambda: T.attention(qkv, h, 0.125, None, None, None, True, side, side)
+            tag = "S" if h == 6 else "B"
+            add(f"attention {tag} B={b} N={n} H={h}", mk_attn)
+            if n == 197 and b != 1024:
+                add(f"attention {tag} B={b} N={n} H={h} + cls rows + column sums", lambda f=mk_attn: f(side=True))
+
+    def mk_attn_bias(b=256, h=6, n=197):
+        qkv, bias = rnd(b, n, 3 * h * 64, dtype=torch.bfloat16), torch.rand(b, n, device=DEV)
+        return lambda: T.attention(qkv, h, 0.125, bias)
+    add("attention S B=256 N=197 H=6 + ToMe log-size bias", mk_attn_bias)
+
+    def mk_attn_ats(b=128, h=12, n=197, m=177):
+        qkv = rnd(b, n, 3 * h * 64, dtype=torch.bfloat16)
+        mask = torch.ones(b, n, dtype=torch.bool, device=DEV)
+        ids = torch.arange(m, device=DEV).expand(b, -1).contiguous()
+        return lambda: T.attention(qkv, h, 0.125, None, mask, ids)
+    add("attention B B=128 N=197 H=12 ATS mask + 177 gathered query rows", mk_attn_ats)
+
+    def mk_attn_scores(b=128, h=12, n=197):
+        qkv = rnd(b, n, 3 * h * 64, dtype=torch.bfloat16)
+        mask = torch.ones(b, n, dtype=torch.bool, device=DEV)
+        return lambda: T.attention(qkv, h, 0.125, None, mask, None, False, True, False)
+    add("attention B B=128 N=197 H=12 scores only (CLS rows, v not read)", mk_attn_scores)
+    # residual add + LayerNorm + bf16 cast
+    for b, n, c in ((256, 197, 384), (256, 97, 384), (128, 197, 768), (1024, 197, 768)):
+        def mk_ln(b=b, n=n, c=c, br=True):
+            x, w, bb = rnd(b, n, c), rnd(c), rnd(c)
+            branch = rnd(b, n, c, dtype=torch.bfloat16) if br else None
+            return lambda: T.add_layernorm(x, branch, w, bb, 1e-6)
+        add(f"add_layernorm B={b} N={n} C={c} (x + branch, LN, bf16)", mk_ln)
+        if b == 256 and n == 197:
+            add(f"add_layernorm B={b} N={n} C={c} (LN, bf16; no branch)", lambda f=mk_ln: f(br=False))
     return out
 
 

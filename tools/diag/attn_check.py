@@ -67,7 +67,9 @@ for (B, N, H) in [(256, 197, 6), (256, 138, 6), (256, 97, 6), (256, 68, 6), (128
     q, k, v = qkv.reshape(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
     t0 = bench(lambda: T.attention(qkv, H, 0.125))
     t1 = bench(lambda: T.attention(qkv, H, 0.125, want_cls=True, want_colsum=True))
+    t1a = bench(lambda: T.attention(qkv, H, 0.125, want_cls=True))
+    t1b = bench(lambda: T.attention(qkv, H, 0.125, want_out=False, want_cls=True))
     t2 = bench(lambda: eager(qkv, H, 0.125)) if B * H * N * N * 4 < 8e9 else float("nan")
     t3 = bench(lambda: F.scaled_dot_product_attention(q, k, v))
     mb = B * N * 4 * H * 64 * 2 / 1e6
-    print(f"B={B} N={N} H={H}: fused {t0:.1f} us ({mb / t0 * 1e-3 * 1e3:.0f} GB/s), +cls+colsum {t1:.1f} us, eager {t2:.1f} us, torch SDPA {t3:.1f} us")
+    print(f"B={B} N={N} H={H}: fused {t0:.1f} us ({mb / t0 * 1e-3 * 1e3:.0f} GB/s), +cls+colsum {t1:.1f} us, +cls {t1a:.1f} us, scores only {t1b:.1f} us, eager {t2:.1f} us, torch SDPA {t3:.1f} us")

@@ -7,14 +7,16 @@ _lib.LIB_PATH = _lib.LIB_PATH.replace(".so", "_dbg.so")
 from tokenreduction_b200 import ops as T
 lib = _lib.load()
 B, N, H = 256, int(sys.argv[1]) if len(sys.argv) > 1 else 197, 6
+MODE = sys.argv[2] if len(sys.argv) > 2 else "plain"
+kw = {"scores": dict(want_out=False, want_cls=True), "colsum": dict(want_cls=True, want_colsum=True), "plain": {}}[MODE]
 qkv = torch.randn(B, N, 3 * H * 64, device="cuda").bfloat16()
 for _ in range(3):
-    T.attention(qkv, H, 0.125)
+    T.attention(qkv, H, 0.125, **kw)
 ncta = min(B * H, 2 * 148)
 st = torch.zeros(ncta * 8 * 32, dtype=torch.int64, device="cuda")
 lib.tokred_debug_set_stamps_attention.argtypes = [ctypes.c_void_p]
 assert lib.tokred_debug_set_stamps_attention(st.data_ptr()) == 0
-T.attention(qkv, H, 0.125)
+T.attention(qkv, H, 0.125, **kw)
 torch.cuda.synchronize()
 lib.tokred_debug_set_stamps_attention(None)
 s = st.view(ncta, 8, 32).cpu().double()
