@@ -28,6 +28,9 @@
 //   store  thread = output row: 32 fp32 -> bf16 -> 64 contiguous bytes of out[b, row, h*64 ..]
 // Rounding points are the reference's: S to bf16, (S*scale) to bf16, P to bf16, O to bf16; everything else fp32.
 #include <cmath>
+#include <mutex>
+
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -56,6 +59,14 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA: one 4-D box of the qkv tensor (d, q/k/v x head, token, image) -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(umma::smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -198,69 +209,70 @@ __device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
   return s;
 }
 
-// one 8-row group of a [rows x 64] bf16 head slice -> canonical K-major core matrices: lane -> row = lane % 8,
-// 16-byte chunks 2*(lane/8) and 2*(lane/8)+1 (8 consecutive lanes fill one contiguous 128-byte core matrix)
-__device__ __forceinline__ void load_group(uint32_t dst_lane, const unsigned char* src_lane, bool ok) {
-  cp_async16(dst_lane, src_lane, ok ? 16u : 0u);
-  cp_async16(dst_lane + 128, src_lane + 16, ok ? 16u : 0u);
-}
-
 template <bool BIAS, bool ROUND2, bool MASK, bool COLSUM>
-__global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_constant__ CUtensorMap tmap, const AttnParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2;          // TMEM lane quarter; 0 = "lower" warp of the pair, 1 = "upper"
   const int N = p.N, H = p.H, C = H * 64, M = p.M;
   const int Np = (N + 15) & ~15;                     // keys: UMMA N of S, UMMA K of P.V
-  const int gq = (M + 7) >> 3, gk = Np >> 3;         // 8-row groups of the Q / K,V tiles
   const int ntiles = (M + 127) >> 7;
   const bool want_out = p.out != nullptr;
   const int nitems = p.B * H;
 
-  // Q | K | V[0] | V[1]: the CTA is persistent; while it works on the last query tile of an item, the next item's q, k
-  // (their area is dead once the last S MMA has completed) and v (other buffer) are already on their way
+  // Q | K | V[0] | V[1], each [8 K-chunks][Np rows][16 B]: the canonical no-swizzle UMMA layout with the 8-row core
+  // matrices of one 16-byte K-chunk back to back (SBO = 128 B) and the chunks Np*16 B apart (LBO) -- exactly what a TMA
+  // box of (8 elements x Np tokens) per chunk writes.  The CTA is persistent: while it works on the last query tile of an
+  // item, the next item's q, k (dead once the last S MMA has completed) and v (other buffer) are already on their way.
+  const uint32_t chunk_bytes = (uint32_t)Np * 16u, mat_bytes = 8u * chunk_bytes;
   unsigned char* Qs = smem;
-  unsigned char* Ks = Qs + (size_t)gq * 1024;
-  unsigned char* Vs = Ks + (size_t)gk * 1024;
-  // the S MMA always reads 128 A rows: the operand area spans at least ntiles*16 row groups past Qs
-  const int ggrp = max(gq + 3 * gk, ntiles * 16);
-  float* bias_s = reinterpret_cast<float*>(smem + (size_t)ggrp * 1024);      // [2][Np]
+  unsigned char* Ks = Qs + mat_bytes;
+  unsigned char* Vs = Ks + mat_bytes;
+  float* bias_s = reinterpret_cast<float*>(smem + 4 * (size_t)mat_bytes);    // [2][Np]
   float* red_max = bias_s + 2 * Np;                                           // [2][128]
   float* red_sum = red_max + 256;                                             // [2][128]
   float* colpart = red_sum + 256;                                             // [8][Np] (COLSUM)
   uint64_t* bar = reinterpret_cast<uint64_t*>(colpart + (COLSUM ? 8 * Np : 0));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* ldbar = bar + 1;                                                  // [2]: operands of item it landed (TMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ldbar + 2);
 
   const uint32_t ncols = Np <= 128 ? 128u : 256u;
   const uint32_t o_col = Np <= 128 ? 64u : 128u;
   TOKRED_STAMP(tid == 0, 0, 0);
   if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
-  if (tid == 0) { umma::mbar_init(bar, 1); umma::fence_mbar_init(); }
+  if (tid == 0) { umma::mbar_init(bar, 1); umma::mbar_init(&ldbar[0], 1); umma::mbar_init(&ldbar[1], 1); umma::fence_mbar_init(); }
+  __syncthreads();
 
-  // ---- loads of one item into (Qs, Ks, V[buf], bias[buf]); asynchronous (cp.async), completed by cp_async_wait_all
-  const int r8 = lane & 7;
-  const uint32_t lane_dst = (uint32_t)(r8 * 16 + (lane >> 3) * 256);
+  // ---- loads of one item into (Qs, Ks, V[buf], bias[buf]).  k, v and (without a row gather) q arrive by TMA: one thread
+  // issues 8 boxes per matrix and moves on (a 75 KB cp.async prefetch kept its issuing warps blocked on the load/store
+  // queue for as long as the copy took); rows past N are zero-filled by the out-of-bounds handling of the tensor map.
+  // Gathered query rows (ATS) or a single query row (scores only) come by cp.async into the same layout.
+  const bool q_by_tma = p.q_ids == nullptr && M == N;
   const size_t row_bytes = (size_t)3 * C * 2;
-  auto issue_loads = [&](int item, int buf, int wi, int nw) {      // warp wi of nw issuing warps
+  auto issue_tma = [&](int item, int buf) {                       // one thread
     const int b = item / H, h = item - b * H;
-    const unsigned char* lane_src = reinterpret_cast<const unsigned char*>(p.qkv + (size_t)b * N * 3 * C + (size_t)h * 64) + (lane >> 3) * 32;
-    // K and V: rows [0, N), zero-filled up to Np
-    const uint32_t k0 = umma::smem_u32(Ks) + lane_dst, v0 = umma::smem_u32(Vs) + (uint32_t)buf * (uint32_t)gk * 1024u + lane_dst;
-    for (int g = wi; g < gk; g += nw) {
-      const int row = g * 8 + r8;
-      const bool ok = row < N;
-      const unsigned char* src = lane_src + (size_t)(ok ? row : 0) * row_bytes;
-      load_group(k0 + g * 1024, src + C * 2, ok);
-      if (want_out) load_group(v0 + g * 1024, src + C * 4, ok);
+    const uint32_t nmat = 1u + (want_out ? 1u : 0u) + (q_by_tma ? 1u : 0u);
+    mbar_expect_tx(&ldbar[buf], nmat * mat_bytes);
+    const uint32_t k0 = umma::smem_u32(Ks), v0 = umma::smem_u32(Vs) + (uint32_t)buf * mat_bytes, q0 = umma::smem_u32(Qs);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      tma_load_4d(k0 + c * chunk_bytes, &tmap, c * 8, H + h, 0, b, &ldbar[buf]);
+      if (want_out) tma_load_4d(v0 + c * chunk_bytes, &tmap, c * 8, 2 * H + h, 0, b, &ldbar[buf]);
+      if (q_by_tma) tma_load_4d(q0 + c * chunk_bytes, &tmap, c * 8, h, 0, b, &ldbar[buf]);
     }
-    const int64_t* ids = p.q_ids ? p.q_ids + (size_t)b * p.ids_stride : nullptr;
-    const uint32_t q0 = umma::smem_u32(Qs) + lane_dst;
-    for (int g = wi; g < gq; g += nw) {
-      const int row = g * 8 + r8;
-      const bool ok = row < M;
-      int srow = ok ? row : 0;
-      if (ids && ok) srow = clamp_idx(ids[row], N);
-      load_group(q0 + g * 1024, lane_src + (size_t)srow * row_bytes, ok);
+  };
+  auto issue_rest = [&](int item, int buf, int wi, int nw) {      // warp wi of nw issuing warps
+    const int b = item / H, h = item - b * H;
+    if (!q_by_tma) {
+      const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.qkv + (size_t)b * N * 3 * C + (size_t)h * 64);
+      const int64_t* ids = p.q_ids ? p.q_ids + (size_t)b * p.ids_stride : nullptr;
+      const int rows = (M + 7) & ~7;                              // pad rows of the last group are zero-filled
+      for (int e = wi * 32 + lane; e < rows * 8; e += nw * 32) {
+        const int row = e >> 3, c = e & 7;
+        const bool ok = row < M;
+        const int srow = ok ? (ids ? clamp_idx(ids[row], N) : row) : 0;
+        cp_async16(umma::smem_u32(Qs) + c * chunk_bytes + row * 16, src0 + (size_t)srow * row_bytes + c * 16, ok ? 16u : 0u);
+      }
     }
     if (BIAS)
       for (int j = wi * 32 + lane; j < Np; j += nw * 32) {
@@ -273,7 +285,10 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
       }
   };
   int item = blockIdx.x;
-  if (item < nitems) issue_loads(item, 0, warp, kThreads / 32);
+  if (item < nitems) {
+    if (tid == 32) issue_tma(item, 0);
+    issue_rest(item, 0, warp, kThreads / 32);
+  }
   if (COLSUM)
     for (int j = tid; j < 8 * Np; j += kThreads) colpart[j] = 0.f;
   cp_async_wait_all();
@@ -304,16 +319,17 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
     const int b = item / H, h = item - b * H;
     const int64_t* ids = p.q_ids ? p.q_ids + (size_t)b * p.ids_stride : nullptr;
     const float* bias_i = bias_s + buf * Np;
-    const uint32_t v_i = umma::smem_u32(Vs) + (uint32_t)buf * (uint32_t)gk * 1024u;
+    const uint32_t v_i = umma::smem_u32(Vs) + (uint32_t)buf * mat_bytes;
+    if (tid == 0) umma::mbar_wait(&ldbar[buf], (uint32_t)((it >> 1) & 1));      // this item's TMA boxes have landed
 
     for (int t = 0; t < ntiles; ++t) {
       // ---- S = Q_t K^T (rows past the Q tile read what lies behind it: finite garbage in accumulator rows nobody reads)
       if (tid == 0) {
-        const uint32_t a0 = umma::smem_u32(Qs) + (uint32_t)t * 16u * 1024u, b0 = umma::smem_u32(Ks);
+        const uint32_t a0 = umma::smem_u32(Qs) + (uint32_t)t * 2048u, b0 = umma::smem_u32(Ks);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma::mma_bf16(tmem, umma::smem_desc_kmajor(a0 + ks * 256, 128, 1024), umma::smem_desc_kmajor(b0 + ks * 256, 128, 1024),
-                         idesc_s, ks > 0 ? 1u : 0u);
+          umma::mma_bf16(tmem, umma::smem_desc_kmajor(a0 + ks * 2 * chunk_bytes, chunk_bytes, 128),
+                         umma::smem_desc_kmajor(b0 + ks * 2 * chunk_bytes, chunk_bytes, 128), idesc_s, ks > 0 ? 1u : 0u);
         umma::mma_commit(bar);
         umma::mbar_wait(bar, phase);       // one thread polls; everybody else parks at the barrier below
       }
@@ -324,13 +340,13 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
       const int row = t * 128 + rl;                          // query row
       const bool active = t * 128 + q * 32 < M;              // uniform over the warp pair of a quarter
       // The last S MMA of this item has completed: q and k are dead, the other v buffer was last read an item ago ->
-      // prefetch the next item.  Issuing 75 KB of cp.async stalls the issuing warp on the load/store queue for about as
-      // long as the copy takes, so the warps of the quarters that hold no query row of this tile (N = 197: rows 128..196
-      // leave quarter 3 idle) do it; only when every quarter is busy do all warps share it.
+      // prefetch the next item (TMA: one thread; the bias vector and cp.async query rows: the warps of quarters that hold
+      // no query row of this tile, all warps only when every quarter is busy).
       if (t == ntiles - 1 && item + (int)gridDim.x < nitems) {
+        if (tid == 32) issue_tma(item + gridDim.x, buf ^ 1);
         const int aq = min(4, (M - t * 128 + 31) >> 5);      // quarters with query rows in this tile
-        if (aq == 4) issue_loads(item + gridDim.x, buf ^ 1, warp, kThreads / 32);
-        else if (!active) issue_loads(item + gridDim.x, buf ^ 1, (q - aq) * 2 + half, (4 - aq) * 2);
+        if (aq == 4) issue_rest(item + gridDim.x, buf ^ 1, warp, kThreads / 32);
+        else if (!active) issue_rest(item + gridDim.x, buf ^ 1, (q - aq) * 2 + half, (4 - aq) * 2);
       }
       if (active) {
         bool row_masked = false;
@@ -440,11 +456,12 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
       __syncthreads();
       if (!want_out) continue;             // scores only (uniform): nothing reads the accumulator again
 
-      // ---- O = P V : A from TMEM, B = v tile MN-major (LBO field = stride between 8-token groups, SBO field = 8-channel cores)
+      // ---- O = P V : A from TMEM, B = v tile MN-major (LBO field = stride between 8-token groups = 128 B, SBO field = stride
+      // between 8-channel cores = one chunk)
       if (tid == 0) {
         umma::tc_fence_after_sync();
         for (int ks = 0; ks < nch; ++ks)
-          mma_bf16_ts(tmem + o_col, tmem + ks * 8, umma::smem_desc_kmajor(v_i + ks * 2048, 1024, 128), idesc_o, ks > 0 ? 1u : 0u);
+          mma_bf16_ts(tmem + o_col, tmem + ks * 8, umma::smem_desc_kmajor(v_i + ks * 256, 128, chunk_bytes), idesc_o, ks > 0 ? 1u : 0u);
         umma::mma_commit(bar);
         umma::mbar_wait(bar, phase);
       }
@@ -501,8 +518,8 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const AttnParams
 
 size_t attn_smem_bytes(int N, int M, bool colsum) {
   const int Np = (N + 15) & ~15;
-  const int groups = (M + 7) / 8 + 3 * (Np / 8), mma_rows = ((M + 127) / 128) * 16;
-  return (size_t)(groups > mma_rows ? groups : mma_rows) * 1024 + (size_t)2 * Np * 4 + 2048 + (colsum ? (size_t)8 * Np * 4 : 0) + 64;
+  (void)M;
+  return (size_t)4 * Np * 128 + (size_t)2 * Np * 4 + 2048 + (colsum ? (size_t)8 * Np * 4 : 0) + 64;
 }
 
 }  // namespace
@@ -510,6 +527,25 @@ size_t attn_smem_bytes(int N, int M, bool colsum) {
 
 using namespace tokred;
 TOKRED_STAMP_SETTER(attention)
+
+namespace {
+// cuTensorMapEncodeTiled through the runtime's driver entry point: the library links cudart only
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+}  // namespace
 
 extern "C" int tokred_attention(const void* qkv, int B, int N, int H, int head_dim, float scale, const float* key_bias,
                                 const uint8_t* mask, const int64_t* q_ids, int64_t ids_stride, int M, void* out,
@@ -538,10 +574,29 @@ extern "C" int tokred_attention(const void* qkv, int B, int N, int H, int head_d
   // persistent CTAs, two per SM (108 KB of shared memory and <= 256 TMEM columns each)
   const int grid = B * H < 2 * kNumSMs ? B * H : 2 * kNumSMs;
   cudaStream_t st = (cudaStream_t)stream;
+  // qkv as a 4-D tensor (d, q/k/v x head, token, image); one box = 8 elements (a 16-byte K-chunk) of Np consecutive tokens
+  // of one (q/k/v, head) slot.  Tokens past N are out of bounds: the copy writes zeros.
+  EncodeTiledFn encode = tensor_map_encoder();
+  if (!encode) {
+    set_error("attention: cuTensorMapEncodeTiled is not available from this driver");
+    return TOKRED_ERR_UNSUPPORTED;
+  }
+  const int C = H * 64, Np = (N + 15) & ~15;
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {64, (cuuint64_t)(3 * H), (cuuint64_t)N, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {128, (cuuint64_t)3 * C * 2, (cuuint64_t)N * 3 * C * 2};
+  const cuuint32_t box[4] = {8, 1, (cuuint32_t)Np, 1}, estr[4] = {1, 1, 1, 1};
+  const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(qkv), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("attention: cuTensorMapEncodeTiled failed (%d) for B=%d N=%d H=%d", (int)cr, B, N, H);
+    return TOKRED_ERR_UNSUPPORTED;
+  }
 #define LAUNCH(BIAS, R2, MASK, CS)                                                                  \
   do {                                                                                              \
     if (int e = allow_smem(attention_kernel<BIAS, R2, MASK, CS>, smem, "attention")) return e;     \
-    attention_kernel<BIAS, R2, MASK, CS><<<grid, kThreads, smem, st>>>(prm);                       \
+    attention_kernel<BIAS, R2, MASK, CS><<<grid, kThreads, smem, st>>>(tmap, prm);                 \
   } while (0)
 #define PICK(BIAS, MASK)                                                                            \
   do {                                                                                              \
