@@ -220,15 +220,18 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
   const bool want_out = p.out != nullptr;
   const int nitems = p.B * H;
 
-  // Q | K | V[0] | V[1], each [8 K-chunks][Np rows][16 B]: the canonical no-swizzle UMMA layout with the 8-row core
-  // matrices of one 16-byte K-chunk back to back (SBO = 128 B) and the chunks Np*16 B apart (LBO) -- exactly what a TMA
-  // box of (8 elements x Np tokens) per chunk writes.  The CTA is persistent: while it works on the last query tile of an
-  // item, the next item's q, k (dead once the last S MMA has completed) and v (other buffer) are already on their way.
-  const uint32_t chunk_bytes = (uint32_t)Np * 16u, mat_bytes = 8u * chunk_bytes;
+  // Q | K | V[0] | V[1], each [Np rows][128 B] in the 128-byte swizzled UMMA layout (16-byte chunk index XOR row % 8) --
+  // exactly what ONE TMA box of (64 elements x Np tokens) with SWIZZLE_128B writes (a first TMA version wrote 8-element
+  // boxes into the no-swizzle layout: 4.7 k 16-byte requests per item kept the copy at 4-5 us and slowed the P.V MMA
+  // running beside it).  The CTA is persistent: while it works on the last query tile of an item, the next item's q, k
+  // (dead once the last S MMA has completed) and v (other buffer) are already on their way.
+  const uint32_t mat_bytes = (uint32_t)Np * 128u;
   unsigned char* Qs = smem;
   unsigned char* Ks = Qs + mat_bytes;
   unsigned char* Vs = Ks + mat_bytes;
-  float* bias_s = reinterpret_cast<float*>(smem + 4 * (size_t)mat_bytes);    // [2][Np]
+  // the S MMA always reads 128 A rows: the operand area spans at least ntiles * 16 KB past Qs
+  const size_t op_bytes = max((size_t)4 * mat_bytes, (size_t)ntiles * 16384);
+  float* bias_s = reinterpret_cast<float*>(smem + op_bytes);                  // [2][Np]
   float* red_max = bias_s + 2 * Np;                                           // [2][128]
   float* red_sum = red_max + 256;                                             // [2][128]
   float* colpart = red_sum + 256;                                             // [8][Np] (COLSUM)
@@ -254,12 +257,9 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
     const uint32_t nmat = 1u + (want_out ? 1u : 0u) + (q_by_tma ? 1u : 0u);
     mbar_expect_tx(&ldbar[buf], nmat * mat_bytes);
     const uint32_t k0 = umma::smem_u32(Ks), v0 = umma::smem_u32(Vs) + (uint32_t)buf * mat_bytes, q0 = umma::smem_u32(Qs);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      tma_load_4d(k0 + c * chunk_bytes, &tmap, c * 8, H + h, 0, b, &ldbar[buf]);
-      if (want_out) tma_load_4d(v0 + c * chunk_bytes, &tmap, c * 8, 2 * H + h, 0, b, &ldbar[buf]);
-      if (q_by_tma) tma_load_4d(q0 + c * chunk_bytes, &tmap, c * 8, h, 0, b, &ldbar[buf]);
-    }
+    tma_load_4d(k0, &tmap, 0, H + h, 0, b, &ldbar[buf]);
+    if (q_by_tma) tma_load_4d(q0, &tmap, 0, h, 0, b, &ldbar[buf]);
+    if (want_out) tma_load_4d(v0, &tmap, 0, 2 * H + h, 0, b, &ldbar[buf]);
   };
   auto issue_rest = [&](int item, int buf, int wi, int nw) {      // warp wi of nw issuing warps
     const int b = item / H, h = item - b * H;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
         const int row = e >> 3, c = e & 7;
         const bool ok = row < M;
         const int srow = ok ? (ids ? clamp_idx(ids[row], N) : row) : 0;
-        cp_async16(umma::smem_u32(Qs) + c * chunk_bytes + row * 16, src0 + (size_t)srow * row_bytes + c * 16, ok ? 16u : 0u);
+        cp_async16(umma::smem_u32(Qs) + row * 128 + ((c ^ (row & 7)) << 4), src0 + (size_t)srow * row_bytes + c * 16, ok ? 16u : 0u);
       }
     }
     if (BIAS)
@@ -325,11 +325,11 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
     for (int t = 0; t < ntiles; ++t) {
       // ---- S = Q_t K^T (rows past the Q tile read what lies behind it: finite garbage in accumulator rows nobody reads)
       if (tid == 0) {
-        const uint32_t a0 = umma::smem_u32(Qs) + (uint32_t)t * 2048u, b0 = umma::smem_u32(Ks);
+        const uint32_t a0 = umma::smem_u32(Qs) + (uint32_t)t * 16384u, b0 = umma::smem_u32(Ks);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma::mma_bf16(tmem, umma::smem_desc_kmajor(a0 + ks * 2 * chunk_bytes, chunk_bytes, 128),
-                         umma::smem_desc_kmajor(b0 + ks * 2 * chunk_bytes, chunk_bytes, 128), idesc_s, ks > 0 ? 1u : 0u);
+          umma::mma_bf16(tmem, umma::smem_desc_sw128(a0 + ks * 32, 16, 1024), umma::smem_desc_sw128(b0 + ks * 32, 16, 1024),
+                         idesc_s, ks > 0 ? 1u : 0u);
         umma::mma_commit(bar);
         umma::mbar_wait(bar, phase);       // one thread polls; everybody else parks at the barrier below
       }
@@ -456,12 +456,11 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
       __syncthreads();
       if (!want_out) continue;             // scores only (uniform): nothing reads the accumulator again
 
-      // ---- O = P V : A from TMEM, B = v tile MN-major (LBO field = stride between 8-token groups = 128 B, SBO field = stride
-      // between 8-channel cores = one chunk)
+      // ---- O = P V : A from TMEM, B = v tile used MN-major (rows = tokens = the K index; 16 tokens per MMA = 2048 bytes)
       if (tid == 0) {
         umma::tc_fence_after_sync();
         for (int ks = 0; ks < nch; ++ks)
-          mma_bf16_ts(tmem + o_col, tmem + ks * 8, umma::smem_desc_kmajor(v_i + ks * 256, 128, chunk_bytes), idesc_o, ks > 0 ? 1u : 0u);
+          mma_bf16_ts(tmem + o_col, tmem + ks * 8, umma::smem_desc_sw128(v_i + ks * 2048, 16, 1024), idesc_o, ks > 0 ? 1u : 0u);
         umma::mma_commit(bar);
         umma::mbar_wait(bar, phase);
       }
@@ -518,8 +517,8 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
 
 size_t attn_smem_bytes(int N, int M, bool colsum) {
   const int Np = (N + 15) & ~15;
-  (void)M;
-  return (size_t)4 * Np * 128 + (size_t)2 * Np * 4 + 2048 + (colsum ? (size_t)8 * Np * 4 : 0) + 64;
+  const size_t ops = (size_t)4 * Np * 128, mma = (size_t)((M + 127) / 128) * 16384;
+  return (ops > mma ? ops : mma) + (size_t)2 * Np * 4 + 2048 + (colsum ? (size_t)8 * Np * 4 : 0) + 64;
 }
 
 }  // namespace
@@ -574,8 +573,8 @@ extern "C" int tokred_attention(const void* qkv, int B, int N, int H, int head_d
   // persistent CTAs, two per SM (108 KB of shared memory and <= 256 TMEM columns each)
   const int grid = B * H < 2 * kNumSMs ? B * H : 2 * kNumSMs;
   cudaStream_t st = (cudaStream_t)stream;
-  // qkv as a 4-D tensor (d, q/k/v x head, token, image); one box = 8 elements (a 16-byte K-chunk) of Np consecutive tokens
-  // of one (q/k/v, head) slot.  Tokens past N are out of bounds: the copy writes zeros.
+  // qkv as a 4-D tensor (d, q/k/v x head, token, image); one box = the 64 elements of Np consecutive tokens of one
+  // (q/k/v, head) slot, written 128-byte swizzled.  Tokens past N are out of bounds: the copy writes zeros.
   EncodeTiledFn encode = tensor_map_encoder();
   if (!encode) {
     set_error("attention: cuTensorMapEncodeTiled is not available from this driver");
@@ -585,9 +584,9 @@ extern "C" int tokred_attention(const void* qkv, int B, int N, int H, int head_d
   CUtensorMap tmap;
   const cuuint64_t dims[4] = {64, (cuuint64_t)(3 * H), (cuuint64_t)N, (cuuint64_t)B};
   const cuuint64_t strides[3] = {128, (cuuint64_t)3 * C * 2, (cuuint64_t)N * 3 * C * 2};
-  const cuuint32_t box[4] = {8, 1, (cuuint32_t)Np, 1}, estr[4] = {1, 1, 1, 1};
+  const cuuint32_t box[4] = {64, 1, (cuuint32_t)Np, 1}, estr[4] = {1, 1, 1, 1};
   const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(qkv), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     set_error("attention: cuTensorMapEncodeTiled failed (%d) for B=%d N=%d H=%d", (int)cr, B, N, H);

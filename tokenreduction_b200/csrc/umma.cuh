@@ -80,6 +80,20 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lb
   d |= (uint64_t)1 << 46;   // descriptor version for sm_100
   return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
+// 128-byte swizzled operand tiles (what a TMA box with CU_TENSOR_MAP_SWIZZLE_128B writes): rows of 128 bytes, the 16-byte
+// chunk index XORed with (row % 8); the tile base must be 1024-byte aligned.  K-major: a row is one M/N index with 64
+// bf16 along K, SBO = 1024 (next 8 rows), LBO unused, a K step of 16 elements advances the start address by 32 bytes.
+// MN-major: a row is one K index with 64 bf16 along M/N, SBO = 1024 (next 8 K indices), LBO = stride to the next 64
+// M/N elements (unused for N = 64).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version for sm_100
+  d |= (uint64_t)2 << 61;   // layout_type SWIZZLE_128B
+  return d;
+}
 enum { FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2 };
 // instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, both operands K-major, dense
 __host__ __device__ constexpr uint32_t instr_desc(uint32_t fmt, uint32_t m, uint32_t n) {
