@@ -306,8 +306,10 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
   const int nch = Np >> 4;
   // Column split of passes A and B between the two warps of a quarter; pass C (cheap, and its in-place writes must trail
   // its reads) is the lower warp's alone, so the lower warp takes fewer columns: 87 a + 27 nch = 87 (nch - a).
-  // (Splitting pass C too, with the upper warp parking its packed half in registers until the lower warp has read, was
-  // measured slower: 128 registers no longer hold it and the spills queue behind the prefetch in the load/store unit.)
+  // (Splitting pass C too was measured twice: with the upper warp parking its whole packed half in registers until the
+  // lower warp has read, 128 registers no longer hold it and the spills made it slower; with at most 32 parked
+  // registers and an even A/B split it came out even (70 vs 72 us at B=256, 477 vs 468 us at B=1024): pass C is bound by
+  // the TMEM load -> convert -> store latency of each chunk, not by the number of chunks per warp.)
   const int nlo = (nch * 11 + 16) >> 5;
   const int c_beg = half ? nlo : 0, c_end = half ? nch : nlo;
   const int c_full = (c_end == nch && c_end > c_beg && (N & 15)) ? c_end - 1 : c_end;      // [c_beg, c_full) full chunks, then the ragged one
