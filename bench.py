@@ -226,6 +226,18 @@ def algorithmic_bytes(name: str, a: tuple) -> float:
     return 0.0
 
 
+def dominant_kernel(rows):
+    """the roofline object describes the DOMINANT tokred kernel: the kernel family with the largest share of the step
+    (sum of avg_us x launches over its launch groups), represented by its largest launch group (first stage)."""
+    if not rows:
+        return None
+    share = {}
+    for r in rows:
+        share[r["kernel"]] = share.get(r["kernel"], 0.0) + r["avg_us"] * r["launches_per_step"]
+    fam = max(share, key=share.get)
+    return max((r for r in rows if r["kernel"] == fam), key=lambda r: r["alg_mb"])
+
+
 def summarise_timeline(timeline, steps, peak_gbs):
     """group launches by (name, shape) -> avg duration, algorithmic GB/s, fraction of the HBM peak."""
     groups = {}
@@ -515,7 +527,7 @@ def run_tokred(a):
                 rr = r.measure(xsteps, xwarm, timeline=True, graph=not a.no_graph)
                 xms, xms_e2e = max_over_ranks(rr["ms"], rr["ms_e2e"])
                 ks = summarise_timeline(rr["timeline"], rr["timeline_steps"], peaks["hbm_gbs"])
-                top = ks[0] if ks else None
+                top = dominant_kernel(ks)
                 m_, s_, kr_, _, amp_ = WORKLOADS[key]
                 extras.append({
                     "workload": label, "baseline_config": cfg_no, "model": f"{m_}_{s_}_patch16_224", "keep_rate": kr_,
@@ -535,7 +547,7 @@ def run_tokred(a):
 
     if rank == 0:
         total = batch * world
-        top = kernels[0] if kernels else None
+        top = dominant_kernel(kernels)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if top and os.path.exists(tpath):
