@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
   float* bias_s = reinterpret_cast<float*>(smem + op_bytes);                  // [2][Np]
   float* red_max = bias_s + 2 * Np;                                           // [2][128]
   float* red_sum = red_max + 256;                                             // [2][128]
-  float* colpart = red_sum + 256;                                             // [8][Np] (COLSUM)
-  uint64_t* bar = reinterpret_cast<uint64_t*>(colpart + (COLSUM ? 8 * Np : 0));
+  float* colpart = red_sum + 256;                                             // [4 quarters][Np] (COLSUM)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(colpart + (COLSUM ? 4 * Np : 0));
   uint64_t* ldbar = bar + 1;                                                  // [2]: operands of item it landed (TMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ldbar + 2);
 
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
     issue_rest(item, 0, warp, kThreads / 32);
   }
   if (COLSUM)
-    for (int j = tid; j < 8 * Np; j += kThreads) colpart[j] = 0.f;
+    for (int j = tid; j < 4 * Np; j += kThreads) colpart[j] = 0.f;
   cp_async_wait_all();
   umma::fence_proxy_async_smem();
   umma::tc_fence_before_sync();
@@ -430,7 +430,9 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = row < M ? __uint_as_float(r[i]) * inv : 0.f;
             const float cs = colsum16(v, lane);
-            if (!(lane & 1)) colpart[(size_t)(t * 4 + q) * Np + c * 16 + (lane >> 1)] = cs;
+            // one slot per quarter: the second query tile adds onto the first (same warp, fixed order: deterministic).
+            // Eight slots pushed the CTA past 113 KB of shared memory: one CTA per SM instead of two, 177 us instead of 95.
+            if (!(lane & 1)) colpart[(size_t)q * Np + c * 16 + (lane >> 1)] += cs;
           });
           pair_sync(q);
         }
@@ -497,12 +499,12 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
       TOKRED_STAMP(tid == 0 && it == 0, t, 7);
     }
     if (COLSUM) {
-      // fixed-order combine of the (tile, quarter) partials: deterministic
+      // fixed-order combine of the quarter partials: deterministic
       float* dst = p.colsum + ((size_t)b * H + h) * N;
       for (int j = tid; j < N; j += kThreads) {
         float s = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { s += colpart[(size_t)k * Np + j]; colpart[(size_t)k * Np + j] = 0.f; }
+        for (int k = 0; k < 4; ++k) { s += colpart[(size_t)k * Np + j]; colpart[(size_t)k * Np + j] = 0.f; }
         dst[j] = s;
       }
     }
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
 size_t attn_smem_bytes(int N, int M, bool colsum) {
   const int Np = (N + 15) & ~15;
   const size_t ops = (size_t)4 * Np * 128, mma = (size_t)((M + 127) / 128) * 16384;
-  return (ops > mma ? ops : mma) + (size_t)2 * Np * 4 + 2048 + (colsum ? (size_t)8 * Np * 4 : 0) + 64;
+  return (ops > mma ? ops : mma) + (size_t)2 * Np * 4 + 2048 + (colsum ? (size_t)4 * Np * 4 : 0) + 64;
 }
 
 }  // namespace
