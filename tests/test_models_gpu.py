@@ -352,3 +352,25 @@ def test_cuda_graph_replay_equals_eager(name):
             want = model(x).clone()
         got = run(x)
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("name", METHODS)
+def test_fp16_autocast_reference_default(name):
+    """validate.py:52-54 evaluates under torch.cuda.amp.autocast() = fp16.  The drop-in runs it: half tensors are converted
+    at the op boundary (fp16 -> fp32 is exact), the fused bf16 producers stay off, and the logits stay within the
+    half-precision noise of the fp32 forward of the same model."""
+    from tokenreduction_b200 import create_model
+    torch.manual_seed(0)
+    model = quiet(create_model, f"{name}_tiny_patch16_224", num_classes=50, args=margs(KR[name])).eval().cuda()
+    x = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(5)).cuda()
+    torch.manual_seed(9)
+    torch.cuda.manual_seed(9)
+    with torch.no_grad():
+        y32 = model(x)
+    torch.manual_seed(9)
+    torch.cuda.manual_seed(9)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        y16 = model(x)
+    assert torch.isfinite(y16).all()
+    rel = ((y16.float() - y32).norm(dim=1) / y32.norm(dim=1)).max()
+    assert float(rel) < 0.35, f"{name}: fp16-autocast logits {float(rel):.3f} away from fp32"
