@@ -95,8 +95,9 @@ class _ReducedViT(VisionTransformer):
     """shared head/tail of every reduced model's forward."""
 
     def _logits(self, x):
-        x = self.norm(x)
-        return self.head(self.pre_logits(x[:, 0]))
+        # LayerNorm is per token: norm(x)[:, 0] == norm(x[:, 0]) bit for bit, and only the class token is read
+        # (e.g. models/topk.py:205-207)
+        return self.head(self.pre_logits(self.norm(x[:, 0])))
 
     def _ret(self, x, viz_data=None):
         if self.training or not self.viz_mode:
