@@ -114,23 +114,37 @@ __device__ __forceinline__ void ld_wait16(uint32_t (&r)[16]) {
                :
                : "memory");
 }
-// f(r, c) over the 16-column chunks [c0, c1) of one accumulator row, the load of chunk c+1 in flight while chunk c is
-// processed (two register sets, loop unrolled by two so they never move)
+// f(r, c) over the 16-column chunks [c0, c1) of one accumulator row, two chunks per round: both loads are issued, then
+// both chunks are processed -- the two bodies are independent, so the scheduler sees twice the instruction-level
+// parallelism of one chunk (a warp shares its scheduler with only three others: its own ILP is what hides latency)
 template <typename F>
 __device__ __forceinline__ void for_chunks(uint32_t trow, int c0, int c1, F&& f) {
-  if (c0 >= c1) return;
-  uint32_t ra[16], rb[16];
-  umma::tmem_ld16(trow + c0 * 16, ra);
+  uint32_t ra[16], rb[16], rc[16];
   int c = c0;
-  while (true) {
+  for (; c + 2 < c1; c += 3) {
+    umma::tmem_ld16(trow + c * 16, ra);
+    umma::tmem_ld16(trow + (c + 1) * 16, rb);
+    umma::tmem_ld16(trow + (c + 2) * 16, rc);
     ld_wait16(ra);
-    if (c + 1 < c1) umma::tmem_ld16(trow + (c + 1) * 16, rb);
-    f(ra, c);
-    if (++c >= c1) break;
     ld_wait16(rb);
-    if (c + 1 < c1) umma::tmem_ld16(trow + (c + 1) * 16, ra);
-    f(rb, c);
-    if (++c >= c1) break;
+    ld_wait16(rc);
+    f(ra, c);
+    f(rb, c + 1);
+    f(rc, c + 2);
+  }
+  if (c + 1 < c1) {
+    umma::tmem_ld16(trow + c * 16, ra);
+    umma::tmem_ld16(trow + (c + 1) * 16, rb);
+    ld_wait16(ra);
+    ld_wait16(rb);
+    f(ra, c);
+    f(rb, c + 1);
+    c += 2;
+  }
+  if (c < c1) {
+    umma::tmem_ld16(trow + c * 16, ra);
+    ld_wait16(ra);
+    f(ra, c);
   }
 }
 __device__ __forceinline__ float bf16r(float v) { return __uint_as_float(pack_bf16x2(v, 0.f) << 16); }
