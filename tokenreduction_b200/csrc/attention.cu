@@ -347,10 +347,9 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
           umma::mma_bf16(tmem, umma::smem_desc_sw128(a0 + ks * 32, 16, 1024), umma::smem_desc_sw128(b0 + ks * 32, 16, 1024),
                          idesc_s, ks > 0 ? 1u : 0u);
         umma::mma_commit(bar);
-        umma::mbar_wait(bar, phase);       // one thread polls; everybody else parks at the barrier below
       }
+      umma::mbar_wait(bar, phase);
       phase ^= 1u;
-      __syncthreads();
       umma::tc_fence_after_sync();
       TOKRED_STAMP(tid == 0 && it == 0, t, 2);
       const int row = t * 128 + rl;                          // query row
@@ -480,10 +479,9 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
         for (int ks = 0; ks < nch; ++ks)
           mma_bf16_ts(tmem + o_col, tmem + ks * 8, umma::smem_desc_sw128(v_i + ks * 2048, 16, 1024), idesc_o, ks > 0 ? 1u : 0u);
         umma::mma_commit(bar);
-        umma::mbar_wait(bar, phase);
       }
+      umma::mbar_wait(bar, phase);
       phase ^= 1u;
-      __syncthreads();
       umma::tc_fence_after_sync();
       TOKRED_STAMP(tid == 0 && it == 0, t, 6);
       if (active) {                                          // whole warp: the TMEM loads are .sync.aligned
