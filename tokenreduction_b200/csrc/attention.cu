@@ -319,12 +319,13 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
   uint32_t phase = 0;
   const int nch = Np >> 4;
   // Column split of passes A and B between the two warps of a quarter; pass C (cheap, and its in-place writes must trail
-  // its reads) is the lower warp's alone, so the lower warp takes fewer columns: 87 a + 27 nch = 87 (nch - a).
+  // its reads) is the lower warp's alone, so the lower warp takes the smaller share of A and B.  Measured at N = 197
+  // (13 chunks): 4/9 64.2 us, 5/8 62.9 us, 6/7 63.1 us (B=256), 431 / 429 / 425 us (B=1024).
   // (Splitting pass C too was measured twice: with the upper warp parking its whole packed half in registers until the
   // lower warp has read, 128 registers no longer hold it and the spills made it slower; with at most 32 parked
-  // registers and an even A/B split it came out even (70 vs 72 us at B=256, 477 vs 468 us at B=1024): pass C is bound by
-  // the TMEM load -> convert -> store latency of each chunk, not by the number of chunks per warp.)
-  const int nlo = (nch * 11 + 16) >> 5;
+  // registers and an even A/B split it came out even: pass C is bound by the TMEM load -> convert -> store latency of
+  // each chunk, not by the number of chunks per warp.)
+  const int nlo = (nch * 15 + 16) >> 5;
   const int c_beg = half ? nlo : 0, c_end = half ? nch : nlo;
   const int c_full = (c_end == nch && c_end > c_beg && (N & 15)) ? c_end - 1 : c_end;      // [c_beg, c_full) full chunks, then the ragged one
   const uint32_t trow = umma::tmem_addr(tmem, (uint32_t)(q * 32), 0);
