@@ -323,8 +323,9 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
   // (13 chunks): 4/9 64.2 us, 5/8 62.9 us, 6/7 63.1 us (B=256), 431 / 429 / 425 us (B=1024).
   // (Splitting pass C too was measured twice: with the upper warp parking its whole packed half in registers until the
   // lower warp has read, 128 registers no longer hold it and the spills made it slower; with at most 32 parked
-  // registers and an even A/B split it came out even: pass C is bound by the TMEM load -> convert -> store latency of
-  // each chunk, not by the number of chunks per warp.)
+  // registers and an even A/B split it came out even, and with 2-3 loads in flight per round on both warps it was
+  // slower again (68 vs 63 us: the pair barrier in the middle and ~125 registers cost more than the halved chunk count
+  // saves).)
   const int nlo = (nch * 15 + 16) >> 5;
   const int c_beg = half ? nlo : 0, c_end = half ? nch : nlo;
   const int c_full = (c_end == nch && c_end > c_beg && (N & 15)) ? c_end - 1 : c_end;      // [c_beg, c_full) full chunks, then the ragged one
