@@ -250,14 +250,16 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
   float* red_sum = red_max + 256;                                             // [2][128]
   float* colpart = red_sum + 256;                                             // [4 quarters][Np] (COLSUM)
   uint64_t* bar = reinterpret_cast<uint64_t*>(colpart + (COLSUM ? 4 * Np : 0));
-  uint64_t* ldbar = bar + 1;                                                  // [2]: operands of item it landed (TMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ldbar + 2);
+  uint64_t* ldbar = bar + 1;                                                  // [2]: q, k of item it landed (TMA)
+  uint64_t* vbar = ldbar + 2;                                                 // [2]: v of item it landed (needed only by P.V)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(vbar + 2);
 
   const uint32_t ncols = Np <= 128 ? 128u : 256u;
   const uint32_t o_col = Np <= 128 ? 64u : 128u;
   TOKRED_STAMP(tid == 0, 0, 0);
   if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
-  if (tid == 0) { umma::mbar_init(bar, 1); umma::mbar_init(&ldbar[0], 1); umma::mbar_init(&ldbar[1], 1); umma::fence_mbar_init(); }
+  if (tid == 0) { umma::mbar_init(bar, 1); umma::mbar_init(&ldbar[0], 1); umma::mbar_init(&ldbar[1], 1);
+                  umma::mbar_init(&vbar[0], 1); umma::mbar_init(&vbar[1], 1); umma::fence_mbar_init(); }
   __syncthreads();
 
   // ---- loads of one item into (Qs, Ks, V[buf], bias[buf]).  k, v and (without a row gather) q arrive by TMA: one thread
@@ -268,12 +270,12 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
   const size_t row_bytes = (size_t)3 * C * 2;
   auto issue_tma = [&](int item, int buf) {                       // one thread
     const int b = item / H, h = item - b * H;
-    const uint32_t nmat = 1u + (want_out ? 1u : 0u) + (q_by_tma ? 1u : 0u);
-    mbar_expect_tx(&ldbar[buf], nmat * mat_bytes);
+    mbar_expect_tx(&ldbar[buf], (q_by_tma ? 2u : 1u) * mat_bytes);
+    if (want_out) mbar_expect_tx(&vbar[buf], mat_bytes);
     const uint32_t k0 = umma::smem_u32(Ks), v0 = umma::smem_u32(Vs) + (uint32_t)buf * mat_bytes, q0 = umma::smem_u32(Qs);
     tma_load_4d(k0, &tmap, 0, H + h, 0, b, &ldbar[buf]);
     if (q_by_tma) tma_load_4d(q0, &tmap, 0, h, 0, b, &ldbar[buf]);
-    if (want_out) tma_load_4d(v0, &tmap, 0, 2 * H + h, 0, b, &ldbar[buf]);
+    if (want_out) tma_load_4d(v0, &tmap, 0, 2 * H + h, 0, b, &vbar[buf]);
   };
   auto issue_rest = [&](int item, int buf, int wi, int nw) {      // warp wi of nw issuing warps
     const int b = item / H, h = item - b * H;
@@ -478,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
       // ---- O = P V : A from TMEM, B = v tile used MN-major (rows = tokens = the K index; 16 tokens per MMA = 2048 bytes)
       if (tid == 0) {
         umma::tc_fence_after_sync();
+        if (t == 0) umma::mbar_wait(&vbar[buf], (uint32_t)((it >> 1) & 1));       // v has its own barrier: S never waits for it
         for (int ks = 0; ks < nch; ++ks)
           mma_bf16_ts(tmem + o_col, tmem + ks * 8, umma::smem_desc_sw128(v_i + ks * 2048, 16, 1024), idesc_o, ks > 0 ? 1u : 0u);
         umma::mma_commit(bar);
@@ -536,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_kernel(const __grid_con
 size_t attn_smem_bytes(int N, int M, bool colsum) {
   const int Np = (N + 15) & ~15;
   const size_t ops = (size_t)4 * Np * 128, mma = (size_t)((M + 127) / 128) * 16384;
-  return (ops > mma ? ops : mma) + (size_t)2 * Np * 4 + 2048 + (colsum ? (size_t)4 * Np * 4 : 0) + 64;
+  return (ops > mma ? ops : mma) + (size_t)2 * Np * 4 + 2048 + (colsum ? (size_t)4 * Np * 4 : 0) + 96;
 }
 
 }  // namespace
