@@ -243,11 +243,9 @@ constexpr int kPoolPhases = kThreads / (kPoolSlice / 8);   // 16
 template <typename T> __device__ __forceinline__ void ld8(const T* p, bool vec, int valid, float (&v)[8]);
 template <> __device__ __forceinline__ void ld8<float>(const float* p, bool vec, int valid, float (&v)[8]) {
   if (vec && valid >= 8) {
-    const int4 a = ld_stream16(p), b = ld_stream16(p + 4);
-    const float* fa = reinterpret_cast<const float*>(&a);
-    const float* fb = reinterpret_cast<const float*>(&b);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { v[i] = fa[i]; v[4 + i] = fb[i]; }
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = i < valid ? p[i] : 0.f;
@@ -267,8 +265,11 @@ template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat
 template <typename T> __device__ __forceinline__ void st8(T* p, bool vec, int valid, const float (&v)[8]);
 template <> __device__ __forceinline__ void st8<float>(float* p, bool vec, int valid, const float (&v)[8]) {
   if (vec && valid >= 8) {
-    st_stream16(p, *reinterpret_cast<const int4*>(&v[0]));
-    st_stream16(p + 4, *reinterpret_cast<const int4*>(&v[4]));
+    // ONE 32-byte store per thread (STG.256; rows are 32-byte aligned on the vector path): two 16-byte stores at a
+    // 32-byte lane stride touch every sector twice
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) if (i < valid) p[i] = v[i];
@@ -286,17 +287,50 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
   }
 }
 
-template <typename TI, typename TO>
-__global__ void __launch_bounds__(kThreads)
+// raw 8-channel chunk of a row: bf16 stays packed in registers (4 instead of 8) until it is consumed, so that more
+// rows can be in flight per thread without pushing the CTA count per SM down
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float f[8]; };
+template <> struct Raw8<__nv_bfloat16> { int4 q; };
+__device__ __forceinline__ void ldraw(const float* p, bool vec, int valid, Raw8<float>& r) { ld8<float>(p, vec, valid, r.f); }
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, bool vec, int valid, Raw8<__nv_bfloat16>& r) {
+  if (vec && valid >= 8) {
+    r.q = ld_stream16(p);
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t lo = 2 * i < valid ? (uint32_t)__bfloat16_as_ushort(p[2 * i]) : 0u;
+      const uint32_t hi = 2 * i + 1 < valid ? (uint32_t)__bfloat16_as_ushort(p[2 * i + 1]) : 0u;
+      w[i] = lo | (hi << 16);
+    }
+    r.q = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+  }
+}
+__device__ __forceinline__ void unraw(const Raw8<float>& r, float (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = r.f[i];
+}
+__device__ __forceinline__ void unraw(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+  const uint32_t w[4] = {(uint32_t)r.q.x, (uint32_t)r.q.y, (uint32_t)r.q.z, (uint32_t)r.q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
+template <typename TI, typename TO, bool vec>
+__global__ void __launch_bounds__(kThreads, 3)
 dyvit_pool_concat_kernel(const TI* __restrict__ h, const float* __restrict__ policy, TO* __restrict__ out, int P, int C,
-                         float eps, int vec) {
+                         float eps) {
   extern __shared__ float smem[];
+  // rows in flight per thread (P = 196: 13 rows per thread -> 2 / 4 rounds); the scalar fallback keeps one
+  constexpr int R = !vec ? 1 : (sizeof(TI) == 2 ? 6 : 4);
   float* part = smem;                              // [kPoolPhases][kPoolSlice]
   float* pol = smem + kPoolPhases * kPoolSlice;    // [P]
   const int b = blockIdx.y, tid = threadIdx.x, half = C / 2;
   const int ct = tid % (kPoolSlice / 8), ph = tid / (kPoolSlice / 8);
   const int c0 = blockIdx.x * kPoolSlice + ct * 8;          // first of this thread's 8 channels (within a half)
   const int valid = half - c0;                              // <= 0: thread idle
+  const int vld = vec ? 8 : valid;                          // vector path: half % 8 == 0, a live chunk is always whole
   const TI* hb = h + (long long)b * P * C;
   for (int p = tid; p < P; p += kThreads) pol[p] = policy[(long long)b * P + p];
   __syncthreads();
@@ -306,17 +340,19 @@ dyvit_pool_concat_kernel(const TI* __restrict__ h, const float* __restrict__ pol
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (valid > 0) {
-    for (int p0 = ph; p0 < P; p0 += 4 * kPoolPhases) {          // 4 rows in flight per thread, consumed in ascending order
-      float v[4][8];
+    for (int p0 = ph; p0 < P; p0 += R * kPoolPhases) {          // R rows in flight per thread, consumed in ascending order
+      Raw8<TI> raw[R];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (p0 + kPoolPhases * u < P) ld8<TI>(hb + (long long)(p0 + kPoolPhases * u) * C + half + c0, vec, valid, v[u]);
+      for (int u = 0; u < R; ++u)
+        if (p0 + kPoolPhases * u < P) ldraw(hb + (long long)(p0 + kPoolPhases * u) * C + half + c0, vec, vld, raw[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < R; ++u)
         if (p0 + kPoolPhases * u < P) {
           const float w = pol[p0 + kPoolPhases * u];
+          float v[8];
+          unraw(raw[u], v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += v[u][i] * w;
+          for (int i = 0; i < 8; ++i) acc[i] += v[i] * w;
         }
     }
   }
@@ -324,26 +360,34 @@ dyvit_pool_concat_kernel(const TI* __restrict__ h, const float* __restrict__ pol
   for (int i = 0; i < 8; ++i) part[ph * kPoolSlice + ct * 8 + i] = acc[i];
   __syncthreads();
   float g[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float s = part[ct * 8 + i];
-#pragma unroll
-    for (int q = 1; q < kPoolPhases; ++q) s += part[q * kPoolSlice + ct * 8 + i];
-    g[i] = s / psum + eps;
+  {
+    // phases combined in ascending order; two 16-byte reads per phase (128 scalar reads scheduled at once held 128 registers)
+    const float4* p4 = reinterpret_cast<const float4*>(part + ct * 8);
+    float4 s0 = p4[0], s1 = p4[1];
+#pragma unroll 4
+    for (int q = 1; q < kPoolPhases; ++q) {
+      const float4 a = p4[q * (kPoolSlice / 4)], c = p4[q * (kPoolSlice / 4) + 1];
+      s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+      s1.x += c.x; s1.y += c.y; s1.z += c.z; s1.w += c.w;
+    }
+    g[0] = s0.x / psum + eps; g[1] = s0.y / psum + eps; g[2] = s0.z / psum + eps; g[3] = s0.w / psum + eps;
+    g[4] = s1.x / psum + eps; g[5] = s1.y / psum + eps; g[6] = s1.z / psum + eps; g[7] = s1.w / psum + eps;
   }
   if (valid > 0) {
     TO* ob = out + (long long)b * P * C;
-    for (int p0 = ph; p0 < P; p0 += 4 * kPoolPhases) {
-      float v[4][8];
+    for (int p0 = ph; p0 < P; p0 += R * kPoolPhases) {
+      Raw8<TI> raw[R];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (p0 + kPoolPhases * u < P) ld8<TI>(hb + (long long)(p0 + kPoolPhases * u) * C + c0, vec, valid, v[u]);
+      for (int u = 0; u < R; ++u)
+        if (p0 + kPoolPhases * u < P) ldraw(hb + (long long)(p0 + kPoolPhases * u) * C + c0, vec, vld, raw[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < R; ++u)
         if (p0 + kPoolPhases * u < P) {
           const long long p = p0 + kPoolPhases * u;
-          st8<TO>(ob + p * C + c0, vec, valid, v[u]);
-          st8<TO>(ob + p * C + half + c0, vec, valid, g);
+          float v[8];
+          unraw(raw[u], v);
+          st8<TO>(ob + p * C + c0, vec, vld, v);
+          st8<TO>(ob + p * C + half + c0, vec, vld, g);
         }
     }
   }
@@ -444,13 +488,16 @@ extern "C" int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float*
   if (B == 0) return TOKRED_OK;
   const int splits = ceil_div(C / 2, kPoolSlice);
   const size_t smem = (size_t)(kPoolPhases * kPoolSlice + P) * 4;
-  const int vec = ((C / 2) % 8 == 0) && aligned16(h) && aligned16(out);
+  // vector path: 8 channels per thread; fp32 sides move 32 bytes per access (LDG.256 / STG.256: 32-byte alignment)
+  const bool al_h = h_dtype == TOKRED_F32 ? (reinterpret_cast<uintptr_t>(h) & 31u) == 0 : aligned16(h);
+  const bool al_o = out_dtype == TOKRED_F32 ? (reinterpret_cast<uintptr_t>(out) & 31u) == 0 : aligned16(out);
+  const int vec = ((C / 2) % 8 == 0) && al_h && al_o;
   dim3 grid(splits, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(TI, TO)                                                                                       \
   do {                                                                                                       \
-    if (int e = allow_smem(dyvit_pool_concat_kernel<TI, TO>, smem, what)) return e;                          \
-    dyvit_pool_concat_kernel<TI, TO><<<grid, kThreads, smem, st>>>((const TI*)h, policy, (TO*)out, P, C, eps, vec);  \
+    if (vec) dyvit_pool_concat_kernel<TI, TO, true><<<grid, kThreads, smem, st>>>((const TI*)h, policy, (TO*)out, P, C, eps);  \
+    else dyvit_pool_concat_kernel<TI, TO, false><<<grid, kThreads, smem, st>>>((const TI*)h, policy, (TO*)out, P, C, eps);    \
   } while (0)
   if (h_dtype == TOKRED_F32 && out_dtype == TOKRED_F32) LAUNCH(float, float);
   else if (h_dtype == TOKRED_BF16 && out_dtype == TOKRED_F32) LAUNCH(__nv_bfloat16, float);

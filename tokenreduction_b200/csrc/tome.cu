@@ -321,7 +321,7 @@ tome_match_tc_kernel(const TM* __restrict__ metric, int N, int D, int r, int cla
 // of sixty-four 2-byte stores per row (721k shared-memory bank conflicts in the round-1 profile), ballot-based
 // compaction of the unmerged list.
 template <bool HEADS>
-__global__ void __launch_bounds__(kTc2Threads)
+__global__ void __launch_bounds__(kTc2Threads, 2)
 tome_match_tc2_kernel(const __nv_bfloat16* __restrict__ metric, long long token_stride, int heads, int N, int r, int class_token,
                       int64_t* __restrict__ unm_idx, int64_t* __restrict__ src_idx, int64_t* __restrict__ dst_idx) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -362,13 +362,17 @@ tome_match_tc2_kernel(const __nv_bfloat16* __restrict__ metric, long long token_
       if (live) {
         const __nv_bfloat16* row = mb + (long long)(2 * i + (isA ? 0 : 1)) * token_stride + cp * 16;
         if (HEADS) {
-          for (int h0 = 0; h0 < heads; h0 += 6) {      // six heads = twelve independent 16-byte loads in flight per lane
-            int4 a[6], c[6];
+          // three heads = six independent 16-byte loads in flight per lane.  (Six heads at once cost 111 registers:
+          // ONE 512-thread CTA per SM, so B=256 ran as 1.73 waves; at <= 64 registers two CTAs are resident, the batch
+          // is a single wave and the SM has the same twelve loads per lane pair in flight.)  Heads are still summed in
+          // ascending order.
+          for (int h0 = 0; h0 < heads; h0 += 3) {
+            int4 a[3], c[3];
 #pragma unroll
-            for (int u = 0; u < 6; ++u)
+            for (int u = 0; u < 3; ++u)
               if (h0 + u < heads) { a[u] = ld_stream16(row + (h0 + u) * 64); c[u] = ld_stream16(row + (h0 + u) * 64 + 8); }
 #pragma unroll
-            for (int u = 0; u < 6; ++u)
+            for (int u = 0; u < 3; ++u)
               if (h0 + u < heads) {
                 const __nv_bfloat16* pa = reinterpret_cast<const __nv_bfloat16*>(&a[u]);
                 const __nv_bfloat16* pc = reinterpret_cast<const __nv_bfloat16*>(&c[u]);
