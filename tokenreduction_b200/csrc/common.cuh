@@ -92,6 +92,28 @@ __device__ __forceinline__ void warp_copy_row16(void* dst, const void* src, int 
   }
   for (; off < bytes; off += 512) st_stream16(d + off, ld_stream16(s + off));
 }
+// One warp copies up to 4 rows of `bytes` each (multiple of 16, 16-B aligned): the loads of ALL rows are issued before
+// the first store -- 8 requests (4 KB per warp) in flight instead of 3, which is what the gather kernels needed to
+// keep HBM busy with few resident warps (small batches).
+__device__ __forceinline__ void warp_copy_rows16x4(char* dbase, const int (&doff)[4], const char* sbase, const int (&soff)[4],
+                                                   int nrows, int bytes, int lane) {
+  for (int off = lane * 16; off < bytes; off += 1024) {
+    int4 a[4], b[4];
+    const bool two = off + 512 < bytes;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u < nrows) {
+        a[u] = ld_stream16(sbase + soff[u] + off);
+        if (two) b[u] = ld_stream16(sbase + soff[u] + off + 512);
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u < nrows) {
+        st_stream16(dbase + doff[u] + off, a[u]);
+        if (two) st_stream16(dbase + doff[u] + off + 512, b[u]);
+      }
+  }
+}
 // Generic fallback (any alignment / size), element type T.
 template <typename T>
 __device__ __forceinline__ void warp_copy_row_elems(T* __restrict__ dst, const T* __restrict__ src, int n, int lane) {
@@ -158,6 +180,34 @@ __device__ __forceinline__ int rank_desc(const float* keys, int n, int i) {
     r += r1 + r2 + r3;
   }
   return r;
+}
+
+// rank_desc for a warp whose lanes rank the elements of one window [ilo, ihi) (warp-uniform bounds, any lane's i
+// inside it).  Keys before the window only need "kj >= ki or NaN" (they win ties), keys after it "kj > ki or NaN":
+// one compare + one add per key and 16-byte broadcast reads, against three compares and the index test of the
+// generic form -- which is kept inside the window.  Same total order, same result as rank_desc.
+template <bool GE>
+__device__ __forceinline__ int count_before(const float* keys, int a, int b, float ki) {
+  int r0 = 0, r1 = 0, r2 = 0, r3 = 0, j = a;
+  for (; j < b && (reinterpret_cast<uintptr_t>(keys + j) & 15u); ++j) { const float kj = keys[j]; r0 += GE ? !(kj < ki) : !(kj <= ki); }
+  for (; j + 3 < b; j += 4) {
+    const float4 k = *reinterpret_cast<const float4*>(keys + j);
+    r0 += GE ? !(k.x < ki) : !(k.x <= ki);
+    r1 += GE ? !(k.y < ki) : !(k.y <= ki);
+    r2 += GE ? !(k.z < ki) : !(k.z <= ki);
+    r3 += GE ? !(k.w < ki) : !(k.w <= ki);
+  }
+  for (; j < b; ++j) { const float kj = keys[j]; r0 += GE ? !(kj < ki) : !(kj <= ki); }
+  return (r0 + r1) + (r2 + r3);
+}
+__device__ __forceinline__ int rank_desc_window(const float* keys, int n, int i, int ilo, int ihi) {
+  const float ki = keys[i];
+  if (ki != ki) return rank_desc(keys, n, i);
+  ilo = ilo < 0 ? 0 : ilo;
+  ihi = ihi > n ? n : ihi;
+  int r = count_before<true>(keys, 0, ilo, ki);
+  for (int j = ilo; j < ihi; ++j) { const float kj = keys[j]; r += !(kj <= ki) || (kj == ki && j < i); }
+  return r + count_before<false>(keys, ihi, n, ki);
 }
 
 // the same count restricted to keys [j0, j1): two lanes split a rank and add their halves

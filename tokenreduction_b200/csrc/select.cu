@@ -47,8 +47,34 @@ __device__ __forceinline__ void copy_row(char* dst, const char* src, int row_byt
   }
 }
 
+// output row j <- token 0 (j == 0) or kept patch sel[j-1]; the rows of this CTA (blockIdx.x of gridDim.x splits) are
+// dealt to its warps four at a time so that every warp has four source rows in flight
+__device__ __forceinline__ void gather_kept_rows(char* ob, const char* xb, const int* sel, int nrows, int row_bytes, int vec16,
+                                                 int elem_size, int warp, int lane) {
+  const int stride = gridDim.x * kWarps;
+  for (int j = blockIdx.x * kWarps + warp; j < nrows; j += 4 * stride) {
+    int so[4], dof[4], nr = 0;        // byte offsets inside the image (an image is far below 2 GB)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int jj = j + u * stride;
+      const bool live = jj < nrows;
+      const int src_row = !live || jj == 0 ? 0 : 1 + sel[jj - 1];
+      so[u] = src_row * row_bytes;
+      dof[u] = (live ? jj : 0) * row_bytes;
+      nr += live;
+    }
+    if (vec16) {
+      warp_copy_rows16x4(ob, dof, xb, so, nr, row_bytes, lane);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nr) copy_row(ob + dof[u], xb + so[u], row_bytes, 0, elem_size, lane);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ Top-K
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 topk_gather_kernel(ScoreSrc ss, const char* __restrict__ x, char* __restrict__ x_out, int64_t* __restrict__ idx_out,
                    int N, int k, int row_bytes, int vec16, int elem_size) {
   extern __shared__ float smem[];
@@ -59,7 +85,7 @@ topk_gather_kernel(ScoreSrc ss, const char* __restrict__ x, char* __restrict__ x
   for (int p = tid; p < P; p += kThreads) keys[p] = fetch_score(ss, b, p, N);
   __syncthreads();
   for (int p = tid; p < P; p += kThreads) {
-    int r = rank_desc(keys, P, p);
+    int r = rank_desc_window(keys, P, p, p - (tid & 31), p - (tid & 31) + 32);
     if (r < k) {
       sel[r] = p;
       if (blockIdx.x == 0) idx_out[(long long)b * k + r] = p;
@@ -70,23 +96,20 @@ topk_gather_kernel(ScoreSrc ss, const char* __restrict__ x, char* __restrict__ x
   const int warp = tid >> 5, lane = tid & 31;
   const char* xb = x + (long long)b * N * row_bytes;
   char* ob = x_out + (long long)b * (k + 1) * row_bytes;
-  for (int j = blockIdx.x * kWarps + warp; j < k + 1; j += gridDim.x * kWarps) {
-    int src_row = j == 0 ? 0 : 1 + sel[j - 1];
-    copy_row(ob + (long long)j * row_bytes, xb + (long long)src_row * row_bytes, row_bytes, vec16, elem_size, lane);
-  }
+  gather_kept_rows(ob, xb, sel, k + 1, row_bytes, vec16, elem_size, warp, lane);
 }
 
 // ------------------------------------------------------------------------------------------ EViT
-// grid.x = number of 512-byte column slices of a token row.  Split s gathers kept rows s*8+w, ... and owns
-// slice s of the fused token: warp w accumulates complement rows w, w+8, ... (ascending patch order), the 8
-// partials are combined in warp order through shared memory -> deterministic.
+// grid.x = number of 1024-byte column slices of a token row (round 1: 512-byte slices -> 768 CTAs at B=128, two waves).
+// Split s gathers its share of the kept rows and owns slice s of the fused token: warp w accumulates complement rows
+// w, w+8, ... (ascending patch order), the 8 partials are combined in warp order through shared memory -> deterministic.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_out, int64_t* __restrict__ idx_out,
                         int64_t* __restrict__ compl_out, int N, int C, int k, int vec16) {
   extern __shared__ float smem[];
   constexpr int VE = 16 / sizeof(T);            // elements per 16-byte lane chunk
-  constexpr int SLICE = 32 * VE;                // elements per 512-byte slice
+  constexpr int SLICE = 2 * 32 * VE;            // elements per 1024-byte slice
   const int P = N - 1, M = P - k, b = blockIdx.y, tid = threadIdx.x;
   float* keys = smem;                                   // [P]
   int* sel = reinterpret_cast<int*>(keys + P);          // [k]
@@ -97,7 +120,7 @@ evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_
   for (int p = tid; p < P; p += kThreads) keys[p] = fetch_score(ss, b, p, N);
   __syncthreads();
   for (int p = tid; p < P; p += kThreads) {
-    int r = rank_desc(keys, P, p);
+    int r = rank_desc_window(keys, P, p, p - (tid & 31), p - (tid & 31) + 32);
     dropped[p] = r >= k;
     if (r < k) {
       sel[r] = p;
@@ -121,37 +144,42 @@ evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_
   const T* xb = x + (long long)b * N * C;
   T* ob = x_out + (long long)b * (k + 2) * C;
   // kept rows
-  for (int j = blockIdx.x * kWarps + warp; j < k + 1; j += gridDim.x * kWarps) {
-    int src_row = j == 0 ? 0 : 1 + sel[j - 1];
-    copy_row(reinterpret_cast<char*>(ob + (long long)j * C), reinterpret_cast<const char*>(xb + (long long)src_row * C),
-             row_bytes, vec16, (int)sizeof(T), lane);
-  }
-  // fused inattentive token, slice blockIdx.x
+  gather_kept_rows(reinterpret_cast<char*>(ob), reinterpret_cast<const char*>(xb), sel, k + 1, row_bytes, vec16, (int)sizeof(T),
+                   warp, lane);
+  // fused inattentive token, slice blockIdx.x (two 16-byte chunks per lane)
   const int e0 = blockIdx.x * SLICE + lane * VE;
-  float acc[VE];
+  float acc[2][VE];
 #pragma unroll
-  for (int i = 0; i < VE; ++i) acc[i] = 0.f;
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < VE; ++i) acc[h][i] = 0.f;
   if (vec16) {
-    // 4 complement rows per step: the 16-byte loads are issued together, then consumed in ascending row order
+    // 4 complement rows x 2 chunks per step: the 16-byte loads are issued together, then consumed in ascending row order
     for (int m0 = warp; m0 < M; m0 += 4 * kWarps) {
-      int4 raw[4];
+      int4 raw[4][2];
       float w[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int m = m0 + u * kWarps;
         w[u] = 0.f;
-        if (m < M && e0 < C) {
+        if (m < M) {
           const int p = cmp[m];
           w[u] = keys[p];
-          raw[u] = ld_stream16(xb + (long long)(1 + p) * C + e0);
+          const T* row = xb + (long long)(1 + p) * C + e0;
+          if (e0 < C) raw[u][0] = ld_stream16(row);
+          if (e0 + 32 * VE < C) raw[u][1] = ld_stream16(row + 32 * VE);
         }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        if (m0 + u * kWarps < M && e0 < C) {
-          const T* v = reinterpret_cast<const T*>(&raw[u]);
+        if (m0 + u * kWarps < M) {
 #pragma unroll
-          for (int i = 0; i < VE; ++i) acc[i] = fmaf(w[u], to_f32(v[i]), acc[i]);
+          for (int h = 0; h < 2; ++h)
+            if (e0 + h * 32 * VE < C) {
+              const T* v = reinterpret_cast<const T*>(&raw[u][h]);
+#pragma unroll
+              for (int i = 0; i < VE; ++i) acc[h][i] = fmaf(w[u], to_f32(v[i]), acc[h][i]);
+            }
         }
       }
     }
@@ -161,12 +189,16 @@ evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_
       const float w = keys[p];
       const T* row = xb + (long long)(1 + p) * C + e0;
 #pragma unroll
-      for (int i = 0; i < VE; ++i)
-        if (e0 + i < C) acc[i] = fmaf(w, to_f32(row[i]), acc[i]);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < VE; ++i)
+          if (e0 + h * 32 * VE + i < C) acc[h][i] = fmaf(w, to_f32(row[h * 32 * VE + i]), acc[h][i]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < VE; ++i) part[warp * SLICE + lane * VE + i] = acc[i];
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < VE; ++i) part[warp * SLICE + h * 32 * VE + lane * VE + i] = acc[h][i];
   __syncthreads();
   for (int e = tid; e < SLICE; e += kThreads) {
     if (blockIdx.x * SLICE + e < C) {
@@ -421,8 +453,9 @@ extern "C" int tokred_topk_gather(const void* x, int x_dtype, const void* scores
   const int vec16 = (row_bytes % 16 == 0) && aligned16(x) && aligned16(x_out);
   const size_t smem = (size_t)(P + k) * 4;
   if (int e = allow_smem(topk_gather_kernel, smem, what)) return e;
+  // every split re-ranks the scores, and a warp moves four rows at a time: as few splits as give every SM two CTAs
   int splits = ceil_div(4 * kNumSMs, B);
-  splits = max(1, min(splits, ceil_div(k + 1, kWarps)));
+  splits = max(1, min(splits, ceil_div(k + 1, 2 * kWarps)));
   ScoreSrc ss{scores, score_dtype, score_stride, score_batch_stride, attn, attn_dtype, H};
   topk_gather_kernel<<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
       ss, (const char*)x, (char*)x_out, idx_out, N, k, row_bytes, vec16, dtype_size(x_dtype));
@@ -443,7 +476,7 @@ extern "C" int tokred_evit_select_fuse(const void* x, int x_dtype, const void* s
   if (B == 0) return TOKRED_OK;
   const int P = N - 1, esz = dtype_size(x_dtype), row_bytes = C * esz;
   const int vec16 = (row_bytes % 16 == 0) && aligned16(x) && aligned16(x_out);
-  const int slice = 512 / esz;
+  const int slice = 1024 / esz;
   const int splits = ceil_div(C, slice);
   const size_t smem = (size_t)(P + k + (P - k) + (P + 3) / 4 + kWarps * slice) * 4;
   ScoreSrc ss{scores, score_dtype, 1, P, attn, attn_dtype, H};

@@ -97,7 +97,7 @@ class _ReducedViT(VisionTransformer):
     def _logits(self, x):
         # LayerNorm is per token: norm(x)[:, 0] == norm(x[:, 0]) bit for bit, and only the class token is read
         # (e.g. models/topk.py:205-207)
-        return self.head(self.pre_logits(self.norm(x[:, 0])))
+        return self.head(self.pre_logits(self.norm(M.cls_value(x))))
 
     def _ret(self, x, viz_data=None):
         if self.training or not self.viz_mode:
@@ -154,9 +154,9 @@ class TopKVisionTransformer(_ReducedViT):
             x, sample_idx = out[0], out[2]
             if self.viz_mode and sample_idx is not None:
                 decisions[i] = _np(sample_idx)
-                features[i] = _np(x)
+                features[i] = _np(M.value(x))
         if self.viz_mode and 11 not in features:
-            features[i] = _np(x)
+            features[i] = _np(M.value(x))
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Features": features})
 
 
@@ -216,9 +216,9 @@ class ToMeVisionTransformer(_ReducedViT):
             x, attn_size, cluster_assign = blk(x, attn_size)
             if self.viz_mode and i in self.pruning_loc and cluster_assign is not None:
                 assignments[i] = _np(cluster_assign)
-                features[i] = _np(x)
+                features[i] = _np(M.value(x))
         if self.viz_mode and 11 not in features:
-            features[i] = _np(x)
+            features[i] = _np(M.value(x))
         return self._ret(self._logits(x), {"Assignment_Maps": assignments, "Features": features})
 
 
@@ -270,6 +270,7 @@ class DPCKNNVisionTransformer(_ClusterLayerViT):
         i = -1
         for i, blk in enumerate(self.blocks):
             if i in self.cluster_loc:
+                x = M.value(x)
                 global_tokens = x[:, :self.num_tokens]
                 x, idx_token, agg_weight, idx_centers, idx_cluster, cluster_centers = self.cluster_layers[cnt](
                     x[:, self.num_tokens:], idx_token, agg_weight, self.viz_mode)
@@ -279,9 +280,9 @@ class DPCKNNVisionTransformer(_ClusterLayerViT):
                     decisions[i], assignments[i], centers_feats[i] = _np(idx_centers), _np(idx_cluster), _np(cluster_centers)
             x = blk(x)
             if self.viz_mode:
-                features[i] = _np(x)
+                features[i] = _np(M.value(x))
         if self.viz_mode and 11 not in features:
-            features[i] = _np(x)
+            features[i] = _np(M.value(x))
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Assignment_Maps": assignments,
                                            "Center_Feats": centers_feats, "Features": features})
 
@@ -324,6 +325,7 @@ class KMedoidsVisionTransformer(_ClusterLayerViT):
         i = -1
         for i, blk in enumerate(self.blocks):
             if i in self.cluster_loc:
+                x = M.value(x)
                 global_tokens = x[:, :self.num_tokens]
                 if attn.dim() == 3:      # per-head column sums [B,H,N] from the fused attention (deterministic order)
                     token_weights = attn.sum(1)[:, self.num_tokens:].unsqueeze(2)
@@ -338,9 +340,9 @@ class KMedoidsVisionTransformer(_ClusterLayerViT):
                 cnt += 1
             x, attn = blk(x)
             if self.viz_mode:
-                features[i] = _np(x)
+                features[i] = _np(M.value(x))
         if self.viz_mode and 11 not in features:
-            features[i] = _np(x)
+            features[i] = _np(M.value(x))
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Assignment_Maps": assignments,
                                            "Center_Feats": centers_feats, "Features": features})
 
@@ -364,6 +366,7 @@ class _SoftClusterViT(_ClusterLayerViT):
         i = -1
         for i, blk in enumerate(self.blocks):
             if i in self.cluster_loc:
+                x = M.value(x)
                 global_tokens = x[:, :self.num_tokens]
                 x, soft_assign = self.cluster_layers[cnt](x[:, self.num_tokens:])
                 x = torch.cat((global_tokens, x.to(global_tokens.dtype)), dim=1)
@@ -376,9 +379,9 @@ class _SoftClusterViT(_ClusterLayerViT):
                 cnt += 1
             x = blk(x)
             if self.viz_mode:
-                features[i] = _np(x)
+                features[i] = _np(M.value(x))
         if self.viz_mode and 11 not in features:
-            features[i] = _np(x)
+            features[i] = _np(M.value(x))
         # key names of models/sinkhorn.py:197, models/patchmerger.py:148, models/sit.py:143
         viz = {"Assignment_Maps": hard_assignment, "Soft_Assignment_Maps": assignments, "Features": features}
         if self._has_center_feats:
@@ -495,9 +498,9 @@ class ATSVisionTransformer(_ReducedViT):
             x, mask, sample_ids = blk(x, mask)
             if self.viz_mode and sample_ids is not None:
                 decisions[i] = _np(sample_ids[:, 1:] - 1)
-                features[i] = _np(x)
+                features[i] = _np(M.value(x))
         if self.viz_mode and 11 not in features:
-            features[i] = _np(x)
+            features[i] = _np(M.value(x))
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Features": features})
 
 
@@ -552,6 +555,7 @@ class DynamicVisionTransformer(_ReducedViT):
         policy = torch.ones(b, init_n + 1, 1, dtype=x.dtype, device=x.device)
         for i, blk in enumerate(self.blocks):
             if i in self.pruning_loc:
+                x = M.value(x)
                 pred_score = self.score_predictor[p_count](x[:, 1:], prev_decision).reshape(b, -1, 2)
                 hard_keep_decision = F.gumbel_softmax(pred_score, hard=True)[:, :, 0:1] * prev_decision
                 out_pred_prob.append(hard_keep_decision.reshape(b, init_n))
@@ -562,7 +566,7 @@ class DynamicVisionTransformer(_ReducedViT):
                 p_count += 1
             else:
                 x = blk(x, policy)
-        x = self.norm(x)
+        x = self.norm(M.value(x))
         features = x[:, 1:]
         x = self.head(self.pre_logits(x[:, 0]))
         if self.dyvit_distillation:
@@ -581,6 +585,7 @@ class DynamicVisionTransformer(_ReducedViT):
         i = -1
         for i, blk in enumerate(self.blocks):
             if i in self.pruning_loc:
+                x = M.value(x)
                 pred_score = self.score_predictor[p_count](x[:, 1:], prev_decision).reshape(b, -1, 2)
                 num_keep = int(init_n * self.token_ratio[p_count])
                 # argsort(desc)[:k] + [CLS, keep+1] gather in one launch; scores read in place (stride 2)
@@ -589,10 +594,10 @@ class DynamicVisionTransformer(_ReducedViT):
                 x = blk(x)
                 if self.viz_mode:
                     decisions[i] = _np(keep_policy)
-                    features_viz[i] = _np(x)
+                    features_viz[i] = _np(M.value(x))
                 p_count += 1
             else:
                 x = blk(x)
         if self.viz_mode and 11 not in features_viz:
-            features_viz[i] = _np(x)
+            features_viz[i] = _np(M.value(x))
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Features": features_viz})

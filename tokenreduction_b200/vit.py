@@ -161,8 +161,9 @@ class Block(nn.Module):
 
     def forward(self, x):
         from . import modules
-        x, y = modules.add_norm(x, self.drop_path(self.attn(modules.norm_lowp(self.norm1, x))), self.norm2)
-        return x + self.drop_path(self.mlp(y))
+        x, y = modules.enter_norm(self.norm1, x)       # x may be the previous block's deferred residual sum
+        x, y = modules.add_norm(x, self.drop_path(self.attn(y)), self.norm2)
+        return modules.defer_add(x, self.drop_path(self.mlp(y)), self.norm1)
 
 
 def _init_vit_weights(module: nn.Module, name: str = "", head_bias: float = 0.0, jax_impl: bool = False):
@@ -291,7 +292,8 @@ class VisionTransformer(nn.Module):
 
     def forward_features(self, x):
         x = self.embed(x)
-        x = self.blocks(x)
+        from . import modules
+        x = modules.value(self.blocks(x))
         x = self.norm(x)
         if self.dist_token is None:
             return self.pre_logits(x[:, 0])
