@@ -92,6 +92,18 @@ TOKRED_API int tokred_tome_merge(const void* x, int x_dtype, const void* size, c
                       const int64_t* src_idx, const int64_t* dst_idx, int B, int N, int C, int r, void* x_out,
                       void* size_out, float* reduced_cluster_idx, int divide, void* stream);
 
+/* ---- a4/a5 with the callers either side fused (bf16-autocast Block_ToMe, models/tome.py:88-104) ----------
+ * x + drop_path(attn branch)  ->  merge_wavg  ->  norm2  in ONE launch over the fp32 residual stream:
+ *   x [B,N,C] fp32; branch [B,N,C] bf16 or NULL (the attention projection's output; added in fp32 on every row read);
+ *   size [B,N] fp32 or NULL; index lists as tokred_tome_merge; gamma, beta [C] fp32, eps: norm2's parameters
+ *   x_out [B,N-r,C] fp32 = merge_wavg(x + branch), size_out [B,N-r] fp32, reduced_cluster_idx [B,N-1] or NULL,
+ *   y [B,N-r,C] bf16 = LayerNorm(x_out) rounded once (what the MLP's first autocast Linear consumes).
+ * Bit-identical to add -> tokred_tome_merge -> tokred_add_layernorm.  C must be a multiple of 128 up to 768.      */
+TOKRED_API int tokred_tome_merge_ln(const float* x, const void* branch, const float* size, const int64_t* unm_idx,
+                         const int64_t* src_idx, const int64_t* dst_idx, int B, int N, int C, int r, const float* gamma,
+                         const float* beta, float eps, float* x_out, float* size_out, float* reduced_cluster_idx, void* y,
+                         void* stream);
+
 /* ---- pairwise distances (building block of a6 / a8, exported for parity checks) ------------------------
  * torch.cdist(x, x) as called at models/dpcknn.py:59 and models/kmedoids.py:68, times post_scale:
  * matmul expansion sqrt(max(|xi|^2+|xj|^2-2xi.xj, 1e-30)) for P > 25, direct differences otherwise.

@@ -258,6 +258,40 @@ def test_tome_merge_bit_exact(T, n, r, c, dtype, with_size):
     assert torch.equal(out.cpu(), out_ref)
 
 
+@pytest.mark.parametrize("b,n,r,c,with_size,with_branch", [(6, 197, 59, 384, False, True), (5, 138, 41, 384, True, True),
+                                                          (3, 197, 59, 768, True, True), (4, 97, 29, 384, True, False),
+                                                          (256, 197, 59, 384, True, True), (7, 50, 24, 128, True, True)])
+def test_tome_merge_ln_fused(T, b, n, r, c, with_size, with_branch):
+    """add + merge + LayerNorm in one launch (bf16-autocast Block_ToMe): merged stream, sizes and source map against the
+    oracle merge of (x + branch) bit for bit (the add is the same fp32 addition), the normalised activations against
+    ATen's layer_norm of the merged stream rounded to bf16, and the whole launch bit-identical to the unfused sequence
+    add -> tome_merge -> add_layernorm.  b=256 is the benchmarked grid."""
+    metric = torch.randn(b, n, 64, generator=g(116))
+    x = torch.randn(b, n, c, generator=g(117))
+    branch = torch.randn(b, n, c, generator=g(118)).to(torch.bfloat16) if with_branch else None
+    size = torch.randint(1, 5, (b, n, 1), generator=g(119)).float() if with_size else None
+    gamma, beta = 1 + 0.1 * torch.randn(c, generator=g(120)), 0.1 * torch.randn(c, generator=g(121))
+    unm, src, dst, _ = O.tome_match(metric[:min(b, 8)], r, True)
+    reps = (b + unm.shape[0] - 1) // unm.shape[0]
+    unm, src, dst = (t.repeat(reps, 1)[:b] for t in (unm, src, dst))
+    xs = x + branch.float() if with_branch else x
+    d = lambda t: None if t is None else t.to(DEV)
+    out, size_out, rci, y = T.tome_merge_ln(d(x), d(branch), d(size), d(unm), d(src), d(dst), d(gamma), d(beta), 1e-6, True)
+    nb = min(b, 8)                                    # oracle (CPU loops) on the first images
+    out_ref, size_ref, rci_ref = O.tome_merge(xs[:nb], None if size is None else size[:nb], unm[:nb], src[:nb], dst[:nb])
+    assert torch.equal(out[:nb].cpu(), out_ref)
+    assert torch.equal(size_out[:nb].cpu(), size_ref)
+    assert torch.equal(rci[:nb].cpu(), rci_ref)
+    y_ref = torch.nn.functional.layer_norm(out_ref, (c,), gamma, beta, 1e-6)
+    assert y.dtype == torch.bfloat16
+    assert_close_rel(y[:nb].float().cpu(), y_ref, 4e-3, "fused norm2 (bf16 output)")
+    # the unfused sequence of the same library, every image
+    out2, size2, rci2 = T.tome_merge(d(xs), d(size), d(unm), d(src), d(dst), True)
+    _, y2 = T.add_layernorm(out2, None, d(gamma), d(beta), 1e-6)
+    assert torch.equal(out, out2) and torch.equal(size_out, size2) and torch.equal(rci, rci2)
+    assert torch.equal(y, y2)
+
+
 def test_tome_merge_properties_full_size(T):
     """BASELINE config 2 size (B=256, DeiT-S): sizes sum to N, CLS row untouched, mass conservation."""
     b, n, r, c = 256, 197, 59, 384

@@ -525,22 +525,55 @@ __device__ __forceinline__ void load_row_chunks(const T* __restrict__ row, int n
   }
 }
 
-template <typename T, int CPL>
+// Fused caller-side work of the bf16-autocast block (models/tome.py:88-104): `x + attn branch` is formed on every row
+// read (the fp32 add the reference runs as its own kernel) and the finished row is LayerNorm-ed and rounded to bf16 for
+// the MLP's first Linear -- add_layernorm's arithmetic, chunk for chunk, so the fused launch is bit-identical to
+// add -> tome_merge -> add_layernorm.
+struct MergeLn {
+  const __nv_bfloat16* branch;   // [N,C] of this image, or nullptr
+  const float* gamma;
+  const float* beta;
+  float eps;
+  __nv_bfloat16* yrow;           // output row of y
+};
+
+template <int CPL>
+__device__ __forceinline__ void load_branch_chunks(const __nv_bfloat16* __restrict__ row, int nchunks, int lane, uint2 (&rb)[CPL]) {
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) rb[i] = *reinterpret_cast<const uint2*>(row + c * 4);
+  }
+}
+__device__ __forceinline__ float bf16_of(const uint2& u, int e) {
+  const uint32_t w = e < 2 ? u.x : u.y;
+  return __uint_as_float((e & 1) ? (w & 0xffff0000u) : (w << 16));
+}
+
+template <typename T, int CPL, bool FUSED = false>
 __device__ __forceinline__ void merge_row_vec(const T* __restrict__ xb, T* __restrict__ orow, int C, int lane, int t0,
                                               int j, const int* __restrict__ src, const int* __restrict__ dst, int r,
-                                              const float* __restrict__ zs, bool has_size, bool divide, float& zsum_out) {
+                                              const float* __restrict__ zs, bool has_size, bool divide, float& zsum_out,
+                                              const MergeLn* ln = nullptr) {
   constexpr int VE = Chunk<T>::VE;
   const int nchunks = C / VE;
   RowAcc<T, CPL> acc;
   int4 raw[CPL];
+  uint2 rb[FUSED ? CPL : 1];
+  const bool has_br = FUSED && ln->branch != nullptr;
   load_row_chunks<T, CPL>(xb + (long long)t0 * C, nchunks, lane, raw);
+  if constexpr (FUSED) { if (has_br) load_branch_chunks<CPL>(ln->branch + (long long)t0 * C, nchunks, lane, rb); }
   const float z0 = zs[t0];
   float zsum = z0;
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
     const T* v = reinterpret_cast<const T*>(&raw[i]);
 #pragma unroll
-    for (int e = 0; e < VE; ++e) acc.v[i][e] = has_size ? mul_as<T>(to_f32(v[e]), z0) : to_f32(v[e]);
+    for (int e = 0; e < VE; ++e) {
+      float xv = to_f32(v[e]);
+      if constexpr (FUSED) { if (has_br) xv = __fadd_rn(xv, bf16_of(rb[i], e)); }
+      acc.v[i][e] = has_size ? mul_as<T>(xv, z0) : xv;
+    }
   }
   if (j >= 0) {
     // sources of odd token j, in src-list order: ballot over the list, then walk the set bits (warp-uniform)
@@ -552,14 +585,18 @@ __device__ __forceinline__ void merge_row_vec(const T* __restrict__ xb, T* __res
         m &= m - 1;
         const int ts = 2 * src[base + bit];
         load_row_chunks<T, CPL>(xb + (long long)ts * C, nchunks, lane, raw);
+        if constexpr (FUSED) { if (has_br) load_branch_chunks<CPL>(ln->branch + (long long)ts * C, nchunks, lane, rb); }
         const float z = zs[ts];
         zsum = add_as<T>(zsum, z);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           const T* v = reinterpret_cast<const T*>(&raw[i]);
 #pragma unroll
-          for (int e = 0; e < VE; ++e)
-            acc.v[i][e] = add_as<T>(acc.v[i][e], has_size ? mul_as<T>(to_f32(v[e]), z) : to_f32(v[e]));
+          for (int e = 0; e < VE; ++e) {
+            float xv = to_f32(v[e]);
+            if constexpr (FUSED) { if (has_br) xv = __fadd_rn(xv, bf16_of(rb[i], e)); }
+            acc.v[i][e] = add_as<T>(acc.v[i][e], has_size ? mul_as<T>(xv, z) : xv);
+          }
         }
       }
     }
@@ -578,11 +615,38 @@ __device__ __forceinline__ void merge_row_vec(const T* __restrict__ xb, T* __res
       for (int e = 0; e < VE; ++e) {
         const float a = round_as<T>(acc.v[i][e]);
         outv[e] = !divide ? from_f32<T>(acc.v[i][e]) : from_f32<T>(pow2 ? __fmul_rn(a, inv) : __fdiv_rn(a, zsum));
+        if constexpr (FUSED) acc.v[i][e] = to_f32(outv[e]);       // the finished row stays in registers for the LayerNorm
       }
       st_stream16(orow + c * VE, *reinterpret_cast<const int4*>(outv));
     }
   }
   zsum_out = zsum;
+  if constexpr (FUSED) {
+    // norm.cu's add_layernorm, operation for operation (C = 128 * CPL: every lane chunk is live)
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) sum += (acc.v[i][0] + acc.v[i][1]) + (acc.v[i][2] + acc.v[i][3]);
+    const float mean = warp_sum(sum) * (1.0f / (float)(128 * CPL));
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const float a = acc.v[i][0] - mean, b = acc.v[i][1] - mean, c = acc.v[i][2] - mean, d = acc.v[i][3] - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / (float)(128 * CPL)) + ln->eps);
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int c4 = (i * 32 + lane) * 4;
+      const float4 g = *reinterpret_cast<const float4*>(ln->gamma + c4), bt = *reinterpret_cast<const float4*>(ln->beta + c4);
+      const float a = (acc.v[i][0] - mean) * rstd * g.x + bt.x, b = (acc.v[i][1] - mean) * rstd * g.y + bt.y;
+      const float c = (acc.v[i][2] - mean) * rstd * g.z + bt.z, d = (acc.v[i][3] - mean) * rstd * g.w + bt.w;
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(ln->yrow + c4) = o;
+    }
+  }
 }
 
 // generic path: any C / alignment, one element per lane-step
@@ -645,6 +709,53 @@ tome_merge_kernel(const T* __restrict__ x, const T* __restrict__ size, const int
     if (lane == 0) size_out[(long long)b * n_out + q] = from_f32<T>(zsum);
   }
 
+  if (rci != nullptr && blockIdx.x == 0) {
+    for (int q = tid; q < n_unm; q += kThreads) rowmap[unm[q]] = q;
+    for (int s = tid; s < r; s += kThreads) rowmap[src[s]] = n_unm + dst[s];
+    __syncthreads();
+    for (int t = 1 + tid; t < N; t += kThreads) {
+      const int row = (t & 1) ? n_unm + (t >> 1) : rowmap[t >> 1];
+      rci[(long long)b * (N - 1) + (t - 1)] = (float)(row - 1);
+    }
+  }
+}
+
+// add + merge + LayerNorm in one launch: tome_merge_kernel's structure on the fp32 residual stream (C = 128 * CPL)
+template <int CPL>
+__global__ void __launch_bounds__(kThreads, CPL <= 3 ? 3 : 2)
+tome_merge_ln_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ branch, const float* __restrict__ size,
+                     const int64_t* __restrict__ unm_idx, const int64_t* __restrict__ src_idx,
+                     const int64_t* __restrict__ dst_idx, int N, int r, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, float* __restrict__ x_out, float* __restrict__ size_out,
+                     float* __restrict__ rci, __nv_bfloat16* __restrict__ y) {
+  extern __shared__ float smem[];
+  constexpr int C = 128 * CPL;
+  const int na = (N + 1) / 2, n_unm = na - r, n_out = N - r;
+  float* zs = smem;
+  int* unm = reinterpret_cast<int*>(zs + N);
+  int* src = unm + n_unm;
+  int* dst = src + r;
+  int* rowmap = dst + r;
+  const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_size = size != nullptr;
+  for (int t = tid; t < N; t += kThreads) zs[t] = has_size ? size[(long long)b * N + t] : 1.f;
+  for (int q = tid; q < n_unm; q += kThreads) unm[q] = clamp_idx(unm_idx[(long long)b * n_unm + q], na);
+  for (int s = tid; s < r; s += kThreads) {
+    src[s] = clamp_idx(src_idx[(long long)b * r + s], na);
+    dst[s] = clamp_idx(dst_idx[(long long)b * r + s], N / 2);
+  }
+  __syncthreads();
+  const float* xb = x + (long long)b * N * C;
+  float* ob = x_out + (long long)b * n_out * C;
+  MergeLn ln{branch ? branch + (long long)b * N * C : nullptr, gamma, beta, eps, nullptr};
+  for (int q = blockIdx.x * kWarps + warp; q < n_out; q += gridDim.x * kWarps) {
+    const int j = q < n_unm ? -1 : q - n_unm;
+    const int t0 = q < n_unm ? 2 * unm[q] : 2 * j + 1;
+    float zsum;
+    ln.yrow = y + ((long long)b * n_out + q) * C;
+    merge_row_vec<float, CPL, true>(xb, ob + (long long)q * C, C, lane, t0, j, src, dst, r, zs, has_size, true, zsum, &ln);
+    if (lane == 0) size_out[(long long)b * n_out + q] = zsum;
+  }
   if (rci != nullptr && blockIdx.x == 0) {
     for (int q = tid; q < n_unm; q += kThreads) rowmap[unm[q]] = q;
     for (int s = tid; s < r; s += kThreads) rowmap[src[s]] = n_unm + dst[s];
@@ -773,6 +884,50 @@ extern "C" int tokred_tome_merge(const void* x, int x_dtype, const void* size, c
   }
   if (x_dtype == TOKRED_F32) { DISPATCH(float) } else { DISPATCH(__nv_bfloat16) }
 #undef DISPATCH
+#undef LAUNCH
+  return finish_launch(what);
+}
+
+extern "C" int tokred_tome_merge_ln(const float* x, const void* branch, const float* size, const int64_t* unm_idx,
+                                    const int64_t* src_idx, const int64_t* dst_idx, int B, int N, int C, int r,
+                                    const float* gamma, const float* beta, float eps, float* x_out, float* size_out,
+                                    float* reduced_cluster_idx, void* y, void* stream) {
+  const char* what = "tokred_tome_merge_ln";
+  if (B == 0) return TOKRED_OK;
+  TOKRED_REQUIRE(x && unm_idx && src_idx && dst_idx && x_out && size_out && gamma && beta && y, "%s: null tensor", what);
+  TOKRED_REQUIRE(B >= 0 && N >= 2 && C >= 1, "%s: bad shape B=%d N=%d C=%d", what, B, N, C);
+  TOKRED_REQUIRE(r >= 1 && r <= N / 2 && r <= (N + 1) / 2, "%s: r=%d outside [1, %d]", what, r, N / 2);
+  TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
+  if (C % 128 != 0 || C > 768) {
+    set_error("%s: C=%d (needs a multiple of 128 up to 768)", what, C);
+    return TOKRED_ERR_UNSUPPORTED;
+  }
+  TOKRED_REQUIRE(aligned16(x) && aligned16(x_out) && aligned16(gamma) && aligned16(beta) &&
+                     (!branch || (reinterpret_cast<uintptr_t>(branch) & 7u) == 0) && (reinterpret_cast<uintptr_t>(y) & 7u) == 0,
+                 "%s: tensors must be 16-byte aligned", what);
+  const int na = (N + 1) / 2, n_unm = na - r, n_out = N - r;
+  const size_t smem = (size_t)(N + n_unm + 2 * r + na) * 4;
+  const int cpl = C / 128;
+  const int resident = kNumSMs * (cpl <= 3 ? 3 : 2);
+  int splits = resident / B;
+  splits = max(1, min(splits, ceil_div(n_out, kWarps)));
+  dim3 grid(splits, B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(CPL)                                                                                                     \
+  do {                                                                                                                  \
+    if (int e = allow_smem(tome_merge_ln_kernel<CPL>, smem, what)) return e;                                            \
+    tome_merge_ln_kernel<CPL><<<grid, kThreads, smem, st>>>(x, (const __nv_bfloat16*)branch, size, unm_idx, src_idx,    \
+                                                            dst_idx, N, r, gamma, beta, eps, x_out, size_out,           \
+                                                            reduced_cluster_idx, (__nv_bfloat16*)y);                    \
+  } while (0)
+  switch (cpl) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    case 5: LAUNCH(5); break;
+    default: LAUNCH(6); break;
+  }
 #undef LAUNCH
   return finish_launch(what);
 }

@@ -444,16 +444,26 @@ class Block_ToMe(nn.Module):
         if self.r <= 0:
             x, y = add_norm(x, self.drop_path(x_attn), self.norm2)
             return defer_add(x, self.drop_path(self.mlp(y)), self.norm1), attn_size, reduced_cluster_idx
-        x = x + self.drop_path(x_attn)
         if self.r > 0:
             _train_guard(self, True)
             re = ops.tome_effective_r(x.shape[1], self.r, self.cls_token, self.dist_token)
             if re > 0 and self.cls_token and not self.dist_token and isinstance(metric, KeyMean):
                 # keys straight from the qkv output: head mean + matching in ONE launch, no [B,N,64] metric tensor
                 unm, src, dst = ops.tome_match_qkv(metric.qkv, metric.num_heads, self.r, True)
-                x, attn_size, reduced_cluster_idx = ops.tome_merge(x, attn_size, unm, src, dst, True, True)
+                branch = self.drop_path(x_attn)
+                if _norm_fusable(self.norm2, x) and ops.tome_merge_ln_supported(x, branch):
+                    # x + branch, merge_wavg and norm2 in ONE launch (:88, :100-101, :104): the residual add and the
+                    # LayerNorm ride on the row the merge already holds in registers
+                    x, attn_size, reduced_cluster_idx, y = ops.tome_merge_ln(
+                        x, branch, attn_size, unm, src, dst, self.norm2.weight, self.norm2.bias, self.norm2.eps, True)
+                    return defer_add(x, self.drop_path(self.mlp(y)), self.norm1), attn_size, reduced_cluster_idx
+                x, attn_size, reduced_cluster_idx = ops.tome_merge(x + branch, attn_size, unm, src, dst, True, True)
                 metric = None
-            elif isinstance(metric, KeyMean):
+                x_attn = None
+        if x_attn is not None:
+            x = x + self.drop_path(x_attn)
+        if self.r > 0:
+            if isinstance(metric, KeyMean):
                 metric = metric.tensor()
             if metric is None:
                 pass

@@ -775,6 +775,56 @@ def add_layernorm(x: Tensor, branch: Optional[Tensor], weight: Tensor, bias: Ten
     return (x_out if branch is not None else x), y
 
 
+@torch.library.custom_op("tokred::tome_merge_ln", mutates_args=(), device_types="cuda")
+def _tome_merge_ln(x: Tensor, branch: Optional[Tensor], size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor,
+                   weight: Tensor, bias: Tensor, eps: float, want_map: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    _need_cuda("tome_merge_ln", x, branch, size, unm, src, dst, weight, bias)
+    b, n, c = x.shape
+    r = src.shape[1]
+    if x.dtype != torch.float32 or c != weight.numel():
+        raise TokredError(f"tome_merge_ln: x {tuple(x.shape)} {x.dtype}; expected fp32 [B,N,{weight.numel()}]")
+    if unm.shape != (b, (n + 1) // 2 - r) or dst.shape != (b, r) or src.shape[0] != b:
+        raise TokredError("tome_merge_ln: index tensors do not match x")
+    if branch is not None and (branch.shape != x.shape or branch.dtype != torch.bfloat16):
+        raise TokredError(f"tome_merge_ln: branch {tuple(branch.shape)} {branch.dtype}; expected bf16 {tuple(x.shape)}")
+    x, unm, src, dst = _c(x), _c(unm), _c(src), _c(dst)
+    if branch is not None:
+        branch = _c(branch)
+    if size is not None:
+        if size.numel() != b * n:
+            raise TokredError(f"tome_merge_ln: size {tuple(size.shape)} does not match x {tuple(x.shape)}")
+        size = _c(size.float())
+    out = torch.empty((b, n - r, c), dtype=torch.float32, device=x.device)
+    size_out = torch.empty((b, n - r, 1), dtype=torch.float32, device=x.device)
+    rci = torch.empty((b, n - 1) if want_map else (0,), dtype=torch.float32, device=x.device)
+    y = torch.empty((b, n - r, c), dtype=torch.bfloat16, device=x.device)
+    _lib.call("tokred_tome_merge_ln", _ptr(x), _ptr(branch), _ptr(size), _ptr(unm), _ptr(src), _ptr(dst), b, n, c, r,
+              _ptr(_c(weight.float())), _ptr(_c(bias.float())), float(eps), _ptr(out), _ptr(size_out),
+              _ptr(rci) if want_map else None, _ptr(y), _stream())
+    return out, size_out, rci, y
+
+
+@_tome_merge_ln.register_fake
+def _(x, branch, size, unm, src, dst, weight, bias, eps, want_map):
+    b, n, c = x.shape
+    r = src.shape[1]
+    return (x.new_empty((b, n - r, c)), x.new_empty((b, n - r, 1)),
+            x.new_empty((b, n - 1) if want_map else (0,), dtype=torch.float32), x.new_empty((b, n - r, c), dtype=torch.bfloat16))
+
+
+def tome_merge_ln_supported(x: Tensor, branch: Optional[Tensor]) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] % 128 == 0 and x.shape[2] <= 768
+            and (branch is None or (branch.dtype == torch.bfloat16 and branch.shape == x.shape)))
+
+
+def tome_merge_ln(x: Tensor, branch: Optional[Tensor], size: Optional[Tensor], unm: Tensor, src: Tensor, dst: Tensor,
+                  weight: Tensor, bias: Tensor, eps: float, want_map: bool = True):
+    """models/tome.py:88 (x + attn branch), :100-101 (merge_wavg), :104 (norm2, as the MLP's autocast Linear consumes it)
+    in ONE launch on the fp32 residual stream: (x_out [B,N-r,C] fp32, size_out [B,N-r,1], map [B,N-1], y bf16).
+    Bit-identical to ``add -> tome_merge -> add_layernorm``."""
+    return torch.ops.tokred.tome_merge_ln(x, branch, size, unm, src, dst, weight, bias, eps, want_map)
+
+
 # ----------------------------------------------------------------------------------------------- f4: autograd formulas
 # SURVEY §8f row 4.  The reference fine-tunes its reduced models with the reduction operators inside the autograd graph
 # (train.py; the discrete selections themselves carry no gradient: topk / argsort / argmax indices).  The forward of
