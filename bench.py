@@ -174,6 +174,17 @@ def algorithmic_bytes(name: str, a: tuple) -> float:
         if g["reduced_cluster_idx"]:
             total += 4 * (n - 1)
         return g["B"] * total
+    if name == "tokred_tome_merge_ln":
+        n, c, r = g["N"], g["C"], g["r"]
+        na = (n + 1) // 2
+        total = n * c * 4 + (n - r) * c * (4 + 2) + (n - r) * 4 + 8 * (na - r) + 16 * r + 8 * c   # x, x_out + y, sizes, lists
+        if g["branch"]:
+            total += n * c * 2
+        if g["size"]:
+            total += n * 4
+        if g["reduced_cluster_idx"]:
+            total += 4 * (n - 1)
+        return g["B"] * total
     if name == "tokred_topk_gather":
         n, c, k = g["N"], g["C"], g["k"]
         sc = (n - 1) * esz(g["score_dtype"]) if g["scores"] else g["H"] * (n - 1) * esz(g["attn_dtype"])

@@ -71,6 +71,12 @@ def cases():
             m, x, size = rnd(b, n, 64, dtype=torch.bfloat16), rnd(b, n, 384), torch.ones(b, n, 1, device=DEV)
             unm, src, dst = T.tome_match(m, r, True, True)
             return lambda: T.tome_merge(x, size, unm, src, dst, True, True)
+        def mk_merge_ln(b=b, n=n, r=r):
+            m, x, size = rnd(b, n, 64, dtype=torch.bfloat16), rnd(b, n, 384), torch.ones(b, n, 1, device=DEV)
+            br, gam, bet = rnd(b, n, 384, dtype=torch.bfloat16), rnd(384), rnd(384)
+            unm, src, dst = T.tome_match(m, r, True, True)
+            return lambda: T.tome_merge_ln(x, br, size, unm, src, dst, gam, bet, 1e-6, True)
+
         def mk_match_qkv(b=b, n=n, r=r):
             qkv = rnd(b, n, 3 * 384, dtype=torch.bfloat16)
             return lambda: T.tome_match_qkv(qkv, 6, r, True)
@@ -79,6 +85,7 @@ def cases():
         add(f"tome_match S B={b} N={n} r={r} lowp ffma", lambda f=mk_match: f("ffma"))
         add(f"tome_match S B={b} N={n} r={r} fp32", lambda f=mk_match: f("fp32"))
         add(f"tome_merge S B={b} N={n} r={r}", mk_merge)
+        add(f"tome_merge_ln S B={b} N={n} r={r} (x + attn branch, merge, norm2 in one launch)", mk_merge_ln)
     # config 3: EViT / DynamicViT B kr 0.5, B=128 (8-GPU shard) and B=1024
     for b in (128, 1024):
         for n, k in ((197, 98), (100, 49), (51, 24)):
