@@ -231,6 +231,17 @@ TOKRED_API int tokred_attention(const void* qkv, int B, int N, int H, int head_d
 TOKRED_API int tokred_add_layernorm(const float* x, const void* branch, int branch_dtype, const float* gamma, const float* beta,
                          float eps, int64_t rows, int C, float* x_out, void* y, void* stream);
 
+/* ---- the data formats in front of the first block (bf16 autocast; models/deit_viz.py PatchEmbed + forward_features) ----
+ * tokred_patchify: image [B,Cin,H,W] fp32 -> out [B,(H/ph)*(W/pw),Cin*ph*pw] bf16 (round-to-nearest-even), row element
+ *   (c*ph+py)*pw+px of patch (gy,gx) = img[b,c,gy*ph+py,gx*pw+px]: the operand of the patch-embedding GEMM (the stride-p
+ *   convolution with its weight viewed as [C,Cin*ph*pw]); replaces ATen's cast + permuting copy.  pw % 4 == 0.
+ * tokred_embed_layernorm: x_out [B,T+P,C] fp32 = cat(tokens [T,C] fp32 (cls[, dist]), patches [B,P,C] bf16) + pos [T+P,C]
+ *   and y [B,T+P,C] bf16 = LayerNorm(x_out; gamma, beta, eps) rounded once (blocks[0].norm1 as the qkv Linear consumes it).
+ *   C a multiple of 128 up to 1024.                                                                              */
+TOKRED_API int tokred_patchify(const float* img, int B, int Cin, int H, int W, int ph, int pw, void* out, void* stream);
+TOKRED_API int tokred_embed_layernorm(const void* patches, const float* tokens, const float* pos, const float* gamma,
+                           const float* beta, float eps, int B, int P, int T, int C, float* x_out, void* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

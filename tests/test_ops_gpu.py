@@ -1210,3 +1210,33 @@ def test_add_layernorm(T, rows, c, bdt):
     yb, yr = y.cpu().float(), y_ref.bfloat16().float()
     assert float((yb == yr).float().mean()) > 0.995
     assert float(((yb - y_ref).abs() / y_ref.abs().clamp_min(1.0)).max()) <= 2 ** -8      # within one bf16 rounding of the fp32 result
+
+
+# ------------------------------------------------------------------------------------------------ in front of block 0
+@pytest.mark.parametrize("b,c,h,w,p", [(3, 3, 224, 224, 16), (2, 3, 64, 96, 16), (256, 3, 224, 224, 16), (2, 1, 32, 32, 8),
+                                       (2, 3, 48, 48, 4)])
+def test_patchify_bit_exact(T, b, c, h, w, p):
+    """cast + patch-major permutation in one pass == ATen's .to(bf16).view.permute.reshape, bit for bit."""
+    x = torch.randn(b, c, h, w, generator=g(300)).to(DEV)
+    gh, gw = h // p, w // p
+    ref = x.to(torch.bfloat16).view(b, c, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(b, gh * gw, c * p * p)
+    out = T.patchify(x, p, p)
+    assert out.dtype == torch.bfloat16 and torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("b,p,t,c", [(4, 196, 1, 384), (3, 196, 2, 768), (256, 196, 1, 384), (2, 9, 1, 128)])
+def test_embed_layernorm(T, b, p, t, c):
+    """cat(tokens, patches) + pos and the first norm1 in one pass: the fp32 stream bit-identical to the ATen sequence, the
+    bf16 activations bit-identical to add_layernorm of that stream and within bf16 rounding of ATen's layer_norm."""
+    patches = torch.randn(b, p, c, generator=g(301)).to(torch.bfloat16).to(DEV)
+    tokens = torch.randn(t, c, generator=g(302)).to(DEV)
+    pos = (0.02 * torch.randn(1, t + p, c, generator=g(303))).to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(c, generator=g(304))).to(DEV), (0.1 * torch.randn(c, generator=g(305))).to(DEV)
+    x_ref = torch.cat((tokens.unsqueeze(0).expand(b, -1, -1), patches), dim=1) + pos
+    assert x_ref.dtype == torch.float32
+    x, y = T.embed_layernorm(patches, tokens, pos[0], gamma, beta, 1e-6)
+    assert torch.equal(x, x_ref)
+    _, y2 = T.add_layernorm(x_ref, None, gamma, beta, 1e-6)
+    assert torch.equal(y, y2)
+    y_ref = torch.nn.functional.layer_norm(x_ref, (c,), gamma, beta, 1e-6)
+    assert_close_rel(y.float(), y_ref, 4e-3, "embed norm1 (bf16 output)")

@@ -1,0 +1,188 @@
+// The data formats in front of the first block (the callers either side of the path), bf16 autocast only:
+//   patchify          image [B,Cin,H,W] fp32 -> [B, gh*gw, Cin*ph*pw] bf16: the operand of the patch-embedding GEMM.  The
+//                     reference's stride-16 convolution (models/deit_viz.py PatchEmbed) is that GEMM; ATen forms the operand
+//                     with a cast kernel and a permuting copy (33 + 117 us at B=256: the permuted copy moves 2-byte elements
+//                     one by one), here it is one pass at HBM speed.
+//   embed_layernorm   x = cat(cls [, dist], patches) + pos_embed  (fp32 residual stream, models/deit_viz.py forward_features)
+//                     and y = blocks[0].norm1(x) rounded to bf16 in the same pass: cat, add, LayerNorm and cast were four
+//                     launches and 44 bytes per element, now 10.
+#include "common.cuh"
+
+namespace tokred {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// grid = (gh, B): one CTA turns the ph image rows x Cin channels of one patch row into gw output rows (contiguous in out).
+// Loads are 16-byte coalesced along the image row; the bf16 patch rows are assembled in shared memory (patch stride padded
+// by 16 bytes: the 8-byte stores of a warp spread over all banks) and leave as 16-byte coalesced stores.
+__global__ void __launch_bounds__(kThreads)
+patchify_kernel(const float* __restrict__ img, int Cin, int H, int W, int ph, int pw, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int gy = blockIdx.x, b = blockIdx.y, gw = W / pw, W4 = W / 4;
+  const int D = Cin * ph * pw;                       // elements per output row
+  const int SP = D * 2 + 16;                         // bytes between patches in shared memory
+  const int items = Cin * ph * W4;
+  const float* ib = img + (long long)b * Cin * H * W + (long long)gy * ph * W;
+  for (int e0 = threadIdx.x; e0 < items; e0 += 4 * kThreads) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kThreads;
+      if (e < items) {
+        const int q = e % W4, r = e / W4, py = r % ph, c = r / ph;
+        v[u] = *reinterpret_cast<const float4*>(ib + ((long long)c * H + py) * W + q * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kThreads;
+      if (e < items) {
+        const int q = e % W4, r = e / W4, py = r % ph, c = r / ph;
+        const int gx = (q * 4) / pw, px = (q * 4) % pw;
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(sm + (size_t)gx * SP + ((size_t)(c * ph + py) * pw + px) * 2) = o;
+      }
+    }
+  }
+  __syncthreads();
+  const int row16 = D / 8;                           // 16-byte units per output row
+  unsigned char* ob = reinterpret_cast<unsigned char*>(out + ((long long)b * gridDim.x + gy) * gw * D);
+  for (int i = threadIdx.x; i < gw * row16; i += kThreads) {
+    const int gx = i / row16, w = i - gx * row16;
+    st_stream16(ob + (size_t)i * 16, *reinterpret_cast<const int4*>(sm + (size_t)gx * SP + (size_t)w * 16));
+  }
+}
+
+__device__ __forceinline__ float4 ld4s(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// one warp per token row; V = float4 chunks per lane (C = 128 * V).  The LayerNorm is norm.cu's, operation for operation.
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+embed_layernorm_kernel(const __nv_bfloat16* __restrict__ patches, const float* __restrict__ tokens, const float* __restrict__ pos,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int B, int P, int T,
+                       float* __restrict__ x_out, __nv_bfloat16* __restrict__ y) {
+  constexpr int C = 128 * V;
+  const int lane = threadIdx.x & 31, N = T + P;
+  const long long rows = (long long)B * N;
+  float4 g[V], bt[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    g[j] = *reinterpret_cast<const float4*>(gamma + (j * 32 + lane) * 4);
+    bt[j] = *reinterpret_cast<const float4*>(beta + (j * 32 + lane) * 4);
+  }
+  for (long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * kWarps) {
+    const int t = (int)(row % N);
+    const long long b = row / N;
+    float4 v[V];
+    if (t < T) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = *reinterpret_cast<const float4*>(tokens + (long long)t * C + (j * 32 + lane) * 4);
+    } else {
+      const __nv_bfloat16* pr = patches + (b * P + (t - T)) * C;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(pr + (j * 32 + lane) * 4);
+        v[j].x = __uint_as_float(raw.x << 16); v[j].y = __uint_as_float(raw.x & 0xffff0000u);
+        v[j].z = __uint_as_float(raw.y << 16); v[j].w = __uint_as_float(raw.y & 0xffff0000u);
+      }
+    }
+    const float* pe = pos + (long long)t * C;
+    float* xo = x_out + row * C;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float4 a = *reinterpret_cast<const float4*>(pe + (j * 32 + lane) * 4);
+      v[j].x += a.x; v[j].y += a.y; v[j].z += a.z; v[j].w += a.w;
+      asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(xo + (j * 32 + lane) * 4), "f"(v[j].x), "f"(v[j].y),
+                   "f"(v[j].z), "f"(v[j].w)
+                   : "memory");
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float a = v[j].x - mean, bb = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + bb * bb) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+    __nv_bfloat16* yr = y + row * C;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float a = (v[j].x - mean) * rstd * g[j].x + bt[j].x, bb = (v[j].y - mean) * rstd * g[j].y + bt[j].y;
+      const float c = (v[j].z - mean) * rstd * g[j].z + bt[j].z, d = (v[j].w - mean) * rstd * g[j].w + bt[j].w;
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(a, bb), hi = __floats2bfloat162_rn(c, d);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(yr + (j * 32 + lane) * 4) = o;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace tokred
+
+using namespace tokred;
+
+extern "C" int tokred_patchify(const float* img, int B, int Cin, int H, int W, int ph, int pw, void* out, void* stream) {
+  const char* what = "tokred_patchify";
+  if (B == 0) return TOKRED_OK;
+  TOKRED_REQUIRE(img && out, "%s: null tensor", what);
+  TOKRED_REQUIRE(B > 0 && Cin >= 1 && ph >= 1 && pw >= 1 && H >= ph && W >= pw && H % ph == 0 && W % pw == 0,
+                 "%s: bad shape B=%d Cin=%d H=%d W=%d patch %dx%d", what, B, Cin, H, W, ph, pw);
+  TOKRED_REQUIRE(B <= 65535, "%s: B=%d > 65535", what, B);
+  if (pw % 4 != 0 || (Cin * ph * pw) % 8 != 0 || !aligned16(img) || !aligned16(out)) {
+    set_error("%s: needs a patch width that is a multiple of 4, rows of whole 16-byte units and 16-byte aligned tensors", what);
+    return TOKRED_ERR_UNSUPPORTED;
+  }
+  const size_t smem = (size_t)(W / pw) * ((size_t)Cin * ph * pw * 2 + 16);
+  if (int e = allow_smem(patchify_kernel, smem, what)) return e;
+  patchify_kernel<<<dim3(H / ph, B), kThreads, smem, (cudaStream_t)stream>>>(img, Cin, H, W, ph, pw, (__nv_bfloat16*)out);
+  return finish_launch(what);
+}
+
+extern "C" int tokred_embed_layernorm(const void* patches, const float* tokens, const float* pos, const float* gamma,
+                                      const float* beta, float eps, int B, int P, int T, int C, float* x_out, void* y,
+                                      void* stream) {
+  const char* what = "tokred_embed_layernorm";
+  if (B == 0) return TOKRED_OK;
+  TOKRED_REQUIRE(patches && tokens && pos && gamma && beta && x_out && y, "%s: null tensor", what);
+  TOKRED_REQUIRE(B > 0 && P >= 1 && T >= 0 && C > 0, "%s: bad shape B=%d P=%d T=%d C=%d", what, B, P, T, C);
+  if (C % 128 != 0 || C > 1024) {
+    set_error("%s: C=%d (needs a multiple of 128 up to 1024)", what, C);
+    return TOKRED_ERR_UNSUPPORTED;
+  }
+  TOKRED_REQUIRE(aligned16(tokens) && aligned16(pos) && aligned16(gamma) && aligned16(beta) && aligned16(x_out) &&
+                     (reinterpret_cast<uintptr_t>(patches) & 7u) == 0 && (reinterpret_cast<uintptr_t>(y) & 7u) == 0,
+                 "%s: tensors must be 16-byte aligned", what);
+  const long long rows = (long long)B * (T + P);
+  const long long want = (rows + kWarps - 1) / kWarps;
+  const int grid = (int)(want < (long long)kNumSMs * 8 ? want : (long long)kNumSMs * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(V)                                                                                                       \
+  embed_layernorm_kernel<V><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)patches, tokens, pos, gamma, beta, eps, B, P, T, \
+                                                      x_out, (__nv_bfloat16*)y)
+  switch (C / 128) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    case 5: LAUNCH(5); break;
+    case 6: LAUNCH(6); break;
+    case 7: LAUNCH(7); break;
+    default: LAUNCH(8); break;
+  }
+#undef LAUNCH
+  return finish_launch(what);
+}

@@ -254,9 +254,11 @@ gather_rows_kernel(const char* __restrict__ src, const int64_t* __restrict__ ids
       dp[u] = out + row * row_bytes;
     }
     if (vec16) {
+      // all four rows' loads before the first store (offsets relative to the first row: a few images apart at most)
+      int so[4], dof[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (u < nrows) warp_copy_row16(dp[u], sp[u], row_bytes, lane);
+      for (int u = 0; u < 4; ++u) { so[u] = (int)(sp[u] - sp[0]); dof[u] = (int)(dp[u] - dp[0]); }
+      warp_copy_rows16x4(dp[0], dof, sp[0], so, nrows, row_bytes, lane);
     } else if (elem_size == 4) {
       copy_rows4<uint32_t>(sp, dp, nrows, row_bytes / 4, lane);
     } else {

@@ -263,8 +263,7 @@ class DPCKNNVisionTransformer(_ClusterLayerViT):
         b, n, _ = x.shape
         idx_token = torch.arange(n, device=x.device)[None, :].repeat(b, 1)
         agg_weight = x.new_ones(b, n, 1)
-        x = torch.cat((self.cls_token.expand(b, -1, -1), x), dim=1)
-        x = self.pos_drop(x + self.pos_embed)
+        x = self.embed_tokens(x)
         cnt = 0
         decisions, assignments, centers_feats, features = {}, {}, {}, {}
         i = -1
@@ -317,8 +316,7 @@ class KMedoidsVisionTransformer(_ClusterLayerViT):
     def forward(self, x):
         x = self.patch_embed(x)
         b = x.shape[0]
-        x = torch.cat((self.cls_token.expand(b, -1, -1), x), dim=1)
-        x = self.pos_drop(x + self.pos_embed)
+        x = self.embed_tokens(x)
         cnt = 0
         attn = None
         decisions, assignments, centers_feats, features = {}, {}, {}, {}
@@ -359,8 +357,7 @@ class _SoftClusterViT(_ClusterLayerViT):
     def forward(self, x):
         x = self.patch_embed(x)
         b = x.shape[0]
-        x = torch.cat((self.cls_token.expand(b, -1, -1), x), dim=1)
-        x = self.pos_drop(x + self.pos_embed)
+        x = self.embed_tokens(x)
         cnt = 0
         assignments, hard_assignment, centers_feats, features = {}, {}, {}, {}
         i = -1
@@ -489,8 +486,7 @@ class ATSVisionTransformer(_ReducedViT):
     def forward(self, x):
         x = self.patch_embed(x)
         b, n = x.shape[:2]
-        x = torch.cat((self.cls_token.expand(b, -1, -1), x), dim=1)
-        x = self.pos_drop(x + self.pos_embed)
+        x = self.embed_tokens(x)
         mask = torch.ones((b, n + self.num_tokens), dtype=torch.bool, device=x.device)
         decisions, features = {}, {}
         i = -1

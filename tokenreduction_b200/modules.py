@@ -123,16 +123,52 @@ class Residual:
         return self.x + self.branch
 
 
+class Embedded:
+    """``cat(cls [, dist], patches) + pos_embed`` that has not been formed yet (models/deit_viz.py forward_features): under
+    bf16 autocast the first block's ``enter_norm`` builds the fp32 stream and norm1's bf16 output from the patch GEMM's
+    output in one pass (ops.embed_layernorm) instead of cat -> add -> layer_norm -> cast."""
+    __slots__ = ("patches", "tokens", "pos")
+
+    def __init__(self, patches: Tensor, tokens: Tensor, pos: Tensor):
+        self.patches, self.tokens, self.pos = patches, tokens, pos        # [B,P,C] bf16, [T,C] fp32, [1,T+P,C] fp32
+
+    @property
+    def shape(self):
+        b, p, c = self.patches.shape
+        return torch.Size((b, p + self.tokens.shape[0], c))
+
+    @property
+    def dtype(self):
+        return self.pos.dtype
+
+    @property
+    def device(self):
+        return self.patches.device
+
+    def value(self) -> Tensor:
+        b = self.patches.shape[0]
+        return torch.cat((self.tokens.unsqueeze(0).expand(b, -1, -1), self.patches), dim=1) + self.pos
+
+
 def value(x):
-    """the tensor a block output stands for (materialises a deferred residual sum)."""
-    return x.value() if isinstance(x, Residual) else x
+    """the tensor a block input / output stands for (materialises a deferred residual sum or embedding)."""
+    return x.value() if isinstance(x, (Residual, Embedded)) else x
+
+
+def embed_tokens(patches: Tensor, tokens: Tensor, pos: Tensor, norm_probe: nn.Module):
+    """``cat(tokens, patches) + pos`` -- deferred to the first block's norm1 where the fused kernel applies."""
+    if (DEFER_RESIDUAL and patches.is_cuda and patches.dtype == torch.bfloat16 and patches.dim() == 3
+            and _norm_fusable(norm_probe, pos) and pos.shape[1] == patches.shape[1] + tokens.shape[0]):
+        return Embedded(patches, tokens, pos)
+    b = patches.shape[0]
+    return torch.cat((tokens.unsqueeze(0).expand(b, -1, -1), patches), dim=1) + pos
 
 
 def cls_value(x) -> Tensor:
     """``value(x)[:, 0]`` without forming the other rows (elementwise add: the same bits)."""
     if isinstance(x, Residual):
         return x.x[:, 0] + x.branch[:, 0]
-    return x[:, 0]
+    return value(x)[:, 0]
 
 
 def defer_add(x: Tensor, branch: Tensor, norm: nn.Module):
@@ -148,6 +184,10 @@ def enter_norm(norm: nn.Module, x) -> Tuple[Tensor, Tensor]:
     if isinstance(x, Residual):
         if _norm_fusable(norm, x.x):
             return ops.add_layernorm(x.x, x.branch, norm.weight, norm.bias, norm.eps)
+        x = x.value()
+    elif isinstance(x, Embedded):
+        if _norm_fusable(norm, x.pos):
+            return ops.embed_layernorm(x.patches, x.tokens, x.pos[0], norm.weight, norm.bias, norm.eps)
         x = x.value()
     return x, norm_lowp(norm, x)
 

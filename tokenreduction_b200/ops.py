@@ -825,6 +825,59 @@ def tome_merge_ln(x: Tensor, branch: Optional[Tensor], size: Optional[Tensor], u
     return torch.ops.tokred.tome_merge_ln(x, branch, size, unm, src, dst, weight, bias, eps, want_map)
 
 
+# ----------------------------------------------------------------------------------------------- in front of block 0
+@torch.library.custom_op("tokred::patchify", mutates_args=(), device_types="cuda")
+def _patchify(img: Tensor, ph: int, pw: int) -> Tensor:
+    _need_cuda("patchify", img)
+    if img.dim() != 4 or img.dtype != torch.float32:
+        raise TokredError(f"patchify: img {tuple(img.shape)} {img.dtype}; expected fp32 [B,C,H,W]")
+    img = _c(img)
+    b, c, h, w = img.shape
+    out = torch.empty((b, (h // ph) * (w // pw), c * ph * pw), dtype=torch.bfloat16, device=img.device)
+    _lib.call("tokred_patchify", _ptr(img), b, c, h, w, ph, pw, _ptr(out), _stream())
+    return out
+
+
+@_patchify.register_fake
+def _(img, ph, pw):
+    b, c, h, w = img.shape
+    return img.new_empty((b, (h // ph) * (w // pw), c * ph * pw), dtype=torch.bfloat16)
+
+
+def patchify(img: Tensor, ph: int, pw: int) -> Tensor:
+    """[B,C,H,W] fp32 -> [B, patches, C*ph*pw] bf16: ``img.to(bf16).view(b,c,gh,ph,gw,pw).permute(0,2,4,1,3,5).reshape``
+    (the patch-embedding GEMM's operand) in one pass."""
+    return torch.ops.tokred.patchify(img, ph, pw)
+
+
+@torch.library.custom_op("tokred::embed_layernorm", mutates_args=(), device_types="cuda")
+def _embed_layernorm(patches: Tensor, tokens: Tensor, pos: Tensor, weight: Tensor, bias: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+    _need_cuda("embed_layernorm", patches, tokens, pos, weight, bias)
+    b, p, c = patches.shape
+    t = tokens.shape[0]
+    if patches.dtype != torch.bfloat16 or tokens.shape != (t, c) or pos.shape != (t + p, c) or weight.numel() != c:
+        raise TokredError(f"embed_layernorm: patches {tuple(patches.shape)} {patches.dtype}, tokens {tuple(tokens.shape)}, "
+                          f"pos {tuple(pos.shape)}")
+    x_out = torch.empty((b, t + p, c), dtype=torch.float32, device=patches.device)
+    y = torch.empty((b, t + p, c), dtype=torch.bfloat16, device=patches.device)
+    _lib.call("tokred_embed_layernorm", _ptr(_c(patches)), _ptr(_c(tokens.float())), _ptr(_c(pos.float())),
+              _ptr(_c(weight.float())), _ptr(_c(bias.float())), float(eps), b, p, t, c, _ptr(x_out), _ptr(y), _stream())
+    return x_out, y
+
+
+@_embed_layernorm.register_fake
+def _(patches, tokens, pos, weight, bias, eps):
+    b, p, c = patches.shape
+    t = tokens.shape[0]
+    return patches.new_empty((b, t + p, c), dtype=torch.float32), patches.new_empty((b, t + p, c))
+
+
+def embed_layernorm(patches: Tensor, tokens: Tensor, pos: Tensor, weight: Tensor, bias: Tensor, eps: float):
+    """(x, y): x = cat(tokens, patches) + pos (fp32), y = LayerNorm(x) rounded to bf16 -- the cat, the positional add, the
+    first block's norm1 and its autocast cast in one pass (models/deit_viz.py forward_features)."""
+    return torch.ops.tokred.embed_layernorm(patches, tokens, pos, weight, bias, eps)
+
+
 # ----------------------------------------------------------------------------------------------- f4: autograd formulas
 # SURVEY §8f row 4.  The reference fine-tunes its reduced models with the reduction operators inside the autograd graph
 # (train.py; the discrete selections themselves carry no gradient: topk / argsort / argmax indices).  The forward of

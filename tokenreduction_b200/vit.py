@@ -96,7 +96,11 @@ class PatchEmbed(nn.Module):
             b, c, _, _ = x.shape
             gh, gw = self.grid_size
             ph, pw = self.patch_size
-            xb = x.to(torch.bfloat16).view(b, c, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(b, gh * gw, c * ph * pw)
+            if x.dtype == torch.float32 and pw % 4 == 0 and (c * ph * pw) % 8 == 0:
+                from . import ops
+                xb = ops.patchify(x, ph, pw)          # cast + patch-major permutation in one pass at HBM speed
+            else:
+                xb = x.to(torch.bfloat16).view(b, c, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(b, gh * gw, c * ph * pw)
             w = self.proj.weight.view(self.proj.weight.shape[0], -1)
             return self.norm(torch.nn.functional.linear(xb, w, self.proj.bias))
         x = self.proj(x)
@@ -282,7 +286,15 @@ class VisionTransformer(nn.Module):
     # -- forward --------------------------------------------------------------------------
     def embed(self, x):
         """patch-embed + cls (+dist) token + positional embedding."""
-        x = self.patch_embed(x)
+        return self.embed_tokens(self.patch_embed(x))
+
+    def embed_tokens(self, x):
+        """cat(cls [, dist], patches) + pos_embed -- handed to the first block unformed where its norm1 can fuse it
+        (modules.Embedded)."""
+        from . import modules
+        if x.dim() == 3 and not (self.training and self.pos_drop.p > 0) and len(self.blocks) > 0 and hasattr(self.blocks[0], "norm1"):
+            tokens = self.cls_token[0] if self.dist_token is None else torch.cat((self.cls_token[0], self.dist_token[0]), dim=0)
+            return modules.embed_tokens(x, tokens, self.pos_embed, self.blocks[0].norm1)
         cls_token = self.cls_token.expand(x.shape[0], -1, -1)
         if self.dist_token is None:
             x = torch.cat((cls_token, x), dim=1)
