@@ -234,6 +234,7 @@ __device__ __forceinline__ void copy_rows4(const char* const (&sp)[4], char* con
   }
 }
 
+template <bool VEC16>       // separate instantiations: the 16-byte path's registers must not cost the word path its occupancy
 __global__ void __launch_bounds__(kThreads)
 gather_rows_kernel(const char* __restrict__ src, const int64_t* __restrict__ ids, long long ids_stride, int G, int N,
                    int M, long long rows, int row_bytes, int vec16, int elem_size, char* __restrict__ out) {
@@ -253,7 +254,7 @@ gather_rows_kernel(const char* __restrict__ src, const int64_t* __restrict__ ids
       sp[u] = src + (bg * N + id) * row_bytes;
       dp[u] = out + row * row_bytes;
     }
-    if (vec16) {
+    if (VEC16) {
       // all four rows' loads before the first store (offsets relative to the first row: a few images apart at most)
       int so[4], dof[4];
 #pragma unroll
@@ -507,8 +508,12 @@ extern "C" int tokred_gather_rows(const void* src, int dtype, const int64_t* ids
   const int vec16 = (row_bytes % 16 == 0) && aligned16(src) && aligned16(out);
   long long blocks = (rows + 4 * kWarps - 1) / (4 * kWarps);
   if (blocks > 32LL * kNumSMs) blocks = 32LL * kNumSMs;
-  gather_rows_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
-      (const char*)src, ids, ids_stride, G, N, M, rows, row_bytes, vec16, dtype_size(dtype), (char*)out);
+  if (vec16)
+    gather_rows_kernel<true><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+        (const char*)src, ids, ids_stride, G, N, M, rows, row_bytes, vec16, dtype_size(dtype), (char*)out);
+  else
+    gather_rows_kernel<false><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+        (const char*)src, ids, ids_stride, G, N, M, rows, row_bytes, vec16, dtype_size(dtype), (char*)out);
   return finish_launch(what);
 }
 

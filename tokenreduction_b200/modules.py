@@ -438,6 +438,17 @@ class KeyMean:
         return self.qkv.view(b, n, 3, self.num_heads, c3 // (3 * self.num_heads))[:, :, 1].mean(2)
 
 
+_LOG_SIZE = [None, None]        # (size tensor, its log) of the last call
+
+
+def _log_size(size: Tensor) -> Tensor:
+    """``size.log()[..., 0]`` (models/tome.py:48).  The sizes only change where tokens merge, so the blocks between two
+    merges are handed the SAME tensor object and reuse its logarithm (three launches per forward instead of eight)."""
+    if _LOG_SIZE[0] is not size:
+        _LOG_SIZE[0], _LOG_SIZE[1] = size, size.log()[..., 0]
+    return _LOG_SIZE[1]
+
+
 class Attention_ToMe(_AttentionBase):
     """models/tome.py:29-59.  forward(x, size) -> (x, metric = k.mean(1))."""
 
@@ -446,7 +457,7 @@ class Attention_ToMe(_AttentionBase):
 
     def forward(self, x, size=None):
         if self._fused(x):
-            bias = None if size is None else size.log()[..., 0]               # proportional attention, :48-49
+            bias = None if size is None else _log_size(size)                  # proportional attention, :48-49
             x, _, _, qkv = self._attend_fused(x, key_bias=bias)
             if not self.need_metric:
                 return x, None
