@@ -189,6 +189,17 @@ def algorithmic_bytes(name: str, a: tuple) -> float:
         n, c, k = g["N"], g["C"], g["k"]
         sc = (n - 1) * esz(g["score_dtype"]) if g["scores"] else g["H"] * (n - 1) * esz(g["attn_dtype"])
         return g["B"] * (sc + 2 * (k + 1) * c * esz(g["x_dtype"]) + 8 * k)
+    if name == "tokred_topk_gather_add":
+        n, c, k = g["N"], g["C"], g["k"]
+        return g["B"] * ((n - 1) * esz(g["score_dtype"]) + (k + 1) * c * (4 + 2 + 4) + 8 * k)
+    if name == "tokred_evit_select_fuse_add":
+        n, c, k = g["N"], g["C"], g["k"]
+        return g["B"] * ((n - 1) * esz(g["score_dtype"]) + n * c * (4 + 2) + (k + 2) * c * 4 + 8 * (k + 1) + 8 * (n - 1 - k))
+    if name == "tokred_patchify":
+        return g["B"] * g["Cin"] * g["H"] * g["W"] * (4 + 2)
+    if name == "tokred_embed_layernorm":
+        n = g["T"] + g["P"]
+        return g["B"] * (g["P"] * g["C"] * 2 + n * g["C"] * (4 + 2)) + (n + g["T"] + 2) * g["C"] * 4
     if name == "tokred_evit_select_fuse":
         n, c, k = g["N"], g["C"], g["k"]
         sc = (n - 1) * esz(g["score_dtype"]) if g["scores"] else g["H"] * (n - 1) * esz(g["attn_dtype"])

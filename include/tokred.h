@@ -92,6 +92,17 @@ TOKRED_API int tokred_tome_merge(const void* x, int x_dtype, const void* size, c
                       const int64_t* src_idx, const int64_t* dst_idx, int B, int N, int C, int r, void* x_out,
                       void* size_out, float* reduced_cluster_idx, int divide, void* stream);
 
+/* ---- a1 / a2 with the block's residual add fused (bf16-autocast Block_TopK / Block_EVIT) --------------------
+ * `x = x + drop_path(attn branch)` (models/topk.py:87, models/evit.py:109) is formed on the fly, as the same fp32 addition,
+ * for the rows that are read: x [B,N,C] fp32, branch [B,N,C] bf16 (the attention projection's output).  Outputs as
+ * tokred_topk_gather / tokred_evit_select_fuse computed on x + branch; rows that are dropped are never added (Top-K).
+ * Rows must be whole 16-byte units (C % 4 == 0), scores given explicitly.                                       */
+TOKRED_API int tokred_topk_gather_add(const float* x, const void* branch, const void* scores, int score_dtype,
+                           int64_t score_stride, int64_t score_batch_stride, int B, int N, int C, int k, float* x_out,
+                           int64_t* idx_out, void* stream);
+TOKRED_API int tokred_evit_select_fuse_add(const float* x, const void* branch, const void* scores, int score_dtype, int B, int N,
+                                int C, int k, float* x_out, int64_t* idx_out, int64_t* compl_out, void* stream);
+
 /* ---- a4/a5 with the callers either side fused (bf16-autocast Block_ToMe, models/tome.py:88-104) ----------
  * x + drop_path(attn branch)  ->  merge_wavg  ->  norm2  in ONE launch over the fp32 residual stream:
  *   x [B,N,C] fp32; branch [B,N,C] bf16 or NULL (the attention projection's output; added in fp32 on every row read);

@@ -1240,3 +1240,32 @@ def test_embed_layernorm(T, b, p, t, c):
     assert torch.equal(y, y2)
     y_ref = torch.nn.functional.layer_norm(x_ref, (c,), gamma, beta, 1e-6)
     assert_close_rel(y.float(), y_ref, 4e-3, "embed norm1 (bf16 output)")
+
+
+# ------------------------------------------------------------------------------------------------ select + residual add
+@pytest.mark.parametrize("b,n,k,c", [(5, 197, 137, 384), (3, 197, 98, 768), (64, 138, 96, 384), (1024, 51, 24, 768), (2, 9, 3, 12)])
+def test_topk_gather_add(T, b, n, k, c):
+    """topk_gather on x + branch with the fp32 add done on the fly == add (ATen) then topk_gather, bit for bit; the kept
+    indices against the oracle."""
+    x = torch.randn(b, n, c, generator=g(400)).to(DEV)
+    br = torch.randn(b, n, c, generator=g(401)).to(torch.bfloat16).to(DEV)
+    sc = tie_free_scores(min(b, 16), n - 1, 402).repeat((b + 15) // 16, 1)[:b].to(DEV)
+    out, idx = T.topk_gather_add(x, br, sc, k)
+    out2, idx2 = T.topk_gather(x + br, sc, k)
+    assert (x + br).dtype == torch.float32
+    assert torch.equal(idx, idx2) and torch.equal(out, out2)
+    nb = min(b, 4)
+    xo_r, idx_r = O.topk_gather((x[:nb] + br[:nb]).cpu(), sc[:nb].cpu(), k)
+    assert torch.equal(idx[:nb].cpu(), idx_r) and torch.equal(out[:nb].cpu(), xo_r)
+
+
+@pytest.mark.parametrize("b,n,k,c", [(5, 197, 98, 768), (4, 100, 49, 768), (128, 197, 98, 768), (3, 51, 24, 384), (2, 9, 3, 12)])
+def test_evit_select_fuse_add(T, b, n, k, c):
+    """evit_select_fuse on x + branch with the add done on the fly == add (ATen) then evit_select_fuse, bit for bit (kept
+    rows, fused inattentive token, both index lists)."""
+    x = torch.randn(b, n, c, generator=g(410)).to(DEV)
+    br = torch.randn(b, n, c, generator=g(411)).to(torch.bfloat16).to(DEV)
+    sc = tie_free_scores(min(b, 16), n - 1, 412).repeat((b + 15) // 16, 1)[:b].to(DEV)
+    out, idx, compl = T.evit_select_fuse_add(x, br, sc, k)
+    out2, idx2, compl2 = T.evit_select_fuse(x + br, sc, k)
+    assert torch.equal(idx, idx2) and torch.equal(compl, compl2) and torch.equal(out, out2)

@@ -23,6 +23,8 @@ SIGNATURES = {
     "tokred_tome_effective_r": [c_int, c_int, c_int],
     "tokred_tome_match": [_P, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tokred_tome_merge": [_P, c_int, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P],
+    "tokred_topk_gather_add": [_P, _P, _P, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P],
+    "tokred_evit_select_fuse_add": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tokred_tome_merge_ln": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P, _P, _P, _P],
     "tokred_pairwise_dist": [_P, c_int, c_int, c_int, c_float, c_int, _P, _P],
     "tokred_dpcknn_cluster": [_P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P],

@@ -16,45 +16,78 @@ constexpr int kWarps = kThreads / 32;
 
 // grid = (gh, B): one CTA turns the ph image rows x Cin channels of one patch row into gw output rows (contiguous in out).
 // Loads are 16-byte coalesced along the image row; the bf16 patch rows are assembled in shared memory (patch stride padded
-// by 16 bytes: the 8-byte stores of a warp spread over all banks) and leave as 16-byte coalesced stores.
+// by 32 bytes: the 8-byte stores of a warp spread over all banks) and leave as 16-byte coalesced stores.
 __global__ void __launch_bounds__(kThreads)
 patchify_kernel(const float* __restrict__ img, int Cin, int H, int W, int ph, int pw, __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char sm[];
   const int gy = blockIdx.x, b = blockIdx.y, gw = W / pw, W4 = W / 4;
   const int D = Cin * ph * pw;                       // elements per output row
-  const int SP = D * 2 + 16;                         // bytes between patches in shared memory
-  const int items = Cin * ph * W4;
+  const int SP = D * 2 + 32;                         // bytes between patches in shared memory (+32: a warp's 8-byte stores tile all banks)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* ib = img + (long long)b * Cin * H * W + (long long)gy * ph * W;
-  for (int e0 = threadIdx.x; e0 < items; e0 += 4 * kThreads) {
-    float4 v[4];
+  // A warp walks image rows r = (c, py); a lane owns the same (up to four) 16-byte column groups q = lane + 32 j of
+  // every row, so the patch / pixel split of a column is computed once per thread, not once per element (the first
+  // version spent its time in integer divisions: 53 % of the HBM rate).
+  constexpr int QMAX = 4;
+  int soff[QMAX];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * kThreads;
-      if (e < items) {
-        const int q = e % W4, r = e / W4, py = r % ph, c = r / ph;
-        v[u] = *reinterpret_cast<const float4*>(ib + ((long long)c * H + py) * W + q * 4);
+  for (int j = 0; j < QMAX; ++j) {
+    const int q = lane + 32 * j;
+    soff[j] = q < W4 ? ((q * 4) / pw) * SP + ((q * 4) % pw) * 2 : -1;
+  }
+  const int nrows = Cin * ph;
+  if (W4 <= 32 * QMAX) {
+    for (int r0 = warp; r0 < nrows; r0 += 2 * kWarps) {          // two rows = up to eight 16-byte loads in flight per lane
+      float4 v[2][QMAX];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int r = r0 + u * kWarps;
+        if (r < nrows) {
+          const float* rowp = ib + ((long long)(r / ph) * H + (r % ph)) * W + lane * 4;
+#pragma unroll
+          for (int j = 0; j < QMAX; ++j)
+            if (soff[j] >= 0) v[u][j] = *reinterpret_cast<const float4*>(rowp + 128 * j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int r = r0 + u * kWarps;
+        if (r < nrows) {
+          unsigned char* dst = sm + (size_t)r * pw * 2;           // (c*ph + py) * pw elements into the patch row
+#pragma unroll
+          for (int j = 0; j < QMAX; ++j)
+            if (soff[j] >= 0) {
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u][j].x, v[u][j].y), hi = __floats2bfloat162_rn(v[u][j].z, v[u][j].w);
+              uint2 o;
+              o.x = *reinterpret_cast<const uint32_t*>(&lo);
+              o.y = *reinterpret_cast<const uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(dst + soff[j]) = o;
+            }
+        }
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = e0 + u * kThreads;
-      if (e < items) {
-        const int q = e % W4, r = e / W4, py = r % ph, c = r / ph;
-        const int gx = (q * 4) / pw, px = (q * 4) % pw;
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+  } else {                                                         // very wide images: generic column loop
+    for (int r = warp; r < nrows; r += kWarps) {
+      const float* rowp = ib + ((long long)(r / ph) * H + (r % ph)) * W;
+      for (int q = lane; q < W4; q += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(rowp + q * 4);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
         uint2 o;
         o.x = *reinterpret_cast<const uint32_t*>(&lo);
         o.y = *reinterpret_cast<const uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(sm + (size_t)gx * SP + ((size_t)(c * ph + py) * pw + px) * 2) = o;
+        *reinterpret_cast<uint2*>(sm + (size_t)((q * 4) / pw) * SP + ((size_t)r * pw + (q * 4) % pw) * 2) = o;
       }
     }
   }
   __syncthreads();
   const int row16 = D / 8;                           // 16-byte units per output row
   unsigned char* ob = reinterpret_cast<unsigned char*>(out + ((long long)b * gridDim.x + gy) * gw * D);
+  int gx = 0, w = threadIdx.x;
+  while (w >= row16) { w -= row16; ++gx; }
   for (int i = threadIdx.x; i < gw * row16; i += kThreads) {
-    const int gx = i / row16, w = i - gx * row16;
     st_stream16(ob + (size_t)i * 16, *reinterpret_cast<const int4*>(sm + (size_t)gx * SP + (size_t)w * 16));
+    w += kThreads;
+    while (w >= row16) { w -= row16; ++gx; }
   }
 }
 
@@ -146,7 +179,7 @@ extern "C" int tokred_patchify(const float* img, int B, int Cin, int H, int W, i
     set_error("%s: needs a patch width that is a multiple of 4, rows of whole 16-byte units and 16-byte aligned tensors", what);
     return TOKRED_ERR_UNSUPPORTED;
   }
-  const size_t smem = (size_t)(W / pw) * ((size_t)Cin * ph * pw * 2 + 16);
+  const size_t smem = (size_t)(W / pw) * ((size_t)Cin * ph * pw * 2 + 32);
   if (int e = allow_smem(patchify_kernel, smem, what)) return e;
   patchify_kernel<<<dim3(H / ph, B), kThreads, smem, (cudaStream_t)stream>>>(img, Cin, H, W, ph, pw, (__nv_bfloat16*)out);
   return finish_launch(what);

@@ -47,10 +47,38 @@ __device__ __forceinline__ void copy_row(char* dst, const char* src, int row_byt
   }
 }
 
+// x + branch on the fly (fp32 stream, bf16 branch: the block's `x = x + drop_path(attn branch)`, e.g. models/topk.py:87, as
+// the same fp32 addition) for the rows that survive only: four rows in flight, one 16-byte + one 8-byte load per row and step
+__device__ __forceinline__ int4 add_bf16x4(const int4& a, const uint2& c) {
+  int4 r;
+  r.x = __float_as_int(__fadd_rn(__int_as_float(a.x), __uint_as_float(c.x << 16)));
+  r.y = __float_as_int(__fadd_rn(__int_as_float(a.y), __uint_as_float(c.x & 0xffff0000u)));
+  r.z = __float_as_int(__fadd_rn(__int_as_float(a.z), __uint_as_float(c.y << 16)));
+  r.w = __float_as_int(__fadd_rn(__int_as_float(a.w), __uint_as_float(c.y & 0xffff0000u)));
+  return r;
+}
+__device__ __forceinline__ void warp_addcopy_rows16x4(char* dbase, const int (&doff)[4], const char* sbase, const char* bbase,
+                                                      const int (&soff)[4], int nrows, int bytes, int lane) {
+  for (int off = lane * 16; off < bytes; off += 512) {
+    int4 a[4];
+    uint2 c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u < nrows) {
+        a[u] = ld_stream16(sbase + soff[u] + off);
+        c[u] = *reinterpret_cast<const uint2*>(bbase + ((soff[u] + off) >> 1));
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u < nrows) st_stream16(dbase + doff[u] + off, add_bf16x4(a[u], c[u]));
+  }
+}
+
 // output row j <- token 0 (j == 0) or kept patch sel[j-1]; the rows of this CTA (blockIdx.x of gridDim.x splits) are
 // dealt to its warps four at a time so that every warp has four source rows in flight
+template <bool ADD = false>
 __device__ __forceinline__ void gather_kept_rows(char* ob, const char* xb, const int* sel, int nrows, int row_bytes, int vec16,
-                                                 int elem_size, int warp, int lane) {
+                                                 int elem_size, int warp, int lane, const char* bb = nullptr) {
   const int stride = gridDim.x * kWarps;
   for (int j = blockIdx.x * kWarps + warp; j < nrows; j += 4 * stride) {
     int so[4], dof[4], nr = 0;        // byte offsets inside the image (an image is far below 2 GB)
@@ -63,7 +91,9 @@ __device__ __forceinline__ void gather_kept_rows(char* ob, const char* xb, const
       dof[u] = (live ? jj : 0) * row_bytes;
       nr += live;
     }
-    if (vec16) {
+    if (ADD) {
+      warp_addcopy_rows16x4(ob, dof, xb, bb, so, nr, row_bytes, lane);      // host: fp32 stream on the vector path only
+    } else if (vec16) {
       warp_copy_rows16x4(ob, dof, xb, so, nr, row_bytes, lane);
     } else {
 #pragma unroll
@@ -74,9 +104,10 @@ __device__ __forceinline__ void gather_kept_rows(char* ob, const char* xb, const
 }
 
 // ------------------------------------------------------------------------------------------ Top-K
-__global__ void __launch_bounds__(kThreads, 4)
-topk_gather_kernel(ScoreSrc ss, const char* __restrict__ x, char* __restrict__ x_out, int64_t* __restrict__ idx_out,
-                   int N, int k, int row_bytes, int vec16, int elem_size) {
+template <bool ADD>       // ADD: x + branch on the rows that are kept (own instantiation: the plain gather keeps its 64 registers)
+__global__ void __launch_bounds__(kThreads, ADD ? 3 : 4)
+topk_gather_kernel(ScoreSrc ss, const char* __restrict__ x, const char* __restrict__ branch, char* __restrict__ x_out,
+                   int64_t* __restrict__ idx_out, int N, int k, int row_bytes, int vec16, int elem_size) {
   extern __shared__ float smem[];
   const int P = N - 1, b = blockIdx.y, tid = threadIdx.x;
   float* keys = smem;
@@ -96,17 +127,18 @@ topk_gather_kernel(ScoreSrc ss, const char* __restrict__ x, char* __restrict__ x
   const int warp = tid >> 5, lane = tid & 31;
   const char* xb = x + (long long)b * N * row_bytes;
   char* ob = x_out + (long long)b * (k + 1) * row_bytes;
-  gather_kept_rows(ob, xb, sel, k + 1, row_bytes, vec16, elem_size, warp, lane);
+  gather_kept_rows<ADD>(ob, xb, sel, k + 1, row_bytes, vec16, elem_size, warp, lane,
+                        ADD ? branch + (long long)b * N * (row_bytes >> 1) : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------ EViT
 // grid.x = number of 1024-byte column slices of a token row (round 1: 512-byte slices -> 768 CTAs at B=128, two waves).
 // Split s gathers its share of the kept rows and owns slice s of the fused token: warp w accumulates complement rows
 // w, w+8, ... (ascending patch order), the 8 partials are combined in warp order through shared memory -> deterministic.
-template <typename T>
+template <typename T, bool ADD = false>
 __global__ void __launch_bounds__(kThreads)
-evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_out, int64_t* __restrict__ idx_out,
-                        int64_t* __restrict__ compl_out, int N, int C, int k, int vec16) {
+evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, const __nv_bfloat16* __restrict__ branch, T* __restrict__ x_out,
+                        int64_t* __restrict__ idx_out, int64_t* __restrict__ compl_out, int N, int C, int k, int vec16) {
   extern __shared__ float smem[];
   constexpr int VE = 16 / sizeof(T);            // elements per 16-byte lane chunk
   constexpr int SLICE = 2 * 32 * VE;            // elements per 1024-byte slice
@@ -144,8 +176,10 @@ evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_
   const T* xb = x + (long long)b * N * C;
   T* ob = x_out + (long long)b * (k + 2) * C;
   // kept rows
-  gather_kept_rows(reinterpret_cast<char*>(ob), reinterpret_cast<const char*>(xb), sel, k + 1, row_bytes, vec16, (int)sizeof(T),
-                   warp, lane);
+  const __nv_bfloat16* bb = nullptr;                                    // x + branch on every row read (fp32 stream only)
+  if constexpr (ADD) bb = branch + (long long)b * N * C;
+  gather_kept_rows<ADD>(reinterpret_cast<char*>(ob), reinterpret_cast<const char*>(xb), sel, k + 1, row_bytes, vec16, (int)sizeof(T),
+                   warp, lane, reinterpret_cast<const char*>(bb));
   // fused inattentive token, slice blockIdx.x (two 16-byte chunks per lane)
   const int e0 = blockIdx.x * SLICE + lane * VE;
   float acc[2][VE];
@@ -157,6 +191,7 @@ evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_
     // 4 complement rows x 2 chunks per step: the 16-byte loads are issued together, then consumed in ascending row order
     for (int m0 = warp; m0 < M; m0 += 4 * kWarps) {
       int4 raw[4][2];
+      uint2 rb[4][2];
       float w[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -168,6 +203,23 @@ evit_select_fuse_kernel(ScoreSrc ss, const T* __restrict__ x, T* __restrict__ x_
           const T* row = xb + (long long)(1 + p) * C + e0;
           if (e0 < C) raw[u][0] = ld_stream16(row);
           if (e0 + 32 * VE < C) raw[u][1] = ld_stream16(row + 32 * VE);
+          if constexpr (ADD) {
+            {
+              const __nv_bfloat16* brow = bb + (long long)(1 + p) * C + e0;
+              if (e0 < C) rb[u][0] = *reinterpret_cast<const uint2*>(brow);
+              if (e0 + 32 * VE < C) rb[u][1] = *reinterpret_cast<const uint2*>(brow + 32 * VE);
+            }
+          }
+        }
+      }
+      if constexpr (ADD) {
+        {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (m0 + u * kWarps < M) {
+              if (e0 < C) raw[u][0] = add_bf16x4(raw[u][0], rb[u][0]);
+              if (e0 + 32 * VE < C) raw[u][1] = add_bf16x4(raw[u][1], rb[u][1]);
+            }
         }
       }
 #pragma unroll
@@ -440,10 +492,9 @@ int check_scores(const void* scores, int score_dtype, const void* attn, int attn
 
 using namespace tokred;
 
-extern "C" int tokred_topk_gather(const void* x, int x_dtype, const void* scores, int score_dtype, int64_t score_stride,
-                                  int64_t score_batch_stride, const void* attn, int attn_dtype, int H, int B, int N,
-                                  int C, int k, void* x_out, int64_t* idx_out, void* stream) {
-  const char* what = "tokred_topk_gather";
+static int launch_topk_gather(const char* what, const void* x, int x_dtype, const void* branch, const void* scores,
+                              int score_dtype, int64_t score_stride, int64_t score_batch_stride, const void* attn, int attn_dtype,
+                              int H, int B, int N, int C, int k, void* x_out, int64_t* idx_out, void* stream) {
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && x_out && idx_out, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(x_dtype), "%s: bad x dtype %d", what, x_dtype);
@@ -455,20 +506,45 @@ extern "C" int tokred_topk_gather(const void* x, int x_dtype, const void* scores
   const int P = N - 1, row_bytes = C * dtype_size(x_dtype);
   const int vec16 = (row_bytes % 16 == 0) && aligned16(x) && aligned16(x_out);
   const size_t smem = (size_t)(P + k) * 4;
-  if (int e = allow_smem(topk_gather_kernel, smem, what)) return e;
+  if (int e = allow_smem(topk_gather_kernel<true>, smem, what)) return e;
+  if (int e = allow_smem(topk_gather_kernel<false>, smem, what)) return e;
   // every split re-ranks the scores, and a warp moves four rows at a time: as few splits as give every SM two CTAs
   int splits = ceil_div(4 * kNumSMs, B);
   splits = max(1, min(splits, ceil_div(k + 1, 2 * kWarps)));
   ScoreSrc ss{scores, score_dtype, score_stride, score_batch_stride, attn, attn_dtype, H};
-  topk_gather_kernel<<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
-      ss, (const char*)x, (char*)x_out, idx_out, N, k, row_bytes, vec16, dtype_size(x_dtype));
+  if (branch && !(x_dtype == TOKRED_F32 && vec16 && (reinterpret_cast<uintptr_t>(branch) & 7u) == 0)) {
+    set_error("%s: the branch add needs an fp32 stream with 16-byte rows and an 8-byte aligned bf16 branch", what);
+    return TOKRED_ERR_UNSUPPORTED;
+  }
+  if (branch)
+    topk_gather_kernel<true><<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
+        ss, (const char*)x, (const char*)branch, (char*)x_out, idx_out, N, k, row_bytes, vec16, dtype_size(x_dtype));
+  else
+    topk_gather_kernel<false><<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
+        ss, (const char*)x, nullptr, (char*)x_out, idx_out, N, k, row_bytes, vec16, dtype_size(x_dtype));
   return finish_launch(what);
 }
 
-extern "C" int tokred_evit_select_fuse(const void* x, int x_dtype, const void* scores, int score_dtype,
-                                       const void* attn, int attn_dtype, int H, int B, int N, int C, int k,
-                                       void* x_out, int64_t* idx_out, int64_t* compl_out, void* stream) {
-  const char* what = "tokred_evit_select_fuse";
+extern "C" int tokred_topk_gather(const void* x, int x_dtype, const void* scores, int score_dtype, int64_t score_stride,
+                                  int64_t score_batch_stride, const void* attn, int attn_dtype, int H, int B, int N,
+                                  int C, int k, void* x_out, int64_t* idx_out, void* stream) {
+  return launch_topk_gather("tokred_topk_gather", x, x_dtype, nullptr, scores, score_dtype, score_stride, score_batch_stride, attn,
+                            attn_dtype, H, B, N, C, k, x_out, idx_out, stream);
+}
+
+extern "C" int tokred_topk_gather_add(const float* x, const void* branch, const void* scores, int score_dtype,
+                                      int64_t score_stride, int64_t score_batch_stride, int B, int N, int C, int k, float* x_out,
+                                      int64_t* idx_out, void* stream) {
+  const char* what = "tokred_topk_gather_add";
+  if (B == 0) return TOKRED_OK;
+  TOKRED_REQUIRE(branch, "%s: null branch", what);
+  return launch_topk_gather(what, x, TOKRED_F32, branch, scores, score_dtype, score_stride, score_batch_stride, nullptr, 0, 0, B,
+                            N, C, k, x_out, idx_out, stream);
+}
+
+static int launch_evit_select_fuse(const char* what, const void* x, int x_dtype, const void* branch, const void* scores,
+                                   int score_dtype, const void* attn, int attn_dtype, int H, int B, int N, int C, int k,
+                                   void* x_out, int64_t* idx_out, int64_t* compl_out, void* stream) {
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(x && x_out && idx_out && compl_out, "%s: null tensor", what);
   TOKRED_REQUIRE(valid_float_dtype(x_dtype), "%s: bad x dtype %d", what, x_dtype);
@@ -483,16 +559,42 @@ extern "C" int tokred_evit_select_fuse(const void* x, int x_dtype, const void* s
   const int splits = ceil_div(C, slice);
   const size_t smem = (size_t)(P + k + (P - k) + (P + 3) / 4 + kWarps * slice) * 4;
   ScoreSrc ss{scores, score_dtype, 1, P, attn, attn_dtype, H};
+  if (branch && !(x_dtype == TOKRED_F32 && vec16 && (reinterpret_cast<uintptr_t>(branch) & 7u) == 0)) {
+    set_error("%s: the branch add needs an fp32 stream with 16-byte rows and an 8-byte aligned bf16 branch", what);
+    return TOKRED_ERR_UNSUPPORTED;
+  }
   if (x_dtype == TOKRED_F32) {
     if (int e = allow_smem(evit_select_fuse_kernel<float>, smem, what)) return e;
-    evit_select_fuse_kernel<float><<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
-        ss, (const float*)x, (float*)x_out, idx_out, compl_out, N, C, k, vec16);
+    if (branch) {
+      if (int e = allow_smem(evit_select_fuse_kernel<float, true>, smem, what)) return e;
+      evit_select_fuse_kernel<float, true><<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
+          ss, (const float*)x, (const __nv_bfloat16*)branch, (float*)x_out, idx_out, compl_out, N, C, k, vec16);
+    } else {
+      evit_select_fuse_kernel<float><<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
+          ss, (const float*)x, nullptr, (float*)x_out, idx_out, compl_out, N, C, k, vec16);
+    }
   } else {
     if (int e = allow_smem(evit_select_fuse_kernel<__nv_bfloat16>, smem, what)) return e;
     evit_select_fuse_kernel<__nv_bfloat16><<<dim3(splits, B), kThreads, smem, (cudaStream_t)stream>>>(
-        ss, (const __nv_bfloat16*)x, (__nv_bfloat16*)x_out, idx_out, compl_out, N, C, k, vec16);
+        ss, (const __nv_bfloat16*)x, nullptr, (__nv_bfloat16*)x_out, idx_out, compl_out, N, C, k, vec16);
   }
   return finish_launch(what);
+}
+
+extern "C" int tokred_evit_select_fuse(const void* x, int x_dtype, const void* scores, int score_dtype,
+                                       const void* attn, int attn_dtype, int H, int B, int N, int C, int k,
+                                       void* x_out, int64_t* idx_out, int64_t* compl_out, void* stream) {
+  return launch_evit_select_fuse("tokred_evit_select_fuse", x, x_dtype, nullptr, scores, score_dtype, attn, attn_dtype, H, B, N, C,
+                                 k, x_out, idx_out, compl_out, stream);
+}
+
+extern "C" int tokred_evit_select_fuse_add(const float* x, const void* branch, const void* scores, int score_dtype, int B, int N,
+                                           int C, int k, float* x_out, int64_t* idx_out, int64_t* compl_out, void* stream) {
+  const char* what = "tokred_evit_select_fuse_add";
+  if (B == 0) return TOKRED_OK;
+  TOKRED_REQUIRE(branch, "%s: null branch", what);
+  return launch_evit_select_fuse(what, x, TOKRED_F32, branch, scores, score_dtype, nullptr, 0, 0, B, N, C, k, x_out, idx_out,
+                                 compl_out, stream);
 }
 
 extern "C" int tokred_gather_rows(const void* src, int dtype, const int64_t* ids, int64_t ids_stride, int B, int G,

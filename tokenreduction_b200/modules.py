@@ -278,8 +278,12 @@ class Block_TopK(nn.Module):
         idx = None
         if cls_attn is not None:
             _train_guard(self, True)
-            x = x + self.drop_path(tmp)
-            x, idx = ops.topk_gather(x, cls_attn, left_tokens)          # select + gather + cat in one launch
+            branch = self.drop_path(tmp)
+            if DEFER_RESIDUAL and ops.select_add_supported(x, branch, cls_attn):
+                x, idx = ops.topk_gather_add(x, branch, cls_attn, left_tokens)    # + the residual add, on the kept rows only
+            else:
+                x = x + branch
+                x, idx = ops.topk_gather(x, cls_attn, left_tokens)      # select + gather + cat in one launch
             y = norm_lowp(self.norm2, x)
         else:
             x, y = add_norm(x, self.drop_path(tmp), self.norm2)
@@ -319,8 +323,12 @@ class Block_EVIT(nn.Module):
         idx = compl = None
         if cls_attn is not None:
             _train_guard(self, True)
-            x = x + self.drop_path(tmp)
-            x, idx, compl = ops.evit_select_fuse(x, cls_attn, left_tokens)
+            branch = self.drop_path(tmp)
+            if DEFER_RESIDUAL and ops.select_add_supported(x, branch, cls_attn):
+                x, idx, compl = ops.evit_select_fuse_add(x, branch, cls_attn, left_tokens)
+            else:
+                x = x + branch
+                x, idx, compl = ops.evit_select_fuse(x, cls_attn, left_tokens)
             y = norm_lowp(self.norm2, x)
         else:
             x, y = add_norm(x, self.drop_path(tmp), self.norm2)

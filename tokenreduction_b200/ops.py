@@ -825,6 +825,70 @@ def tome_merge_ln(x: Tensor, branch: Optional[Tensor], size: Optional[Tensor], u
     return torch.ops.tokred.tome_merge_ln(x, branch, size, unm, src, dst, weight, bias, eps, want_map)
 
 
+# ----------------------------------------------------------------------------------------------- select + residual add
+def select_add_supported(x: Tensor, branch: Tensor, scores: Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] % 4 == 0 and branch.dtype == torch.bfloat16
+            and branch.shape == x.shape and scores.dtype in (torch.float32, torch.bfloat16)
+            and not (torch.is_grad_enabled() and (x.requires_grad or branch.requires_grad)))
+
+
+@torch.library.custom_op("tokred::topk_gather_add", mutates_args=(), device_types="cuda")
+def _topk_gather_add(x: Tensor, branch: Tensor, scores: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    _need_cuda("topk_gather_add", x, branch, scores)
+    b, n, c = x.shape
+    if x.dtype != torch.float32 or branch.dtype != torch.bfloat16 or branch.shape != x.shape:
+        raise TokredError(f"topk_gather_add: x {tuple(x.shape)} {x.dtype}, branch {tuple(branch.shape)} {branch.dtype}")
+    if scores.dim() != 2 or scores.shape[0] != b or scores.shape[1] != n - 1:
+        raise TokredError(f"topk_gather_add: scores {tuple(scores.shape)} does not match x {tuple(x.shape)}")
+    x, branch = _c(x), _c(branch)
+    out = torch.empty((b, k + 1, c), dtype=torch.float32, device=x.device)
+    idx = torch.empty((b, k), dtype=torch.int64, device=x.device)
+    _lib.call("tokred_topk_gather_add", _ptr(x), _ptr(branch), _ptr(scores), _dt(scores), scores.stride(1), scores.stride(0),
+              b, n, c, k, _ptr(out), _ptr(idx), _stream())
+    return out, idx
+
+
+@_topk_gather_add.register_fake
+def _(x, branch, scores, k):
+    b, n, c = x.shape
+    return x.new_empty((b, k + 1, c)), x.new_empty((b, k), dtype=torch.int64)
+
+
+def topk_gather_add(x: Tensor, branch: Tensor, scores: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """``topk_gather(x + branch, scores, k)`` without materialising the sum (models/topk.py:87 + :62, :89-93): the fp32 add
+    happens on the kept rows as they are gathered.  Inference path of the bf16-autocast blocks."""
+    return torch.ops.tokred.topk_gather_add(x, branch, scores, k)
+
+
+@torch.library.custom_op("tokred::evit_select_fuse_add", mutates_args=(), device_types="cuda")
+def _evit_select_fuse_add(x: Tensor, branch: Tensor, scores: Tensor, k: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("evit_select_fuse_add", x, branch, scores)
+    b, n, c = x.shape
+    if x.dtype != torch.float32 or branch.dtype != torch.bfloat16 or branch.shape != x.shape:
+        raise TokredError(f"evit_select_fuse_add: x {tuple(x.shape)} {x.dtype}, branch {tuple(branch.shape)} {branch.dtype}")
+    if scores.dim() != 2 or scores.shape[0] != b or scores.shape[1] != n - 1:
+        raise TokredError(f"evit_select_fuse_add: scores {tuple(scores.shape)} does not match x {tuple(x.shape)}")
+    x, branch, scores = _c(x), _c(branch), _c(scores)
+    out = torch.empty((b, k + 2, c), dtype=torch.float32, device=x.device)
+    idx = torch.empty((b, k + 1), dtype=torch.int64, device=x.device)
+    compl = torch.empty((b, n - 1 - k), dtype=torch.int64, device=x.device)
+    _lib.call("tokred_evit_select_fuse_add", _ptr(x), _ptr(branch), _ptr(scores), _dt(scores), b, n, c, k, _ptr(out), _ptr(idx),
+              _ptr(compl), _stream())
+    return out, idx, compl
+
+
+@_evit_select_fuse_add.register_fake
+def _(x, branch, scores, k):
+    b, n, c = x.shape
+    return (x.new_empty((b, k + 2, c)), x.new_empty((b, k + 1), dtype=torch.int64),
+            x.new_empty((b, n - 1 - k), dtype=torch.int64))
+
+
+def evit_select_fuse_add(x: Tensor, branch: Tensor, scores: Tensor, k: int):
+    """``evit_select_fuse(x + branch, scores, k)`` without materialising the sum (models/evit.py:109 + :84, :111-123)."""
+    return torch.ops.tokred.evit_select_fuse_add(x, branch, scores, k)
+
+
 # ----------------------------------------------------------------------------------------------- in front of block 0
 @torch.library.custom_op("tokred::patchify", mutates_args=(), device_types="cuda")
 def _patchify(img: Tensor, ph: int, pw: int) -> Tensor:
