@@ -379,6 +379,7 @@ class Runner:
                                  drop_path_rate=0.0, drop_block_rate=None, img_size=224,
                                  args=model_args(kr, viz_mode=world > 1, tokred_device_viz=True))
         self.model = model.eval().to(dev)
+        self.model.viz_features = False        # only the kept / assignment indices are gathered across ranks, not feature maps
         gen = torch.Generator().manual_seed(1 + rank)
         self.host_images = torch.randn(batch, 3, 224, 224, generator=gen).pin_memory()
         self.images = self.host_images.to(dev)

