@@ -350,9 +350,10 @@ def run_reference(a):
 DECISION_KEYS = ("Kept_Tokens", "Assignment_Maps")
 
 
-def pack_decisions(viz):
-    """every stage's kept-token / assignment indices of this rank's shard as ONE int32 tensor [B, total] (device)."""
-    cols = []
+def pack_decisions(viz, logits=None):
+    """the logits (fp32 bit patterns) and every stage's kept-token / assignment indices of this rank's shard as ONE int32
+    tensor [B, total] (device)."""
+    cols = [] if logits is None else [logits.contiguous().view(torch.int32)]
     for key in DECISION_KEYS:
         for i in sorted(viz.get(key, {})):
             t = viz[key][i]
@@ -408,14 +409,14 @@ class Runner:
             return out.float()
         y, viz = out
         y = y.float()
-        # the path's only exchange: logits and kept / assignment indices of every shard (two all_gathers, KBs-MBs)
-        self.dist.all_gather_into_tensor(self.g_logits, y)
-        dec = pack_decisions(viz)
-        if dec is not None:
-            if self.g_dec is None or self.g_dec.shape[1] != dec.shape[1]:
-                self.g_dec = torch.empty(self.world * dec.shape[0], dec.shape[1], dtype=torch.int32, device=self.dev)
-                self.dec_cols = dec.shape[1]
-            self.dist.all_gather_into_tensor(self.g_dec, dec.contiguous())
+        # the path's only exchange: logits and kept / assignment indices of every shard, packed into ONE int32 tensor
+        # [B, 1000 + index columns] (the logits as their fp32 bit patterns) -> one all_gather per step (KBs-MBs)
+        dec = pack_decisions(viz, y)
+        if self.g_dec is None or self.g_dec.shape[1] != dec.shape[1]:
+            self.g_dec = torch.empty(self.world * dec.shape[0], dec.shape[1], dtype=torch.int32, device=self.dev)
+            self.dec_cols = dec.shape[1] - y.shape[1]
+        self.dist.all_gather_into_tensor(self.g_dec, dec)
+        self.g_logits = self.g_dec[:, :y.shape[1]].view(torch.float32)     # every rank holds all logits and all indices
         return y
 
     def barrier(self):
@@ -598,7 +599,7 @@ def run_tokred(a):
                                     "one CUDA graph replay per step (tokenreduction_b200.graph.GraphedForward); the per-kernel "
                                     "timeline is a separate untimed eager pass",
                        "exchange": "none (1 GPU)" if world == 1 else
-                                   f"per step: NCCL all_gather of logits [B,1000] f32 + kept/assignment indices [B,{dec_cols}] i32",
+                                   f"per step: ONE NCCL all_gather of logits [B,1000] f32 + kept/assignment indices [B,{dec_cols}] i32 (packed)",
                        "e2e_pipeline": "per step: H2D of the batch (pinned, copy stream, 2 device buffers; overlaps the "
                                        "previous step's forward) + forward + D2H of the logits + stream sync"},
             "e2e": {"value": round(total * a.steps / (ms_e2e * 1e-3), 1), "unit": "images/s",
