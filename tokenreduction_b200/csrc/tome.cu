@@ -722,7 +722,7 @@ tome_merge_kernel(const T* __restrict__ x, const T* __restrict__ size, const int
 
 // add + merge + LayerNorm in one launch: tome_merge_kernel's structure on the fp32 residual stream (C = 128 * CPL)
 template <int CPL>
-__global__ void __launch_bounds__(kThreads, CPL <= 3 ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, CPL <= 3 ? 4 : 2)
 tome_merge_ln_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ branch, const float* __restrict__ size,
                      const int64_t* __restrict__ unm_idx, const int64_t* __restrict__ src_idx,
                      const int64_t* __restrict__ dst_idx, int N, int r, const float* __restrict__ gamma,
@@ -908,9 +908,10 @@ extern "C" int tokred_tome_merge_ln(const float* x, const void* branch, const fl
   const int na = (N + 1) / 2, n_unm = na - r, n_out = N - r;
   const size_t smem = (size_t)(N + n_unm + 2 * r + na) * 4;
   const int cpl = C / 128;
-  // measured at B=256, N=197 (3 CTAs per SM resident): 256 CTAs 54.0 us, 512 CTAs 57.0 us, 768 CTAs 47.3 us, 1024 CTAs
-  // 49.7 us -- about five CTAs per SM: small enough that the second, partial wave costs little
-  int splits = ceil_div(5 * kNumSMs, B);
+  // ONE wave of resident CTAs (4 per SM at 64 registers up to C = 384, else 2), like tome_merge.  Measured at B=256, N=197:
+  // 512 CTAs 43.1 us, 768 CTAs 47.9 us, 1024 CTAs 44.5 us, 1536 CTAs 44.8 us (at 72 registers / 3 CTAs per SM: 54 / 47 us)
+  const int resident = kNumSMs * (cpl <= 3 ? 4 : 2);
+  int splits = resident / B;
   splits = max(1, min(splits, ceil_div(n_out, kWarps)));
   dim3 grid(splits, B);
   cudaStream_t st = (cudaStream_t)stream;
