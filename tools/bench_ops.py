@@ -210,6 +210,29 @@ def cases():
         add(f"add_layernorm B={b} N={n} C={c} (x + branch, LN, bf16)", mk_ln)
         if b == 256 and n == 197:
             add(f"add_layernorm B={b} N={n} C={c} (LN, bf16; no branch)", lambda f=mk_ln: f(br=False))
+    # in front of block 0: image -> bf16 patch rows; cat(cls, patches) + pos_embed + the first norm1
+    for b, c in ((256, 384), (128, 768), (1024, 768)):
+        def mk_patch(b=b):
+            img = rnd(b, 3, 224, 224)
+            return lambda: T.patchify(img, 16, 16)
+
+        def mk_embed(b=b, c=c):
+            patches, tok, pos, w, bb = rnd(b, 196, c, dtype=torch.bfloat16), rnd(1, c), rnd(197, c), rnd(c), rnd(c)
+            return lambda: T.embed_layernorm(patches, tok, pos, w, bb, 1e-6)
+        if c != 384 or b == 256:
+            add(f"patchify B={b} 3x224x224 -> [196, 768] bf16", mk_patch)
+        add(f"embed_layernorm B={b} N=197 C={c} (cat cls + pos_embed + norm1, bf16)", mk_embed)
+    # the residual add on the rows a select kernel reads (bf16-autocast Top-K / EViT blocks)
+    for b, n, k in ((128, 197, 98), (1024, 197, 98)):
+        def mk_topk_add(b=b, n=n, k=k):
+            x, br, s = rnd(b, n, 768), rnd(b, n, 768, dtype=torch.bfloat16), spread_scores(b, n - 1, 1).to(DEV)
+            return lambda: T.topk_gather_add(x, br, s, k)
+
+        def mk_evit_add(b=b, n=n, k=k):
+            x, br, s = rnd(b, n, 768), rnd(b, n, 768, dtype=torch.bfloat16), spread_scores(b, n - 1, 1).to(DEV)
+            return lambda: T.evit_select_fuse_add(x, br, s, k)
+        add(f"topk_gather_add B B={b} N={n} k={k} (x + attn branch on the kept rows)", mk_topk_add)
+        add(f"evit_select_fuse_add B B={b} N={n} k={k} (x + attn branch on every row read)", mk_evit_add)
     return out
 
 
