@@ -151,6 +151,12 @@ TOKRED_API int tokred_attn_colsum(const void* attn, int attn_dtype, int B, int H
 TOKRED_API int tokred_kmedoids_fit(const float* x, int64_t x_batch_stride, const float* token_weight, int B, int P, int C, int K, int iters,
                                    int exact_fp32, float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream);
 
+/* The same with caller-supplied initial medoids init_idx [B,K] int64 (models/kmedoids.py:43-61: the equal_weight variant's
+ * farthest-point initialisation, built by the caller from tokred_pairwise_dist); token_weight may then be NULL (= ones, :61). */
+TOKRED_API int tokred_kmedoids_fit_init(const float* x, int64_t x_batch_stride, const float* token_weight, const int64_t* init_idx,
+                                        int B, int P, int C, int K, int iters, int exact_fp32, float* centres,
+                                        int64_t* cluster_idx, int64_t* assignment, void* stream);
+
 /* Scratch for the bulk-copy fed tensor-core path of the three soft merges (a9, a12, a13): the caller passes a device
  * buffer of at least this many bytes, 128-byte aligned (bf16 token tiles + packed Q).  With workspace = NULL the
  * entry points use the scratch-free tensor-core kernel instead (slower).  The library never allocates.            */

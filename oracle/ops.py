@@ -210,7 +210,7 @@ def attn_colsum(attn: Tensor, num_tokens: int = 1) -> Tensor:
 
 
 def kmedoids_fit(x: Tensor, cluster_num: int, iters: int, token_weight: Tensor, dist: Optional[Tensor] = None):
-    """models/kmedoids.py:62-85 (token_weight given; the equal_weight numpy-RNG path :43-61 is out of scope).
+    """models/kmedoids.py:62-85 (token_weight given; the equal_weight path :43-61 is kmedoids_fit_equal below).
 
     The reference's K x iters loop of masked clones is restated through S_i = sum_j (D_ij * w_i): rows outside
     cluster k are masked to 1e6 in EVERY column, so they sum to P*1e6 (exact in fp32 for P <= 4096) and an
@@ -223,6 +223,44 @@ def kmedoids_fit(x: Tensor, cluster_num: int, iters: int, token_weight: Tensor, 
     big = torch.tensor(1.0e6 * p, dtype=s.dtype, device=s.device)         # P copies of 1e6 sum exactly in fp32
     for _ in range(iters):
         assign = torch.gather(d, 2, centre.unsqueeze(1).expand(-1, p, -1)).argmin(dim=-1)   # [b,p]
+        for k in range(cluster_num):
+            cand = torch.where(assign == k, s, big.expand_as(s))
+            centre[:, k] = cand.argmin(dim=1)
+    assign = torch.gather(d, 2, centre.unsqueeze(1).expand(-1, p, -1)).argmin(dim=-1)
+    return gather_rows(x, centre), centre, assign
+
+
+def kmedoids_init_equal(x: Tensor, cluster_num: int, first: int, dist: Optional[Tensor] = None) -> Tensor:
+    """models/kmedoids.py:43-59 -- the equal_weight initialisation, loop for loop: medoid 0 = ``first`` (the reference's
+    one ``np.random.choice`` draw, shared by the batch); then k = 1..K-1: distances of every token to the medoids so far
+    (cdist(x, centers), here columns of the full matrix), rows of chosen medoids zeroed, max over the medoid axis, max
+    over tokens.  -> cluster_idx [B,K]."""
+    b, n, _ = x.shape
+    cluster_idx = torch.ones((b, 1), dtype=torch.long, device=x.device) * int(first)
+    for k in range(1, cluster_num):
+        if dist is None:
+            inter = torch.cdist(x, gather_rows(x, cluster_idx))                                 # [b,n,k], the reference's call (:48-49)
+        else:
+            inter = torch.gather(dist, 2, cluster_idx.unsqueeze(1).expand(-1, n, -1)).clone()   # columns of a given matrix
+        for i in range(b):
+            for kt in range(k):
+                inter[i, cluster_idx[i, kt]] = 0
+        max_dist, _ = torch.max(inter, dim=-1)
+        _, new = torch.max(max_dist, dim=-1)
+        cluster_idx = torch.cat((cluster_idx, new.reshape(b, -1)), dim=-1)
+    return cluster_idx
+
+
+def kmedoids_fit_equal(x: Tensor, cluster_num: int, iters: int, first: int, dist: Optional[Tensor] = None):
+    """models/kmedoids.py:40-85 with token_weight=None: kmedoids_init_equal, unit weights (:61), then the iterations of
+    kmedoids_fit.  -> (centres, cluster_idx, assignment)."""
+    b, p, c = x.shape
+    d = pairwise_dist(x) if dist is None else dist
+    centre = kmedoids_init_equal(x, cluster_num, first, dist).clone()
+    s = (d * x.new_ones(b, p, 1)).sum(dim=-1)
+    big = torch.tensor(1.0e6 * p, dtype=s.dtype, device=s.device)
+    for _ in range(iters):
+        assign = torch.gather(d, 2, centre.unsqueeze(1).expand(-1, p, -1)).argmin(dim=-1)
         for k in range(cluster_num):
             cand = torch.where(assign == k, s, big.expand_as(s))
             centre[:, k] = cand.argmin(dim=1)

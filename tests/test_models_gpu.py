@@ -422,3 +422,31 @@ def test_deferred_sums_are_bit_identical(name, viz, monkeypatch):
                 assert torch.equal(ta, tb), f"{name}: viz output {key}[{i}] differs"
     else:
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["kmedoids", "dpcknn"])
+@pytest.mark.parametrize("amp", [False, True])
+def test_equal_weight_models_run(name, amp):
+    """`--equal_weight` (train.py flag; models/kmedoids.py:43-61, models/dpcknn.py:151-158): the drop-in models run it -- round 1
+    raised NotImplementedError for K-Medoids.  Same numpy / torch seeds -> same logits; a different first medoid -> the
+    K-Medoids logits move."""
+    import numpy as np
+    from tokenreduction_b200 import create_model
+    torch.manual_seed(0)
+    args = margs(KR[name])
+    args.equal_weight = True
+    model = quiet(create_model, f"{name}_small_patch16_224", num_classes=100, args=args).eval().cuda()
+    x = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(21)).cuda()
+
+    def run(seed):
+        np.random.seed(seed)
+        torch.manual_seed(9)
+        torch.cuda.manual_seed(9)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            return model(x).float()
+
+    a, b, c = run(1), run(1), run(2)
+    assert bool(torch.isfinite(a).all()) and a.shape == (4, 100)
+    assert torch.equal(a, b)
+    if name == "kmedoids":
+        assert not torch.equal(a, c)

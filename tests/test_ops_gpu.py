@@ -487,6 +487,35 @@ def test_kmedoids_fit_at_bench_batch(T, p, k):
     _check_kmedoids(T, x, tw, k, 3, False, min_own=0.6, min_e2e=0.5, floor_e2e=0.9)
 
 
+@pytest.mark.parametrize("p,k,first", [(196, 49, 17), (49, 12, 0), (12, 3, 11), (196, 49, 195)])
+def test_kmedoids_fit_equal_weight(T, p, k, first):
+    """--equal_weight (models/kmedoids.py:43-61): farthest-point initialisation from the drawn token + unit weights.
+    (1) the initialisation on the product's own distance matrix equals the oracle's loop on that matrix, bit for bit;
+    (2) with that matrix the whole fit (medoids, assignment, medoid rows) equals the oracle's on every image;
+    (3) end to end against the oracle on the reference's cdist: an image may differ only where the two distance matrices
+        disagree by more than the decision margin -- on this well-separated data none does."""
+    b, c = 16, 384
+    x = clustered_tokens(b, p, c, max(k // 2, 2), 133).to(DEV)
+    d_own = T.pairwise_dist(x, 1.0, False)
+    init = T.kmedoids_init_farthest(d_own, k, first)
+    assert torch.equal(init.cpu(), O.kmedoids_init_equal(x.cpu(), k, first, dist=d_own.cpu()))
+    cen, ci, asg = T.kmedoids_fit_equal(x, k, 3, first)
+    cen_o, ci_o, asg_o = O.kmedoids_fit_equal(x.cpu(), k, 3, first, dist=d_own.cpu())
+    assert torch.equal(ci.cpu(), ci_o) and torch.equal(asg.cpu(), asg_o) and torch.equal(cen.cpu(), cen_o)
+    cen_r, ci_r, asg_r = O.kmedoids_fit_equal(x.cpu(), k, 3, first)
+    same = (ci.cpu() == ci_r).all(dim=1) & (asg.cpu() == asg_r).all(dim=1)
+    assert bool(same.all()), f"images {(~same).nonzero().flatten().tolist()} differ from the oracle on cdist"
+    # module level: the drop-in function draws the first medoid with the reference's numpy call
+    import numpy as np
+    from tokenreduction_b200 import modules as M
+    np.random.seed(3)
+    want_first = int(np.random.choice(np.arange(p), 1)[0])
+    np.random.seed(3)
+    cen_m, ci_m, asg_m = M.k_medoids_fit(x, k, 3, None)
+    cen_w, ci_w, asg_w = T.kmedoids_fit_equal(x, k, 3, want_first)
+    assert torch.equal(ci_m, ci_w) and torch.equal(asg_m, asg_w) and torch.equal(cen_m, cen_w)
+
+
 # ------------------------------------------------------------------------------------------------ soft merges
 @pytest.mark.parametrize("p,k,c", [(196, 176, 768), (176, 158, 768), (158, 142, 768), (196, 176, 384), (60, 20, 100)])
 def test_sinkhorn_fp32(T, p, k, c):

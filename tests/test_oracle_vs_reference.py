@@ -119,6 +119,22 @@ def test_kmedoids(ref, p, k):
     assert torch.equal(ci, ci_ref) and torch.equal(asg, as_ref) and torch.equal(cen, c_ref)
 
 
+@pytest.mark.parametrize("p,k", [(196, 49), (49, 12), (12, 3)])
+def test_kmedoids_equal_weight(ref, p, k):
+    """--equal_weight (models/kmedoids.py:43-61): token_weight=None -> one numpy draw, farthest-point initialisation, unit
+    weights.  The oracle takes the drawn index as an argument; same numpy seed on both sides."""
+    import numpy as np
+    K = ref["kmedoids"]
+    b, c = 3, 64
+    x = torch.randn(b, p, c, generator=g(114))
+    np.random.seed(5)
+    c_ref, ci_ref, as_ref = K.k_medoids_fit(x, k, 3, None)
+    np.random.seed(5)
+    first = int(np.random.choice(np.arange(p), 1)[0])
+    cen, ci, asg = O.kmedoids_fit_equal(x, k, 3, first, dist=None)
+    assert torch.equal(ci, ci_ref) and torch.equal(asg, as_ref) and torch.equal(cen, c_ref)
+
+
 @pytest.mark.parametrize("p,k", [(196, 176), (176, 158), (60, 20)])
 def test_sinkhorn(ref, p, k):
     S = ref["sinkhorn"]

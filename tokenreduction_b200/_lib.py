@@ -31,6 +31,7 @@ SIGNATURES = {
     "tokred_dpcknn_merge": [_P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tokred_attn_colsum": [_P, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "tokred_kmedoids_fit": [_P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "tokred_kmedoids_fit_init": [_P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tokred_sinkhorn_merge": [_P, c_int, c_int64, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P],
     "tokred_patchmerger": [_P, c_int, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, c_int, _P, c_int, _P, _P, c_size_t, _P],
     "tokred_sit_merge": [_P, c_int, c_int64, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_size_t, _P],

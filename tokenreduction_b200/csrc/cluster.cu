@@ -292,13 +292,13 @@ template <int NT, class Sync>
 __device__ __forceinline__ void kmed_epilogue(const float* D, int DS, int P, int C, int K, int iters, const float* __restrict__ tw_b,
                                               const float* __restrict__ xb, float* extra, int tid, Sync sync,
                                               float* __restrict__ centres_b, int64_t* __restrict__ cidx_b,
-                                              int64_t* __restrict__ assign_b) {
+                                              int64_t* __restrict__ assign_b, const int64_t* __restrict__ init_b = nullptr) {
   float* w = extra;
   float* S = w + P;
   int* assign = reinterpret_cast<int*>(S + P);   // [P]
   int* centre = assign + P;                       // [K]
   const int warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < P; i += NT) w[i] = tw_b[i];
+  for (int i = tid; i < P; i += NT) w[i] = tw_b ? tw_b[i] : 1.f;      // no weights: the equal_weight variant (:61)
   sync();
   // S_i = sum_j (D_ij * w_i); initial centres = top-K token weights (descending, lowest index on ties)
   for (int i = tid; i < P; i += NT) {
@@ -310,6 +310,10 @@ __device__ __forceinline__ void kmed_epilogue(const float* D, int DS, int P, int
     if (rk < K) centre[rk] = i;
   }
   sync();
+  if (init_b) {        // caller-supplied initial medoids (the equal_weight farthest-point initialisation, :43-59)
+    for (int k = tid; k < K; k += NT) centre[k] = clamp_idx(init_b[k], P);
+    sync();
+  }
   // Medoid update: c_k = argmin_{i: assign_i = k} S_i with the lowest i on ties, empty cluster -> token 0 (every
   // masked row sums to P * 1e6 > any S).  One shared-memory atomicMin per token on the key (S bits, i):
   // S > 0, so the fp32 bit pattern orders like the value -- replaces K serial scans of P by 49 threads.
@@ -385,7 +389,8 @@ dpcknn_cluster_kernel(const float* __restrict__ x, long long xbs, const float* _
 
 template <bool LIGHT>
 __global__ void __launch_bounds__(LIGHT ? kLightThreads : kThreads, 1)
-kmedoids_fit_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ token_weight, int P, int C, int K, int iters,
+kmedoids_fit_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ token_weight,
+                    const int64_t* __restrict__ init_idx, int P, int C, int K, int iters,
                     float* __restrict__ centres, int64_t* __restrict__ cluster_idx, int64_t* __restrict__ assignment) {
   constexpr int NT = LIGHT ? kLightThreads : kThreads;
   extern __shared__ __align__(128) float smem[];
@@ -394,15 +399,16 @@ kmedoids_fit_kernel(const float* __restrict__ x, long long xbs, const float* __r
   const float* xb = x + (long long)b * xbs;
   pairdist_to_smem<LIGHT>(xb, P, C, cx, 1.0f);
   __syncthreads();
-  kmed_epilogue<NT>(cx.D, cx.DS, P, C, K, iters, token_weight + (long long)b * P, xb, cx.extra, (int)threadIdx.x, BlockSync(),
-                    centres + (long long)b * K * C, cluster_idx + (long long)b * K, assignment + (long long)b * P);
+  kmed_epilogue<NT>(cx.D, cx.DS, P, C, K, iters, token_weight ? token_weight + (long long)b * P : nullptr, xb, cx.extra,
+                    (int)threadIdx.x, BlockSync(), centres + (long long)b * K * C, cluster_idx + (long long)b * K,
+                    assignment + (long long)b * P, init_idx ? init_idx + (long long)b * K : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------ pipelined kernels
 struct PipeParams {
   const float* x; long long xbs; int B, P, C; float post_scale;
   const float* noise; int K, knn; int64_t* idx_cluster; int64_t* index_down;                    // DPC-KNN
-  const float* tw; int iters; float* centres; int64_t* cidx; int64_t* assign;                   // K-Medoids
+  const float* tw; const int64_t* init; int iters; float* centres; int64_t* cidx; int64_t* assign;   // K-Medoids
   float* out;                                                                                   // plain cdist
 };
 enum { EPI_PLAIN = 0, EPI_DPC = 1, EPI_KMED = 2 };
@@ -429,8 +435,9 @@ __global__ void __launch_bounds__(pipe::kThreads, 1) dist_pipe_kernel(const Pipe
         dpc_epilogue<pipe::kBack>(cx.D, cx.DS, p.P, p.K, p.knn, p.noise + b * p.P, cx.extra, bt, BackSync(),
                                   p.idx_cluster + b * p.P, p.index_down + b * p.K, it);
       } else {
-        kmed_epilogue<pipe::kBack>(cx.D, cx.DS, p.P, p.C, p.K, p.iters, p.tw + b * p.P, p.x + b * p.xbs, cx.extra, bt, BackSync(),
-                                   p.centres + b * (long long)p.K * p.C, p.cidx + b * p.K, p.assign + b * p.P);
+        kmed_epilogue<pipe::kBack>(cx.D, cx.DS, p.P, p.C, p.K, p.iters, p.tw ? p.tw + b * p.P : nullptr, p.x + b * p.xbs, cx.extra,
+                                   bt, BackSync(), p.centres + b * (long long)p.K * p.C, p.cidx + b * p.K, p.assign + b * p.P,
+                                   p.init ? p.init + b * p.K : nullptr);
       }
       pipe::bar_sync(pipe::BAR_BACK, pipe::kBack);       // D and the epilogue vectors are free for the next image
       TOKRED_STAMP(bt == 0, it, 14);
@@ -728,11 +735,11 @@ extern "C" int tokred_dpcknn_cluster(const float* x, int64_t x_batch_stride, con
   return finish_launch(what);
 }
 
-extern "C" int tokred_kmedoids_fit(const float* x, int64_t x_batch_stride, const float* token_weight, int B, int P, int C, int K, int iters,
-                                   int exact_fp32, float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream) {
-  const char* what = "tokred_kmedoids_fit";
+static int launch_kmedoids_fit(const char* what, const float* x, int64_t x_batch_stride, const float* token_weight,
+                               const int64_t* init_idx, int B, int P, int C, int K, int iters, int exact_fp32, float* centres,
+                               int64_t* cluster_idx, int64_t* assignment, void* stream) {
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
-  TOKRED_REQUIRE(x && token_weight && centres && cluster_idx && assignment, "%s: null tensor", what);
+  TOKRED_REQUIRE(x && (token_weight || init_idx) && centres && cluster_idx && assignment, "%s: null tensor", what);
   TOKRED_REQUIRE(B >= 0 && P >= 1 && C >= 1, "%s: bad shape B=%d P=%d C=%d", what, B, P, C);
   TOKRED_REQUIRE(K >= 1 && K <= P, "%s: cluster_num=%d outside [1, P=%d]", what, K, P);
   TOKRED_REQUIRE(iters >= 0, "%s: iters=%d < 0", what, iters);
@@ -743,19 +750,38 @@ extern "C" int tokred_kmedoids_fit(const float* x, int64_t x_batch_stride, const
   if (pick_pipe(P, exact_fp32)) {
     PipeParams p{};
     p.x = x; p.xbs = xbs; p.B = B; p.P = P; p.C = C; p.post_scale = 1.0f;
-    p.tw = token_weight; p.K = K; p.iters = iters; p.centres = centres; p.cidx = cluster_idx; p.assign = assignment;
+    p.tw = token_weight; p.init = init_idx; p.K = K; p.iters = iters; p.centres = centres; p.cidx = cluster_idx; p.assign = assignment;
     return launch_pipe<EPI_KMED>(p, kmed_extra_floats(P, K), what, st);
   }
   const int light = P <= 25;
   const size_t smem = dist_smem_bytes(P, kmed_extra_floats(P, K), light);
   if (light) {
     if (int e = allow_smem(kmedoids_fit_kernel<true>, smem, what)) return e;
-    kmedoids_fit_kernel<true><<<B, kLightThreads, smem, st>>>(x, xbs, token_weight, P, C, K, iters, centres, cluster_idx, assignment);
+    kmedoids_fit_kernel<true><<<B, kLightThreads, smem, st>>>(x, xbs, token_weight, init_idx, P, C, K, iters, centres, cluster_idx, assignment);
   } else {
     if (int e = allow_smem(kmedoids_fit_kernel<false>, smem, what)) return e;
-    kmedoids_fit_kernel<false><<<B, kThreads, smem, st>>>(x, xbs, token_weight, P, C, K, iters, centres, cluster_idx, assignment);
+    kmedoids_fit_kernel<false><<<B, kThreads, smem, st>>>(x, xbs, token_weight, init_idx, P, C, K, iters, centres, cluster_idx, assignment);
   }
   return finish_launch(what);
+}
+
+extern "C" int tokred_kmedoids_fit(const float* x, int64_t x_batch_stride, const float* token_weight, int B, int P, int C, int K, int iters,
+                                   int exact_fp32, float* centres, int64_t* cluster_idx, int64_t* assignment, void* stream) {
+  const char* what = "tokred_kmedoids_fit";
+  if (B == 0) return TOKRED_OK;
+  TOKRED_REQUIRE(token_weight, "%s: null token_weight", what);
+  return launch_kmedoids_fit(what, x, x_batch_stride, token_weight, nullptr, B, P, C, K, iters, exact_fp32, centres, cluster_idx,
+                             assignment, stream);
+}
+
+extern "C" int tokred_kmedoids_fit_init(const float* x, int64_t x_batch_stride, const float* token_weight, const int64_t* init_idx,
+                                        int B, int P, int C, int K, int iters, int exact_fp32, float* centres,
+                                        int64_t* cluster_idx, int64_t* assignment, void* stream) {
+  const char* what = "tokred_kmedoids_fit_init";
+  if (B == 0) return TOKRED_OK;
+  TOKRED_REQUIRE(init_idx, "%s: null init_idx", what);
+  return launch_kmedoids_fit(what, x, x_batch_stride, token_weight, init_idx, B, P, C, K, iters, exact_fp32, centres, cluster_idx,
+                             assignment, stream);
 }
 
 extern "C" int tokred_dpcknn_merge(const float* x, int64_t x_batch_stride, const int64_t* idx_token, const float* agg_weight,

@@ -592,8 +592,11 @@ class CTM(nn.Module):
 def k_medoids_fit(x: Tensor, cluster_num: int, iterations: int = 5, token_weight: Optional[Tensor] = None):
     """models/kmedoids.py:40-85 -> (centres, cluster_idx, assignment)."""
     if token_weight is None:
-        raise NotImplementedError("k_medoids_fit: the equal_weight initialisation (numpy RNG, models/kmedoids.py:43-61) "
-                                  "is not on the accelerated path")
+        # --equal_weight (:43-61): one numpy draw picks the first medoid for the whole batch -- the same call, so the same
+        # generator position as the reference -- then the farthest-point initialisation and unit weights
+        import numpy as np
+        first = int(np.random.choice(np.arange(x.shape[1]), 1)[0])
+        return ops.kmedoids_fit_equal(x, cluster_num, iterations, first, False)
     return ops.kmedoids_fit(x, token_weight, cluster_num, iterations, False)
 
 

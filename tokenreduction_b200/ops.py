@@ -447,6 +447,60 @@ def _(x, token_weight, cluster_num, iters, exact_fp32):
             x.new_empty((b, p), dtype=torch.int64))
 
 
+@torch.library.custom_op("tokred::kmedoids_fit_init", mutates_args=(), device_types="cuda")
+def _kmedoids_fit_init(x: Tensor, init_idx: Tensor, iters: int, exact_fp32: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda("kmedoids_fit_init", x, init_idx)
+    b, p, c = x.shape
+    if x.dtype != torch.float32:
+        raise TokredError("kmedoids_fit_init: x must be float32 (cdist runs in fp32)")
+    if init_idx.dim() != 2 or init_idx.shape[0] != b or init_idx.dtype != torch.int64 or not 1 <= init_idx.shape[1] <= p:
+        raise TokredError(f"kmedoids_fit_init: init_idx {tuple(init_idx.shape)} {init_idx.dtype}; expected int64 [B,K<=P]")
+    k = init_idx.shape[1]
+    (x, xbs), init_idx = _rows(x), _c(init_idx)
+    centres = torch.empty((b, k, c), dtype=torch.float32, device=x.device)
+    cidx = torch.empty((b, k), dtype=torch.int64, device=x.device)
+    assign = torch.empty((b, p), dtype=torch.int64, device=x.device)
+    _lib.call("tokred_kmedoids_fit_init", _ptr(x), xbs, None, _ptr(init_idx), b, p, c, k, iters, int(exact_fp32), _ptr(centres),
+              _ptr(cidx), _ptr(assign), _stream())
+    return centres, cidx, assign
+
+
+@_kmedoids_fit_init.register_fake
+def _(x, init_idx, iters, exact_fp32):
+    b, p, c = x.shape
+    k = init_idx.shape[1]
+    return (x.new_empty((b, k, c)), x.new_empty((b, k), dtype=torch.int64), x.new_empty((b, p), dtype=torch.int64))
+
+
+def kmedoids_init_farthest(dist: Tensor, cluster_num: int, first: int) -> Tensor:
+    """models/kmedoids.py:43-59, the equal_weight initialisation, on a full distance matrix [B,P,P]: start from token
+    ``first`` (the reference's one numpy draw, shared by the batch); k-th medoid = the token whose LARGEST distance to
+    the medoids chosen so far is largest (``torch.max`` over the medoid axis, then over tokens: first index on ties), the
+    rows of chosen medoids zeroed (:53-55).  A running maximum replaces the reference's growing [B,P,k] cdist.
+    -> init_idx [B,K] int64."""
+    b, p, _ = dist.shape
+    idx = torch.full((b, 1), int(first), dtype=torch.int64, device=dist.device)
+    chosen = torch.zeros((b, p), dtype=torch.bool, device=dist.device)
+    chosen[:, int(first)] = True
+    far = dist[:, :, int(first)].clone()
+    for _ in range(1, cluster_num):
+        new = far.masked_fill(chosen, 0.0).argmax(dim=-1, keepdim=True)                  # [B,1]
+        idx = torch.cat((idx, new), dim=-1)
+        chosen.scatter_(1, new, True)
+        far = torch.maximum(far, torch.gather(dist, 2, new.unsqueeze(1).expand(-1, p, -1)).squeeze(-1))
+    return idx
+
+
+def kmedoids_fit_equal(x: Tensor, cluster_num: int, iters: int, first: int, exact_fp32: bool = False):
+    """models/kmedoids.py:40-85 with token_weight=None (``--equal_weight``): farthest-point initialisation from token
+    ``first`` on the product's distance matrix, then the medoid iterations with unit weights in the K-Medoids kernel."""
+    xf = _up(x)[0]
+    dist = torch.ops.tokred.pairwise_dist(xf, 1.0, exact_fp32)
+    init = kmedoids_init_farthest(dist, cluster_num, first)
+    centres, cidx, assign = torch.ops.tokred.kmedoids_fit_init(xf, init, iters, exact_fp32)
+    return _down(centres, x), cidx, assign
+
+
 def attn_colsum(attn: Tensor, num_tokens: int = 1) -> Tensor:
     """models/kmedoids.py:240: token weights [B,P,1] = sum over heads and query rows of attention columns."""
     return torch.ops.tokred.attn_colsum(_up(attn)[0], num_tokens)
