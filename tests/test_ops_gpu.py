@@ -901,6 +901,18 @@ def test_dyvit_pool_concat(T, p, c, hdtype):
     assert_close_rel(out[:, :, c // 2:], ref[:, :, c // 2:], RTOL32, "pooled half")
 
 
+@pytest.mark.parametrize("b,p,c", [(4, 196, 768), (128, 98, 768), (3, 49, 384), (2, 7, 16)])
+def test_dyvit_pool_concat_lowp_out(T, b, p, c):
+    """bf16 output (what out_conv's autocast Linear casts the fp32 concatenation to): bit-identical to rounding the fp32
+    result of the same kernel -- the local half is an exact copy, the pooled half is rounded once either way."""
+    h = torch.randn(b, p, c, generator=g(159)).to(torch.bfloat16).to(DEV)
+    policy = (torch.rand(b, p, 1, generator=g(160)) > 0.3).float().to(DEV)
+    out32 = T.dyvit_pool_concat(h, policy)
+    out16 = T.dyvit_pool_concat(h, policy, lowp_out=True)
+    assert out32.dtype == torch.float32 and out16.dtype == torch.bfloat16
+    assert torch.equal(out16, out32.to(torch.bfloat16))
+
+
 # ------------------------------------------------------------------------------------------------ benchmarked grids
 def test_evit_and_dyvit_keep_at_bench_batch(T):
     """BASELINE config 3 grid: DeiT-B, keep_rate 0.5, B=1024 on one GPU (splits depend on B: 1 CTA row per image

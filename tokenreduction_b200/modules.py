@@ -839,7 +839,10 @@ class PredictorLG(nn.Module):
 
     def forward(self, x, policy):
         h = self.in_conv(x)
-        return self.out_conv(ops.dyvit_pool_concat(h, policy, self.eps))
+        # under bf16 autocast out_conv's first Linear casts its input to bf16: ask the kernel for that tensor directly
+        lowp = (h.is_cuda and h.dtype == torch.bfloat16 and torch.is_autocast_enabled("cuda")
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16 and isinstance(self.out_conv[0], nn.Linear))
+        return self.out_conv(ops.dyvit_pool_concat(h, policy, self.eps, lowp_out=lowp))
 
 
 class Policy_Attention(_AttentionBase):

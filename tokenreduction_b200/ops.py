@@ -728,8 +728,30 @@ def _(h, policy, eps):
     return h.new_empty(h.shape, dtype=torch.promote_types(h.dtype, policy.dtype))
 
 
-def dyvit_pool_concat(h: Tensor, policy: Tensor, eps: float = 1e-6) -> Tensor:
-    """models/dyvit.py:114-118: [local half | masked mean of the global half + eps]."""
+@torch.library.custom_op("tokred::dyvit_pool_concat_lowp", mutates_args=(), device_types="cuda")
+def _dyvit_pool_concat_lowp(h: Tensor, policy: Tensor, eps: float) -> Tensor:
+    _need_cuda("dyvit_pool_concat_lowp", h, policy)
+    b, p, c = h.shape
+    if policy.numel() != b * p or h.dtype != torch.bfloat16:
+        raise TokredError("dyvit_pool_concat_lowp: h must be bf16 [B,P,C], policy [B,P,1]")
+    h, pol = _c(h), _c(policy.float())
+    out = torch.empty((b, p, c), dtype=torch.bfloat16, device=h.device)
+    _lib.call("tokred_dyvit_pool_concat", _ptr(h), _dt(h), _ptr(pol), b, p, c, float(eps), _ptr(out), _dt(out), _stream())
+    return out
+
+
+@_dyvit_pool_concat_lowp.register_fake
+def _(h, policy, eps):
+    return h.new_empty(h.shape)
+
+
+def dyvit_pool_concat(h: Tensor, policy: Tensor, eps: float = 1e-6, lowp_out: bool = False) -> Tensor:
+    """models/dyvit.py:114-118: [local half | masked mean of the global half + eps].
+    lowp_out (bf16 h, inference under bf16 autocast): emit the concatenation in bf16 -- what the autocast Linear that
+    consumes it (out_conv, :119) would cast the reference's fp32 ``torch.cat`` result to: the local half is bf16 already,
+    the pooled half is rounded once either way, so the Linear sees the same bits and the fp32 tensor + its cast disappear."""
+    if lowp_out and h.dtype == torch.bfloat16 and not (torch.is_grad_enabled() and (h.requires_grad or policy.requires_grad)):
+        return torch.ops.tokred.dyvit_pool_concat_lowp(h, policy, eps)
     hf, pf = _up(h, policy)
     out = torch.ops.tokred.dyvit_pool_concat(hf, pf, eps)
     return out.to(torch.promote_types(h.dtype, policy.dtype))      # torch.cat's promotion (models/dyvit.py:118)
