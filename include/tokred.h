@@ -211,10 +211,11 @@ TOKRED_API int tokred_gather_rows(const void* src, int dtype, const int64_t* ids
 
 /* ---- a11 DynamicViT predictor pooling ----------------------------------------------------------------
  * models/dyvit.py:114-118: out = [h[:,:,:C/2] | (sum_p h[:,p,C/2:]*policy[p]) / sum_p policy[p] + eps].
- *   h [B,P,C] h_dtype (bf16 under autocast), policy [B,P] fp32 -> out [B,P,C] out_dtype (fp32 under autocast:
- *   the reference's cat promotes)                                                                       */
-TOKRED_API int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float* policy, int B, int P, int C, float eps,
-                             void* out, int out_dtype, void* stream);
+ *   h [B,P,C] h_dtype (bf16 under autocast), images h_batch_stride elements apart (0 = dense P*C; the [:, 1:] view of a
+ *   [B,P+1,C] tensor is read in place), policy [B,P] fp32 -> out [B,P,C] out_dtype (fp32: the reference's cat promotes;
+ *   bf16: what the autocast Linear consuming it, :119, casts that to -- the same bits)                   */
+TOKRED_API int tokred_dyvit_pool_concat(const void* h, int h_dtype, int64_t h_batch_stride, const float* policy, int B, int P,
+                             int C, float eps, void* out, int out_dtype, void* stream);
 
 /* ---- f1 / f2: attention that emits only what the reduction operators read ---------------------------
  * models/topk.py:44-52,59-61; evit.py:66-87; tome.py:44-58 (proportional attention :48-49); kmedoids.py:105-112,240;

@@ -38,7 +38,7 @@ SIGNATURES = {
     "tokred_soft_merge_workspace_bytes": [c_int, c_int, c_int, c_int],
     "tokred_ats_sample": [_P, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P],
     "tokred_gather_rows": [_P, c_int, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P],
-    "tokred_dyvit_pool_concat": [_P, c_int, _P, c_int, c_int, c_int, c_float, _P, c_int, _P],
+    "tokred_dyvit_pool_concat": [_P, c_int, c_int64, _P, c_int, c_int, c_int, c_float, _P, c_int, _P],
     "tokred_add_layernorm": [_P, _P, c_int, _P, _P, c_float, c_int64, c_int, _P, _P, _P],
     "tokred_patchify": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "tokred_embed_layernorm": [_P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, _P, _P, _P],

@@ -406,8 +406,8 @@ __device__ __forceinline__ void unraw(const Raw8<__nv_bfloat16>& r, float (&v)[8
 
 template <typename TI, typename TO, bool vec>
 __global__ void __launch_bounds__(kThreads, 3)
-dyvit_pool_concat_kernel(const TI* __restrict__ h, const float* __restrict__ policy, TO* __restrict__ out, int P, int C,
-                         float eps) {
+dyvit_pool_concat_kernel(const TI* __restrict__ h, long long hbs, const float* __restrict__ policy, TO* __restrict__ out, int P,
+                         int C, float eps) {
   extern __shared__ float smem[];
   // rows in flight per thread (P = 196: 13 rows per thread -> 2 / 4 rounds); the scalar fallback keeps one
   constexpr int R = !vec ? 1 : (sizeof(TI) == 2 ? 6 : 4);
@@ -418,7 +418,7 @@ dyvit_pool_concat_kernel(const TI* __restrict__ h, const float* __restrict__ pol
   const int c0 = blockIdx.x * kPoolSlice + ct * 8;          // first of this thread's 8 channels (within a half)
   const int valid = half - c0;                              // <= 0: thread idle
   const int vld = vec ? 8 : valid;                          // vector path: half % 8 == 0, a live chunk is always whole
-  const TI* hb = h + (long long)b * P * C;
+  const TI* hb = h + (long long)b * hbs;          // hbs: elements between images (h may be the [:, 1:] view of [B,P+1,C])
   for (int p = tid; p < P; p += kThreads) pol[p] = policy[(long long)b * P + p];
   __syncthreads();
   float psum = 0.f;
@@ -619,8 +619,8 @@ extern "C" int tokred_gather_rows(const void* src, int dtype, const int64_t* ids
   return finish_launch(what);
 }
 
-extern "C" int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float* policy, int B, int P, int C,
-                                        float eps, void* out, int out_dtype, void* stream) {
+extern "C" int tokred_dyvit_pool_concat(const void* h, int h_dtype, int64_t h_batch_stride, const float* policy, int B, int P,
+                                        int C, float eps, void* out, int out_dtype, void* stream) {
   const char* what = "tokred_dyvit_pool_concat";
   if (B == 0) return TOKRED_OK;   // empty batch: nothing to enqueue (tensors may be null)
   TOKRED_REQUIRE(h && policy && out, "%s: null tensor", what);
@@ -633,13 +633,17 @@ extern "C" int tokred_dyvit_pool_concat(const void* h, int h_dtype, const float*
   // vector path: 8 channels per thread; fp32 sides move 32 bytes per access (LDG.256 / STG.256: 32-byte alignment)
   const bool al_h = h_dtype == TOKRED_F32 ? (reinterpret_cast<uintptr_t>(h) & 31u) == 0 : aligned16(h);
   const bool al_o = out_dtype == TOKRED_F32 ? (reinterpret_cast<uintptr_t>(out) & 31u) == 0 : aligned16(out);
-  const int vec = ((C / 2) % 8 == 0) && al_h && al_o;
+  TOKRED_REQUIRE(h_batch_stride == 0 || h_batch_stride >= (int64_t)P * C, "%s: h_batch_stride=%lld < P*C", what,
+                 (long long)h_batch_stride);
+  const long long hbs = h_batch_stride ? (long long)h_batch_stride : (long long)P * C;
+  const bool al_s = (hbs * dtype_size(h_dtype)) % (h_dtype == TOKRED_F32 ? 32 : 16) == 0;
+  const int vec = ((C / 2) % 8 == 0) && al_h && al_o && al_s;
   dim3 grid(splits, B);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(TI, TO)                                                                                       \
   do {                                                                                                       \
-    if (vec) dyvit_pool_concat_kernel<TI, TO, true><<<grid, kThreads, smem, st>>>((const TI*)h, policy, (TO*)out, P, C, eps);  \
-    else dyvit_pool_concat_kernel<TI, TO, false><<<grid, kThreads, smem, st>>>((const TI*)h, policy, (TO*)out, P, C, eps);    \
+    if (vec) dyvit_pool_concat_kernel<TI, TO, true><<<grid, kThreads, smem, st>>>((const TI*)h, hbs, policy, (TO*)out, P, C, eps);  \
+    else dyvit_pool_concat_kernel<TI, TO, false><<<grid, kThreads, smem, st>>>((const TI*)h, hbs, policy, (TO*)out, P, C, eps);    \
   } while (0)
   if (h_dtype == TOKRED_F32 && out_dtype == TOKRED_F32) LAUNCH(float, float);
   else if (h_dtype == TOKRED_BF16 && out_dtype == TOKRED_F32) LAUNCH(__nv_bfloat16, float);

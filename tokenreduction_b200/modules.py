@@ -826,6 +826,16 @@ def batch_index_select(x: Tensor, idx: Tensor) -> Tensor:
     raise NotImplementedError
 
 
+def _slice_base(x: Tensor) -> Optional[Tensor]:
+    """the contiguous [B,N,C] tensor of which ``x`` is the ``[:, 1:]`` view, or None."""
+    base = x._base
+    if (base is None or x.dim() != 3 or base.dim() != 3 or not base.is_contiguous() or base.dtype != x.dtype
+            or base.shape[0] != x.shape[0] or base.shape[1] != x.shape[1] + 1 or base.shape[2] != x.shape[2]
+            or x.stride() != base.stride() or x.data_ptr() != base.data_ptr() + base.shape[2] * base.element_size()):
+        return None
+    return base
+
+
 class PredictorLG(nn.Module):
     """models/dyvit.py:91-119.  forward(x, policy) -> log-softmax keep/drop scores [B,P,2]."""
 
@@ -838,7 +848,15 @@ class PredictorLG(nn.Module):
         self.eps = eps
 
     def forward(self, x, policy):
-        h = self.in_conv(x)
+        full = _slice_base(x)
+        if full is not None and _norm_fusable(self.in_conv[0], full) and not self.training:
+            # x is the [:, 1:] view of the contiguous token tensor (models/dyvit.py:232): ATen's layer_norm would copy the
+            # view (fp32), normalise it and cast it for the Linear -- three passes.  LayerNorm, Linear and GELU are per
+            # token, so they run on ALL tokens from one add_layernorm pass (the fused LayerNorm every block uses under
+            # bf16 autocast: one rounding to bf16) and the class row is skipped by the pooling kernel's batch stride.
+            h = self.in_conv[2](self.in_conv[1](norm_lowp(self.in_conv[0], full)))[:, 1:]
+        else:
+            h = self.in_conv(x)
         # under bf16 autocast out_conv's first Linear casts its input to bf16: ask the kernel for that tensor directly
         lowp = (h.is_cuda and h.dtype == torch.bfloat16 and torch.is_autocast_enabled("cuda")
                 and torch.get_autocast_dtype("cuda") == torch.bfloat16 and isinstance(self.out_conv[0], nn.Linear))

@@ -715,11 +715,11 @@ def _dyvit_pool_concat(h: Tensor, policy: Tensor, eps: float) -> Tensor:
     b, p, c = h.shape
     if policy.numel() != b * p:
         raise TokredError("dyvit_pool_concat: policy must be [B,P,1]")
-    h = _c(h)
+    h, hbs = _rows(h)
     pol = _c(policy.float())
     odt = torch.promote_types(h.dtype, policy.dtype)      # the reference's torch.cat promotes (models/dyvit.py:118)
     out = torch.empty((b, p, c), dtype=odt, device=h.device)
-    _lib.call("tokred_dyvit_pool_concat", _ptr(h), _dt(h), _ptr(pol), b, p, c, float(eps), _ptr(out), _dt(out), _stream())
+    _lib.call("tokred_dyvit_pool_concat", _ptr(h), _dt(h), hbs, _ptr(pol), b, p, c, float(eps), _ptr(out), _dt(out), _stream())
     return out
 
 
@@ -734,9 +734,9 @@ def _dyvit_pool_concat_lowp(h: Tensor, policy: Tensor, eps: float) -> Tensor:
     b, p, c = h.shape
     if policy.numel() != b * p or h.dtype != torch.bfloat16:
         raise TokredError("dyvit_pool_concat_lowp: h must be bf16 [B,P,C], policy [B,P,1]")
-    h, pol = _c(h), _c(policy.float())
+    (h, hbs), pol = _rows(h), _c(policy.float())
     out = torch.empty((b, p, c), dtype=torch.bfloat16, device=h.device)
-    _lib.call("tokred_dyvit_pool_concat", _ptr(h), _dt(h), _ptr(pol), b, p, c, float(eps), _ptr(out), _dt(out), _stream())
+    _lib.call("tokred_dyvit_pool_concat", _ptr(h), _dt(h), hbs, _ptr(pol), b, p, c, float(eps), _ptr(out), _dt(out), _stream())
     return out
 
 
