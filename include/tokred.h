@@ -253,12 +253,15 @@ TOKRED_API int tokred_add_layernorm(const float* x, const void* branch, int bran
  * tokred_patchify: image [B,Cin,H,W] fp32 -> out [B,(H/ph)*(W/pw),Cin*ph*pw] bf16 (round-to-nearest-even), row element
  *   (c*ph+py)*pw+px of patch (gy,gx) = img[b,c,gy*ph+py,gx*pw+px]: the operand of the patch-embedding GEMM (the stride-p
  *   convolution with its weight viewed as [C,Cin*ph*pw]); replaces ATen's cast + permuting copy.  pw % 4 == 0.
- * tokred_embed_layernorm: x_out [B,T+P,C] fp32 = cat(tokens [T,C] fp32 (cls[, dist]), patches [B,P,C] bf16) + pos [T+P,C]
- *   and y [B,T+P,C] bf16 = LayerNorm(x_out; gamma, beta, eps) rounded once (blocks[0].norm1 as the qkv Linear consumes it).
- *   C a multiple of 128 up to 1024.                                                                              */
+ * tokred_embed_layernorm: x_out [B,T+P,C] fp32 = cat(tokens, patches [B,P,C] bf16 | fp32) (+ pos [T+P,C] unless NULL)
+ *   and y [B,T+P,C] bf16 = LayerNorm(x_out; gamma, beta, eps) rounded once (the next block's norm1 as its qkv Linear consumes
+ *   it).  tokens [T,C] fp32 shared by the batch (tokens_batch_stride = 0: the cls / dist parameters, forward_features) or
+ *   per image, tokens_batch_stride elements apart (the class rows x[:, :T] of a [B,N,C] stream read in place: the
+ *   re-concatenation after a cluster layer, e.g. models/sinkhorn.py:168, models/dpcknn.py:262).  C a multiple of 128 <= 1024. */
 TOKRED_API int tokred_patchify(const float* img, int B, int Cin, int H, int W, int ph, int pw, void* out, void* stream);
-TOKRED_API int tokred_embed_layernorm(const void* patches, const float* tokens, const float* pos, const float* gamma,
-                           const float* beta, float eps, int B, int P, int T, int C, float* x_out, void* y, void* stream);
+TOKRED_API int tokred_embed_layernorm(const void* patches, int patch_dtype, const float* tokens, int64_t tokens_batch_stride,
+                           const float* pos, const float* gamma, const float* beta, float eps, int B, int P, int T, int C,
+                           float* x_out, void* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1310,3 +1310,22 @@ def test_evit_select_fuse_add(T, b, n, k, c):
     out, idx, compl = T.evit_select_fuse_add(x, br, sc, k)
     out2, idx2, compl2 = T.evit_select_fuse(x + br, sc, k)
     assert torch.equal(idx, idx2) and torch.equal(compl, compl2) and torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("b,n,k,c,pdtype", [(4, 197, 176, 768, torch.bfloat16), (128, 197, 176, 768, torch.bfloat16),
+                                            (5, 197, 49, 384, torch.float32), (256, 50, 12, 384, torch.float32),
+                                            (3, 10, 4, 128, torch.bfloat16)])
+def test_embed_layernorm_concat_after_cluster_layer(T, b, n, k, c, pdtype):
+    """the re-concatenation after a cluster layer (class rows x[:, :1] read in place through their batch stride, merged
+    tokens bf16 or fp32, no positional add) fused with the next norm1: the fp32 stream bit-identical to ATen's
+    cat((global, merged.to(fp32))), the bf16 activations bit-identical to add_layernorm of it."""
+    x_old = torch.randn(b, n, c, generator=g(501)).to(DEV)
+    merged = torch.randn(b, k, c, generator=g(502)).to(pdtype).to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(c, generator=g(503))).to(DEV), (0.1 * torch.randn(c, generator=g(504))).to(DEV)
+    glob = x_old[:, :1]
+    x_ref = torch.cat((glob, merged.to(glob.dtype)), dim=1)
+    x, y = T.embed_layernorm(merged, glob, None, gamma, beta, 1e-6)
+    assert torch.equal(x, x_ref)
+    _, y2 = T.add_layernorm(x_ref, None, gamma, beta, 1e-6)
+    assert torch.equal(y, y2)
+

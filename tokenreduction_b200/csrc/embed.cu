@@ -98,11 +98,14 @@ __device__ __forceinline__ float4 ld4s(const float* p) {
 }
 
 // one warp per token row; V = float4 chunks per lane (C = 128 * V).  The LayerNorm is norm.cu's, operation for operation.
-template <int V>
+// TP: dtype of the patch rows (bf16: GEMM / soft-merge outputs; fp32: merged cluster tokens).  tok_bs: elements between the
+// images' token rows (0: one shared set -- cls / dist parameters; N*C: the class rows x[:, :T] of a [B,N,C] stream, read in
+// place); pos may be null (the re-concatenation after a cluster layer, e.g. models/sinkhorn.py:168, adds nothing).
+template <int V, typename TP>
 __global__ void __launch_bounds__(kThreads)
-embed_layernorm_kernel(const __nv_bfloat16* __restrict__ patches, const float* __restrict__ tokens, const float* __restrict__ pos,
-                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int B, int P, int T,
-                       float* __restrict__ x_out, __nv_bfloat16* __restrict__ y) {
+embed_layernorm_kernel(const TP* __restrict__ patches, const float* __restrict__ tokens, long long tok_bs,
+                       const float* __restrict__ pos, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                       int B, int P, int T, float* __restrict__ x_out, __nv_bfloat16* __restrict__ y) {
   constexpr int C = 128 * V;
   const int lane = threadIdx.x & 31, N = T + P;
   const long long rows = (long long)B * N;
@@ -118,22 +121,28 @@ embed_layernorm_kernel(const __nv_bfloat16* __restrict__ patches, const float* _
     float4 v[V];
     if (t < T) {
 #pragma unroll
-      for (int j = 0; j < V; ++j) v[j] = *reinterpret_cast<const float4*>(tokens + (long long)t * C + (j * 32 + lane) * 4);
+      for (int j = 0; j < V; ++j) v[j] = *reinterpret_cast<const float4*>(tokens + b * tok_bs + (long long)t * C + (j * 32 + lane) * 4);
     } else {
-      const __nv_bfloat16* pr = patches + (b * P + (t - T)) * C;
+      const TP* pr = patches + (b * P + (t - T)) * C;
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(pr + (j * 32 + lane) * 4);
-        v[j].x = __uint_as_float(raw.x << 16); v[j].y = __uint_as_float(raw.x & 0xffff0000u);
-        v[j].z = __uint_as_float(raw.y << 16); v[j].w = __uint_as_float(raw.y & 0xffff0000u);
+        if constexpr (sizeof(TP) == 2) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(pr + (j * 32 + lane) * 4);
+          v[j].x = __uint_as_float(raw.x << 16); v[j].y = __uint_as_float(raw.x & 0xffff0000u);
+          v[j].z = __uint_as_float(raw.y << 16); v[j].w = __uint_as_float(raw.y & 0xffff0000u);
+        } else {
+          v[j] = ld4s(reinterpret_cast<const float*>(pr) + (j * 32 + lane) * 4);
+        }
       }
     }
-    const float* pe = pos + (long long)t * C;
+    const float* pe = pos ? pos + (long long)t * C : nullptr;
     float* xo = x_out + row * C;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const float4 a = *reinterpret_cast<const float4*>(pe + (j * 32 + lane) * 4);
-      v[j].x += a.x; v[j].y += a.y; v[j].z += a.z; v[j].w += a.w;
+      if (pe) {
+        const float4 a = *reinterpret_cast<const float4*>(pe + (j * 32 + lane) * 4);
+        v[j].x += a.x; v[j].y += a.y; v[j].z += a.z; v[j].w += a.w;
+      }
       asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(xo + (j * 32 + lane) * 4), "f"(v[j].x), "f"(v[j].y),
                    "f"(v[j].z), "f"(v[j].w)
                    : "memory");
@@ -185,27 +194,38 @@ extern "C" int tokred_patchify(const float* img, int B, int Cin, int H, int W, i
   return finish_launch(what);
 }
 
-extern "C" int tokred_embed_layernorm(const void* patches, const float* tokens, const float* pos, const float* gamma,
-                                      const float* beta, float eps, int B, int P, int T, int C, float* x_out, void* y,
-                                      void* stream) {
+extern "C" int tokred_embed_layernorm(const void* patches, int patch_dtype, const float* tokens, int64_t tokens_batch_stride,
+                                      const float* pos, const float* gamma, const float* beta, float eps, int B, int P, int T,
+                                      int C, float* x_out, void* y, void* stream) {
   const char* what = "tokred_embed_layernorm";
   if (B == 0) return TOKRED_OK;
-  TOKRED_REQUIRE(patches && tokens && pos && gamma && beta && x_out && y, "%s: null tensor", what);
+  TOKRED_REQUIRE(patches && (tokens || T == 0) && gamma && beta && x_out && y, "%s: null tensor", what);
+  TOKRED_REQUIRE(valid_float_dtype(patch_dtype), "%s: bad patch dtype %d", what, patch_dtype);
+  TOKRED_REQUIRE(tokens_batch_stride >= 0 && tokens_batch_stride % 4 == 0, "%s: tokens_batch_stride=%lld", what,
+                 (long long)tokens_batch_stride);
   TOKRED_REQUIRE(B > 0 && P >= 1 && T >= 0 && C > 0, "%s: bad shape B=%d P=%d T=%d C=%d", what, B, P, T, C);
   if (C % 128 != 0 || C > 1024) {
     set_error("%s: C=%d (needs a multiple of 128 up to 1024)", what, C);
     return TOKRED_ERR_UNSUPPORTED;
   }
   TOKRED_REQUIRE(aligned16(tokens) && aligned16(pos) && aligned16(gamma) && aligned16(beta) && aligned16(x_out) &&
-                     (reinterpret_cast<uintptr_t>(patches) & 7u) == 0 && (reinterpret_cast<uintptr_t>(y) & 7u) == 0,
+                     (reinterpret_cast<uintptr_t>(patches) & (patch_dtype == TOKRED_F32 ? 15u : 7u)) == 0 &&
+                     (reinterpret_cast<uintptr_t>(y) & 7u) == 0,
                  "%s: tensors must be 16-byte aligned", what);
   const long long rows = (long long)B * (T + P);
   const long long want = (rows + kWarps - 1) / kWarps;
   const int grid = (int)(want < (long long)kNumSMs * 8 ? want : (long long)kNumSMs * 8);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(V)                                                                                                       \
-  embed_layernorm_kernel<V><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)patches, tokens, pos, gamma, beta, eps, B, P, T, \
-                                                      x_out, (__nv_bfloat16*)y)
+  do {                                                                                                                  \
+    if (patch_dtype == TOKRED_F32)                                                                                      \
+      embed_layernorm_kernel<V, float><<<grid, kThreads, 0, st>>>((const float*)patches, tokens, (long long)tokens_batch_stride, \
+                                                                  pos, gamma, beta, eps, B, P, T, x_out, (__nv_bfloat16*)y); \
+    else                                                                                                                \
+      embed_layernorm_kernel<V, __nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16*)patches, tokens,          \
+                                                                          (long long)tokens_batch_stride, pos, gamma, beta, \
+                                                                          eps, B, P, T, x_out, (__nv_bfloat16*)y);         \
+  } while (0)
   switch (C / 128) {
     case 1: LAUNCH(1); break;
     case 2: LAUNCH(2); break;

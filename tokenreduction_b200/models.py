@@ -281,7 +281,7 @@ class DPCKNNVisionTransformer(_ClusterLayerViT):
                 global_tokens = x[:, :self.num_tokens]
                 x, idx_token, agg_weight, idx_centers, idx_cluster, cluster_centers = self.cluster_layers[cnt](
                     x[:, self.num_tokens:], idx_token, agg_weight, self.viz_mode)
-                x = torch.cat((global_tokens, x), dim=1)
+                x = M.concat_tokens(global_tokens, x, blk.norm1)
                 cnt += 1
                 if self.viz_mode:
                     decisions[i], assignments[i], centers_feats[i] = _np(idx_centers), _np(idx_cluster), _np(cluster_centers)
@@ -342,7 +342,7 @@ class KMedoidsVisionTransformer(_ClusterLayerViT):
                 x, idx_centers, idx_cluster = self.cluster_layers[cnt](x[:, self.num_tokens:], token_weights)
                 if self.viz_mode:
                     decisions[i], assignments[i], centers_feats[i] = _np(idx_centers), _np(idx_cluster), _np(x)
-                x = torch.cat((global_tokens, x), dim=1)
+                x = M.concat_tokens(global_tokens, x, blk.norm1)
                 cnt += 1
             x, attn = blk(x)
             if self.viz_mode:
@@ -374,7 +374,7 @@ class _SoftClusterViT(_ClusterLayerViT):
                 x = M.value(x)
                 global_tokens = x[:, :self.num_tokens]
                 x, soft_assign = self.cluster_layers[cnt](x[:, self.num_tokens:])
-                x = torch.cat((global_tokens, x.to(global_tokens.dtype)), dim=1)
+                x = M.concat_tokens(global_tokens, x, blk.norm1)
                 if self.viz_mode:
                     assignments[i] = _np(soft_assign)
                     hard_assignment[i] = _np(torch.argmax(soft_assign, dim=-2))

@@ -129,17 +129,19 @@ class Embedded:
     output in one pass (ops.embed_layernorm) instead of cat -> add -> layer_norm -> cast."""
     __slots__ = ("patches", "tokens", "pos")
 
-    def __init__(self, patches: Tensor, tokens: Tensor, pos: Tensor):
-        self.patches, self.tokens, self.pos = patches, tokens, pos        # [B,P,C] bf16, [T,C] fp32, [1,T+P,C] fp32
+    def __init__(self, patches: Tensor, tokens: Tensor, pos: Optional[Tensor]):
+        # [B,P,C] bf16 | fp32; [T,C] fp32 shared or [B,T,C] fp32 per image (the class rows kept aside around a cluster
+        # layer, e.g. models/sinkhorn.py:166-168); [1,T+P,C] fp32 or None
+        self.patches, self.tokens, self.pos = patches, tokens, pos
 
     @property
     def shape(self):
         b, p, c = self.patches.shape
-        return torch.Size((b, p + self.tokens.shape[0], c))
+        return torch.Size((b, p + self.tokens.shape[-2], c))
 
     @property
     def dtype(self):
-        return self.pos.dtype
+        return self.tokens.dtype
 
     @property
     def device(self):
@@ -147,7 +149,9 @@ class Embedded:
 
     def value(self) -> Tensor:
         b = self.patches.shape[0]
-        return torch.cat((self.tokens.unsqueeze(0).expand(b, -1, -1), self.patches), dim=1) + self.pos
+        tok = self.tokens.unsqueeze(0).expand(b, -1, -1) if self.tokens.dim() == 2 else self.tokens
+        x = torch.cat((tok, self.patches.to(tok.dtype)), dim=1)
+        return x if self.pos is None else x + self.pos
 
 
 def value(x):
@@ -179,6 +183,18 @@ def defer_add(x: Tensor, branch: Tensor, norm: nn.Module):
     return x + branch
 
 
+def concat_tokens(tokens: Tensor, x: Tensor, norm_probe: nn.Module):
+    """``torch.cat((global_tokens, x.to(global_tokens.dtype)), dim=1)`` after a cluster layer (models/sinkhorn.py:168,
+    patchmerger.py:119, sit.py:119, dpcknn.py:262, kmedoids.py:249) -- deferred to the next block's norm1 where the fused kernel
+    applies: ATen's cat of the fp32 stream ran at 1.4 TB/s (100 us per stage at B=128 DeiT-B) after a separate bf16 -> fp32
+    conversion of the merged tokens."""
+    if (DEFER_RESIDUAL and x.is_cuda and x.dim() == 3 and x.dtype in (torch.bfloat16, torch.float32)
+            and tokens.dtype == torch.float32 and tokens.dim() == 3 and tokens.shape[0] == x.shape[0]
+            and tokens.shape[2] == x.shape[2] and _norm_fusable(norm_probe, tokens)):
+        return Embedded(x, tokens, None)
+    return torch.cat((tokens, x.to(tokens.dtype)), dim=1)
+
+
 def enter_norm(norm: nn.Module, x) -> Tuple[Tensor, Tensor]:
     """(x, norm(x) as the next autocast Linear consumes it) for a block input that may be a deferred residual sum."""
     if isinstance(x, Residual):
@@ -186,8 +202,8 @@ def enter_norm(norm: nn.Module, x) -> Tuple[Tensor, Tensor]:
             return ops.add_layernorm(x.x, x.branch, norm.weight, norm.bias, norm.eps)
         x = x.value()
     elif isinstance(x, Embedded):
-        if _norm_fusable(norm, x.pos):
-            return ops.embed_layernorm(x.patches, x.tokens, x.pos[0], norm.weight, norm.bias, norm.eps)
+        if _norm_fusable(norm, x.tokens):
+            return ops.embed_layernorm(x.patches, x.tokens, None if x.pos is None else x.pos[0], norm.weight, norm.bias, norm.eps)
         x = x.value()
     return x, norm_lowp(norm, x)
 

@@ -991,16 +991,27 @@ def patchify(img: Tensor, ph: int, pw: int) -> Tensor:
 
 
 @torch.library.custom_op("tokred::embed_layernorm", mutates_args=(), device_types="cuda")
-def _embed_layernorm(patches: Tensor, tokens: Tensor, pos: Tensor, weight: Tensor, bias: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+def _embed_layernorm(patches: Tensor, tokens: Tensor, pos: Optional[Tensor], weight: Tensor, bias: Tensor,
+                     eps: float) -> Tuple[Tensor, Tensor]:
     _need_cuda("embed_layernorm", patches, tokens, pos, weight, bias)
     b, p, c = patches.shape
-    t = tokens.shape[0]
-    if patches.dtype != torch.bfloat16 or tokens.shape != (t, c) or pos.shape != (t + p, c) or weight.numel() != c:
-        raise TokredError(f"embed_layernorm: patches {tuple(patches.shape)} {patches.dtype}, tokens {tuple(tokens.shape)}, "
-                          f"pos {tuple(pos.shape)}")
+    if patches.dtype not in (torch.bfloat16, torch.float32) or weight.numel() != c or tokens.dtype != torch.float32:
+        raise TokredError(f"embed_layernorm: patches {tuple(patches.shape)} {patches.dtype}, tokens {tokens.dtype}")
+    if tokens.dim() == 2:                                  # [T,C]: shared by the batch
+        t, tok, tok_bs = tokens.shape[0], _c(tokens), 0
+    else:                                                  # [B,T,C]: per image, rows dense (e.g. the x[:, :T] view)
+        t = tokens.shape[1]
+        if tokens.shape[0] != b or tokens.shape[2] != c:
+            raise TokredError(f"embed_layernorm: tokens {tuple(tokens.shape)} do not match patches {tuple(patches.shape)}")
+        if not (tokens.stride(2) == 1 and (t == 1 or tokens.stride(1) == c) and tokens.stride(0) % 4 == 0 and tokens.stride(0) >= t * c):
+            tokens = tokens.contiguous()
+        tok, tok_bs = tokens, (int(tokens.stride(0)) if b > 1 else t * c)
+    if tok.shape[-1] != c or (pos is not None and tuple(pos.shape) != (t + p, c)):
+        raise TokredError(f"embed_layernorm: tokens {tuple(tokens.shape)} / pos do not match patches {tuple(patches.shape)}")
+    patches = _c(patches)
     x_out = torch.empty((b, t + p, c), dtype=torch.float32, device=patches.device)
     y = torch.empty((b, t + p, c), dtype=torch.bfloat16, device=patches.device)
-    _lib.call("tokred_embed_layernorm", _ptr(_c(patches)), _ptr(_c(tokens.float())), _ptr(_c(pos.float())),
+    _lib.call("tokred_embed_layernorm", _ptr(patches), _dt(patches), _ptr(tok), tok_bs, _ptr(_c(pos.float())) if pos is not None else None,
               _ptr(_c(weight.float())), _ptr(_c(bias.float())), float(eps), b, p, t, c, _ptr(x_out), _ptr(y), _stream())
     return x_out, y
 
@@ -1008,13 +1019,15 @@ def _embed_layernorm(patches: Tensor, tokens: Tensor, pos: Tensor, weight: Tenso
 @_embed_layernorm.register_fake
 def _(patches, tokens, pos, weight, bias, eps):
     b, p, c = patches.shape
-    t = tokens.shape[0]
-    return patches.new_empty((b, t + p, c), dtype=torch.float32), patches.new_empty((b, t + p, c))
+    t = tokens.shape[-2]
+    return (patches.new_empty((b, t + p, c), dtype=torch.float32), patches.new_empty((b, t + p, c), dtype=torch.bfloat16))
 
 
-def embed_layernorm(patches: Tensor, tokens: Tensor, pos: Tensor, weight: Tensor, bias: Tensor, eps: float):
-    """(x, y): x = cat(tokens, patches) + pos (fp32), y = LayerNorm(x) rounded to bf16 -- the cat, the positional add, the
-    first block's norm1 and its autocast cast in one pass (models/deit_viz.py forward_features)."""
+def embed_layernorm(patches: Tensor, tokens: Tensor, pos: Optional[Tensor], weight: Tensor, bias: Tensor, eps: float):
+    """(x, y): x = cat(tokens, patches) (+ pos) in fp32, y = LayerNorm(x) rounded to bf16 -- the cat, the positional add, the
+    next norm1 and its autocast cast in one pass.  tokens [T,C] (the cls / dist parameters: models/deit_viz.py
+    forward_features) or [B,T,C] (the class rows kept aside around a cluster layer, e.g. models/sinkhorn.py:166-168; the
+    x[:, :T] view is read in place); patches bf16 or fp32; pos [T+P,C] or None."""
     return torch.ops.tokred.embed_layernorm(patches, tokens, pos, weight, bias, eps)
 
 
