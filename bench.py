@@ -195,6 +195,8 @@ def algorithmic_bytes(name: str, a: tuple) -> float:
     if name == "tokred_evit_select_fuse_add":
         n, c, k = g["N"], g["C"], g["k"]
         return g["B"] * ((n - 1) * esz(g["score_dtype"]) + n * c * (4 + 2) + (k + 2) * c * 4 + 8 * (k + 1) + 8 * (n - 1 - k))
+    if name == "tokred_residual_add":
+        return g["n"] * (4 + 2 + 4)
     if name == "tokred_patchify":
         return g["B"] * g["Cin"] * g["H"] * g["W"] * (4 + 2)
     if name == "tokred_embed_layernorm":

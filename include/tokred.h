@@ -249,6 +249,10 @@ TOKRED_API int tokred_attention(const void* qkv, int B, int N, int H, int head_d
 TOKRED_API int tokred_add_layernorm(const float* x, const void* branch, int branch_dtype, const float* gamma, const float* beta,
                          float eps, int64_t rows, int C, float* x_out, void* y, void* stream);
 
+/* out[i] = x[i] + float(branch[i]), i < n (n % 4 == 0): the fp32 residual sum alone, for a consumer that is not a LayerNorm
+ * (x fp32, branch bf16; the same fp32 addition as ATen's mixed-dtype add, e.g. models/dpcknn.py:258 reading x after :104).  */
+TOKRED_API int tokred_residual_add(const float* x, const void* branch, int64_t n, float* out, void* stream);
+
 /* ---- the data formats in front of the first block (bf16 autocast; models/deit_viz.py PatchEmbed + forward_features) ----
  * tokred_patchify: image [B,Cin,H,W] fp32 -> out [B,(H/ph)*(W/pw),Cin*ph*pw] bf16 (round-to-nearest-even), row element
  *   (c*ph+py)*pw+px of patch (gy,gx) = img[b,c,gy*ph+py,gx*pw+px]: the operand of the patch-embedding GEMM (the stride-p

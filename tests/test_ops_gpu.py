@@ -1329,3 +1329,12 @@ def test_embed_layernorm_concat_after_cluster_layer(T, b, n, k, c, pdtype):
     _, y2 = T.add_layernorm(x_ref, None, gamma, beta, 1e-6)
     assert torch.equal(y, y2)
 
+
+@pytest.mark.parametrize("shape", [(256, 197, 384), (5, 50, 768), (3, 7, 4), (1, 1, 12)])
+def test_residual_add(T, shape):
+    """the deferred residual sum when something other than a LayerNorm reads it: bit-identical to ATen's fp32 + bf16 add."""
+    x = torch.randn(*shape, generator=g(601)).to(DEV)
+    br = torch.randn(*shape, generator=g(602)).to(torch.bfloat16).to(DEV)
+    assert torch.equal(T.residual_add(x, br), x + br)
+    assert torch.equal(T.residual_add(x, br.float()), x + br.float())          # other dtypes: ATen
+

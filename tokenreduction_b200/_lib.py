@@ -42,6 +42,7 @@ SIGNATURES = {
     "tokred_add_layernorm": [_P, _P, c_int, _P, _P, c_float, c_int64, c_int, _P, _P, _P],
     "tokred_patchify": [_P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "tokred_embed_layernorm": [_P, c_int, _P, c_int64, _P, _P, _P, c_float, c_int, c_int, c_int, c_int, _P, _P, _P],
+    "tokred_residual_add": [_P, _P, c_int64, _P, _P],
     "tokred_attention": [_P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, c_int64, c_int, _P, _P, _P, _P],
 }
 EXPORTS = ["tokred_abi_version", "tokred_last_error", "tokred_launch_count", *SIGNATURES]

@@ -85,10 +85,54 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_kernel(const float* __
   }
 }
 
+// x + branch alone (fp32 stream, bf16 branch): what a consumer other than a LayerNorm reads when a block's residual sum was
+// deferred (modules.value(): the slices in front of a cluster layer, the DynamicViT predictor).  ATen's mixed-dtype add runs
+// its unrolled, non-vectorised kernel at ~3.3 TB/s; this is the same fp32 addition with 16-byte accesses.
+__global__ void __launch_bounds__(kThreads) residual_add_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ branch,
+                                                                 long long n4, float* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x; i0 < n4; i0 += 4 * stride) {
+    float4 v[4];
+    uint2 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        v[u] = ld4(x + i * 4);
+        r[u] = *reinterpret_cast<const uint2*>(branch + i * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        v[u].x += __uint_as_float(r[u].x << 16); v[u].y += __uint_as_float(r[u].x & 0xffff0000u);
+        v[u].z += __uint_as_float(r[u].y << 16); v[u].w += __uint_as_float(r[u].y & 0xffff0000u);
+        st4(out + i * 4, v[u]);
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace tokred
 
 using namespace tokred;
+
+extern "C" int tokred_residual_add(const float* x, const void* branch, int64_t n, float* out, void* stream) {
+  const char* what = "tokred_residual_add";
+  if (n == 0) return TOKRED_OK;
+  TOKRED_REQUIRE(x && branch && out, "%s: null tensor", what);
+  TOKRED_REQUIRE(n > 0, "%s: n=%lld", what, (long long)n);
+  if (n % 4 != 0 || !aligned16(x) || !aligned16(out) || (reinterpret_cast<uintptr_t>(branch) & 7u)) {
+    set_error("%s: needs a multiple of 4 elements and 16-byte aligned tensors", what);
+    return TOKRED_ERR_UNSUPPORTED;
+  }
+  const long long n4 = n / 4, want = (n4 + 4LL * kThreads - 1) / (4LL * kThreads);
+  const int grid = (int)(want < (long long)kNumSMs * 8 ? want : (long long)kNumSMs * 8);
+  residual_add_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)branch, n4, out);
+  return finish_launch(what);
+}
 
 extern "C" int tokred_add_layernorm(const float* x, const void* branch, int branch_dtype, const float* gamma, const float* beta,
                                     float eps, int64_t rows, int C, float* x_out, void* y, void* stream) {

@@ -120,7 +120,7 @@ class Residual:
         return self.x.shape
 
     def value(self) -> Tensor:
-        return self.x + self.branch
+        return ops.residual_add(self.x, self.branch)
 
 
 class Embedded:

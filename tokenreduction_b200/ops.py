@@ -1031,6 +1031,31 @@ def embed_layernorm(patches: Tensor, tokens: Tensor, pos: Optional[Tensor], weig
     return torch.ops.tokred.embed_layernorm(patches, tokens, pos, weight, bias, eps)
 
 
+@torch.library.custom_op("tokred::residual_add", mutates_args=(), device_types="cuda")
+def _residual_add(x: Tensor, branch: Tensor) -> Tensor:
+    _need_cuda("residual_add", x, branch)
+    if x.dtype != torch.float32 or branch.dtype != torch.bfloat16 or branch.shape != x.shape or x.numel() % 4 != 0:
+        raise TokredError(f"residual_add: x {tuple(x.shape)} {x.dtype}, branch {tuple(branch.shape)} {branch.dtype}")
+    x, branch = _c(x), _c(branch)
+    out = torch.empty_like(x)
+    _lib.call("tokred_residual_add", _ptr(x), _ptr(branch), x.numel(), _ptr(out), _stream())
+    return out
+
+
+@_residual_add.register_fake
+def _(x, branch):
+    return torch.empty_like(x)
+
+
+def residual_add(x: Tensor, branch: Tensor) -> Tensor:
+    """``x + branch`` for an fp32 stream and a bf16 branch (the same fp32 addition as ATen's mixed-dtype add, with 16-byte
+    accesses); anything else falls back to ATen."""
+    if (x.is_cuda and x.dtype == torch.float32 and branch.dtype == torch.bfloat16 and branch.shape == x.shape
+            and x.numel() % 4 == 0 and x.numel() > 0 and not (torch.is_grad_enabled() and (x.requires_grad or branch.requires_grad))):
+        return torch.ops.tokred.residual_add(x, branch)
+    return x + branch
+
+
 # ----------------------------------------------------------------------------------------------- f4: autograd formulas
 # SURVEY §8f row 4.  The reference fine-tunes its reduced models with the reduction operators inside the autograd graph
 # (train.py; the discrete selections themselves carry no gradient: topk / argsort / argmax indices).  The forward of
