@@ -450,3 +450,22 @@ def test_equal_weight_models_run(name, amp):
     assert torch.equal(a, b)
     if name == "kmedoids":
         assert not torch.equal(a, c)
+
+
+def test_standalone_block_returns_tensors():
+    """the drop-in blocks keep the reference's return types when called on their own: residual sums are deferred only inside the
+    block loops of this package's models (which set ``defer_out`` on their blocks and materialise on every other read)."""
+    from tokenreduction_b200 import modules as M
+    torch.manual_seed(0)
+    x = torch.randn(4, 197, 384, device="cuda")
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for blk in (M.Block_ToMe(384, 6, qkv_bias=True, r=59), M.Block_TopK(384, 6, qkv_bias=True, keep_rate=0.7),
+                    M.Block_EVIT(384, 6, qkv_bias=True, keep_rate=0.7), M.BlockWithProbs(384, 6, qkv_bias=True)):
+            blk = blk.eval().cuda()
+            out = blk(x)
+            first = out[0] if isinstance(out, tuple) else out
+            assert isinstance(first, torch.Tensor) and first.dtype == torch.float32 and bool(torch.isfinite(first).all())
+            blk.defer_out = True                      # what a model of this package sets on the blocks of its loop
+            out2 = blk(x)
+            first2 = out2[0] if isinstance(out2, tuple) else out2
+            assert isinstance(first2, M.Residual) and torch.equal(first2.value(), first)

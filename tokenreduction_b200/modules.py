@@ -175,10 +175,13 @@ def cls_value(x) -> Tensor:
     return value(x)[:, 0]
 
 
-def defer_add(x: Tensor, branch: Tensor, norm: nn.Module):
+def defer_add(x: Tensor, branch: Tensor, norm: nn.Module, owner: Optional[nn.Module] = None):
     """``x + branch`` -- deferred to the next block's norm1 where that block can fuse it (``norm``: a LayerNorm of the
-    stream's width, used as the probe for the fused kernel's conditions)."""
-    if DEFER_RESIDUAL and _norm_fusable(norm, x) and branch.shape == x.shape and branch.is_cuda:
+    stream's width, used as the probe for the fused kernel's conditions).  Only a block whose ``defer_out`` flag was set by
+    the model that owns the block loop (VisionTransformer.embed_tokens) defers: a block called on its own returns a plain
+    tensor, like the reference's."""
+    if (DEFER_RESIDUAL and getattr(owner, "defer_out", False) and _norm_fusable(norm, x) and branch.shape == x.shape
+            and branch.is_cuda):
         return Residual(x, branch)
     return x + branch
 
@@ -303,7 +306,7 @@ class Block_TopK(nn.Module):
             y = norm_lowp(self.norm2, x)
         else:
             x, y = add_norm(x, self.drop_path(tmp), self.norm2)
-        x = defer_add(x, self.drop_path(self.mlp(y)), self.norm1)
+        x = defer_add(x, self.drop_path(self.mlp(y)), self.norm1, self)
         return x, x.shape[1] - 1, idx
 
 
@@ -348,7 +351,7 @@ class Block_EVIT(nn.Module):
             y = norm_lowp(self.norm2, x)
         else:
             x, y = add_norm(x, self.drop_path(tmp), self.norm2)
-        x = defer_add(x, self.drop_path(self.mlp(y)), self.norm1)
+        x = defer_add(x, self.drop_path(self.mlp(y)), self.norm1, self)
         return x, x.shape[1] - 1, idx, compl
 
 
@@ -518,7 +521,7 @@ class Block_ToMe(nn.Module):
         reduced_cluster_idx = None
         if self.r <= 0:
             x, y = add_norm(x, self.drop_path(x_attn), self.norm2)
-            return defer_add(x, self.drop_path(self.mlp(y)), self.norm1), attn_size, reduced_cluster_idx
+            return defer_add(x, self.drop_path(self.mlp(y)), self.norm1, self), attn_size, reduced_cluster_idx
         if self.r > 0:
             _train_guard(self, True)
             re = ops.tome_effective_r(x.shape[1], self.r, self.cls_token, self.dist_token)
@@ -531,7 +534,7 @@ class Block_ToMe(nn.Module):
                     # LayerNorm ride on the row the merge already holds in registers
                     x, attn_size, reduced_cluster_idx, y = ops.tome_merge_ln(
                         x, branch, attn_size, unm, src, dst, self.norm2.weight, self.norm2.bias, self.norm2.eps, True)
-                    return defer_add(x, self.drop_path(self.mlp(y)), self.norm1), attn_size, reduced_cluster_idx
+                    return defer_add(x, self.drop_path(self.mlp(y)), self.norm1, self), attn_size, reduced_cluster_idx
                 x, attn_size, reduced_cluster_idx = ops.tome_merge(x + branch, attn_size, unm, src, dst, True, True)
                 metric = None
                 x_attn = None
@@ -555,7 +558,7 @@ class Block_ToMe(nn.Module):
                 merge, _ = bipartite_soft_matching(metric, self.r, self.cls_token, self.dist_token)
                 reduced_cluster_idx = _reduced_cluster_idx(merge_source(merge, x, None), self.cls_token)
                 x, attn_size = merge_wavg(merge, x, attn_size)
-        x = defer_add(x, self.drop_path(self.mlp(norm_lowp(self.norm2, x))), self.norm1)
+        x = defer_add(x, self.drop_path(self.mlp(norm_lowp(self.norm2, x))), self.norm1, self)
         return x, attn_size, reduced_cluster_idx
 
 
@@ -665,7 +668,7 @@ class BlockWithProbs(nn.Module):
         x, y = enter_norm(self.norm1, x)
         x_attn, attn = self.attn(y)
         x, y = add_norm(x, self.drop_path(x_attn), self.norm2)
-        x = defer_add(x, self.drop_path(self.mlp(y)), self.norm1)
+        x = defer_add(x, self.drop_path(self.mlp(y)), self.norm1, self)
         return x, attn
 
 
@@ -827,7 +830,7 @@ class ATSBlock(nn.Module):
         if sample_ids is not None:
             x = ops.gather_rows(x, sample_ids)
         x, y = add_norm(x, self.drop_path1(x_tmp), self.norm2)
-        x = defer_add(x, self.drop_path2(self.mlp(y)), self.norm1)
+        x = defer_add(x, self.drop_path2(self.mlp(y)), self.norm1, self)
         return x, mask, sample_ids
 
 
@@ -925,4 +928,4 @@ class Block_DyVIT(nn.Module):
     def forward(self, x, policy=None):
         x, y = enter_norm(self.norm1, x)
         x, y = add_norm(x, self.drop_path(self.attn(y, policy=policy)), self.norm2)
-        return defer_add(x, self.drop_path(self.mlp(y)), self.norm1)
+        return defer_add(x, self.drop_path(self.mlp(y)), self.norm1, self)

@@ -167,7 +167,7 @@ class Block(nn.Module):
         from . import modules
         x, y = modules.enter_norm(self.norm1, x)       # x may be the previous block's deferred residual sum
         x, y = modules.add_norm(x, self.drop_path(self.attn(y)), self.norm2)
-        return modules.defer_add(x, self.drop_path(self.mlp(y)), self.norm1)
+        return modules.defer_add(x, self.drop_path(self.mlp(y)), self.norm1, self)
 
 
 def _init_vit_weights(module: nn.Module, name: str = "", head_bias: float = 0.0, jax_impl: bool = False):
@@ -292,6 +292,12 @@ class VisionTransformer(nn.Module):
         """cat(cls [, dist], patches) + pos_embed -- handed to the first block unformed where its norm1 can fuse it
         (modules.Embedded)."""
         from . import modules
+        if not getattr(self, "_defer_flags_set", False):
+            # the models of this package own their block loops and materialise a deferred sum wherever something other than
+            # the next block reads it (modules.value): their blocks may hand residual sums over un-added
+            for blk in self.blocks:
+                blk.defer_out = True
+            self._defer_flags_set = True
         if x.dim() == 3 and not (self.training and self.pos_drop.p > 0) and len(self.blocks) > 0 and hasattr(self.blocks[0], "norm1"):
             tokens = self.cls_token[0] if self.dist_token is None else torch.cat((self.cls_token[0], self.dist_token[0]), dim=0)
             return modules.embed_tokens(x, tokens, self.pos_embed, self.blocks[0].norm1)
