@@ -504,6 +504,8 @@ static int launch_topk_gather(const char* what, const void* x, int x_dtype, cons
   if (int e = check_scores(scores, score_dtype, attn, attn_dtype, H, what)) return e;
   if (B == 0) return TOKRED_OK;
   const int P = N - 1, row_bytes = C * dtype_size(x_dtype);
+  TOKRED_REQUIRE((long long)N * row_bytes <= 0x7fffffffLL, "%s: an image of %d x %d bytes exceeds 2 GB (32-bit row offsets)", what, N,
+                 row_bytes);
   const int vec16 = (row_bytes % 16 == 0) && aligned16(x) && aligned16(x_out);
   const size_t smem = (size_t)(P + k) * 4;
   if (int e = allow_smem(topk_gather_kernel<true>, smem, what)) return e;
@@ -554,6 +556,8 @@ static int launch_evit_select_fuse(const char* what, const void* x, int x_dtype,
   if (int e = check_scores(scores, score_dtype, attn, attn_dtype, H, what)) return e;
   if (B == 0) return TOKRED_OK;
   const int P = N - 1, esz = dtype_size(x_dtype), row_bytes = C * esz;
+  TOKRED_REQUIRE((long long)N * row_bytes <= 0x7fffffffLL, "%s: an image of %d x %d bytes exceeds 2 GB (32-bit row offsets)", what, N,
+                 row_bytes);
   const int vec16 = (row_bytes % 16 == 0) && aligned16(x) && aligned16(x_out);
   const int slice = 1024 / esz;
   const int splits = ceil_div(C, slice);
@@ -607,7 +611,9 @@ extern "C" int tokred_gather_rows(const void* src, int dtype, const int64_t* ids
   const long long rows = (long long)B * G * M;
   if (rows == 0) return TOKRED_OK;
   const int row_bytes = W * dtype_size(dtype);
-  const int vec16 = (row_bytes % 16 == 0) && aligned16(src) && aligned16(out);
+  // the 16-byte path addresses the four rows of a group by 32-bit offsets from the first (at most four (b, g) slices apart)
+  const int vec16 = (row_bytes % 16 == 0) && aligned16(src) && aligned16(out) && 5LL * N * row_bytes <= 0x7fffffffLL &&
+                    4LL * row_bytes <= 0x7fffffffLL;
   long long blocks = (rows + 4 * kWarps - 1) / (4 * kWarps);
   if (blocks > 32LL * kNumSMs) blocks = 32LL * kNumSMs;
   if (vec16)
