@@ -1,6 +1,7 @@
-"""diagnostic: where does the tcgen05 bf16 matching differ from the oracle on 'decidable' images?"""
+"""diagnostic (test infrastructure: it uses the oracle, so it lives under tests/; not collected by pytest): where does the
+tcgen05 bf16 matching differ from the oracle on decidable images?"""
 import sys, os, math, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import ops as O
 import margins as MG
