@@ -397,23 +397,31 @@ class Runner:
         from tokenreduction_b200.graph import GraphedForward
         g = self.graphs.get(buf.data_ptr())
         if g is None:
-            g = GraphedForward(self.model, buf, torch.bfloat16 if self.amp else None, static_input=buf)
+            g = GraphedForward(self._step, buf, torch.bfloat16 if self.amp else None, static_input=buf)
             self.graphs[buf.data_ptr()] = g
         return g
+
+    def _step(self, x):
+        """the forward as it is captured into the CUDA graph.  world > 1: the model runs in viz mode and the shard's logits
+        (fp32 bit patterns) and kept / assignment indices are packed into ONE int32 tensor [B, 1000 + index columns] inside
+        the same graph, so the only work outside it is the all_gather."""
+        out = self.model(x)
+        if self.world == 1:
+            return out.float()
+        y, viz = out
+        y = y.float()
+        return y, pack_decisions(viz, y)
 
     def forward(self, x, graph=False):
         if graph:
             out = self.graphed(x)(x)
         else:
             with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
-                out = self.model(x)
+                out = self._step(x)
         if self.world == 1:
-            return out.float()
-        y, viz = out
-        y = y.float()
-        # the path's only exchange: logits and kept / assignment indices of every shard, packed into ONE int32 tensor
-        # [B, 1000 + index columns] (the logits as their fp32 bit patterns) -> one all_gather per step (KBs-MBs)
-        dec = pack_decisions(viz, y)
+            return out
+        y, dec = out
+        # the path's only exchange: one all_gather per step of the packed tensor (KBs-MBs)
         if self.g_dec is None or self.g_dec.shape[1] != dec.shape[1]:
             self.g_dec = torch.empty(self.world * dec.shape[0], dec.shape[1], dtype=torch.int32, device=self.dev)
             self.dec_cols = dec.shape[1] - y.shape[1]
