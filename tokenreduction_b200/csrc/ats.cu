@@ -137,19 +137,39 @@ ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long
   for (int q = tid; q < n_steps; q += kThreads) {
     const float t = steps[q];
     const float m2t = -2.0f * t, tt = __fmul_rn(t, t);
-    float best = CUDART_INF_F;
     int bp = 0;
-    for (int p = 0; p < P; ++p) {
-      const float c = cdf[p];
-      float d;
-      if (use_mm) {
-        // ATen cdist matmul expansion on 1-d points: ((-2t)*c + t^2) + c^2, clamp, sqrt
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(m2t, c), tt), __fmul_rn(c, c));
-        d = sqrtf(fmaxf(d2, 1e-30f));
-      } else {
-        d = fabsf(t - c);
+    if (use_mm) {
+      // ATen cdist matmul expansion on 1-d points: d = sqrt(max(((-2t)*c + t^2) + c^2, 1e-30)); argmin with the lowest
+      // index on ties.  sqrtf is monotone, so the winners are exactly the entries whose radicand lies in [xmin, X], X the
+      // largest float with sqrtf(X) == sqrtf(xmin) (at most three floats share a square root): one pass for xmin, a few
+      // ulp steps for X, one pass for the first index -- the same index as the sqrt-per-entry loop (IEEE sqrtf with its
+      // slow-path branches was a third of the kernel's stall samples) without a square root per entry.
+      float xmin = CUDART_INF_F;
+#pragma unroll 4
+      for (int p = 0; p < P; ++p) {
+        const float c = cdf[p];
+        xmin = fminf(xmin, fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(m2t, c), tt), __fmul_rn(c, c)), 1e-30f));
       }
-      if (d < best) { best = d; bp = p; }
+      const float dmin = sqrtf(xmin);
+      float X = xmin;
+      for (int s = 0; s < 8; ++s) {
+        const float nx = __uint_as_float(__float_as_uint(X) + 1u);          // next float up (X > 0, finite)
+        if (!(sqrtf(nx) == dmin)) break;
+        X = nx;
+      }
+      bp = P;
+      for (int p = P - 1; p >= 0; --p) {
+        const float c = cdf[p];
+        const float x = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(m2t, c), tt), __fmul_rn(c, c)), 1e-30f);
+        bp = x <= X ? p : bp;
+      }
+      bp = (bp == P || !(xmin < CUDART_INF_F)) ? 0 : bp;                    // nothing below +inf: the strict "<" loop keeps index 0
+    } else {
+      float best = CUDART_INF_F;
+      for (int p = 0; p < P; ++p) {
+        const float d = fabsf(t - cdf[p]);
+        if (d < best) { best = d; bp = p; }
+      }
     }
     hit[1 + bp] = 1;
   }
