@@ -518,6 +518,30 @@ class Runner:
         return res
 
 
+def bind_to_gpu_numa_node(dev):
+    """Multi-GPU end-to-end path: every rank streams its 154 MB batch from pinned host memory each step.  Pinned pages are
+    placed on the NUMA node of the thread that first touches them, so the rank is bound to the CPUs NVML reports as local to
+    its GPU BEFORE it allocates the pinned batch -- otherwise about half of the eight copies cross the socket interconnect.
+    Returns the CPU count bound to, or None (no NVML / TOKRED_BENCH_NO_AFFINITY=1 / any error: the default placement stays)."""
+    if os.environ.get("TOKRED_BENCH_NO_AFFINITY") == "1" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = {i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1} & allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 def run_tokred(a):
     import torch.distributed as dist
     from tokenreduction_b200 import _lib
@@ -529,6 +553,7 @@ def run_tokred(a):
         raise SystemExit("bench.py: no CUDA device; the tokred kernels have no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(dev) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -617,6 +642,8 @@ def run_tokred(a):
                        "execution": "eager (one Python-issued launch per kernel)" if a.no_graph else
                                     "one CUDA graph replay per step (tokenreduction_b200.graph.GraphedForward); the per-kernel "
                                     "timeline is a separate untimed eager pass",
+                       "host_affinity": (f"rank bound to the {affinity} CPUs NVML reports local to its GPU before the pinned batch is "
+                                         "allocated (first-touch NUMA placement)") if affinity else "default",
                        "exchange": "none (1 GPU)" if world == 1 else
                                    f"per step: ONE NCCL all_gather of logits [B,1000] f32 + kept/assignment indices [B,{dec_cols}] i32 (packed)",
                        "e2e_pipeline": "per step: H2D of the batch (pinned, copy stream, 2 device buffers; overlaps the "
