@@ -175,28 +175,39 @@ ats_sample_kernel(const TV* __restrict__ v, long long vs_b, long long vs_h, long
   }
   __syncthreads();
 
-  // sorted unique ids by compaction
+  // sorted unique ids by ballot compaction: position = hits in earlier chunks + earlier warps + lower lanes (the first
+  // version counted with one thread and ranked every hit by a scan over all earlier flags)
   const int W = n_steps + 1;
   int64_t* ids_b = ids_out + (long long)b * W;
   uint8_t* m_b = mask_out + (long long)b * W;
-  if (tid == 0) {
-    int c = 0;
-    for (int t = 1; t < N; ++t) c += hit[t];
-    *count_s = c;
-    atomicMax(max_count, c);
-    ids_b[0] = 0;
-    m_b[0] = 1;
-  }
-  for (int t = 1 + tid; t < N; t += kThreads) {
-    if (hit[t]) {
-      int pos = 0;
-      for (int q = 1; q < t; ++q) pos += hit[q];
+  int* wcnt = count_s + 1;                             // [kWarps]
+  int base = 0;
+  for (int t0 = 1; t0 < N; t0 += kThreads) {
+    const int t = t0 + tid;
+    const bool h = t < N && hit[t] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, h);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int pos = base + __popc(bal & ((1u << lane) - 1u)), tot = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const int c = wcnt[w];
+      pos += w < warp ? c : 0;
+      tot += c;
+    }
+    if (h) {
       ids_b[1 + pos] = t;
       m_b[1 + pos] = 1;
     }
+    base += tot;
+    __syncthreads();
   }
-  __syncthreads();
-  const int cnt = *count_s;
+  const int cnt = base;
+  if (tid == 0) {
+    atomicMax(max_count, cnt);
+    ids_b[0] = 0;
+    m_b[0] = 1;
+  }
   for (int j = 1 + cnt + tid; j < W; j += kThreads) { ids_b[j] = 0; m_b[j] = 0; }
 }
 
@@ -223,7 +234,7 @@ extern "C" int tokred_ats_sample(const void* v, int v_dtype, int64_t v_stride_b,
   const long long ahs = attn_head_stride > 0 ? attn_head_stride : (long long)N * N;
   TOKRED_REQUIRE(ahs >= N, "%s: attn_head_stride %lld < N", what, ahs);
   const int P = N - 1;
-  const size_t smem = ((size_t)H * P + P + kWarps + N + 1) * 4;
+  const size_t smem = ((size_t)H * P + P + kWarps + N + 1 + kWarps) * 4;
   const int use_mm = (n_steps > 25 || P > 25) ? 1 : 0;     // ATen: matmul expansion when either side has > 25 points
   cudaStream_t st = (cudaStream_t)stream;
   if (v_dtype == TOKRED_F32) {
