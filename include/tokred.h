@@ -28,7 +28,9 @@
 extern "C" {
 #endif
 
-#define TOKRED_ABI_VERSION 3   /* 2: x_batch_stride on a6-a9, a12, a13; 3: tokred_attention (f1) */
+#define TOKRED_ABI_VERSION 4   /* 2: x_batch_stride on a6-a9, a12, a13; 3: tokred_attention (f1); 4: h_batch_stride on
+                                   tokred_dyvit_pool_concat, the fused / deferred entry points (tome_merge_ln, *_add, patchify,
+                                   embed_layernorm, residual_add, kmedoids_fit_init) */
 #define TOKRED_API __attribute__((visibility("default")))
 
 enum { TOKRED_F32 = 0, TOKRED_BF16 = 1 };
